@@ -1,0 +1,128 @@
+/*
+ * upsnet_b200.h -- C ABI of libupsnet_b200.so: hand-written sm_100a CUDA for the UPSNet
+ * per-image inference hot path.  Plain pointers and sizes only; no
+ * torch types.  Every entry point
+ *   - takes DEVICE pointers unless the name ends in _host,
+ *   - enqueues on `stream` (a cudaStream_t passed as void*) and does not synchronise,
+ *   - never allocates (caller-owned outputs and workspaces; sizes from *_workspace_bytes),
+ *   - is re-entrant (no global state) and returns 0 on success, a positive cudaError_t
+ *     value on a CUDA failure, or a negative UPSNET_E_* code on an argument error.
+ * Paths in "replaces:" comments are relative to /root/reference/upsnet/.
+ */
+#ifndef UPSNET_B200_H_
+#define UPSNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPSNET_E_BADARG (-1)
+#define UPSNET_E_UNSUPPORTED (-2)
+#define UPSNET_E_WORKSPACE (-3)
+
+#define UPSNET_LAYOUT_NCHW 0
+#define UPSNET_LAYOUT_NHWC 1
+
+/* epilogue flags for the convolution entry points */
+#define UPSNET_EPI_RELU 1
+
+/* precision of the tensor-core convolution path */
+#define UPSNET_PREC_FP32_SIMT 0 /* fp32 FFMA tiles (exact-order-free fp32)            */
+#define UPSNET_PREC_BF16X3 1    /* tcgen05 kind::f16, 3-term bf16 split (~fp32 result) */
+#define UPSNET_PREC_BF16 2      /* tcgen05 kind::f16, single bf16 pass                 */
+
+/* library / build identification: returns e.g. 100 for sm_100a, fills `n_sm` if non-NULL */
+int upsnet_version(int *n_sm);
+
+/* ---------------------------------------------------------------------------------------
+ * ROIAlign forward (sampling grid sr x sr, no half-pixel shift).
+ * replaces: operators/src/roi_align_cuda.cpp:39-75 roi_align_forward_cuda
+ *           -> operators/src/roi_align_kernel.cu:351 roi_align_forward_gpu_kernel_launcher
+ * feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC) fp32; rois [R,5] = (batch,x1,y1,x2,y2);
+ * out [R,C,PH,PW] (NCHW) or [R,PH,PW,C] (NHWC) -- same layout flag as feat.
+ */
+int upsnet_roi_align_forward(const float *feat, int B, int C, int H, int W, int layout,
+                             const float *rois, int R, int PH, int PW, int sampling_ratio,
+                             float spatial_scale, float *out, void *stream);
+
+/* FPN ROIAlign: level assignment + 4 pyramid levels + un-permute in ONE launch.
+ * replaces: operators/modules/fpn_roi_align.py:32-62 FPNRoIAlign.forward (host bucketing,
+ *           4 launches, cat, index_select).  feats[l] has spatial size (Hs[l],Ws[l]) and
+ *           scale scales[l]; level(roi) = clip(floor(2+log2(sqrt(w*h)/224+1e-6)),0,3).
+ * levels_out (optional, may be NULL): int32 [R] chosen level per roi. */
+int upsnet_roi_align_fpn_forward(const float *const feats[4], const int Hs[4], const int Ws[4],
+                                 const float scales[4], int B, int C, int layout,
+                                 const float *rois, int R, int PH, int PW, int sampling_ratio,
+                                 float *out, int *levels_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * NMS (IoU with the legacy +1 box area, suppress when IoU > thresh).
+ * replaces: nms/gpu_nms.hpp:14 _nms  (nms/nms_kernel.cu:40-84 nms_kernel + :97-150 host sweep)
+ *
+ * Device-resident, segmented: S independent problems in one launch pair.  boxes [total,4]
+ * fp32 (x1,y1,x2,y2), already sorted by descending score inside each segment;
+ * seg_offsets int32 [S+1] on the DEVICE; max_seg_len = host-known upper bound of a segment
+ * length (<= 65536).  keep_out int32 [S, max_seg_len]: positions (relative to the segment
+ * start) of kept boxes in ascending order; keep_cnt int32 [S].  Nothing returns to the host.
+ */
+int upsnet_nms_workspace_bytes(int S, int max_seg_len, size_t *bytes);
+int upsnet_nms_segmented(const float *boxes, const int *seg_offsets, int S, int max_seg_len,
+                         float thresh, int *keep_out, int *keep_cnt, void *workspace,
+                         size_t workspace_bytes, void *stream);
+/* Drop-in for the reference's host-pointer entry (same arguments as _nms): boxes_host
+ * [n,boxes_dim>=4] sorted by score desc; keep_out/num_out on the host; synchronises. */
+int upsnet_nms_host(int *keep_out, int *num_out, const float *boxes_host, int boxes_num,
+                    int boxes_dim, float thresh, int device_id);
+
+/* ---------------------------------------------------------------------------------------
+ * Deformable convolution v1 / v2 forward, fused (no column buffer in HBM).
+ * replaces: operators/functions/deform_conv.py:26-57 DeformConvFunction.forward
+ *           (= deform_conv_cuda.deform_im2col, operators/src/deform_conv_cuda.cpp:49-68,
+ *              kernel operators/src/deform_conv_kernel.cu:194-242, + torch.mm + bias)
+ *           operators/functions/mod_deform_conv.py:25-59 for mask != NULL
+ *           (kernel operators/src/mod_deform_conv_kernel.cu:187-249).
+ * x [N,Cin,H,W]; offset [N,dg*2*kh*kw,Ho,Wo] (pairs (dh,dw) per tap); mask [N,dg*kh*kw,Ho,Wo]
+ * or NULL (already activated: 2*sigmoid); weight [Cout,Cin,kh,kw]; bias [Cout] or NULL;
+ * y [N,Cout,Ho,Wo].  All fp32 NCHW contiguous.  groups must be 1 (the reference ignores it).
+ */
+int upsnet_dcn_forward(const float *x, const float *offset, const float *mask,
+                       const float *weight, const float *bias, float *y, int N, int Cin, int H,
+                       int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                       int pad_w, int dil_h, int dil_w, int deformable_groups, int epi_flags,
+                       int precision, void *stream);
+
+/* Dense convolution forward with fused bias / residual-add / ReLU epilogue (frozen BN is
+ * folded into weight+bias by the caller).
+ * replaces: the cuDNN conv + BN + ReLU + add chains of models/resnet.py:80-100,
+ *           models/fpn.py:78-104, models/rpn.py:52-56, models/rcnn.py:79-87,132-141.
+ * x [N,Cin,H,W]; weight [Cout,Cin,kh,kw]; bias/residual may be NULL; residual, y [N,Cout,Ho,Wo]. */
+int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias,
+                          const float *residual, float *y, int N, int Cin, int H, int W,
+                          int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                          int pad_w, int dil_h, int dil_w, int epi_flags, int precision,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Parameter-free panoptic head, fused: MaskRemoval + SegTerm + void/concat/argmax.
+ * replaces: models/resnet_upsnet.py:223-240 with operators/modules/mask_removal.py:29-93,
+ *           operators/modules/unary_logits.py:78-105.  Never materialises the [1,k,H,W] planes.
+ * fcn [S,H,W] fp32 (fcn_output of one image); boxes [n,4] (mask_rois[:,1:]); cls_prob [n];
+ * mask_logit [n,28,28] (logit of the predicted class); cls_idx int64 [n] (1-based thing class,
+ * <= num_thing); num_stuff = S - num_thing.
+ * keep_out int64 [max(n,1)] original indices of kept instances in score order, k_out int32[1];
+ * labels int64 [H,W] (255 = void); sem_labels int64 [H,W] or NULL (argmax_c fcn).
+ */
+int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thing, size_t *bytes);
+int upsnet_panoptic_head(const float *fcn, int S, int H, int W, const float *boxes,
+                         const float *cls_prob, const float *mask_logit, const int64_t *cls_idx,
+                         int n, int num_stuff, double fraction_threshold, int64_t *keep_out,
+                         int *k_out, int64_t *labels, int64_t *sem_labels, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPSNET_B200_H_ */

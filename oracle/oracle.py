@@ -53,7 +53,7 @@ def lib():
         L.oracle_clip_boxes.argtypes = [f32p, C.c_int, C.c_float, C.c_float]
         L.oracle_mask_resize.argtypes = [f32p, C.c_int, C.c_int, f32p]
         L.oracle_panoptic_head.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, i64p, C.c_int,
-                                           C.c_int, C.c_float, i64p, i32p, i64p, C.c_void_p]
+                                           C.c_int, C.c_double, i64p, i32p, i64p, C.c_void_p]
         L.oracle_panoptic_head.restype = C.c_int
         L.oracle_conv2d.argtypes = [f32p, f32p, C.c_void_p, f32p] + [C.c_int] * 14
     return _LIB

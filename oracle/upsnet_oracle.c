@@ -342,7 +342,7 @@ static inline float round_half_even(float v) { return nearbyintf(v); }
 ORACLE_API int oracle_panoptic_head(const float *fcn, int S, int H, int W, const float *boxes,
                                     const float *cls_prob, const float *mask_logit,
                                     const int64_t *cls_idx, int n, int num_stuff,
-                                    float fraction_threshold, int64_t *keep_out, int *k_out,
+                                    double fraction_threshold, int64_t *keep_out, int *k_out,
                                     int64_t *labels, int64_t *sem_labels) {
   const size_t HW = (size_t)H * W;
   /* ---- MaskRemoval (mask_removal.py:43-93) ---- */
@@ -386,7 +386,7 @@ ORACLE_API int oracle_panoptic_head(const float *fcn, int S, int H, int W, const
           }
         }
       }
-      if (mask_sum == 0 || ((double)overlap / (double)mask_sum > (double)fraction_threshold)) continue;
+      if (mask_sum == 0 || ((double)overlap / (double)mask_sum > fraction_threshold)) continue;
       keep_out[k++] = i;
       if (mi)
         for (int y = y0; y < y1; ++y) {

@@ -1,0 +1,85 @@
+"""ctypes binding of libupsnet_b200.so (the C ABI declared in include/upsnet_b200.h).
+
+There is deliberately NO fallback: if the CUDA library cannot be loaded, or a tensor is not a
+CUDA tensor, the ops raise.  (The reference does the same for non-CUDA tensors:
+operators/functions/deform_conv.py:40-41, functions/roialign.py:34-35.)
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libupsnet_b200.so")
+_lib = None
+
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+EPI_RELU = 1
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+
+_ERR = {-1: "bad argument", -2: "unsupported configuration", -3: "workspace too small"}
+
+
+class UpsnetError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build  # in-tree nvcc build; raises if nvcc is missing
+            _build.build()
+        L = C.CDLL(LIB_PATH)
+        vp, i, f, d, sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
+        L.upsnet_version.argtypes = [C.POINTER(i)]
+        L.upsnet_roi_align_forward.argtypes = [vp, i, i, i, i, i, vp, i, i, i, i, f, vp, vp]
+        L.upsnet_roi_align_fpn_forward.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(f),
+                                                   i, i, i, vp, i, i, i, i, vp, vp, vp]
+        L.upsnet_nms_workspace_bytes.argtypes = [i, i, C.POINTER(sz)]
+        L.upsnet_nms_segmented.argtypes = [vp, vp, i, i, f, vp, vp, vp, sz, vp]
+        L.upsnet_nms_host.argtypes = [vp, vp, vp, i, i, f, i]
+        L.upsnet_dcn_forward.argtypes = [vp] * 6 + [i] * 16 + [vp]
+        L.upsnet_conv2d_forward.argtypes = [vp] * 5 + [i] * 15 + [vp]
+        L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
+        L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, d, vp, vp, vp, vp, vp, sz, vp]
+        for name in dir(L):
+            pass
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "upsnet_version", "upsnet_roi_align_forward", "upsnet_roi_align_fpn_forward",
+    "upsnet_nms_workspace_bytes", "upsnet_nms_segmented", "upsnet_nms_host", "upsnet_dcn_forward",
+    "upsnet_conv2d_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head",
+]
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise UpsnetError("%s: %s (%d)" % (what, _ERR.get(rc, "error"), rc))
+    raise UpsnetError("%s: CUDA error %d" % (what, rc))
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise UpsnetError("upsnet_b200 ops are CUDA-only (sm_100a); got a %s tensor" % t.device)
+
+
+def f32c(t):
+    """fp32 + contiguous (NCHW), no copy when already so."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

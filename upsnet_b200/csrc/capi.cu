@@ -1,0 +1,73 @@
+// capi.cu -- convolution / deformable-convolution entry points of the C ABI and dispatch
+// between the fp32 CUDA-core tiles (igemm_simt.cu) and the tcgen05 tensor-core tiles
+// (igemm_tc.cu).  See include/upsnet_b200.h for the contract of every symbol.
+#include "common.cuh"
+
+namespace ups {
+struct ConvParams {
+  const float* x; const float* offset; const float* mask; const float* weight;
+  const float* bias; const float* residual; float* y;
+  int N, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo, relu;
+};
+int launch_igemm_simt(const ConvParams& p, cudaStream_t stream);
+}  // namespace ups
+
+extern "C" int upsnet_version(int* n_sm) {
+  if (n_sm) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      *n_sm = sms;
+    else
+      *n_sm = -1;
+  }
+  return 100;
+}
+
+static int conv_common(const float* x, const float* offset, const float* mask, const float* weight,
+                       const float* bias, const float* residual, float* y, int N, int Cin, int H,
+                       int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                       int dw, int dg, int epi_flags, int precision, void* stream) {
+  if (!x || !weight || !y) return UPSNET_E_BADARG;
+  if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 ||
+      sw <= 0 || ph < 0 || pw < 0 || dh <= 0 || dw <= 0 || dg <= 0 || Cin % dg != 0)
+    return UPSNET_E_BADARG;
+  ups::ConvParams p;
+  p.x = x; p.offset = offset; p.mask = mask; p.weight = weight; p.bias = bias;
+  p.residual = residual; p.y = y;
+  p.N = N; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.kh = kh; p.kw = kw; p.sh = sh;
+  p.sw = sw; p.ph = ph; p.pw = pw; p.dh = dh; p.dw = dw; p.dg = dg;
+  p.Ho = ups::conv_out_size(H, ph, dh, kh, sh);
+  p.Wo = ups::conv_out_size(W, pw, dw, kw, sw);
+  p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
+  if (p.Ho <= 0 || p.Wo <= 0) return UPSNET_E_BADARG;
+  if ((size_t)Cin * H * W >= (1ull << 31)) return UPSNET_E_UNSUPPORTED;  // int32 plane offsets
+  switch (precision) {
+    case UPSNET_PREC_FP32_SIMT:
+      return ups::launch_igemm_simt(p, (cudaStream_t)stream);
+    default:
+      return UPSNET_E_UNSUPPORTED;
+  }
+}
+
+extern "C" int upsnet_dcn_forward(const float* x, const float* offset, const float* mask,
+                                  const float* weight, const float* bias, float* y, int N, int Cin,
+                                  int H, int W, int Cout, int kh, int kw, int stride_h,
+                                  int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                  int deformable_groups, int epi_flags, int precision,
+                                  void* stream) {
+  if (!offset) return UPSNET_E_BADARG;
+  return conv_common(x, offset, mask, weight, bias, nullptr, y, N, Cin, H, W, Cout, kh, kw,
+                     stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups, epi_flags,
+                     precision, stream);
+}
+
+extern "C" int upsnet_conv2d_forward(const float* x, const float* weight, const float* bias,
+                                     const float* residual, float* y, int N, int Cin, int H, int W,
+                                     int Cout, int kh, int kw, int stride_h, int stride_w,
+                                     int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags,
+                                     int precision, void* stream) {
+  return conv_common(x, nullptr, nullptr, weight, bias, residual, y, N, Cin, H, W, Cout, kh, kw,
+                     stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, 1, epi_flags, precision,
+                     stream);
+}

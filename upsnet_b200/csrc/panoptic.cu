@@ -1,0 +1,407 @@
+// panoptic.cu -- fused parameter-free panoptic head for sm_100a.
+//
+// Restates models/resnet_upsnet.py:223-240 of the reference:
+//   MaskRemoval  (operators/modules/mask_removal.py:29-93)  score-ordered overlap pruning
+//   SegTerm      (operators/modules/unary_logits.py:78-105) boxed copy of the thing logit
+//   void = max(thing logits) - max_i(seg_inst);  cat;  argmax;  void -> 255
+// without ever materialising the three [1,k,H,W] fp32 planes (0.8-8 GB each in the reference).
+//
+// Kernels
+//   pan_prep     1 CTA : rank instances by score (counting rank, stable), integer geometry.
+//   pan_removal  1 CTA per thing class: serial over that class's instances in score order,
+//                parallel over the pixels of the paste window; class occupancy kept as a
+//                1-bit/pixel plane; warp ballots build 32-pixel words, popc gives |mask| and
+//                |mask & occupied|.
+//   pan_compact  1 CTA : kept list in score order (ballot prefix sums), k==0 fallback.
+//   pan_fuse     CTA per 128x8 pixel tile: bins the kept instances against the tile, then every
+//                thread streams the S semantic logits of 4 consecutive pixels (float4, coalesced)
+//                and runs the ordered argmax over [stuff | instances | void].
+// pan_fuse is the bandwidth kernel: algorithmic bytes = 4*S*H*W + 8*H*W (+8*H*W with
+// sem_labels) + n*(3136+24); see DESIGN.md.  Arithmetic of the 28x28 -> (w,h) resize is the
+// oracle-of-record formula (oracle/upsnet_oracle.c resized_logit) in un-fused fp32 (_rn
+// intrinsics) so label maps are bit-exact.
+#include "common.cuh"
+
+namespace ups {
+
+constexpr int kMaskS = 28;
+constexpr int kMaskElems = kMaskS * kMaskS;
+
+// per-instance integer geometry, SoA with stride n (indexed by ORIGINAL instance id)
+struct PanGeom {
+  int* bx0; int* by0; int* w; int* h;        // truncated box origin and size
+  int* gx0; int* gy0; int* gx1; int* gy1;    // mask paste window (image coords, clamped)
+  int* sx0; int* sy0; int* sx1; int* sy1;    // SegTerm window (python-slice clamped)
+  int* cls;                                  // 1-based thing class (0 = dummy)
+};
+
+struct PanWorkspace {
+  int* order;       // [n]  rank -> original index (score desc, stable)
+  int* kept_flag;   // [n]  by rank
+  int* kept_list;   // [n]  compacted: original indices in score order
+  int* meta;        // [4]  k, zero_mask, ...
+  PanGeom g;
+  unsigned int* occ;      // [num_thing][H][Ww]  occupancy bit planes
+  unsigned int* scratch;  // [num_thing][H][Ww]  candidate mask words of the current instance
+};
+
+static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorkspace* ws,
+                                                char* base) {
+  const int nn = n > 0 ? n : 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_order = take(sizeof(int) * nn), o_flag = take(sizeof(int) * nn);
+  const size_t o_list = take(sizeof(int) * nn), o_meta = take(sizeof(int) * 4);
+  const size_t o_geom = take(sizeof(int) * nn * 13);
+  const int Ww = ceil_div(W, 32);
+  const size_t plane = (size_t)num_thing * H * Ww * sizeof(unsigned int);
+  const size_t o_occ = take(plane), o_scr = take(plane);
+  if (ws) {
+    ws->order = (int*)(base + o_order); ws->kept_flag = (int*)(base + o_flag);
+    ws->kept_list = (int*)(base + o_list); ws->meta = (int*)(base + o_meta);
+    int* g = (int*)(base + o_geom);
+    ws->g.bx0 = g; ws->g.by0 = g + nn; ws->g.w = g + 2 * nn; ws->g.h = g + 3 * nn;
+    ws->g.gx0 = g + 4 * nn; ws->g.gy0 = g + 5 * nn; ws->g.gx1 = g + 6 * nn; ws->g.gy1 = g + 7 * nn;
+    ws->g.sx0 = g + 8 * nn; ws->g.sy0 = g + 9 * nn; ws->g.sx1 = g + 10 * nn; ws->g.sy1 = g + 11 * nn;
+    ws->g.cls = g + 12 * nn;
+    ws->occ = (unsigned int*)(base + o_occ); ws->scratch = (unsigned int*)(base + o_scr);
+  }
+  return off;
+}
+
+// ---- resize coefficients: oracle resize_coef_x / resize_coef_y, un-fused ----
+__device__ __forceinline__ void coef_x(int d, int n_dst, int& s, float& f) {
+  const double scale = __ddiv_rn((double)kMaskS, (double)n_dst);
+  float fv = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  int sv = (int)floorf(fv);
+  fv = __fsub_rn(fv, (float)sv);
+  if (sv < 0) { sv = 0; fv = 0.f; }
+  if (sv >= kMaskS - 1) { sv = kMaskS - 1; fv = 0.f; }
+  s = sv; f = fv;
+}
+__device__ __forceinline__ void coef_y(int d, int n_dst, int& s, float& f) {
+  const double scale = __ddiv_rn((double)kMaskS, (double)n_dst);
+  float fv = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  const int sv = (int)floorf(fv);
+  s = sv; f = __fsub_rn(fv, (float)sv);
+}
+__device__ __forceinline__ float blend(const float* __restrict__ S, int sx, float fx, int sy, float fy) {
+  const int sx1 = min(sx + 1, kMaskS - 1);
+  const int y0 = min(max(sy, 0), kMaskS - 1), y1 = min(max(sy + 1, 0), kMaskS - 1);
+  const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
+  const float h0 = __fadd_rn(__fmul_rn(S[y0 * kMaskS + sx], a0), __fmul_rn(S[y0 * kMaskS + sx1], a1));
+  const float h1 = __fadd_rn(__fmul_rn(S[y1 * kMaskS + sx], a0), __fmul_rn(S[y1 * kMaskS + sx1], a1));
+  return __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
+                const int64_t* __restrict__ cls_idx, int n, int H, int W, PanWorkspace ws) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float p = prob[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float q = prob[j];
+      rank += (q > p) || (q == p && j < i);
+    }
+    ws.order[rank] = i;
+    const float* b = boxes + (size_t)i * 4;
+    const int bx0 = (int)b[0], by0 = (int)b[1], bx1 = (int)b[2], by1 = (int)b[3];  // astype(int32)
+    const int w = max(bx1 - bx0 + 1, 1), h = max(by1 - by0 + 1, 1);
+    ws.g.bx0[i] = bx0; ws.g.by0[i] = by0; ws.g.w[i] = w; ws.g.h[i] = h;
+    ws.g.gx0[i] = max(bx0, 0); ws.g.gx1[i] = min(bx1 + 1, W);
+    ws.g.gy0[i] = max(by0, 0); ws.g.gy1[i] = min(by1 + 1, H);
+    const int c = (int)cls_idx[i];
+    // unary_logits.py:92-103: boxes*4.0*0.25 is exact in binary fp; int() truncates, round() is
+    // numpy half-to-even (rintf); python slices clamp to the array extent.
+    const float fb0 = __fmul_rn(__fmul_rn(b[0], 4.0f), 0.25f), fb1 = __fmul_rn(__fmul_rn(b[1], 4.0f), 0.25f);
+    const float fb2 = __fmul_rn(__fmul_rn(b[2], 4.0f), 0.25f), fb3 = __fmul_rn(__fmul_rn(b[3], 4.0f), 0.25f);
+    int sx0 = min((int)fb0, W), sy0 = min((int)fb1, H);
+    int sx1 = min((int)(rintf(fb2) + 1.f), W), sy1 = min((int)(rintf(fb3) + 1.f), H);
+    if (c == 0) { sx1 = sx0; sy1 = sy0; }
+    ws.g.sx0[i] = sx0; ws.g.sy0[i] = sy0; ws.g.sx1[i] = sx1; ws.g.sy1[i] = sy1;
+    ws.g.cls[i] = c;
+  }
+}
+
+// one CTA per thing class (blockIdx.x = class-1)
+__global__ void __launch_bounds__(1024)
+pan_removal_kernel(const float* __restrict__ mask_logit, int n, int H, int W,
+                   double fraction_threshold, PanWorkspace ws) {
+  __shared__ float S[kMaskElems];
+  __shared__ unsigned int s_sum, s_ovl;
+  __shared__ int s_keep;
+  const int c = blockIdx.x;  // 0-based class
+  const int Ww = ceil_div(W, 32);
+  unsigned int* occ = ws.occ + (size_t)c * H * Ww;
+  unsigned int* scr = ws.scratch + (size_t)c * H * Ww;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool dummy_single = (n == 1 && ws.g.cls[0] == 0);  // mask_removal.py:55-57
+
+  for (int r = 0; r < n; ++r) {
+    const int i = ws.order[r];
+    if (ws.g.cls[i] - 1 != c || dummy_single) continue;  // uniform across the CTA
+    const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], w = ws.g.w[i], h = ws.g.h[i];
+    const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
+    __syncthreads();  // previous instance fully retired (S, counters, occ updates)
+    for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x) S[t] = mask_logit[(size_t)i * kMaskElems + t];
+    if (threadIdx.x == 0) { s_sum = 0; s_ovl = 0; }
+    __syncthreads();
+    const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;  // word columns [wx0, wx1)
+    const int nwc = max(wx1 - wx0, 0), rows = max(y1 - y0, 0);
+    unsigned int my_sum = 0, my_ovl = 0;
+    for (int item = warp; item < nwc * rows; item += nwarps) {
+      const int wy = y0 + item / nwc, wc = wx0 + item % nwc;
+      const int x = wc * 32 + lane;
+      bool bit = false;
+      const int dx = x - bx0, dy = wy - by0;
+      if (x >= x0 && x < x1 && dx >= 0 && dx < w && dy >= 0 && dy < h) {
+        int sx, sy; float fx, fy;
+        coef_x(dx, w, sx, fx);
+        coef_y(dy, h, sy, fy);
+        bit = blend(S, sx, fx, sy, fy) > 0.f;
+      }
+      const unsigned int word = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0) {
+        scr[(size_t)wy * Ww + wc] = word;
+        my_sum += __popc(word);
+        my_ovl += __popc(word & occ[(size_t)wy * Ww + wc]);
+      }
+    }
+    if (lane == 0 && (my_sum | my_ovl)) { atomicAdd(&s_sum, my_sum); atomicAdd(&s_ovl, my_ovl); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int ms = s_sum, ov = s_ovl;
+      // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
+      const bool drop = (ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold);
+      s_keep = drop ? 0 : 1;
+      ws.kept_flag[r] = drop ? 0 : 1;
+    }
+    __syncthreads();
+    if (s_keep) {
+      for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {
+        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
+        occ[o] |= scr[o];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+pan_compact_kernel(int n, PanWorkspace ws, int64_t* __restrict__ keep_out, int* __restrict__ k_out) {
+  const int lane = threadIdx.x;
+  int k = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int r = base + lane;
+    const bool kept = r < n && ws.kept_flag[r] != 0;
+    const unsigned int m = __ballot_sync(0xffffffffu, kept);
+    if (kept) {
+      const int pos = k + __popc(m & ((1u << lane) - 1u));
+      const int i = ws.order[r];
+      ws.kept_list[pos] = i;
+      keep_out[pos] = i;
+    }
+    k += __popc(m);
+  }
+  if (lane == 0) {
+    int zero_mask = 0;
+    if (k == 0) {  // mask_removal.py:89-92 (and :55-57): keep=[0] with an all-zero mask plane
+      ws.kept_list[0] = 0; keep_out[0] = 0; k = 1; zero_mask = 1;
+    }
+    ws.meta[0] = k; ws.meta[1] = zero_mask;
+    k_out[0] = k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kTileW = 128, kTileH = 8, kFuseThreads = 256, kMaxList = 2048;
+
+struct Best { float v; int i; };
+__device__ __forceinline__ void feed(Best& b, float v, int i) { if (v > b.v) { b.v = v; b.i = i; } }
+
+__global__ void __launch_bounds__(kFuseThreads)
+pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuff,
+                const float* __restrict__ mask_logit, PanWorkspace ws,
+                int64_t* __restrict__ labels, int64_t* __restrict__ sem_labels) {
+  __shared__ unsigned short list[kMaxList];
+  __shared__ int s_cnt, s_first_unlisted;
+  __shared__ int s_warp_cnt[kFuseThreads / 32];
+  const int k = ws.meta[0], zero_mask = ws.meta[1];
+  const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+  const int tx1 = min(tx0 + kTileW, W), ty1 = min(ty0 + kTileH, H);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_cnt = 0; s_first_unlisted = k; }
+  __syncthreads();
+  // ---- bin kept instances against this tile (ascending j preserved) ----
+  for (int base = 0; base < k; base += kFuseThreads) {
+    const int j = base + threadIdx.x;
+    bool hit = false;
+    if (j < k) {
+      const int i = ws.kept_list[j];
+      const bool hit_seg = ws.g.sx0[i] < tx1 && ws.g.sx1[i] > tx0 && ws.g.sy0[i] < ty1 && ws.g.sy1[i] > ty0;
+      const bool hit_msk = !zero_mask && ws.g.gx0[i] < tx1 && ws.g.gx1[i] > tx0 && ws.g.gy0[i] < ty1 &&
+                           ws.g.gy1[i] > ty0;
+      hit = hit_seg || hit_msk;
+      if (!hit) atomicMin(&s_first_unlisted, j);
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = s_cnt;
+    for (int w2 = 0; w2 < warp; ++w2) off += s_warp_cnt[w2];
+    if (hit) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      if (pos < kMaxList) list[pos] = (unsigned short)j;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w2 = 0; w2 < kFuseThreads / 32; ++w2) tot += s_warp_cnt[w2];
+      s_cnt += tot;
+    }
+    __syncthreads();
+  }
+  const int cnt = min(s_cnt, kMaxList);
+  const int u0 = s_first_unlisted;  // smallest kept index whose windows miss the tile (value 0)
+  const bool any_unlisted = u0 < k;
+
+  // ---- per-thread: 4 consecutive pixels of one row ----
+  const int x = tx0 + (threadIdx.x & 31) * 4, y = ty0 + (threadIdx.x >> 5);
+  if (y >= H || x >= W) return;
+  const size_t HW = (size_t)H * W;
+  const size_t p = (size_t)y * W + x;
+  const bool vec = (x + 3 < W) && ((W & 3) == 0);
+  const int npx = vec ? 4 : min(4, W - x);
+
+  Best best[4], sem[4];
+  float thing_max[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { best[q].v = -INFINITY; best[q].i = 0; sem[q].v = -INFINITY; sem[q].i = 0; thing_max[q] = -INFINITY; }
+  for (int c = 0; c < S; ++c) {
+    float v[4];
+    if (vec) {
+      const float4 t = __ldg((const float4*)(fcn + (size_t)c * HW + p));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = q < npx ? __ldg(fcn + (size_t)c * HW + p + q) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (c == 0) { best[q].v = v[q]; sem[q].v = v[q]; }
+      else {
+        if (c < num_stuff) feed(best[q], v[q], c);
+        feed(sem[q], v[q], c);
+      }
+      if (c >= num_stuff) thing_max[q] = (c == num_stuff) ? v[q] : fmaxf(thing_max[q], v[q]);
+    }
+  }
+  // ---- instances, ascending kept index; unlisted instances contribute the value 0 at u0 ----
+  float inst_max[4];
+  bool inst_init[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { inst_max[q] = 0.f; inst_init[q] = any_unlisted; }
+  bool fed_unlisted = !any_unlisted;
+  for (int li = 0; li < cnt; ++li) {
+    const int j = list[li];
+    if (!fed_unlisted && j > u0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) feed(best[q], 0.f, num_stuff + u0);
+      fed_unlisted = true;
+    }
+    const int i = ws.kept_list[j];
+    const int sx0 = ws.g.sx0[i], sx1 = ws.g.sx1[i], sy0 = ws.g.sy0[i], sy1 = ws.g.sy1[i];
+    const int gx0 = ws.g.gx0[i], gx1 = ws.g.gx1[i], gy0 = ws.g.gy0[i], gy1 = ws.g.gy1[i];
+    const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], bw = ws.g.w[i], bh = ws.g.h[i];
+    const bool row_seg = y >= sy0 && y < sy1;
+    const int dy = y - by0;
+    const bool row_msk = !zero_mask && y >= gy0 && y < gy1 && dy >= 0 && dy < bh;
+    const float* seg_plane = fcn + (size_t)(num_stuff + ws.g.cls[i] - 1) * HW + p;
+    const float* Sm = mask_logit + (size_t)i * kMaskElems;
+    int sy = 0; float fy = 0.f;
+    if (row_msk) coef_y(dy, bh, sy, fy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= npx) break;
+      const int xx = x + q;
+      float seg = 0.f;
+      if (row_seg && xx >= sx0 && xx < sx1) seg = __ldg(seg_plane + q);
+      float m = 0.f;
+      const int dx = xx - bx0;
+      if (row_msk && xx >= gx0 && xx < gx1 && dx >= 0 && dx < bw) {
+        int sx; float fx;
+        coef_x(dx, bw, sx, fx);
+        m = blend(Sm, sx, fx, sy, fy);
+      }
+      feed(best[q], __fadd_rn(seg, m), num_stuff + j);
+      if (!inst_init[q]) { inst_max[q] = seg; inst_init[q] = true; } else inst_max[q] = fmaxf(inst_max[q], seg);
+    }
+  }
+  if (!fed_unlisted) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) feed(best[q], 0.f, num_stuff + u0);
+  }
+  long long out[4], semo[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float voidv = __fsub_rn(thing_max[q], inst_max[q]);
+    feed(best[q], voidv, num_stuff + k);
+    out[q] = (best[q].i == num_stuff + k) ? 255 : best[q].i;
+    semo[q] = sem[q].i;
+  }
+  if (vec) {
+    longlong2* o = (longlong2*)(labels + p);
+    o[0] = make_longlong2(out[0], out[1]);
+    o[1] = make_longlong2(out[2], out[3]);
+    if (sem_labels) {
+      longlong2* so = (longlong2*)(sem_labels + p);
+      so[0] = make_longlong2(semo[0], semo[1]);
+      so[1] = make_longlong2(semo[2], semo[3]);
+    }
+  } else {
+    for (int q = 0; q < npx; ++q) { labels[p + q] = out[q]; if (sem_labels) sem_labels[p + q] = semo[q]; }
+  }
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thing, size_t* bytes) {
+  if (!bytes || n < 0 || H <= 0 || W <= 0 || num_thing <= 0) return UPSNET_E_BADARG;
+  *bytes = ups::pan_ws_layout(n, H, W, num_thing, nullptr, nullptr);
+  return 0;
+}
+
+extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const float* boxes,
+                                    const float* cls_prob, const float* mask_logit,
+                                    const int64_t* cls_idx, int n, int num_stuff,
+                                    double fraction_threshold, int64_t* keep_out, int* k_out,
+                                    int64_t* labels, int64_t* sem_labels, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  using namespace ups;
+  if (!fcn || !boxes || !cls_prob || !mask_logit || !cls_idx || !keep_out || !k_out || !labels || !workspace)
+    return UPSNET_E_BADARG;
+  const int num_thing = S - num_stuff;
+  if (n < 1 || H <= 0 || W <= 0 || num_thing <= 0 || num_stuff < 1) return UPSNET_E_BADARG;
+  if (n > kMaxList) return UPSNET_E_UNSUPPORTED;  // per-tile instance list capacity
+  if (((uintptr_t)fcn & 15) || ((uintptr_t)labels & 15) || (sem_labels && ((uintptr_t)sem_labels & 15)))
+    return UPSNET_E_BADARG;
+  PanWorkspace ws;
+  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace);
+  if (workspace_bytes < need) return UPSNET_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ww = ceil_div(W, 32);
+  UPS_CUDA(cudaMemsetAsync(ws.occ, 0, (size_t)num_thing * H * Ww * sizeof(unsigned int), st));
+  UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
+  pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, H, W, ws);
+  UPS_CHECK_LAUNCH();
+  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, H, W, fraction_threshold, ws);
+  UPS_CHECK_LAUNCH();
+  pan_compact_kernel<<<1, 32, 0, st>>>(n, ws, keep_out, k_out);
+  UPS_CHECK_LAUNCH();
+  dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH));
+  pan_fuse_kernel<<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels,
+                                                 sem_labels);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,220 @@
+// roi_align.cu -- ROIAlign / FPN-ROIAlign forward for sm_100a.
+//
+// Semantics follow operators/src/roi_align_kernel.cu:43-95 (bilinear) and :163-235 (forward)
+// of the reference: no half-pixel shift, roi extent forced >= 1, sampling grid sr x sr,
+// out-of-map test y<-1 || y>H.  The FPN variant folds fpn_roi_align.py:32-62 (level
+// assignment, four per-level launches, cat + index_select) into one launch.
+//
+// Two data layouts:
+//   NCHW  (reference API parity): thread per output element, pw fastest.
+//   NHWC  (engine layout): one CTA per (roi, ph), lanes over channels -> every bilinear tap is
+//         one contiguous C*4-byte read and every output write is coalesced.
+// HBM-bound gather: algorithmic bytes = 4*R*C*PH*PW (write) + unique feature reads.
+#include "common.cuh"
+
+namespace ups {
+
+struct FpnFeats {
+  const float* p[4];
+  int H[4], W[4];
+  float scale[4];
+  int nlevels;  // 1 => plain RoIAlign (level 0 always)
+};
+
+// Level thresholds on x = sqrtf(w*h)/224 + 1e-6 (float32): level = #{t : x >= thr[t]}.
+// They are the smallest float32 x for which numpy's floor(2+log2(x)) reaches 1, 2, 3
+// (fpn_roi_align.py:37 evaluated in float32): 0.5, 1.0 and 1.9999999 -- the last sits one ulp
+// below 2 because 2 + log2f(x) rounds up to 3.0 there.  Pinned by tests/test_host_logic.py.
+__device__ __forceinline__ int fpn_level_of(float x1, float y1, float x2, float y2) {
+  const float w = x2 - x1 + 1.f, h = y2 - y1 + 1.f;
+  const float x = __fadd_rn(__fdiv_rn(__fsqrt_rn(__fmul_rn(w, h)), 224.f), 1e-6f);
+  const float t1 = __uint_as_float(0x3f000000u);  // 0.5
+  const float t2 = __uint_as_float(0x3f800000u);  // 1.0
+  const float t3 = __uint_as_float(0x3fffffffu);  // 1.9999999
+  return (x >= t1) + (x >= t2) + (x >= t3);
+}
+
+struct SamplePos {
+  int o00, o01, o10, o11;  // element offsets (in pixels) of the four taps
+  float w00, w01, w10, w11;
+};
+
+// roi_align_kernel.cu:43-95 -- returns weights/offsets instead of the value so that the NHWC
+// kernel can reuse them across channels.  An out-of-range sample has all weights 0.
+__device__ __forceinline__ SamplePos roi_sample(int H, int W, float y, float x) {
+  SamplePos s;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+    s.o00 = s.o01 = s.o10 = s.o11 = 0;
+    s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
+    return s;
+  }
+  if (y <= 0) y = 0;
+  if (x <= 0) x = 0;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+  s.o00 = yl * W + xl; s.o01 = yl * W + xh; s.o10 = yh * W + xl; s.o11 = yh * W + xh;
+  s.w00 = hy * hx; s.w01 = hy * lx; s.w10 = ly * hx; s.w11 = ly * lx;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW: thread per output element (n, c, ph, pw)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+roi_align_nchw_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, int PH, int PW,
+                      int sr, float* __restrict__ out, int* __restrict__ levels_out) {
+  const long long total = (long long)R * C * PH * PW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int pw = (int)(idx % PW);
+    const int ph = (int)((idx / PW) % PH);
+    const int c = (int)((idx / PW / PH) % C);
+    const int n = (int)(idx / PW / PH / C);
+    const float* r = rois + (size_t)n * 5;
+    const int b = (int)roundf(r[0]);
+    const float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+    const int lv = f.nlevels > 1 ? fpn_level_of(rx1, ry1, rx2, ry2) : 0;
+    if (levels_out && c == 0 && ph == 0 && pw == 0) levels_out[n] = lv;
+    const int H = f.H[lv], W = f.W[lv];
+    const float sc = f.scale[lv];
+    const float rsw = rx1 * sc, rsh = ry1 * sc, rew = rx2 * sc, reh = ry2 * sc;
+    const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
+    const float bsh = rh / (float)PH, bsw = rw / (float)PW;
+    const int gh = sr > 0 ? sr : (int)ceilf(rh / PH), gw = sr > 0 ? sr : (int)ceilf(rw / PW);
+    const float* d = f.p[lv] + ((size_t)b * C + c) * H * W;
+    float acc = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = rsw + pw * bsw + (float)(ix + .5f) * bsw / (float)gw;
+        const SamplePos s = roi_sample(H, W, y, x);
+        acc += (s.w00 * __ldg(d + s.o00) + s.w01 * __ldg(d + s.o01) + s.w10 * __ldg(d + s.o10) +
+                s.w11 * __ldg(d + s.o11));
+      }
+    }
+    out[idx] = acc / (float)(gh * gw);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NHWC: CTA per (roi, ph); threads over channels (float4 per thread); loop over pw.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, int PH, int PW,
+                      int sr, float* __restrict__ out, int* __restrict__ levels_out) {
+  const int n = blockIdx.x / PH, ph = blockIdx.x % PH;
+  const float* r = rois + (size_t)n * 5;
+  const int b = (int)roundf(r[0]);
+  const float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+  const int lv = f.nlevels > 1 ? fpn_level_of(rx1, ry1, rx2, ry2) : 0;
+  if (levels_out && ph == 0 && threadIdx.x == 0) levels_out[n] = lv;
+  const int H = f.H[lv], W = f.W[lv];
+  const float sc = f.scale[lv];
+  const float rsw = rx1 * sc, rsh = ry1 * sc, rew = rx2 * sc, reh = ry2 * sc;
+  const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
+  const float bsh = rh / (float)PH, bsw = rw / (float)PW;
+  const int gh = sr > 0 ? sr : (int)ceilf(rh / PH), gw = sr > 0 ? sr : (int)ceilf(rw / PW);
+  const float inv_count_div = (float)(gh * gw);
+  const float* base = f.p[lv] + (size_t)b * H * W * C;
+  for (int c = threadIdx.x * VEC; c < C; c += blockDim.x * VEC) {
+    for (int pw = 0; pw < PW; ++pw) {
+      float acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          const float x = rsw + pw * bsw + (float)(ix + .5f) * bsw / (float)gw;
+          const SamplePos s = roi_sample(H, W, y, x);
+          if (VEC == 4) {
+            const float4 v00 = __ldg((const float4*)(base + (size_t)s.o00 * C + c));
+            const float4 v01 = __ldg((const float4*)(base + (size_t)s.o01 * C + c));
+            const float4 v10 = __ldg((const float4*)(base + (size_t)s.o10 * C + c));
+            const float4 v11 = __ldg((const float4*)(base + (size_t)s.o11 * C + c));
+            acc[0] += (s.w00 * v00.x + s.w01 * v01.x + s.w10 * v10.x + s.w11 * v11.x);
+            acc[1 % VEC] += (s.w00 * v00.y + s.w01 * v01.y + s.w10 * v10.y + s.w11 * v11.y);
+            acc[2 % VEC] += (s.w00 * v00.z + s.w01 * v01.z + s.w10 * v10.z + s.w11 * v11.z);
+            acc[3 % VEC] += (s.w00 * v00.w + s.w01 * v01.w + s.w10 * v10.w + s.w11 * v11.w);
+          } else {
+            acc[0] += (s.w00 * __ldg(base + (size_t)s.o00 * C + c) +
+                       s.w01 * __ldg(base + (size_t)s.o01 * C + c) +
+                       s.w10 * __ldg(base + (size_t)s.o10 * C + c) +
+                       s.w11 * __ldg(base + (size_t)s.o11 * C + c));
+          }
+        }
+      }
+      float* o = out + (((size_t)n * PH + ph) * PW + pw) * C + c;
+      if (VEC == 4) {
+        float4 v;
+        v.x = acc[0] / inv_count_div; v.y = acc[1 % VEC] / inv_count_div;
+        v.z = acc[2 % VEC] / inv_count_div; v.w = acc[3 % VEC] / inv_count_div;
+        *(float4*)o = v;
+      } else {
+        o[0] = acc[0] / inv_count_div;
+      }
+    }
+  }
+}
+
+static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, const float* rois, int R,
+                            int PH, int PW, int sr, float* out, int* levels_out,
+                            cudaStream_t stream) {
+  if (R < 0 || C <= 0 || PH <= 0 || PW <= 0 || B <= 0) return UPSNET_E_BADARG;
+  if (R == 0) return 0;
+  if (layout == UPSNET_LAYOUT_NCHW) {
+    const long long total = (long long)R * C * PH * PW;
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 64) blocks = kNumSMs * 64;
+    roi_align_nchw_kernel<<<(int)blocks, 256, 0, stream>>>(f, C, rois, R, PH, PW, sr, out,
+                                                           levels_out);
+  } else if (layout == UPSNET_LAYOUT_NHWC) {
+    bool vec4 = (C % 4 == 0);
+    for (int l = 0; l < f.nlevels; ++l) vec4 = vec4 && (((uintptr_t)f.p[l] & 15) == 0);
+    vec4 = vec4 && (((uintptr_t)out & 15) == 0);
+    if (vec4) {
+      int threads = C / 4 < 32 ? 32 : (C / 4 > 256 ? 256 : (C / 4 + 31) / 32 * 32);
+      roi_align_nhwc_kernel<4><<<R * PH, threads, 0, stream>>>(f, C, rois, R, PH, PW, sr, out,
+                                                              levels_out);
+    } else {
+      int threads = C < 32 ? 32 : (C > 256 ? 256 : (C + 31) / 32 * 32);
+      roi_align_nhwc_kernel<1><<<R * PH, threads, 0, stream>>>(f, C, rois, R, PH, PW, sr, out,
+                                                              levels_out);
+    }
+  } else {
+    return UPSNET_E_BADARG;
+  }
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_roi_align_forward(const float* feat, int B, int C, int H, int W, int layout,
+                                        const float* rois, int R, int PH, int PW,
+                                        int sampling_ratio, float spatial_scale, float* out,
+                                        void* stream) {
+  if (!feat || !out || (!rois && R > 0)) return UPSNET_E_BADARG;
+  ups::FpnFeats f{};
+  f.p[0] = feat; f.H[0] = H; f.W[0] = W; f.scale[0] = spatial_scale; f.nlevels = 1;
+  return ups::launch_roi_align(f, B, C, layout, rois, R, PH, PW, sampling_ratio, out, nullptr,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int upsnet_roi_align_fpn_forward(const float* const feats[4], const int Hs[4],
+                                            const int Ws[4], const float scales[4], int B, int C,
+                                            int layout, const float* rois, int R, int PH, int PW,
+                                            int sampling_ratio, float* out, int* levels_out,
+                                            void* stream) {
+  if (!feats || !Hs || !Ws || !scales || !out || (!rois && R > 0)) return UPSNET_E_BADARG;
+  ups::FpnFeats f{};
+  for (int l = 0; l < 4; ++l) {
+    if (!feats[l]) return UPSNET_E_BADARG;
+    f.p[l] = feats[l]; f.H[l] = Hs[l]; f.W[l] = Ws[l]; f.scale[l] = scales[l];
+  }
+  f.nlevels = 4;
+  return ups::launch_roi_align(f, B, C, layout, rois, R, PH, PW, sampling_ratio, out, levels_out,
+                               (cudaStream_t)stream);
+}

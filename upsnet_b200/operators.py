@@ -1,0 +1,407 @@
+"""Host-side mirror of the reference's operator API (upsnet/operators/modules/*, upsnet/nms/nms.py)
+on top of the sm_100a C ABI.  Same class names, constructor arguments, parameter names/shapes
+(so reference checkpoints load) and forward signatures; all compute is in libupsnet_b200.so.
+
+Reference interfaces mirrored (paths relative to /root/reference/upsnet/):
+  DeformConv, DeformConvWithOffset      operators/modules/deform_conv.py:27-78
+  ModDeformConv(+WithOffsetMask)        operators/modules/mod_deform_conv.py:24-81  (exported as
+                                        ModulatedDeformConv too, the name BASELINE.json uses)
+  RoIAlign / RoIAlignFunction           operators/modules/roialign.py:20-29, functions/roialign.py:21-43
+  FPNRoIAlign                           operators/modules/fpn_roi_align.py:22-62
+  gpu_nms_wrapper / nms                 nms/nms.py:43-46, nms/gpu_nms.pyx:23-38
+  MaskRemoval, SegTerm, PanopticHead    operators/modules/mask_removal.py:23-93,
+                                        operators/modules/unary_logits.py:69-105,
+                                        models/resnet_upsnet.py:217-247 (F1: no such class there)
+Forward only: the inference hot path; backward kernels are the training
+config and out of this round's scope.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _pair
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
+
+# default arithmetic of the convolution tiles; switched by upsnet_b200.set_precision()
+_PRECISION = {"conv": _lib.PREC_FP32_SIMT}
+
+
+def set_precision(name):
+    """'fp32' (CUDA-core fp32 tiles), 'bf16x3' or 'bf16' (tcgen05 tiles)."""
+    _PRECISION["conv"] = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.PREC_BF16}[name]
+
+
+def _conv_out(n, pad, dil, k, stride):
+    return (n + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# functional layer
+# ------------------------------------------------------------------------------------------------
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None):
+    """Dense conv + fused bias / residual / ReLU epilogue (upsnet_conv2d_forward)."""
+    require_cuda(x, weight, bias, residual)
+    x, weight = f32c(x), f32c(weight)
+    bias = None if bias is None else f32c(bias)
+    residual = None if residual is None else f32c(residual)
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    N, Cin, H, W = x.shape
+    Cout, Cin_w, kh, kw = weight.shape
+    assert Cin_w == Cin, "groups != 1 is not supported"
+    Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
+    y = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    if residual is not None:
+        assert residual.shape == y.shape
+    prec = _PRECISION["conv"] if precision is None else precision
+    with torch.cuda.device(x.device):
+        check(lib().upsnet_conv2d_forward(ptr(x), ptr(weight), ptr(bias), ptr(residual), ptr(y), N, Cin, H, W,
+                                          Cout, kh, kw, sh, sw, ph, pw, dh, dw, _lib.EPI_RELU if relu else 0,
+                                          prec, stream_ptr(x.device)), "conv2d")
+    return y
+
+
+def linear(x, weight, bias=None, relu=False, precision=None):
+    """y = x @ weight.T + bias as a 1x1 convolution over N 'images' of 1x1 pixels."""
+    N, K = x.shape
+    y = conv2d(x.reshape(N, K, 1, 1), weight.reshape(weight.shape[0], K, 1, 1), bias, relu=relu,
+               precision=precision)
+    return y.reshape(N, weight.shape[0])
+
+
+def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1,
+                mask=None, relu=False, precision=None):
+    """DeformConvFunction.forward (functions/deform_conv.py:26-57); with `mask` (already 2*sigmoid)
+    ModDeformConvFunction.forward (functions/mod_deform_conv.py:25-59).  One fused launch."""
+    require_cuda(data, offset, weight, bias, mask)
+    data, offset, weight = f32c(data), f32c(offset), f32c(weight)
+    bias = None if bias is None else f32c(bias)
+    mask = None if mask is None else f32c(mask)
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    N, Cin, H, W = data.shape
+    Cout, Cin_w, kh, kw = weight.shape
+    assert Cin_w == Cin, "groups != 1 is not supported (the reference ignores `groups`)"
+    Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
+    assert tuple(offset.shape) == (N, 2 * kh * kw * deformable_groups, Ho, Wo), offset.shape
+    if mask is not None:
+        assert tuple(mask.shape) == (N, kh * kw * deformable_groups, Ho, Wo), mask.shape
+    y = torch.empty((N, Cout, Ho, Wo), device=data.device, dtype=torch.float32)
+    prec = _PRECISION["conv"] if precision is None else precision
+    with torch.cuda.device(data.device):
+        check(lib().upsnet_dcn_forward(ptr(data), ptr(offset), ptr(mask), ptr(weight), ptr(bias), ptr(y), N, Cin,
+                                       H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, deformable_groups,
+                                       _lib.EPI_RELU if relu else 0, prec, stream_ptr(data.device)),
+              "deform_conv")
+    return y
+
+
+def roi_align(features, rois, pooled_height, pooled_width, spatial_scale, sampling_ratio=2, layout="nchw"):
+    require_cuda(features, rois)
+    features, rois = f32c(features), f32c(rois)
+    assert rois.dim() == 2 and rois.shape[1] == 5
+    R = rois.shape[0]
+    if layout == "nchw":
+        B, Cc, H, W = features.shape
+        out = torch.empty((R, Cc, pooled_height, pooled_width), device=features.device, dtype=torch.float32)
+        lay = _lib.LAYOUT_NCHW
+    else:
+        B, H, W, Cc = features.shape
+        out = torch.empty((R, pooled_height, pooled_width, Cc), device=features.device, dtype=torch.float32)
+        lay = _lib.LAYOUT_NHWC
+    with torch.cuda.device(features.device):
+        check(lib().upsnet_roi_align_forward(ptr(features), B, Cc, H, W, lay, ptr(rois), R, pooled_height,
+                                             pooled_width, sampling_ratio, float(spatial_scale), ptr(out),
+                                             stream_ptr(features.device)), "roi_align")
+    return out
+
+
+def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, sampling_ratio=2, layout="nchw",
+                  return_levels=False):
+    """FPNRoIAlign.forward in one launch (level assignment on device, output already in roi order)."""
+    assert len(feats) == 4 and len(spatial_scales) == 4
+    require_cuda(rois, *feats)
+    feats = [f32c(f) for f in feats]
+    rois = f32c(rois)
+    R = rois.shape[0]
+    if layout == "nchw":
+        B, Cc = feats[0].shape[0], feats[0].shape[1]
+        Hs = [f.shape[2] for f in feats]; Ws = [f.shape[3] for f in feats]
+        out = torch.empty((R, Cc, pooled_height, pooled_width), device=rois.device, dtype=torch.float32)
+        lay = _lib.LAYOUT_NCHW
+    else:
+        B, Cc = feats[0].shape[0], feats[0].shape[3]
+        Hs = [f.shape[1] for f in feats]; Ws = [f.shape[2] for f in feats]
+        out = torch.empty((R, pooled_height, pooled_width, Cc), device=rois.device, dtype=torch.float32)
+        lay = _lib.LAYOUT_NHWC
+    levels = torch.empty((R,), device=rois.device, dtype=torch.int32) if return_levels else None
+    fp = (C.c_void_p * 4)(*[f.data_ptr() for f in feats])
+    hs = (C.c_int * 4)(*Hs); ws = (C.c_int * 4)(*Ws)
+    sc = (C.c_float * 4)(*[float(s) for s in spatial_scales])
+    with torch.cuda.device(rois.device):
+        check(lib().upsnet_roi_align_fpn_forward(fp, hs, ws, sc, B, Cc, lay, ptr(rois), R, pooled_height,
+                                                 pooled_width, sampling_ratio, ptr(out), ptr(levels),
+                                                 stream_ptr(rois.device)), "fpn_roi_align")
+    return (out, levels) if return_levels else out
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS
+# ------------------------------------------------------------------------------------------------
+class _Workspace:
+    """Caller-owned, grow-only device scratch (the C ABI never allocates)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, device, nbytes):
+        b = self.buf.get(device)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+            self.buf[device] = b
+        return b
+
+
+_nms_ws = _Workspace()
+_pan_ws = _Workspace()
+
+
+def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
+    """boxes_sorted [total,4] fp32 sorted by descending score inside each segment; seg_offsets int32
+    [S+1] (device).  Returns (keep [S,max_seg_len] int32 positions relative to segment start,
+    counts [S] int32) -- both on the device, no host synchronisation."""
+    require_cuda(boxes_sorted, seg_offsets)
+    boxes_sorted = f32c(boxes_sorted)
+    assert seg_offsets.dtype == torch.int32
+    S = seg_offsets.numel() - 1
+    dev = boxes_sorted.device
+    nbytes = C.c_size_t(0)
+    check(lib().upsnet_nms_workspace_bytes(S, max_seg_len, C.byref(nbytes)), "nms_workspace_bytes")
+    ws = _nms_ws.get(dev, nbytes.value)
+    keep = torch.empty((S, max_seg_len), dtype=torch.int32, device=dev)
+    cnt = torch.empty((S,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().upsnet_nms_segmented(ptr(boxes_sorted), ptr(seg_offsets), S, max_seg_len, float(thresh),
+                                         ptr(keep), ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev)), "nms")
+    return keep, cnt
+
+
+def nms(boxes, scores, thresh):
+    """Device API: boxes [N,4], scores [N] (CUDA) -> int64 indices of kept boxes, descending score
+    (== order[keep] of nms/gpu_nms.pyx:32-38).  One D2H of the count only."""
+    require_cuda(boxes, scores)
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    _, order = torch.sort(scores.float(), descending=True, stable=True)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=boxes.device)
+    keep, cnt = nms_segmented(boxes.float()[order], seg, n, thresh)
+    k = int(cnt.item())
+    return order[keep[0, :k].long()]
+
+
+def gpu_nms(dets, thresh, device_id=0):
+    """nms/gpu_nms.pyx:23-38: dets np.float32 [N,5] on the HOST -> list[int]."""
+    dets = np.ascontiguousarray(dets, dtype=np.float32)
+    if dets.shape[0] == 0:
+        return []
+    d = torch.from_numpy(dets).to(torch.device("cuda", device_id))
+    return nms(d[:, :4], d[:, 4], thresh).cpu().tolist()
+
+
+def gpu_nms_wrapper(thresh, device_id):
+    """nms/nms.py:43-46."""
+    def _nms(dets):
+        return gpu_nms(dets, thresh, device_id)
+    return _nms
+
+
+# ------------------------------------------------------------------------------------------------
+# modules (reference names / signatures / parameter names)
+# ------------------------------------------------------------------------------------------------
+class DeformConv(nn.Module):
+    """operators/modules/deform_conv.py:27-64.  Parameters are created on CUDA like the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__()
+        assert in_channels % groups == 0, 'in_channels must be divisible by groups'
+        assert out_channels % groups == 0, 'out_channels must be divisible by groups'
+        assert out_channels % deformable_groups == 0, 'out_channels must be divisible by deformable groups'
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride = _pair(kernel_size), _pair(stride)
+        self.padding, self.dilation = _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        dev = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        self.weight = Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size, device=dev))
+        if bias:
+            self.bias = Parameter(torch.empty(out_channels, device=dev))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, data, offset):
+        return deform_conv(data, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                           self.deformable_groups)
+
+
+class DeformConvWithOffset(nn.Module):
+    """operators/modules/deform_conv.py:67-78 (submodules `conv_offset`, `conv`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__()
+        self.conv_offset = nn.Conv2d(in_channels, kernel_size * kernel_size * 2 * deformable_groups,
+                                     kernel_size=3, stride=1, padding=1)
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+        self.conv = DeformConv(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                               padding=padding, dilation=dilation, groups=groups,
+                               deformable_groups=deformable_groups, bias=bias)
+
+    def forward(self, x):
+        offset = conv2d(x, self.conv_offset.weight, self.conv_offset.bias, 1, 1, 1)
+        return self.conv(x, offset)
+
+
+class ModDeformConv(DeformConv):
+    """operators/modules/mod_deform_conv.py:24-67: forward(data, offset_mask) with
+    offset = cat(chunk0, chunk1), mask = 2*sigmoid(chunk2)."""
+
+    def forward(self, data, offset_mask):
+        offset_1, offset_2, mask = torch.chunk(offset_mask, 3, dim=1)
+        offset = torch.cat((offset_1, offset_2), dim=1)
+        mask = torch.sigmoid(mask) * 2
+        return deform_conv(data, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                           self.deformable_groups, mask=mask)
+
+
+ModulatedDeformConv = ModDeformConv
+
+
+class ModDeformConvWithOffsetMask(nn.Module):
+    """operators/modules/mod_deform_conv.py:70-81 (submodules `conv_offset_mask`, `conv`)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__()
+        self.conv_offset_mask = nn.Conv2d(in_channels, kernel_size * kernel_size * 3 * deformable_groups,
+                                          kernel_size=3, stride=1, padding=1)
+        self.conv_offset_mask.weight.data.zero_()
+        self.conv_offset_mask.bias.data.zero_()
+        self.conv = ModDeformConv(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                                  padding=padding, dilation=dilation, groups=groups,
+                                  deformable_groups=deformable_groups, bias=bias)
+
+    def forward(self, x):
+        om = conv2d(x, self.conv_offset_mask.weight, self.conv_offset_mask.bias, 1, 1, 1)
+        return self.conv(x, om)
+
+
+class RoIAlignFunction:
+    """functions/roialign.py:21-43 call shape: RoIAlignFunction(ph, pw, scale)(features, rois)."""
+
+    def __init__(self, pooled_height, pooled_width, spatial_scale, sampling_ratio=2):
+        self.pooled_width, self.pooled_height = int(pooled_width), int(pooled_height)
+        self.spatial_scale, self.sampling_ratio = float(spatial_scale), sampling_ratio
+
+    def __call__(self, features, rois):
+        if not features.is_cuda:
+            raise Exception('not implemented')
+        return roi_align(features, rois, self.pooled_height, self.pooled_width, self.spatial_scale,
+                         self.sampling_ratio)
+
+
+class RoIAlign(nn.Module):
+    """operators/modules/roialign.py:20-29."""
+
+    def __init__(self, pooled_height, pooled_width, spatial_scale):
+        super().__init__()
+        self.pooled_width, self.pooled_height = int(pooled_width), int(pooled_height)
+        self.spatial_scale = float(spatial_scale)
+
+    def forward(self, features, rois):
+        return RoIAlignFunction(self.pooled_height, self.pooled_width, self.spatial_scale)(features, rois)
+
+
+ROIAlign = RoIAlign
+
+
+class FPNRoIAlign(nn.Module):
+    """operators/modules/fpn_roi_align.py:22-62; forward([P2..P5], rois[N,5]) -> [N,C,ph,pw]."""
+
+    def __init__(self, pooled_height, pooled_width, spatial_scale, with_expand=False):
+        super().__init__()
+        self.pooled_width, self.pooled_height = int(pooled_width), int(pooled_height)
+        self.spatial_scale = spatial_scale
+        self.with_expand = with_expand
+
+    def forward(self, feat, rois):
+        return fpn_roi_align(list(feat), rois, self.pooled_height, self.pooled_width, self.spatial_scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# panoptic head
+# ------------------------------------------------------------------------------------------------
+def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
+                  want_sem=False):
+    """Fused MaskRemoval + SegTerm + void/argmax (upsnet_panoptic_head).
+    fcn_output [1,S,H,W]; mask_rois [n,4]; cls_prob [n]; mask_logit [n,1,28,28] or [n,28,28];
+    cls_idx int64 [n].  Returns (keep_inds int64 [k], panoptic_output int64 [1,H,W][, sem int64 [1,H,W]])."""
+    require_cuda(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx)
+    assert fcn_output.dim() == 4 and fcn_output.shape[0] == 1, "only support batch size = 1"
+    fcn = f32c(fcn_output)
+    _, S, H, W = fcn.shape
+    boxes, prob, ml = f32c(mask_rois), f32c(cls_prob).reshape(-1), f32c(mask_logit)
+    cls = cls_idx.to(torch.int64).contiguous()
+    n = boxes.shape[0]
+    assert boxes.shape == (n, 4) and prob.numel() == n and ml.numel() == n * 784 and cls.numel() == n
+    dev = fcn.device
+    num_thing = S - num_stuff
+    nbytes = C.c_size_t(0)
+    check(lib().upsnet_panoptic_workspace_bytes(n, H, W, num_thing, C.byref(nbytes)), "panoptic_workspace_bytes")
+    ws = _pan_ws.get(dev, nbytes.value)
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    k = torch.empty((1,), dtype=torch.int32, device=dev)
+    labels = torch.empty((1, H, W), dtype=torch.int64, device=dev)
+    sem = torch.empty((1, H, W), dtype=torch.int64, device=dev) if want_sem else None
+    with torch.cuda.device(dev):
+        check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, num_stuff,
+                                         float(fraction_threshold), ptr(keep), ptr(k), ptr(labels), ptr(sem),
+                                         ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
+    keep = keep[:int(k.item())]
+    return (keep, labels, sem) if want_sem else (keep, labels)
+
+
+class PanopticHead(nn.Module):
+    """The parameter-free panoptic head of models/resnet_upsnet.py:217-247 as one module (the
+    reference has no such class: SURVEY.md F1).  forward takes what lines 220-227 consume."""
+
+    def __init__(self, num_seg_classes, num_classes, fraction_threshold=0.3):
+        super().__init__()
+        self.num_seg_classes, self.num_classes = num_seg_classes, num_classes
+        self.num_stuff = num_seg_classes - num_classes + 1  # unary_logits.py:72
+        self.fraction_threshold = fraction_threshold
+
+    def forward(self, fcn_output, mask_rois, cls_prob, mask_score, cls_idx, want_sem=False):
+        """mask_rois [n,5] (batch,x1,y1,x2,y2) or [n,4]; mask_score [n,1,28,28] = logit of the predicted
+        class (resnet_upsnet.py:220).  Returns dict(keep_inds, panoptic_outputs[, fcn_outputs])."""
+        boxes = mask_rois[:, 1:] if mask_rois.shape[1] == 5 else mask_rois
+        out = panoptic_fuse(fcn_output, boxes, cls_prob, mask_score, cls_idx, self.num_stuff,
+                            self.fraction_threshold, want_sem)
+        res = {'keep_inds': out[0], 'panoptic_outputs': out[1]}
+        if want_sem:
+            res['fcn_outputs'] = out[2]
+        return res
