@@ -1,0 +1,185 @@
+"""Device-resident restatement of the reference's CPU detection glue that sits between the hot
+kernels (F8: >=6 host round trips per image in the reference).
+
+  generate_anchors / level anchors      rpn/generate_anchors.py:50-76,156-206;
+                                        operators/functions/pyramid_proposal.py:73-100
+  bbox_transform / clip_boxes           bbox/bbox_transform.py:290-330, :45-60
+  pyramid_proposals                     operators/functions/pyramid_proposal.py:41-222 +
+                                        operators/modules/pyramid_proposal.py:36-67
+  mask_roi                              operators/modules/mask_roi.py:36-146
+
+Tensors stay on the GPU; NMS is the segmented device kernel (one launch for all levels / classes).
+The remaining host synchronisations are size reads (counts), noted inline.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .operators import nms_segmented
+
+BBOX_XFORM_CLIP = math.log(1000. / 16.)
+
+
+def generate_anchors(stride, sizes, aspect_ratios=(0.5, 1, 2)):
+    """Anchors (x1,y1,x2,y2) centred on (stride-1)/2: ratio enumeration with np.round on the
+    widths/heights of the base window, then scale enumeration (float64, like the reference)."""
+    scales = np.array(sizes, dtype=np.float64) / stride
+    ratios = np.array(aspect_ratios, dtype=np.float64)
+    base = float(stride)
+    ctr = 0.5 * (base - 1)
+    area = base * base
+    ws = np.round(np.sqrt(area / ratios))
+    hs = np.round(ws * ratios)
+    out = []
+    for w, h in zip(ws, hs):
+        for s in scales:
+            W, H = w * s, h * s
+            out.append([ctr - 0.5 * (W - 1), ctr - 0.5 * (H - 1), ctr + 0.5 * (W - 1), ctr + 0.5 * (H - 1)])
+    return np.array(out, dtype=np.float64)
+
+
+def level_anchors(stride, height, width, scales=(8,), ratios=(0.5, 1, 2)):
+    """All shifted anchors of one level, rows ordered (h, w, a) (pyramid_proposal.py:83-100),
+    cast to float32 as bbox_transform does (bbox_transform.py:298)."""
+    sub = generate_anchors(stride, np.array(scales) * stride, ratios)
+    sx, sy = np.meshgrid(np.arange(0, width) * stride, np.arange(0, height) * stride)
+    shifts = np.vstack((sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel())).transpose()
+    A, K = sub.shape[0], shifts.shape[0]
+    anchors = sub.reshape((1, A, 4)) + shifts.reshape((1, K, 4)).transpose((1, 0, 2))
+    return anchors.reshape((K * A, 4)).astype(np.float32)
+
+
+def bbox_transform(boxes, deltas, weights=(1., 1., 1., 1.)):
+    """boxes [N,4], deltas [N,4K] -> [N,4K] (float32 arithmetic, same operation order)."""
+    widths = boxes[:, 2] - boxes[:, 0] + 1.0
+    heights = boxes[:, 3] - boxes[:, 1] + 1.0
+    ctr_x = boxes[:, 0] + 0.5 * widths
+    ctr_y = boxes[:, 1] + 0.5 * heights
+    wx, wy, ww, wh = weights
+    dx = deltas[:, 0::4] / wx
+    dy = deltas[:, 1::4] / wy
+    dw = torch.clamp(deltas[:, 2::4] / ww, max=BBOX_XFORM_CLIP)
+    dh = torch.clamp(deltas[:, 3::4] / wh, max=BBOX_XFORM_CLIP)
+    pcx = dx * widths[:, None] + ctr_x[:, None]
+    pcy = dy * heights[:, None] + ctr_y[:, None]
+    pw = torch.exp(dw) * widths[:, None]
+    ph = torch.exp(dh) * heights[:, None]
+    out = torch.empty_like(deltas)
+    out[:, 0::4] = pcx - 0.5 * pw
+    out[:, 1::4] = pcy - 0.5 * ph
+    out[:, 2::4] = pcx + 0.5 * pw - 1
+    out[:, 3::4] = pcy + 0.5 * ph - 1
+    return out
+
+
+def clip_boxes(boxes, im_h, im_w):
+    boxes[:, 0::4].clamp_(min=0, max=im_w - 1)
+    boxes[:, 1::4].clamp_(min=0, max=im_h - 1)
+    boxes[:, 2::4].clamp_(min=0, max=im_w - 1)
+    boxes[:, 3::4].clamp_(min=0, max=im_h - 1)
+    return boxes
+
+
+class ProposalGenerator:
+    """PyramidProposal (individual_proposals=True, the shipped setting: config.py:123)."""
+
+    def __init__(self, feat_stride=(4, 8, 16, 32, 64), scales=(8,), ratios=(0.5, 1, 2), pre_nms_top_n=1000,
+                 post_nms_top_n=1000, nms_thresh=0.7, min_size=0):
+        self.feat_stride, self.scales, self.ratios = feat_stride, scales, ratios
+        self.pre, self.post, self.thresh, self.min_size = pre_nms_top_n, post_nms_top_n, nms_thresh, min_size
+        self._anchors = {}
+
+    def anchors(self, lvl, h, w, device):
+        key = (lvl, h, w, str(device))
+        if key not in self._anchors:
+            self._anchors[key] = torch.from_numpy(
+                level_anchors(self.feat_stride[lvl], h, w, self.scales, self.ratios)).to(device)
+        return self._anchors[key]
+
+    def __call__(self, cls_probs, bbox_preds, im_info):
+        """cls_probs[l] [1,A,h,w] (sigmoid), bbox_preds[l] [1,4A,h,w]; im_info (H, W, scale).
+        Returns rois [R<=post,5] (batch 0), scores [R]."""
+        dev = cls_probs[0].device
+        im_h, im_w, im_scale = float(im_info[0]), float(im_info[1]), float(im_info[2])
+        L = len(cls_probs)
+        boxes_l, scores_l, lens = [], [], []
+        for l in range(L):
+            A = cls_probs[l].shape[1]
+            h, w = cls_probs[l].shape[-2:]
+            scores = cls_probs[l][0].permute(1, 2, 0).reshape(-1)                 # (h, w, a)
+            deltas = bbox_preds[l][0].reshape(A, 4, h, w).permute(2, 3, 0, 1).reshape(-1, 4)
+            k = min(self.pre, scores.numel()) if self.pre > 0 else scores.numel()
+            top_s, top_i = torch.topk(scores, k, sorted=True)                     # descending
+            props = bbox_transform(self.anchors(l, h, w, dev)[top_i], deltas[top_i])
+            props = clip_boxes(props, im_h, im_w)
+            if self.min_size > 0:  # config.test.rpn_min_size = 0 in every shipped yaml
+                ws = props[:, 2] - props[:, 0] + 1
+                hs = props[:, 3] - props[:, 1] + 1
+                keep = (ws >= self.min_size * im_scale) & (hs >= self.min_size * im_scale)
+                props, top_s = props[keep], top_s[keep]                           # host sync (size)
+            boxes_l.append(props); scores_l.append(top_s); lens.append(props.shape[0])
+        boxes = torch.cat(boxes_l)
+        scores = torch.cat(scores_l)
+        offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        max_len = max(max(lens), 1)
+        keep, cnt = nms_segmented(boxes, offs, max_len, self.thresh)             # one launch, all levels
+        # gather kept boxes of every level without leaving the device
+        pos = torch.arange(max_len, device=dev)[None, :]
+        limit = cnt.clamp(max=self.post if self.post > 0 else max_len)[:, None]
+        valid = pos < limit
+        gidx = (keep.long() + offs[:-1, None].long())[valid]
+        out_boxes, out_scores = boxes[gidx], scores[gidx]
+        # modules/pyramid_proposal.py:61-67: final top-N over levels by score
+        _, idx = torch.sort(-out_scores, dim=0, stable=True)
+        idx = idx[:self.post]
+        rois = torch.cat([torch.zeros((idx.numel(), 1), device=dev), out_boxes[idx]], 1)
+        return rois, out_scores[idx]
+
+
+class MaskROI:
+    """operators/modules/mask_roi.py:24-146 on the device (decode, clip, per-class threshold + NMS,
+    global top-`top_n`).  Output order = the reference's: class-major, NMS (descending score) order."""
+
+    def __init__(self, top_n, num_classes, nms_thresh=0.5, class_agnostic=False, score_thresh=0.05,
+                 bbox_reg_weights=(10., 10., 5., 5.)):
+        self.top_n, self.num_classes = top_n, num_classes
+        self.nms_thresh, self.class_agnostic, self.score_thresh = nms_thresh, class_agnostic, score_thresh
+        self.weights = bbox_reg_weights
+
+    def __call__(self, rois, bbox_delta, cls_prob, im_info):
+        dev = rois.device
+        C = self.num_classes
+        proposal = bbox_transform(rois[:, 1:], bbox_delta, self.weights)
+        proposal = clip_boxes(proposal, float(im_info[0]), float(im_info[1])).reshape(-1, C, 4)
+        prob = cls_prob[:, 1:]                                    # skip background (j = 0)
+        cand = prob > self.score_thresh
+        ridx, cidx = torch.nonzero(cand, as_tuple=True)           # host sync (size); row-major = roi order
+        if ridx.numel() == 0:                                     # mask_roi.py:132-139
+            return (torch.ones(1, device=dev), torch.zeros(1, 5, device=dev),
+                    torch.zeros(1, dtype=torch.long, device=dev))
+        sc = prob[ridx, cidx]
+        bx = proposal[ridx, cidx + 1]
+        cls = cidx + 1
+        seg_key = torch.zeros_like(cls) if self.class_agnostic else cls - 1
+        nseg = 1 if self.class_agnostic else C - 1
+        # order: segment ascending, score descending (stable => ties keep roi order)
+        o1 = torch.sort(sc, descending=True, stable=True)[1]
+        o2 = torch.sort(seg_key[o1], stable=True)[1]
+        order = o1[o2]
+        sc, bx, cls, seg_key = sc[order], bx[order], cls[order], seg_key[order]
+        counts = torch.bincount(seg_key, minlength=nseg)
+        offs = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
+        offs[1:] = torch.cumsum(counts, 0).int()
+        max_len = int(counts.max().item())                       # host sync (size)
+        keep, cnt = nms_segmented(bx, offs, max_len, self.nms_thresh)
+        pos = torch.arange(max_len, device=dev)[None, :]
+        valid = pos < cnt[:, None]
+        gidx = (keep.long() + offs[:-1, None].long())[valid]      # class-major, NMS order inside
+        sc, bx, cls = sc[gidx], bx[gidx], cls[gidx]
+        if self.top_n > 0 and sc.numel() > self.top_n:            # mask_roi.py:106-121
+            thresh = torch.sort(sc)[0][-self.top_n]
+            sel = sc >= thresh
+            sc, bx, cls = sc[sel], bx[sel], cls[sel]
+        boxes = torch.cat([torch.zeros((bx.shape[0], 1), device=dev), bx], 1)
+        return sc, boxes, cls.long()

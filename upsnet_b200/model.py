@@ -1,0 +1,460 @@
+"""resnet_upsnet inference engine: the host-side mirror of upsnet/models/{resnet,fpn,rpn,rcnn,fcn,
+resnet_upsnet}.py running on the sm_100a C ABI.
+
+* Same module tree / parameter names as the reference, so its checkpoints load with
+  load_state_dict (e.g. resnet_backbone.res3.layers.0.conv2_offset.weight,
+  fcn_head.fcn_subnet.conv.0.0.conv_offset.weight; SURVEY.md section 5 "Checkpoint / resume").
+* forward(data, label=None) -> the reference's result dict (models/resnet_upsnet.py:209-247):
+  cls_probs, pred_boxes, mask_probs, fcn_outputs, cls_inds, panoptic_cls_inds,
+  panoptic_cls_probs, panoptic_outputs.
+* Frozen BatchNorm (models/resnet.py:69-78: always eval, requires_grad False) is folded into the
+  preceding convolution once (prepare()); bias/ReLU/residual live in the conv epilogue.
+* Inference only (label must be None): training is BASELINE config #4, outside this round.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import operators as ops
+from .detection import MaskROI, ProposalGenerator
+from .operators import DeformConv, DeformConvWithOffset
+
+
+class UPSNetConfig:
+    """The hot-path knobs of upsnet/config/config.py + experiments/*.yaml."""
+
+    def __init__(self, **kw):
+        self.num_classes = 9              # dataset.num_classes (Cityscapes: 8 things + bg)
+        self.num_seg_classes = 19         # dataset.num_seg_classes
+        self.backbone_with_dconv = 100    # network.backbone_with_dconv (3 => DCN in res3..res5)
+        self.backbone_with_dilation = False
+        self.backbone_with_dpyramid = False
+        self.fpn_feature_dim = 256
+        self.fpn_with_gap = False
+        self.fcn_num_layers = 2
+        self.num_anchors = 3
+        self.anchor_scales = (8,)
+        self.anchor_ratios = (0.5, 1, 2)
+        self.rpn_feat_stride = (4, 8, 16, 32, 64)
+        self.mask_size = 28
+        self.bbox_reg_weights = (10., 10., 5., 5.)
+        self.rpn_pre_nms_top_n = 1000
+        self.rpn_post_nms_top_n = 1000
+        self.rpn_nms_thresh = 0.7
+        self.rpn_min_size = 0
+        self.nms_thresh = 0.5
+        self.max_det = 100
+        self.score_thresh = 0.05
+        self.panoptic_score_thresh = 0.6
+        self.panoptic_box_keep_fraction = 0.7   # < 1 => enable_void (resnet_upsnet.py:66-67)
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+    @classmethod
+    def cityscapes_r50(cls):      # experiments/upsnet_resnet50_cityscapes_16gpu.yaml
+        return cls()
+
+    @classmethod
+    def coco_r101_dcn(cls):       # experiments/upsnet_resnet101_dcn_coco_3x_16gpu.yaml
+        return cls(num_classes=81, num_seg_classes=133, backbone_with_dconv=3, fpn_with_gap=True,
+                   fcn_num_layers=3)
+
+
+def _fold_bn(conv_w, bn):
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return (conv_w * scale.view(-1, 1, 1, 1)).contiguous(), (bn.bias - bn.running_mean * scale).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# backbone (models/resnet.py)
+# ---------------------------------------------------------------------------------------------
+class Bottleneck(nn.Module):
+    """models/resnet.py:53-100 (and :102-153 when deformable): 1x1(stride) -> 3x3 -> 1x1, +res."""
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, deformable=False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=stride, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.deformable = deformable
+        if deformable:
+            self.conv2_offset = nn.Conv2d(planes, 18, 3, 1, 1)
+            self.conv2_offset.weight.data.zero_()
+            self.conv2_offset.bias.data.zero_()
+            self.conv2 = DeformConv(planes, planes, 3, stride=1, padding=dilation, dilation=dilation, bias=False)
+        else:
+            self.conv2 = nn.Conv2d(planes, planes, 3, 1, dilation, dilation, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+        self.stride, self.dilation = stride, dilation
+        self._f = None
+
+    def prepare(self):
+        f = {}
+        f["w1"], f["b1"] = _fold_bn(self.conv1.weight, self.bn1)
+        f["w2"], f["b2"] = _fold_bn(self.conv2.weight, self.bn2)
+        f["w3"], f["b3"] = _fold_bn(self.conv3.weight, self.bn3)
+        if self.downsample is not None:
+            f["wd"], f["bd"] = _fold_bn(self.downsample[0].weight, self.downsample[1])
+        self._f = {k: v.detach() for k, v in f.items()}
+
+    def forward(self, x):
+        f = self._f
+        out = ops.conv2d(x, f["w1"], f["b1"], stride=self.stride, relu=True)
+        if self.deformable:
+            offset = ops.conv2d(out, self.conv2_offset.weight, self.conv2_offset.bias, 1, 1, 1)
+            out = ops.deform_conv(out, offset, f["w2"], f["b2"], 1, self.dilation, self.dilation, relu=True)
+        else:
+            out = ops.conv2d(out, f["w2"], f["b2"], 1, self.dilation, self.dilation, relu=True)
+        residual = x if self.downsample is None else ops.conv2d(x, f["wd"], f["bd"], stride=self.stride)
+        return ops.conv2d(out, f["w3"], f["b3"], residual=residual, relu=True)
+
+
+class Stem(nn.Module):
+    """models/resnet.py:155-175 `conv1`: 7x7/2 conv + BN + ReLU + 3x3/2 max-pool."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self._f = None
+
+    def prepare(self):
+        w, b = _fold_bn(self.conv1.weight, self.bn1)
+        self._f = (w.detach(), b.detach())
+
+    def forward(self, x):
+        x = ops.conv2d(x, self._f[0], self._f[1], stride=2, padding=3, relu=True)
+        return F.max_pool2d(x, 3, 2, 1)
+
+
+class ResBlock(nn.Module):
+    """models/resnet.py:177-207 res_block; parameters live under `.layers.<i>`."""
+
+    def __init__(self, planes, blocks, stride=1, dilation=1, deformable=False, with_dpyramid=False):
+        super().__init__()
+        inplanes = planes * 2 if planes != 64 else planes
+        downsample = None
+        if stride != 1 or inplanes != planes * 4:
+            downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                       nn.BatchNorm2d(planes * 4))
+        layers = [Bottleneck(inplanes, planes, stride, dilation, downsample, deformable)]
+        for _ in range(1, blocks - 1):
+            layers.append(Bottleneck(planes * 4, planes, dilation=dilation, deformable=deformable))
+        layers.append(Bottleneck(planes * 4, planes, dilation=dilation, deformable=deformable or with_dpyramid))
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class ResNetBackbone(nn.Module):
+    """models/resnet.py:314-356."""
+
+    def __init__(self, blocks, cfg):
+        super().__init__()
+        d = cfg.backbone_with_dconv
+        self.conv1 = Stem()
+        self.res2 = ResBlock(64, blocks[0])
+        self.res3 = ResBlock(128, blocks[1], 2, deformable=d <= 3, with_dpyramid=cfg.backbone_with_dpyramid)
+        self.res4 = ResBlock(256, blocks[2], 2, deformable=d <= 4, with_dpyramid=cfg.backbone_with_dpyramid)
+        s5, d5 = (1, 2) if cfg.backbone_with_dilation else (2, 1)
+        self.res5 = ResBlock(512, blocks[3], s5, d5, deformable=d <= 5)
+
+    def forward(self, x):
+        c1 = self.conv1(x)
+        r2 = self.res2(c1)
+        r3 = self.res3(r2)
+        r4 = self.res4(r3)
+        return r2, r3, r4, self.res5(r4)
+
+
+# ---------------------------------------------------------------------------------------------
+# FPN / RPN / heads (models/fpn.py, rpn.py, rcnn.py, fcn.py)
+# ---------------------------------------------------------------------------------------------
+class FPN(nn.Module):
+    """models/fpn.py:25-104 (with_norm='none', nearest upsampling, P6 = stride-2 subsample of P5)."""
+
+    def __init__(self, feature_dim, with_gap):
+        super().__init__()
+        self.feature_dim = feature_dim
+        if with_gap:
+            self.fpn_gap = nn.Linear(2048, feature_dim)
+        for name, cin in (("fpn_p5_1x1", 2048), ("fpn_p4_1x1", 1024), ("fpn_p3_1x1", 512), ("fpn_p2_1x1", 256)):
+            setattr(self, name, nn.Conv2d(cin, feature_dim, 1))
+        for name in ("fpn_p5", "fpn_p4", "fpn_p3", "fpn_p2"):
+            setattr(self, name, nn.Conv2d(feature_dim, feature_dim, 3, padding=1))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight.data, a=1)
+                m.bias.data.zero_()
+
+    @staticmethod
+    def _c(m, x, residual=None, padding=0):
+        return ops.conv2d(x, m.weight, m.bias, padding=padding, residual=residual)
+
+    def forward(self, res2, res3, res4, res5):
+        p5_1x1 = self._c(self.fpn_p5_1x1, res5)
+        if hasattr(self, "fpn_gap"):
+            gap = ops.linear(res5.mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias)
+            p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1)
+        up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")  # noqa: E731
+        p4_plus = self._c(self.fpn_p4_1x1, res4, residual=up(p5_1x1))   # lateral + top-down fused
+        p3_plus = self._c(self.fpn_p3_1x1, res3, residual=up(p4_plus))
+        p2_plus = self._c(self.fpn_p2_1x1, res2, residual=up(p3_plus))
+        p5 = self._c(self.fpn_p5, p5_1x1, padding=1)
+        p4 = self._c(self.fpn_p4, p4_plus, padding=1)
+        p3 = self._c(self.fpn_p3, p3_plus, padding=1)
+        p2 = self._c(self.fpn_p2, p2_plus, padding=1)
+        p6 = p5[:, :, ::2, ::2].contiguous()                            # MaxPool2d(kernel 1, stride 2)
+        return p2, p3, p4, p5, p6
+
+
+class RPN(nn.Module):
+    """models/rpn.py:26-57."""
+
+    def __init__(self, num_anchors, input_dim):
+        super().__init__()
+        self.num_anchors = num_anchors
+        self.conv_proposal = nn.Sequential(nn.Conv2d(input_dim, input_dim, 3, padding=1), nn.ReLU(inplace=True))
+        self.cls_score = nn.Conv2d(input_dim, num_anchors, 1)
+        self.bbox_pred = nn.Conv2d(input_dim, num_anchors * 4, 1)
+        for m in (self.conv_proposal[0], self.cls_score, self.bbox_pred):
+            nn.init.normal_(m.weight.data, 0, 0.01)
+            m.bias.data.zero_()
+        self._f = None
+
+    def prepare(self):  # the two 1x1 heads share their input: one GEMM with Cout = A + 4A
+        self._f = (torch.cat([self.cls_score.weight, self.bbox_pred.weight]).detach().contiguous(),
+                   torch.cat([self.cls_score.bias, self.bbox_pred.bias]).detach().contiguous())
+
+    def forward(self, x):
+        c = self.conv_proposal[0]
+        t = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
+        both = ops.conv2d(t, self._f[0], self._f[1])
+        cls_score, bbox_pred = both[:, :self.num_anchors], both[:, self.num_anchors:]
+        return cls_score, bbox_pred, torch.sigmoid(cls_score)
+
+
+class RCNN(nn.Module):
+    """models/rcnn.py:89-146."""
+
+    def __init__(self, num_classes, num_reg_classes, pool_size=7, dim_in=256, dim_hidden=1024):
+        super().__init__()
+        self.pool_size = pool_size
+        self.roi_pooling = ops.FPNRoIAlign(pool_size, pool_size, [1.0 / 4, 1.0 / 8, 1.0 / 16, 1.0 / 32])
+        self.fc6 = nn.Sequential(nn.Linear(pool_size ** 2 * dim_in, dim_hidden), nn.ReLU(inplace=True))
+        self.fc7 = nn.Sequential(nn.Linear(dim_hidden, dim_hidden), nn.ReLU(inplace=True))
+        self.cls_score = nn.Linear(dim_hidden, num_classes)
+        self.bbox_pred = nn.Linear(dim_hidden, num_reg_classes * 4)
+        for m in (self.fc6[0], self.fc7[0]):
+            nn.init.kaiming_uniform_(m.weight.data, a=1)
+            m.bias.data.fill_(0)
+        nn.init.normal_(self.cls_score.weight.data, 0, 0.01)
+        self.cls_score.bias.data.fill_(0)
+        nn.init.normal_(self.bbox_pred.weight.data, 0, 0.001)
+        self.bbox_pred.bias.data.fill_(0)
+        self.num_classes = num_classes
+        self._f = None
+
+    def prepare(self):
+        self._f = (torch.cat([self.cls_score.weight, self.bbox_pred.weight]).detach().contiguous(),
+                   torch.cat([self.cls_score.bias, self.bbox_pred.bias]).detach().contiguous())
+
+    def forward(self, feat, rois):
+        pool = self.roi_pooling(feat, rois)
+        x = pool.view(pool.size(0), -1)
+        fc6 = ops.linear(x, self.fc6[0].weight, self.fc6[0].bias, relu=True)
+        fc7 = ops.linear(fc6, self.fc7[0].weight, self.fc7[0].bias, relu=True)
+        both = ops.linear(fc7, self._f[0], self._f[1])
+        return {"cls_score": both[:, :self.num_classes].contiguous(),
+                "bbox_pred": both[:, self.num_classes:].contiguous(), "fc_feat": fc7}
+
+
+class MaskBranch(nn.Module):
+    """models/rcnn.py:34-87: ROIAlign 14x14 -> 4 x (3x3 + ReLU) -> deconv 2x2/2 + ReLU -> 1x1."""
+
+    def __init__(self, num_classes, mask_size=28, dim_in=256, dim_hidden=256):
+        super().__init__()
+        self.roi_pooling = ops.FPNRoIAlign(mask_size // 2, mask_size // 2, [1.0 / 4, 1.0 / 8, 1.0 / 16, 1.0 / 32])
+        for i, cin in enumerate((dim_in, dim_hidden, dim_hidden, dim_hidden), start=1):
+            setattr(self, "mask_conv%d" % i, nn.Sequential(nn.Conv2d(cin, dim_hidden, 3, 1, 1), nn.ReLU(inplace=True)))
+        self.mask_deconv1 = nn.Sequential(nn.ConvTranspose2d(dim_hidden, dim_hidden, 2, 2, 0), nn.ReLU(inplace=True))
+        self.mask_score = nn.Conv2d(dim_hidden, num_classes, 1)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.kaiming_normal_(m.weight.data, mode="fan_in")
+                m.bias.data.zero_()
+        self._f = None
+
+    def prepare(self):
+        # ConvTranspose2d(k=2,s=2): out[n,co,2i+a,2j+b] = sum_ci x[n,ci,i,j] W[ci,co,a,b] + bias[co]
+        # == 1x1 conv to 4*Cout channels ordered (a,b,co) followed by a pixel shuffle.
+        w = self.mask_deconv1[0].weight                      # [Cin, Cout, 2, 2]
+        cin, cout = w.shape[0], w.shape[1]
+        w1 = w.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1).detach().contiguous()
+        b1 = self.mask_deconv1[0].bias.repeat(4).detach().contiguous()
+        self._f = (w1, b1, cout)
+
+    def forward(self, feat, rois):
+        x = self.roi_pooling(feat, rois)
+        for i in range(1, 5):
+            c = getattr(self, "mask_conv%d" % i)[0]
+            x = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
+        w1, b1, cout = self._f
+        y = ops.conv2d(x, w1, b1, relu=True)                 # [n, 4*Cout, h, w]
+        n, _, h, w = y.shape
+        y = y.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
+        return ops.conv2d(y, self.mask_score.weight, self.mask_score.bias)
+
+
+class FCNSubNet(nn.Module):
+    """models/fcn.py:29-73: num_layers x (DeformConvWithOffset + ReLU); channel drop at layer n-2."""
+
+    def __init__(self, in_channels, out_channels, num_layers):
+        super().__init__()
+        assert num_layers >= 2
+        self.num_layers = num_layers
+        self.conv = nn.ModuleList()
+        for i in range(num_layers):
+            if i == num_layers - 2:
+                layer = DeformConvWithOffset(in_channels, out_channels, 3, stride=1, padding=1, dilation=1)
+                in_channels = out_channels
+            else:
+                layer = DeformConvWithOffset(in_channels, in_channels, 3, stride=1, padding=1, dilation=1)
+            self.conv.append(nn.Sequential(layer, nn.ReLU(inplace=True)))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.fill_(0)
+                m.bias.data.fill_(0)
+            elif isinstance(m, DeformConv):
+                nn.init.kaiming_normal_(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.fill_(0)
+
+    def forward(self, x):
+        for i in range(self.num_layers):
+            l = self.conv[i][0]
+            offset = ops.conv2d(x, l.conv_offset.weight, l.conv_offset.bias, 1, 1, 1)
+            x = ops.deform_conv(x, offset, l.conv.weight, l.conv.bias, l.conv.stride, l.conv.padding,
+                                l.conv.dilation, l.conv.deformable_groups, relu=True)   # ReLU fused
+        return x
+
+
+class FCNHead(nn.Module):
+    """models/fcn.py:76-108."""
+
+    def __init__(self, in_channels, num_classes, num_layers, upsample_rate=4):
+        super().__init__()
+        self.fcn_subnet = FCNSubNet(in_channels, 128, num_layers)
+        self.upsample_rate = upsample_rate
+        self.score = nn.Conv2d(512, num_classes, 1)
+        nn.init.normal_(self.score.weight.data, 0, 0.01)
+        self.score.bias.data.zero_()
+
+    def forward(self, p2, p3, p4, p5):
+        p2, p3, p4, p5 = (self.fcn_subnet(p) for p in (p2, p3, p4, p5))
+        p3 = F.interpolate(p3, None, 2, mode="bilinear", align_corners=False)
+        p4 = F.interpolate(p4, None, 4, mode="bilinear", align_corners=False)
+        p5 = F.interpolate(p5, None, 8, mode="bilinear", align_corners=False)
+        feat = torch.cat([p2, p3, p4, p5], dim=1)
+        score = ops.conv2d(feat, self.score.weight, self.score.bias)
+        ret = {"fcn_score": score, "fcn_feat": feat}
+        if self.upsample_rate != 1:
+            ret["fcn_output"] = F.interpolate(score, None, self.upsample_rate, mode="bilinear", align_corners=False)
+        return ret
+
+
+# ---------------------------------------------------------------------------------------------
+class resnet_upsnet(nn.Module):
+    """models/resnet_upsnet.py:38-248 (test branch)."""
+
+    def __init__(self, backbone_depth, cfg=None):
+        super().__init__()
+        cfg = cfg or UPSNetConfig()
+        self.cfg = cfg
+        self.num_classes, self.num_seg_classes = cfg.num_classes, cfg.num_seg_classes
+        self.num_reg_classes = cfg.num_classes
+        self.resnet_backbone = ResNetBackbone(backbone_depth, cfg)
+        self.fpn = FPN(cfg.fpn_feature_dim, cfg.fpn_with_gap)
+        self.rpn = RPN(cfg.num_anchors, cfg.fpn_feature_dim)
+        self.rcnn = RCNN(self.num_classes, self.num_reg_classes, dim_in=cfg.fpn_feature_dim)
+        self.mask_branch = MaskBranch(self.num_classes, cfg.mask_size, dim_in=cfg.fpn_feature_dim)
+        self.fcn_head = FCNHead(cfg.fpn_feature_dim, self.num_seg_classes, cfg.fcn_num_layers)
+        self.enable_void = cfg.panoptic_box_keep_fraction < 1
+        assert self.enable_void, "all shipped configs enable the void channel"
+        self.pyramid_proposal = ProposalGenerator(cfg.rpn_feat_stride, cfg.anchor_scales, cfg.anchor_ratios,
+                                                  cfg.rpn_pre_nms_top_n, cfg.rpn_post_nms_top_n,
+                                                  cfg.rpn_nms_thresh, cfg.rpn_min_size)
+        self.mask_roi = MaskROI(cfg.max_det, self.num_classes, cfg.nms_thresh, False, cfg.score_thresh,
+                                cfg.bbox_reg_weights)
+        self.mask_roi_panoptic = MaskROI(cfg.max_det, self.num_classes, 0.5, True, cfg.panoptic_score_thresh,
+                                         cfg.bbox_reg_weights)
+        self.panoptic_head = ops.PanopticHead(self.num_seg_classes, self.num_classes, 0.3)
+        self._prepared = False
+        self.eval()
+
+    def prepare(self):
+        """Fold frozen BN, fuse sibling 1x1 heads, reshape the deconv: call after loading weights."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "prepare"):
+                m.prepare()
+        self._prepared = True
+        return self
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._prepared = False
+        return r
+
+    @torch.no_grad()
+    def forward(self, data, label=None):
+        if label is not None:
+            raise NotImplementedError("training forward (BASELINE config #4) is outside this round's scope")
+        if not self._prepared:
+            self.prepare()
+        x = data["data"]
+        im_info = np.asarray(data["im_info"], dtype=np.float32).reshape(-1, 3)
+        assert x.shape[0] == 1 and im_info.shape[0] == 1, "one image per device (SURVEY F9)"
+        res2, res3, res4, res5 = self.resnet_backbone(x)
+        p2, p3, p4, p5, p6 = self.fpn(res2, res3, res4, res5)
+        rpn_cls_prob, rpn_bbox_pred = [], []
+        for feat in (p2, p3, p4, p5, p6):
+            _, bbox, prob = self.rpn(feat)
+            rpn_cls_prob.append(prob)
+            rpn_bbox_pred.append(bbox)
+        rois, _ = self.pyramid_proposal(rpn_cls_prob, rpn_bbox_pred, im_info[0])
+        fcn_output = self.fcn_head(p2, p3, p4, p5)
+        feats = [p2, p3, p4, p5]
+        rcnn_output = self.rcnn(feats, rois)
+        cls_prob = F.softmax(rcnn_output["cls_score"], dim=1)
+        bbox_pred = rcnn_output["bbox_pred"]
+
+        cls_prob_all, mask_rois, cls_idx = self.mask_roi(rois, bbox_pred, cls_prob, im_info[0])
+        mask_prob = torch.sigmoid(self.mask_branch(feats, mask_rois))
+        results = {"cls_probs": cls_prob_all, "pred_boxes": mask_rois, "mask_probs": mask_prob, "cls_inds": cls_idx}
+
+        # ---- panoptic head (resnet_upsnet.py:217-247) ----
+        pcls_prob, pmask_rois, pcls_idx = self.mask_roi_panoptic(rois, bbox_pred, cls_prob, im_info[0])
+        mask_score = self.mask_branch(feats, pmask_rois)
+        ms = self.cfg.mask_size
+        mask_score = mask_score.gather(1, pcls_idx.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
+        pan = self.panoptic_head(fcn_output["fcn_output"], pmask_rois, pcls_prob, mask_score, pcls_idx, want_sem=True)
+        keep = pan["keep_inds"]
+        results.update({"fcn_outputs": pan["fcn_outputs"], "panoptic_cls_inds": pcls_idx[keep],
+                        "panoptic_cls_probs": pcls_prob[keep], "panoptic_outputs": pan["panoptic_outputs"]})
+        return results
+
+
+def resnet_50_upsnet(cfg=None):
+    return resnet_upsnet([3, 4, 6, 3], cfg)
+
+
+def resnet_101_upsnet(cfg=None):
+    return resnet_upsnet([3, 4, 23, 3], cfg)
