@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- panoptic images/sec of the UPSNet-50 Cityscapes inference hot path (BASELINE.json
+configs[1]: synthetic 1x3x1024x2048, batch 1 per GPU) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...   # the reference's CPU path on the host cores
+
+One "step" = one full per-image forward (backbone -> FPN -> RPN -> proposals -> semantic head (DCN)
+-> RCNN -> MaskROI -> mask head x2 -> fused panoptic head).  Images are independent, so ranks are
+replicas with no data-path collective ("weak" scaling).
+
+JSON line:  value = whole-job images/s with the input image already resident in HBM (CUDA events,
+max over ranks); e2e = same metric through the public API with HOST buffers (pinned H2D of the image
+and D2H of the result maps inside the timed region); roofline = achieved TFLOP/s of the dominant
+kernel family measured with CUDA events around its launches, against MEASURED_PEAKS.json;
+cpu_baseline = the CPU path (oracle/cpu_model.py) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "panoptic images/sec at 1024x2048"
+H, W = 1024, 2048
+WORKLOAD = "UPSNet-50 Cityscapes inference, synthetic 1x3x1024x2048, batch 1 per GPU (BASELINE configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path for the same workload on the host cores."""
+    import torch
+    if rank != 0:
+        return
+    from oracle.cpu_model import cpu_ops
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    model = synthetic_model(UPSNetConfig.cityscapes_r50(), seed=0, device="cpu")
+    inputs = [synthetic_input(H, W, seed=s) for s in range(2)]
+    budget_s, t_begin = 280.0, time.perf_counter()
+    with cpu_ops():
+        done_w = 0
+        for i in range(args.warmup):
+            model(inputs[i % 2]); done_w += 1
+            if time.perf_counter() - t_begin > budget_s / 3:
+                break
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(args.steps):
+            model(inputs[i % 2]); done += 1
+            if time.perf_counter() - t_begin > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    val = done / dt
+    sample = "%d full 1024x2048 images through torch-CPU fp32 convs + C/OpenMP restated ops (oracle/cpu_model.py)" % done
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": done, "warmup": done_w, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    import torch
+    from oracle.cpu_model import cpu_ops
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    model = synthetic_model(UPSNetConfig.cityscapes_r50(), seed=0, device="cpu")
+    inp = synthetic_input(H, W, seed=0)
+    with cpu_ops():
+        model(inp)  # warm-up (thread pools, oneDNN primitive caches)
+        t0 = time.perf_counter(); n = 0
+        while n < 2 or (time.perf_counter() - t0 < 15.0 and n < 8):
+            model(inp); n += 1
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "%d full 1024x2048 images (after 1 warm-up), torch-CPU fp32 convs + C/OpenMP restated ops" % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("UPSNET_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as ops
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    U.set_precision(args.precision)
+    model = synthetic_model(UPSNetConfig.cityscapes_r50(), seed=0, device=dev)
+    n_img = 4  # rotate distinct images; one step touches >1 GB of activations (>> 126 MB L2)
+    host_imgs = [synthetic_input(H, W, seed=100 * rank + s)["data"].pin_memory() for s in range(n_img)]
+    dev_imgs = [h.to(dev) for h in host_imgs]
+    im_info = synthetic_input(8, 8)["im_info"]; im_info[0, :2] = (H, W)
+
+    def step_resident(i):
+        return model({"data": dev_imgs[i % n_img], "im_info": im_info})
+
+    def step_e2e(i):
+        x = host_imgs[i % n_img].to(dev, non_blocking=True)
+        out = model({"data": x, "im_info": im_info})
+        pan = out["panoptic_outputs"].to("cpu", non_blocking=True)
+        sem = out["fcn_outputs"].to("cpu", non_blocking=True)
+        boxes = out["pred_boxes"].to("cpu", non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pan, sem, boxes
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.STATS["launches"]
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ops.STATS["launches"] - l0
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    out = step_e2e(0)
+    h2d = host_imgs[0].numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in out)
+
+    # ---- roofline leg: CUDA events around every C-ABI call of a few more steps ----
+    ops.STATS["trace"] = []
+    torch.cuda.synchronize()
+    n_trace = min(3, args.steps)
+    for i in range(n_trace):
+        step_resident(i)
+    torch.cuda.synchronize()
+    trace, ops.STATS["trace"] = ops.STATS["trace"], None
+    fam = {}
+    for kind, a, b, work in trace:
+        f = fam.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
+        f["ms"] += a.elapsed_time(b); f["calls"] += 1
+        f["flops"] += work.get("flops", 0.0); f["bytes"] += work.get("bytes", 0.0)
+    pk = peaks()
+    tot_ms = sum(f["ms"] for f in fam.values())
+    conv = {"ms": fam.get("conv2d", {"ms": 0})["ms"] + fam.get("dcn", {"ms": 0})["ms"],
+            "flops": fam.get("conv2d", {"flops": 0})["flops"] + fam.get("dcn", {"flops": 0})["flops"],
+            "calls": fam.get("conv2d", {"calls": 0})["calls"] + fam.get("dcn", {"calls": 0})["calls"]}
+    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    roofline = {"kernel": "igemm (conv2d + dcn tiles), precision=%s" % args.precision, "bound": "tensor",
+                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + " (sustained bf16)",
+                "traffic": None, "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
+                "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
+                "flops_per_step": conv["flops"] / n_trace,
+                "families_ms_per_step": {k: round(v["ms"] / n_trace, 4) for k, v in sorted(fam.items())}}
+    if "panoptic_head" in fam:
+        f = fam["panoptic_head"]
+        roofline["panoptic_head_gbs"] = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+        roofline["panoptic_head_frac_hbm"] = roofline["panoptic_head_gbs"] / pk["hbm_gbs"]
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_leg()
+        line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "fp32", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "parallelism": "replicas x%d (one image per GPU, no collective)" % world,
+                           "l2": "no flush: each step streams >1 GB of activations (>> 126 MB L2) and rotates %d images" % n_img,
+                           "weights": "random-init (upsnet_b200/synthetic.py), frozen BN folded"},
+                "clocks": clocks,
+                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

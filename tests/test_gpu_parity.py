@@ -342,3 +342,37 @@ def test_panoptic_head_module(dev):
     assert out["keep_inds"].cpu().tolist() == wk.tolist()
     assert np.array_equal(out["panoptic_outputs"][0].cpu().numpy(), wl)
     assert np.array_equal(out["fcn_outputs"][0].cpu().numpy(), ws)
+
+
+# ------------------------------- whole engine ---------------------------------------------------
+def test_engine_forward_matches_cpu_path(dev):
+    """resnet_upsnet on the GPU (C ABI kernels) vs the same host logic on the CPU path
+    (torch-CPU convs + oracle ops).  Dense outputs within 1e-3 (relative to their scale); discrete
+    outputs (NMS / top-k decisions feed everything downstream) must agree on almost every pixel."""
+    from oracle.cpu_model import cpu_ops
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    cfg = UPSNetConfig.cityscapes_r50()
+    m_cpu = synthetic_model(cfg, depth=(1, 1, 1, 1), seed=3)
+    m_gpu = synthetic_model(cfg, depth=(1, 1, 1, 1), seed=3, device=dev)
+    Hh, Ww = 256, 384
+    inp = synthetic_input(Hh, Ww, seed=4)
+    with cpu_ops(), torch.no_grad():
+        r2, r3, r4, r5 = m_cpu.resnet_backbone(inp["data"])
+        p_cpu = m_cpu.fpn(r2, r3, r4, r5)
+        fcn_cpu = m_cpu.fcn_head(*p_cpu[:4])["fcn_output"]
+        out_cpu = m_cpu(inp)
+    gin = {"data": inp["data"].to(dev), "im_info": inp["im_info"]}
+    with torch.no_grad():
+        g2, g3, g4, g5 = m_gpu.resnet_backbone(gin["data"])
+        p_gpu = m_gpu.fpn(g2, g3, g4, g5)
+        fcn_gpu = m_gpu.fcn_head(*p_gpu[:4])["fcn_output"]
+        out_gpu = m_gpu(gin)
+    for a, b in zip(p_gpu, p_cpu):
+        assert (a.cpu() - b).abs().max() <= TOL * max(1.0, float(b.abs().max()))
+    assert (fcn_gpu.cpu() - fcn_cpu).abs().max() <= TOL * max(1.0, float(fcn_cpu.abs().max()))
+    sem_agree = (out_gpu["fcn_outputs"].cpu() == out_cpu["fcn_outputs"]).float().mean().item()
+    pan_agree = (out_gpu["panoptic_outputs"].cpu() == out_cpu["panoptic_outputs"]).float().mean().item()
+    assert sem_agree > 0.999, sem_agree
+    assert pan_agree > 0.98, pan_agree
+    assert out_gpu["panoptic_outputs"].dtype == torch.int64 and out_gpu["panoptic_outputs"].shape == (1, Hh, Ww)

@@ -36,6 +36,33 @@ def set_precision(name):
     _PRECISION["conv"] = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.PREC_BF16}[name]
 
 
+# launch accounting (bench.py reports gpu_launches) and optional per-call CUDA-event timing of the
+# kernels behind one C-ABI call (bench.py's roofline leg; off in normal operation)
+STATS = {"launches": 0, "trace": None}
+
+
+class _Timed:
+    """with _Timed(kind, n_kernels, work, device): <C-ABI call> -- counts launches; when
+    STATS["trace"] is a list also brackets the call with events on the current stream."""
+
+    def __init__(self, kind, n_kernels, work, device):
+        self.kind, self.n, self.work, self.device = kind, n_kernels, work, device
+        self.ev = None
+
+    def __enter__(self):
+        STATS["launches"] += self.n
+        if STATS["trace"] is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record(torch.cuda.current_stream(self.device))
+            STATS["trace"].append((self.kind, self.ev[0], self.ev[1], self.work))
+        return False
+
+
 def _conv_out(n, pad, dil, k, stride):
     return (n + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
 
@@ -58,7 +85,9 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
     if residual is not None:
         assert residual.shape == y.shape
     prec = _PRECISION["conv"] if precision is None else precision
-    with torch.cuda.device(x.device):
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "bytes": 4.0 * (x.numel() + weight.numel() + y.numel() * (2 if residual is not None else 1))}
+    with torch.cuda.device(x.device), _Timed("conv2d", 1, work, x.device):
         check(lib().upsnet_conv2d_forward(ptr(x), ptr(weight), ptr(bias), ptr(residual), ptr(y), N, Cin, H, W,
                                           Cout, kh, kw, sh, sw, ph, pw, dh, dw, _lib.EPI_RELU if relu else 0,
                                           prec, stream_ptr(x.device)), "conv2d")
@@ -91,7 +120,10 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
         assert tuple(mask.shape) == (N, kh * kw * deformable_groups, Ho, Wo), mask.shape
     y = torch.empty((N, Cout, Ho, Wo), device=data.device, dtype=torch.float32)
     prec = _PRECISION["conv"] if precision is None else precision
-    with torch.cuda.device(data.device):
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "bytes": 4.0 * (data.numel() + offset.numel() + weight.numel() + y.numel() +
+                            (mask.numel() if mask is not None else 0))}
+    with torch.cuda.device(data.device), _Timed("dcn", 1, work, data.device):
         check(lib().upsnet_dcn_forward(ptr(data), ptr(offset), ptr(mask), ptr(weight), ptr(bias), ptr(y), N, Cin,
                                        H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, deformable_groups,
                                        _lib.EPI_RELU if relu else 0, prec, stream_ptr(data.device)),
@@ -112,7 +144,7 @@ def roi_align(features, rois, pooled_height, pooled_width, spatial_scale, sampli
         B, H, W, Cc = features.shape
         out = torch.empty((R, pooled_height, pooled_width, Cc), device=features.device, dtype=torch.float32)
         lay = _lib.LAYOUT_NHWC
-    with torch.cuda.device(features.device):
+    with torch.cuda.device(features.device), _Timed("roi_align", 1, {"bytes": 4.0 * out.numel()}, features.device):
         check(lib().upsnet_roi_align_forward(ptr(features), B, Cc, H, W, lay, ptr(rois), R, pooled_height,
                                              pooled_width, sampling_ratio, float(spatial_scale), ptr(out),
                                              stream_ptr(features.device)), "roi_align")
@@ -141,7 +173,7 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
     fp = (C.c_void_p * 4)(*[f.data_ptr() for f in feats])
     hs = (C.c_int * 4)(*Hs); ws = (C.c_int * 4)(*Ws)
     sc = (C.c_float * 4)(*[float(s) for s in spatial_scales])
-    with torch.cuda.device(rois.device):
+    with torch.cuda.device(rois.device), _Timed("roi_align_fpn", 1, {"bytes": 4.0 * out.numel()}, rois.device):
         check(lib().upsnet_roi_align_fpn_forward(fp, hs, ws, sc, B, Cc, lay, ptr(rois), R, pooled_height,
                                                  pooled_width, sampling_ratio, ptr(out), ptr(levels),
                                                  stream_ptr(rois.device)), "fpn_roi_align")
@@ -183,7 +215,7 @@ def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
     ws = _nms_ws.get(dev, nbytes.value)
     keep = torch.empty((S, max_seg_len), dtype=torch.int32, device=dev)
     cnt = torch.empty((S,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("nms", 2, {"bytes": 20.0 * boxes_sorted.shape[0]}, dev):
         check(lib().upsnet_nms_segmented(ptr(boxes_sorted), ptr(seg_offsets), S, max_seg_len, float(thresh),
                                          ptr(keep), ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev)), "nms")
     return keep, cnt
@@ -377,7 +409,8 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     k = torch.empty((1,), dtype=torch.int32, device=dev)
     labels = torch.empty((1, H, W), dtype=torch.int64, device=dev)
     sem = torch.empty((1, H, W), dtype=torch.int64, device=dev) if want_sem else None
-    with torch.cuda.device(dev):
+    work = {"bytes": 4.0 * S * H * W + 8.0 * H * W * (2 if want_sem else 1) + n * (4.0 * 784 + 24)}
+    with torch.cuda.device(dev), _Timed("panoptic_head", 4, work, dev):
         check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, num_stuff,
                                          float(fraction_threshold), ptr(keep), ptr(k), ptr(labels), ptr(sem),
                                          ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")

@@ -1,0 +1,61 @@
+"""Synthetic weights / inputs of the benchmark workloads: there is no network
+access for checkpoints or datasets, so bench.py and the tests use random-init weights of the reference
+architecture and Cityscapes-/COCO-shaped random images."""
+import numpy as np
+import torch
+
+
+def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
+    """Random-init resnet_upsnet per SURVEY.md section 8d config 2: reference initialisers, except
+    (a) offset convs get N(0, 0.5)-scaled weights so DCN offsets are non-zero (the reference zero-inits
+    them, modules/deform_conv.py:72-73 -- zero offsets would hide DCN bugs), (b) BN statistics are
+    randomised so folding is exercised, (c) the class / mask heads are biased so that several dozen
+    detections survive score > 0.6 and reach the panoptic head."""
+    from upsnet_b200.model import resnet_upsnet, Bottleneck
+    from upsnet_b200.operators import DeformConvWithOffset
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        m = resnet_upsnet(list(depth), cfg)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.copy_(torch.empty_like(mod.weight).uniform_(0.5, 1.5, generator=g))
+                mod.bias.copy_(torch.empty_like(mod.bias).normal_(0, 0.1, generator=g))
+                mod.running_mean.copy_(torch.empty_like(mod.running_mean).normal_(0, 0.1, generator=g))
+                mod.running_var.copy_(torch.empty_like(mod.running_var).uniform_(0.5, 1.5, generator=g))
+            elif isinstance(mod, DeformConvWithOffset):
+                w = mod.conv_offset.weight
+                w.copy_(torch.empty(w.shape).normal_(0, 0.5 / (w.shape[1] * 9) ** 0.5, generator=g).to(w.device))
+                cw = mod.conv.weight
+                cw.copy_(torch.empty(cw.shape).normal_(0, (2.0 / (cw.shape[1] * 9)) ** 0.5, generator=g).to(cw.device))
+                mod.conv.bias.zero_()
+            elif isinstance(mod, Bottleneck):
+                for c in (mod.conv1, mod.conv2, mod.conv3):
+                    w = c.weight
+                    fan = w.shape[1] * w.shape[2] * w.shape[3]
+                    w.copy_(torch.empty(w.shape).normal_(0, (2.0 / fan) ** 0.5, generator=g).to(w.device))
+                if mod.deformable:
+                    w = mod.conv2_offset.weight
+                    w.copy_(torch.empty(w.shape).normal_(0, 0.5 / (w.shape[1] * 9) ** 0.5, generator=g))
+                if mod.downsample is not None:
+                    w = mod.downsample[0].weight
+                    w.copy_(torch.empty(w.shape).normal_(0, (1.0 / w.shape[1]) ** 0.5, generator=g))
+                mod.bn3.weight.mul_(0.3)  # keep the residual stream bounded at random init
+        sw = m.resnet_backbone.conv1.conv1.weight
+        sw.copy_(torch.empty(sw.shape).normal_(0, (2.0 / 147) ** 0.5 / 50, generator=g))
+        # heads: make detections plentiful and confident enough for the panoptic branch
+        m.rpn.cls_score.weight.copy_(torch.empty_like(m.rpn.cls_score.weight).normal_(0, 0.05, generator=g))
+        m.rpn.bbox_pred.weight.copy_(torch.empty_like(m.rpn.bbox_pred.weight).normal_(0, 0.01, generator=g))
+        m.rcnn.cls_score.weight.copy_(torch.empty_like(m.rcnn.cls_score.weight).normal_(0, 0.25, generator=g))
+        m.rcnn.cls_score.bias[0] = -1.0
+        m.rcnn.bbox_pred.weight.copy_(torch.empty_like(m.rcnn.bbox_pred.weight).normal_(0, 0.02, generator=g))
+        m.mask_branch.mask_score.bias.fill_(0.2)
+        m.fcn_head.score.weight.copy_(torch.empty_like(m.fcn_head.score.weight).normal_(0, 0.1, generator=g))
+    m = m.to(device)
+    m.prepare()
+    return m
+
+
+def synthetic_input(H=1024, W=2048, seed=0, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    data = (torch.randn(1, 3, H, W, generator=g) * 50).to(device)   # mean-subtracted BGR scale
+    return {"data": data, "im_info": np.array([[H, W, 1.0]], np.float32)}
