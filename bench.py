@@ -183,9 +183,10 @@ def main():
         torch.cuda.current_stream().synchronize()
         return pan, sem, boxes
 
+    from upsnet_b200 import replicas
+
     def sync_all():
-        if world > 1:
-            dist.barrier()
+        replicas.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps):
@@ -197,10 +198,8 @@ def main():
             fn(i)
         e1.record()
         sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), ops.STATS["launches"] - l0
+        ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev)   # slowest rank
+        return ms, ops.STATS["launches"] - l0
 
     for i in range(args.warmup):
         step_resident(i)

@@ -106,6 +106,26 @@ int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias
                           void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * tcgen05 implicit-GEMM convolution / deformable convolution (engine entry point).
+ * Same arithmetic contract as upsnet_conv2d_forward / upsnet_dcn_forward, but
+ *   - x is NHWC fp32 [N,H,W,Cin] (Cin % 64 == 0), y / residual are NHWC or NCHW (out_layout),
+ *   - weights are pre-packed once with upsnet_igemm_pack_weight (bf16 hi/lo planes,
+ *     [Cout_pad][kh*kw][Cin]); `packed` must hold upsnet_igemm_packed_weight_bytes bytes,
+ *   - offset [N,2*kh*kw,Ho,Wo] / mask [N,kh*kw,Ho,Wo] stay NCHW (reference layout), NULL for a
+ *     dense convolution; deformable_groups must be 1,
+ *   - precision is UPSNET_PREC_BF16X3 (fp32-grade result) or UPSNET_PREC_BF16.
+ * replaces: the same reference call sites as upsnet_conv2d_forward / upsnet_dcn_forward.
+ */
+int upsnet_igemm_packed_weight_bytes(int Cout, int Cin, int kh, int kw, size_t *bytes);
+int upsnet_igemm_pack_weight(const float *weight, int Cout, int Cin, int kh, int kw, void *packed,
+                             void *stream);
+int upsnet_igemm_forward(const float *x_nhwc, const float *offset, const float *mask,
+                         const void *packed, const float *bias, const float *residual, float *y,
+                         int N, int H, int W, int Cin, int Cout, int kh, int kw, int stride_h,
+                         int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int out_layout,
+                         int epi_flags, int precision, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Parameter-free panoptic head, fused: MaskRemoval + SegTerm + void/concat/argmax.
  * replaces: models/resnet_upsnet.py:223-240 with operators/modules/mask_removal.py:29-93,
  *           operators/modules/unary_logits.py:78-105.  Never materialises the [1,k,H,W] planes.

@@ -16,7 +16,8 @@ import torch.nn.functional as F
 from . import oracle as O
 
 
-def _conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None):
+def _conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
+            out_format=None):
     y = F.conv2d(x.float(), weight.float(), None if bias is None else bias.float(), stride, padding, dilation)
     if residual is not None:
         y = y + residual
@@ -33,7 +34,7 @@ def _pair(v):
 
 
 def _deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1, mask=None,
-                 relu=False, precision=None):
+                 relu=False, precision=None, out_format=None):
     """Reference structure (functions/deform_conv.py:44-57): per image, deformable im2col (C oracle,
     OpenMP) into a column buffer, then torch.mm on the host cores, then bias."""
     s, p, d = _pair(stride)[0], _pair(padding)[0], _pair(dilation)[0]
@@ -62,8 +63,8 @@ def _roi_align(features, rois, ph, pw, scale, sampling_ratio=2, layout="nchw"):
 
 
 def _fpn_roi_align(feats, rois, ph, pw, scales, sampling_ratio=2, layout="nchw", return_levels=False):
-    assert layout == "nchw"
-    out = torch.from_numpy(O.fpn_roi_align([f.detach().numpy() for f in feats], rois.detach().numpy(), ph, pw, scales))
+    assert layout in ("nchw", "auto")
+    out = torch.from_numpy(O.fpn_roi_align([f.detach().contiguous().numpy() for f in feats], rois.detach().numpy(), ph, pw, scales))
     if return_levels:
         return out, torch.from_numpy(O.fpn_level_numpy(rois.detach().numpy()))
     return out

@@ -41,6 +41,9 @@ def lib():
         L.upsnet_nms_host.argtypes = [vp, vp, vp, i, i, f, i]
         L.upsnet_dcn_forward.argtypes = [vp] * 6 + [i] * 16 + [vp]
         L.upsnet_conv2d_forward.argtypes = [vp] * 5 + [i] * 15 + [vp]
+        L.upsnet_igemm_packed_weight_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
+        L.upsnet_igemm_pack_weight.argtypes = [vp, i, i, i, i, vp, vp]
+        L.upsnet_igemm_forward.argtypes = [vp] * 7 + [i] * 16 + [vp]
         L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
         L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, d, vp, vp, vp, vp, vp, sz, vp]
         for name in dir(L):
@@ -52,7 +55,8 @@ def lib():
 EXPORTED_SYMBOLS = [
     "upsnet_version", "upsnet_roi_align_forward", "upsnet_roi_align_fpn_forward",
     "upsnet_nms_workspace_bytes", "upsnet_nms_segmented", "upsnet_nms_host", "upsnet_dcn_forward",
-    "upsnet_conv2d_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head",
+    "upsnet_conv2d_forward", "upsnet_igemm_packed_weight_bytes", "upsnet_igemm_pack_weight",
+    "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head",
 ]
 
 

@@ -10,6 +10,18 @@ struct ConvParams {
   int N, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo, relu;
 };
 int launch_igemm_simt(const ConvParams& p, cudaStream_t stream);
+
+struct TcParams {
+  const float* x; const float* offset; const float* mask;
+  const uint16_t* w_hi; const uint16_t* w_lo;
+  const float* bias; const float* residual; float* y;
+  int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+  int relu, out_nhwc, BN, stages, x3;
+};
+size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
+int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream);
+bool tc_supported(int Cin, int kh, int kw, int dg);
+int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream);
 }  // namespace ups
 
 extern "C" int upsnet_version(int* n_sm) {
@@ -70,4 +82,45 @@ extern "C" int upsnet_conv2d_forward(const float* x, const float* weight, const 
   return conv_common(x, nullptr, nullptr, weight, bias, residual, y, N, Cin, H, W, Cout, kh, kw,
                      stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, 1, epi_flags, precision,
                      stream);
+}
+
+extern "C" int upsnet_igemm_packed_weight_bytes(int Cout, int Cin, int kh, int kw, size_t* bytes) {
+  if (!bytes || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0) return UPSNET_E_BADARG;
+  if (!ups::tc_supported(Cin, kh, kw, 1)) return UPSNET_E_UNSUPPORTED;
+  *bytes = ups::tc_packed_weight_bytes(Cout, Cin, kh, kw);
+  return 0;
+}
+
+extern "C" int upsnet_igemm_pack_weight(const float* weight, int Cout, int Cin, int kh, int kw,
+                                        void* packed, void* stream) {
+  if (!weight || !packed || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0) return UPSNET_E_BADARG;
+  if (!ups::tc_supported(Cin, kh, kw, 1)) return UPSNET_E_UNSUPPORTED;
+  return ups::tc_pack_weight(weight, Cout, Cin, kh, kw, packed, (cudaStream_t)stream);
+}
+
+extern "C" int upsnet_igemm_forward(const float* x_nhwc, const float* offset, const float* mask,
+                                    const void* packed, const float* bias, const float* residual,
+                                    float* y, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                                    int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                                    int dil_w, int out_layout, int epi_flags, int precision,
+                                    void* stream) {
+  if (!x_nhwc || !packed || !y) return UPSNET_E_BADARG;
+  if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride_h <= 0 ||
+      stride_w <= 0 || pad_h < 0 || pad_w < 0 || dil_h <= 0 || dil_w <= 0)
+    return UPSNET_E_BADARG;
+  if (precision != UPSNET_PREC_BF16X3 && precision != UPSNET_PREC_BF16) return UPSNET_E_BADARG;
+  if (out_layout != UPSNET_LAYOUT_NCHW && out_layout != UPSNET_LAYOUT_NHWC) return UPSNET_E_BADARG;
+  if (mask && !offset) return UPSNET_E_BADARG;
+  if ((size_t)H * W >= (1ull << 31)) return UPSNET_E_UNSUPPORTED;
+  ups::TcParams p{};
+  p.x = x_nhwc; p.offset = offset; p.mask = mask; p.bias = bias; p.residual = residual; p.y = y;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.sh = stride_h;
+  p.sw = stride_w; p.ph = pad_h; p.pw = pad_w; p.dh = dil_h; p.dw = dil_w;
+  p.Ho = ups::conv_out_size(H, pad_h, dil_h, kh, stride_h);
+  p.Wo = ups::conv_out_size(W, pad_w, dil_w, kw, stride_w);
+  if (p.Ho <= 0 || p.Wo <= 0) return UPSNET_E_BADARG;
+  p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
+  p.out_nhwc = out_layout == UPSNET_LAYOUT_NHWC;
+  p.x3 = precision == UPSNET_PREC_BF16X3;
+  return ups::launch_igemm_tc(p, packed, (cudaStream_t)stream);
 }

@@ -1,0 +1,515 @@
+// igemm_tc.cu -- tcgen05 implicit-GEMM convolution / deformable convolution for sm_100a.
+//
+// One warp-specialised kernel covers the dense k x k convolutions of the backbone / FPN / RPN /
+// heads, the fully connected layers and the FUSED deformable conv v1/v2 (im2col never leaves the
+// SM; reference: deformable_im2col -> 1.2 GB col buffer -> torch.mm, operators/functions/
+// deform_conv.py:44-57 + operators/src/deform_conv_kernel.cu:194-242).
+//
+//   D[128 pixels x BN couts] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem)  *  B[BN x 64]^T (bf16, smem)
+//
+// * A (activations, NHWC fp32 in HBM) is GATHERED by 8 producer warps: for k-block (tap, 64
+//   channels) every (pixel,8-channel) item is one or -- when deformable -- four 32-byte reads
+//   (the four bilinear corners; weights/offsets come from a per-tile sample table computed once
+//   per (tap,pixel), reused by all channels), blended in fp32, converted to bf16 and stored with
+//   one 16-byte st.shared into the K-major SWIZZLE_128B layout tcgen05 consumes.
+// * B (weights) is pre-packed once to bf16 [Cout_pad][tap][Cin] and copied by the same warps.
+// * One elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) per 16-column slice;
+//   tcgen05.commit releases the smem stage to the producers through an mbarrier; accumulators
+//   live in TMEM and are drained with tcgen05.ld (32x32b.x16) by all 8 producer warps.
+// * Precision modes: BF16 (one pass) and BF16X3 (x = hi + lo split of both operands, three
+//   MMAs: hi*hi + lo*hi + hi*lo; error ~2^-16 relative, i.e. fp32-grade results for the
+//   "fp32 logits within 1e-3" contract at 3x the tensor work).
+// Roofline: tensor pipe (flops = 2*P*Cout*Cin*kh*kw); the deformable variant is bounded by the
+// LSU gather rate of the producers (4 corner reads per element) -- see DESIGN.md.
+#include <cuda_bf16.h>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace ups {
+
+constexpr int TC_BM = 128;         // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;          // bf16 elements per k-block row (= 128 bytes, one swizzle span)
+constexpr int TC_PRODUCERS = 256;  // 8 warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_MAX_STAGES = 6;
+
+struct TcParams {
+  const float* x;        // NHWC fp32 [N,H,W,Cin]
+  const float* offset;   // NCHW fp32 [N,2*KHW,Ho,Wo] or null
+  const float* mask;     // NCHW fp32 [N,KHW,Ho,Wo] or null
+  const uint16_t* w_hi;  // bf16 [Cout_pad][KHW*Cin]
+  const uint16_t* w_lo;  // bf16 residual plane (BF16X3) or null
+  const float* bias; const float* residual; float* y;
+  int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+  int relu, out_nhwc, BN, stages, x3;
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+        printf("upsnet igemm_tc: mbarrier timeout (bar=%u parity=%u block=%d,%d thread=%d)\n", bar, parity,
+               (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
+// bits [0,14), LBO [16,30) (unused for swizzled K-major), SBO>>4 = 1024>>4 in [32,46) (8 rows of
+// 128 B), version 1 in [46,48), layout type SWIZZLE_128B (=2) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (1) @4, a/b format
+// bf16 (1) @7/@10, a/b major K (0) @15/@16, N>>3 @17, M>>4 @24.
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// shared-memory carve-up (offsets from the 1024-aligned base)
+struct TcSmem {
+  uint32_t bars;      // full[6], empty[6], accum (13 x 8 B) then tmem ptr
+  uint32_t rowbase;   // long long [128]
+  uint32_t table;     // deform: float4 [KHW][128] + int4 [KHW][128]; dense: int [KHW][128]
+  uint32_t stages;    // 1024-aligned
+  uint32_t a_bytes, b_bytes, stage_bytes, total;
+};
+__host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, int stages, bool x3) {
+  TcSmem s;
+  s.bars = 0;
+  s.rowbase = 128;
+  s.table = s.rowbase + TC_BM * 8;
+  const uint32_t tbytes = deform ? KHW * TC_BM * 32 : KHW * TC_BM * 4;
+  s.stages = (uint32_t)((s.table + tbytes + 1023) / 1024 * 1024);
+  s.a_bytes = TC_BM * 128;
+  s.b_bytes = BN * 128;
+  s.stage_bytes = (s.a_bytes + s.b_bytes) * (x3 ? 2 : 1);
+  s.total = s.stages + s.stage_bytes * stages;
+  return s;
+}
+
+template <bool DEFORM>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+igemm_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  // 1024-byte alignment of the stage buffers is required by SWIZZLE_128B
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_dyn + (base - raw);
+
+  const int KHW = p.kh * p.kw;
+  const bool x3 = p.x3 != 0;
+  const TcSmem L = tc_smem_layout(DEFORM, KHW, p.BN, p.stages, x3);
+  const uint32_t bar_full = base + L.bars, bar_empty = bar_full + 8 * TC_MAX_STAGES;
+  const uint32_t bar_accum = bar_empty + 8 * TC_MAX_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + L.bars + 8 * (2 * TC_MAX_STAGES + 1));
+  long long* rowbase = reinterpret_cast<long long*>(sm + L.rowbase);
+  float4* tw = reinterpret_cast<float4*>(sm + L.table);
+  int4* to = reinterpret_cast<int4*>(sm + L.table + (DEFORM ? KHW * TC_BM * 16 : 0));
+  int* ti = reinterpret_cast<int*>(sm + L.table);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HoWo = p.Ho * p.Wo;
+  const long long Ptot = (long long)p.N * HoWo;
+  const long long p0 = (long long)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int cchunks = p.Cin / TC_BK;
+  const int num_kb = KHW * cchunks;
+  const int Kp = KHW * p.Cin;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+
+  // ---------------- one-time setup ----------------
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+  }
+  for (int r = tid; r < TC_BM; r += TC_THREADS) {
+    const long long pg = p0 + r;
+    rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
+  }
+  // per-tile sample table (channel independent): one entry per (tap, pixel)
+  for (int e = tid; e < KHW * TC_BM; e += TC_THREADS) {
+    const int tap = e / TC_BM, r = e - tap * TC_BM;
+    const long long pg = p0 + r;
+    const int ki = tap / p.kw, kj = tap - ki * p.kw;
+    if (DEFORM) {
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      int4 ov = make_int4(0, 0, 0, 0);
+      if (pg < Ptot) {
+        const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+        const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+        const float* offp = p.offset + ((size_t)n * 2 * KHW + 2 * tap) * HoWo + pp;
+        const float oh = __ldg(offp), ow = __ldg(offp + HoWo);
+        const float h = (float)(ho * p.sh - p.ph + ki * p.dh) + oh;
+        const float w = (float)(wo * p.sw - p.pw + kj * p.dw) + ow;
+        if (h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {  // deform_conv_kernel.cu:229
+          const int hl = (int)floorf(h), wl = (int)floorf(w), hh = hl + 1, wh = wl + 1;
+          const float lh = h - hl, lw = w - wl, ch = 1.f - lh, cw = 1.f - lw;
+          const bool t_ok = hl >= 0, b_ok = hh <= p.H - 1, l_ok = wl >= 0, r_ok = wh <= p.W - 1;
+          float m = 1.f;
+          if (p.mask) m = __ldg(p.mask + ((size_t)n * KHW + tap) * HoWo + pp);
+          wv.x = (t_ok && l_ok) ? ch * cw * m : 0.f;
+          wv.y = (t_ok && r_ok) ? ch * lw * m : 0.f;
+          wv.z = (b_ok && l_ok) ? lh * cw * m : 0.f;
+          wv.w = (b_ok && r_ok) ? lh * lw * m : 0.f;
+          ov.x = (t_ok && l_ok) ? hl * p.W + wl : 0;
+          ov.y = (t_ok && r_ok) ? hl * p.W + wh : 0;
+          ov.z = (b_ok && l_ok) ? hh * p.W + wl : 0;
+          ov.w = (b_ok && r_ok) ? hh * p.W + wh : 0;
+        }
+      }
+      tw[e] = wv;
+      to[e] = ov;
+    } else {
+      int o = -1;
+      if (pg < Ptot) {
+        const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+        const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+        const int hi = ho * p.sh - p.ph + ki * p.dh, wi = wo * p.sw - p.pw + kj * p.dw;
+        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) o = hi * p.W + wi;
+      }
+      ti[e] = o;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 8) {
+    // =============================== PRODUCERS ===============================
+    const int j = tid & 7;         // 16-byte chunk (8 channels) inside the 128-byte row
+    const int r_first = tid >> 3;  // 32 rows per pass
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % p.stages, it = kb / p.stages;
+      mbar_wait(bar_empty + 8 * s, (uint32_t)((it & 1) ^ 1));
+      uint8_t* stage = sm + L.stages + (size_t)s * L.stage_bytes;
+      uint8_t* a_hi = stage;
+      uint8_t* b_hi = stage + L.a_bytes;
+      uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
+      uint8_t* b_lo = a_lo + L.a_bytes;
+      const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
+      // ---- A: gather 128 rows x 8 chunks ----
+#pragma unroll 2
+      for (int pass = 0; pass < TC_BM / 32; ++pass) {
+        const int r = r_first + pass * 32;
+        const long long rb = rowbase[r];
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+        if (rb >= 0) {
+          const float* xb = p.x + rb + c0;
+          if (DEFORM) {
+            const float4 wv = tw[tap * TC_BM + r];
+            const int4 ov = to[tap * TC_BM + r];
+            const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin);
+            const float4* c01 = reinterpret_cast<const float4*>(xb + (size_t)ov.y * p.Cin);
+            const float4* c10 = reinterpret_cast<const float4*>(xb + (size_t)ov.z * p.Cin);
+            const float4* c11 = reinterpret_cast<const float4*>(xb + (size_t)ov.w * p.Cin);
+            const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
+            const float4 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
+            v[0] = wv.x * a0.x + wv.y * b0.x + wv.z * d0.x + wv.w * e0.x;
+            v[1] = wv.x * a0.y + wv.y * b0.y + wv.z * d0.y + wv.w * e0.y;
+            v[2] = wv.x * a0.z + wv.y * b0.z + wv.z * d0.z + wv.w * e0.z;
+            v[3] = wv.x * a0.w + wv.y * b0.w + wv.z * d0.w + wv.w * e0.w;
+            v[4] = wv.x * a1.x + wv.y * b1.x + wv.z * d1.x + wv.w * e1.x;
+            v[5] = wv.x * a1.y + wv.y * b1.y + wv.z * d1.y + wv.w * e1.y;
+            v[6] = wv.x * a1.z + wv.y * b1.z + wv.z * d1.z + wv.w * e1.z;
+            v[7] = wv.x * a1.w + wv.y * b1.w + wv.z * d1.w + wv.w * e1.w;
+          } else {
+            const int o = ti[tap * TC_BM + r];
+            if (o >= 0) {
+              const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)o * p.Cin);
+              const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1);
+              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+              v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+            }
+          }
+        }
+        const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+        uint4 hi;
+        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+        if (x3) {
+          uint4 lo;
+          lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+          lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+          lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+          lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+          *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+        }
+      }
+      // ---- B: copy BN rows x 8 chunks of packed bf16 weights ----
+      for (int r = r_first; r < p.BN; r += 32) {
+        const size_t g = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
+        const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_hi + g));
+        if (x3) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_lo + g));
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+    }
+
+    // =============================== EPILOGUE ===============================
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    const long long pg = p0 + m;
+    const bool row_ok = pg < Ptot;
+    const int n_img = row_ok ? (int)(pg / HoWo) : 0;
+    const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
+    const int cols_half = p.BN / 2;
+    const bool vec_ptrs_ok = (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
+                             (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
+    for (int cb = 0; cb < cols_half; cb += 16) {
+      const int col = half * cols_half + cb;
+      uint32_t rr[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, rr);  // warp-collective
+      if (!row_ok) continue;
+      const int co0 = n0 + col;
+      if (p.out_nhwc) {
+        float* yo = p.y + (size_t)pg * p.Cout + co0;
+        const float* ro = p.residual ? p.residual + (size_t)pg * p.Cout + co0 : nullptr;
+        if (co0 + 15 < p.Cout && (p.Cout & 3) == 0 && vec_ptrs_ok) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            float4 o;
+            o.x = __uint_as_float(rr[g4 * 4 + 0]); o.y = __uint_as_float(rr[g4 * 4 + 1]);
+            o.z = __uint_as_float(rr[g4 * 4 + 2]); o.w = __uint_as_float(rr[g4 * 4 + 3]);
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g4 * 4));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (ro) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(ro + g4 * 4));
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(yo + g4 * 4) = o;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (co0 + e >= p.Cout) break;
+            float o = __uint_as_float(rr[e]);
+            if (p.bias) o += __ldg(p.bias + co0 + e);
+            if (ro) o += __ldg(ro + e);
+            if (p.relu) o = fmaxf(o, 0.f);
+            yo[e] = o;
+          }
+        }
+      } else {  // NCHW: for a fixed cout the 32 lanes of a warp write 32 consecutive pixels
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int co = co0 + e;
+          if (co >= p.Cout) break;
+          const size_t oidx = ((size_t)n_img * p.Cout + co) * HoWo + pp;
+          float o = __uint_as_float(rr[e]);
+          if (p.bias) o += __ldg(p.bias + co);
+          if (p.residual) o += __ldg(p.residual + oidx);
+          if (p.relu) o = fmaxf(o, 0.f);
+          p.y[oidx] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =============================== MMA ISSUER (warp 8, lane 0) ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(TC_BM, p.BN);
+      const uint32_t stage0 = base + L.stages;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages, it = kb / p.stages;
+        mbar_wait(bar_full + 8 * s, (uint32_t)(it & 1));
+        tc_fence_after();
+        const uint32_t a_hi = stage0 + (uint32_t)s * L.stage_bytes;
+        const uint32_t b_hi = a_hi + L.a_bytes;
+        const uint32_t a_lo = b_hi + L.b_bytes;
+        const uint32_t b_lo = a_lo + L.a_bytes;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 = 32 bytes inside the swizzle span
+          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          if (x3) {
+            umma_bf16(tmem_base, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, first);
+            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
+            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, first);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);  // frees the stage once the MMAs above have read it
+      }
+      umma_commit(bar_accum);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// weight pre-pack: fp32 [Cout,Cin,kh,kw] -> bf16 hi / lo planes [Cout_pad][KHW*Cin], k = tap*Cin + c
+// ----------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int Cout_pad,
+                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const size_t total = (size_t)Cout_pad * KHW * Cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % ((size_t)KHW * Cin));
+    const int co = (int)(i / ((size_t)KHW * Cin));
+    const int tap = kk / Cin, c = kk - tap * Cin;
+    const float v = co < Cout ? w[((size_t)co * Cin + c) * KHW + tap] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+  }
+}
+
+static int tc_cout_pad(int Cout) { return Cout <= 32 ? 32 : (Cout + 63) / 64 * 64; }
+
+size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw) {
+  return (size_t)2 * tc_cout_pad(Cout) * kh * kw * Cin * sizeof(uint16_t);
+}
+
+int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream) {
+  const int Cout_pad = tc_cout_pad(Cout), KHW = kh * kw;
+  uint16_t* hi = reinterpret_cast<uint16_t*>(packed);
+  uint16_t* lo = hi + (size_t)Cout_pad * KHW * Cin;
+  const size_t total = (size_t)Cout_pad * KHW * Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, KHW, Cout_pad, hi, lo);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+bool tc_supported(int Cin, int kh, int kw, int dg) { return (Cin % TC_BK) == 0 && dg == 1 && kh * kw <= 49; }
+
+int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
+  const int KHW = p.kh * p.kw;
+  if (!tc_supported(p.Cin, p.kh, p.kw, 1)) return UPSNET_E_UNSUPPORTED;
+  if ((((uintptr_t)p.x) & 15) || (((uintptr_t)packed) & 15) || (((uintptr_t)p.y) & 15)) return UPSNET_E_BADARG;
+  p.Cout_pad = tc_cout_pad(p.Cout);
+  p.w_hi = reinterpret_cast<const uint16_t*>(packed);
+  p.w_lo = p.w_hi + (size_t)p.Cout_pad * KHW * p.Cin;
+  const bool deform = p.offset != nullptr;
+  // tile N: as wide as possible (each gathered A tile is reused by BN couts)
+  int BN = p.Cout_pad;
+  const int bn_cap = p.x3 ? 128 : 256;
+  if (BN > bn_cap) BN = (p.Cout_pad % bn_cap == 0) ? bn_cap : ((p.Cout_pad % 128 == 0) ? 128 : 64);
+  p.BN = BN;
+  int stages = TC_MAX_STAGES;
+  TcSmem L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
+  const uint32_t budget = 200 * 1024;
+  while (stages > 2 && L.total + 1024 > budget) { --stages; L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0); }
+  if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  const int num_kb = KHW * (p.Cin / TC_BK);
+  if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
+  L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
+  p.stages = stages;
+  const long long Ptot = (long long)p.N * p.Ho * p.Wo;
+  if (Ptot <= 0) return 0;
+  const long long gx = (Ptot + TC_BM - 1) / TC_BM;
+  if (gx > 2147483647LL) return UPSNET_E_UNSUPPORTED;
+  dim3 grid((unsigned)gx, (unsigned)(p.Cout_pad / BN));
+  const size_t smem = L.total + 1024;
+  if (deform) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    igemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
+  } else {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    igemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
+  }
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ups

@@ -108,7 +108,7 @@ class Bottleneck(nn.Module):
         f = self._f
         out = ops.conv2d(x, f["w1"], f["b1"], stride=self.stride, relu=True)
         if self.deformable:
-            offset = ops.conv2d(out, self.conv2_offset.weight, self.conv2_offset.bias, 1, 1, 1)
+            offset = ops.conv2d(out, self.conv2_offset.weight, self.conv2_offset.bias, 1, 1, 1, out_format="nchw")
             out = ops.deform_conv(out, offset, f["w2"], f["b2"], 1, self.dilation, self.dilation, relu=True)
         else:
             out = ops.conv2d(out, f["w2"], f["b2"], 1, self.dilation, self.dilation, relu=True)
@@ -237,7 +237,7 @@ class RPN(nn.Module):
     def forward(self, x):
         c = self.conv_proposal[0]
         t = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
-        both = ops.conv2d(t, self._f[0], self._f[1])
+        both = ops.conv2d(t, self._f[0], self._f[1], out_format="nchw")
         cls_score, bbox_pred = both[:, :self.num_anchors], both[:, self.num_anchors:]
         return cls_score, bbox_pred, torch.sigmoid(cls_score)
 
@@ -269,7 +269,7 @@ class RCNN(nn.Module):
 
     def forward(self, feat, rois):
         pool = self.roi_pooling(feat, rois)
-        x = pool.view(pool.size(0), -1)
+        x = pool.reshape(pool.size(0), -1)
         fc6 = ops.linear(x, self.fc6[0].weight, self.fc6[0].bias, relu=True)
         fc7 = ops.linear(fc6, self.fc7[0].weight, self.fc7[0].bias, relu=True)
         both = ops.linear(fc7, self._f[0], self._f[1])
@@ -310,8 +310,8 @@ class MaskBranch(nn.Module):
         w1, b1, cout = self._f
         y = ops.conv2d(x, w1, b1, relu=True)                 # [n, 4*Cout, h, w]
         n, _, h, w = y.shape
-        y = y.view(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
-        return ops.conv2d(y, self.mask_score.weight, self.mask_score.bias)
+        y = y.reshape(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
+        return ops.conv2d(y, self.mask_score.weight, self.mask_score.bias, out_format="nchw")
 
 
 class FCNSubNet(nn.Module):
@@ -341,7 +341,7 @@ class FCNSubNet(nn.Module):
     def forward(self, x):
         for i in range(self.num_layers):
             l = self.conv[i][0]
-            offset = ops.conv2d(x, l.conv_offset.weight, l.conv_offset.bias, 1, 1, 1)
+            offset = ops.conv2d(x, l.conv_offset.weight, l.conv_offset.bias, 1, 1, 1, out_format="nchw")
             x = ops.deform_conv(x, offset, l.conv.weight, l.conv.bias, l.conv.stride, l.conv.padding,
                                 l.conv.dilation, l.conv.deformable_groups, relu=True)   # ReLU fused
         return x
@@ -364,7 +364,7 @@ class FCNHead(nn.Module):
         p4 = F.interpolate(p4, None, 4, mode="bilinear", align_corners=False)
         p5 = F.interpolate(p5, None, 8, mode="bilinear", align_corners=False)
         feat = torch.cat([p2, p3, p4, p5], dim=1)
-        score = ops.conv2d(feat, self.score.weight, self.score.bias)
+        score = ops.conv2d(feat, self.score.weight, self.score.bias, out_format="nchw")  # panoptic kernel reads planes
         ret = {"fcn_score": score, "fcn_feat": feat}
         if self.upsample_rate != 1:
             ret["fcn_output"] = F.interpolate(score, None, self.upsample_rate, mode="bilinear", align_corners=False)

@@ -68,11 +68,83 @@ def _conv_out(n, pad, dil, k, stride):
 
 
 # ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) path plumbing: NHWC views and the packed-weight cache
+# ------------------------------------------------------------------------------------------------
+def _nhwc(x):
+    """[N,C,H,W] logical tensor -> contiguous [N,H,W,C] storage (no copy if already channels_last)."""
+    xp = x.permute(0, 2, 3, 1)
+    return xp if xp.is_contiguous() else xp.contiguous()
+
+
+_packed_cache = {}
+
+
+def _packed_weight(weight):
+    """bf16 hi/lo planes [Cout_pad][kh*kw][Cin] (upsnet_igemm_pack_weight), cached per weight version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    hit = _packed_cache.get(key)
+    if hit is not None:
+        return hit
+    Cout, Cin, kh, kw = weight.shape
+    nbytes = C.c_size_t(0)
+    check(lib().upsnet_igemm_packed_weight_bytes(Cout, Cin, kh, kw, C.byref(nbytes)), "igemm_packed_weight_bytes")
+    buf = torch.empty(nbytes.value, dtype=torch.uint8, device=weight.device)
+    w = f32c(weight.detach())
+    with torch.cuda.device(weight.device):
+        check(lib().upsnet_igemm_pack_weight(ptr(w), Cout, Cin, kh, kw, ptr(buf), stream_ptr(weight.device)),
+              "igemm_pack_weight")
+    STATS["launches"] += 1
+    if len(_packed_cache) > 4096:
+        _packed_cache.clear()
+    _packed_cache[key] = buf
+    return buf
+
+
+def _tc_ok(Cin, kh, kw, dg):
+    return Cin % 64 == 0 and dg == 1 and kh * kw <= 49
+
+
+def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format):
+    """upsnet_igemm_forward: x logical NCHW (any memory format), result logical NCHW whose storage is
+    NHWC (channels_last view, the engine layout) unless out_format == 'nchw'."""
+    sh, sw = stride; ph, pw = padding; dh, dw = dilation
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
+    xs = _nhwc(x if x.dtype == torch.float32 else x.float())
+    packed = _packed_weight(weight)
+    nhwc_out = out_format != "nchw"
+    if nhwc_out:
+        store = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+        y = store.permute(0, 3, 1, 2)
+        res = None if residual is None else _nhwc(residual.float())
+    else:
+        store = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+        y = store
+        res = None if residual is None else f32c(residual)
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * (3 if prec == _lib.PREC_BF16X3 else 1),
+            "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "bytes": 4.0 * (x.numel() + weight.numel() + store.numel() * (2 if residual is not None else 1))}
+    with torch.cuda.device(x.device), _Timed(kind, 1, work, x.device):
+        check(lib().upsnet_igemm_forward(ptr(xs), ptr(offset), ptr(mask), ptr(packed), ptr(bias), ptr(res),
+                                         ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                                         _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW,
+                                         _lib.EPI_RELU if relu else 0, prec, stream_ptr(x.device)), kind)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
 # functional layer
 # ------------------------------------------------------------------------------------------------
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None):
-    """Dense conv + fused bias / residual / ReLU epilogue (upsnet_conv2d_forward)."""
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
+           out_format=None):
+    """Dense conv + fused bias / residual / ReLU epilogue.  fp32 precision -> upsnet_conv2d_forward
+    (NCHW CUDA-core tiles); bf16x3 / bf16 -> upsnet_igemm_forward (tcgen05 tiles, NHWC storage)."""
     require_cuda(x, weight, bias, residual)
+    prec = _PRECISION["conv"] if precision is None else precision
+    if prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], 1):
+        return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
+                         _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format)
     x, weight = f32c(x), f32c(weight)
     bias = None if bias is None else f32c(bias)
     residual = None if residual is None else f32c(residual)
@@ -84,10 +156,10 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
     y = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
     if residual is not None:
         assert residual.shape == y.shape
-    prec = _PRECISION["conv"] if precision is None else precision
-    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+    prec = _lib.PREC_FP32_SIMT
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
             "bytes": 4.0 * (x.numel() + weight.numel() + y.numel() * (2 if residual is not None else 1))}
-    with torch.cuda.device(x.device), _Timed("conv2d", 1, work, x.device):
+    with torch.cuda.device(x.device), _Timed("conv2d_simt", 1, work, x.device):
         check(lib().upsnet_conv2d_forward(ptr(x), ptr(weight), ptr(bias), ptr(residual), ptr(y), N, Cin, H, W,
                                           Cout, kh, kw, sh, sw, ph, pw, dh, dw, _lib.EPI_RELU if relu else 0,
                                           prec, stream_ptr(x.device)), "conv2d")
@@ -103,14 +175,26 @@ def linear(x, weight, bias=None, relu=False, precision=None):
 
 
 def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1,
-                mask=None, relu=False, precision=None):
+                mask=None, relu=False, precision=None, out_format=None):
     """DeformConvFunction.forward (functions/deform_conv.py:26-57); with `mask` (already 2*sigmoid)
     ModDeformConvFunction.forward (functions/mod_deform_conv.py:25-59).  One fused launch."""
     require_cuda(data, offset, weight, bias, mask)
-    data, offset, weight = f32c(data), f32c(offset), f32c(weight)
+    prec = _PRECISION["conv"] if precision is None else precision
+    use_tc = prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], deformable_groups)
+    offset = f32c(offset)
     bias = None if bias is None else f32c(bias)
     mask = None if mask is None else f32c(mask)
     sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    if use_tc:
+        N, Cin, H, W = data.shape
+        kh, kw = weight.shape[2], weight.shape[3]
+        Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
+        assert tuple(offset.shape) == (N, 2 * kh * kw, Ho, Wo), offset.shape
+        if mask is not None:
+            assert tuple(mask.shape) == (N, kh * kw, Ho, Wo), mask.shape
+        return _igemm_tc("dcn", data, offset, mask, weight, bias, None, (sh, sw), (ph, pw), (dh, dw), relu, prec,
+                         out_format)
+    data, weight = f32c(data), f32c(weight)
     N, Cin, H, W = data.shape
     Cout, Cin_w, kh, kw = weight.shape
     assert Cin_w == Cin, "groups != 1 is not supported (the reference ignores `groups`)"
@@ -119,11 +203,11 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
     if mask is not None:
         assert tuple(mask.shape) == (N, kh * kw * deformable_groups, Ho, Wo), mask.shape
     y = torch.empty((N, Cout, Ho, Wo), device=data.device, dtype=torch.float32)
-    prec = _PRECISION["conv"] if precision is None else precision
-    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+    prec = _lib.PREC_FP32_SIMT
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
             "bytes": 4.0 * (data.numel() + offset.numel() + weight.numel() + y.numel() +
                             (mask.numel() if mask is not None else 0))}
-    with torch.cuda.device(data.device), _Timed("dcn", 1, work, data.device):
+    with torch.cuda.device(data.device), _Timed("dcn_simt", 1, work, data.device):
         check(lib().upsnet_dcn_forward(ptr(data), ptr(offset), ptr(mask), ptr(weight), ptr(bias), ptr(y), N, Cin,
                                        H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, deformable_groups,
                                        _lib.EPI_RELU if relu else 0, prec, stream_ptr(data.device)),
@@ -156,9 +240,18 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
     """FPNRoIAlign.forward in one launch (level assignment on device, output already in roi order)."""
     assert len(feats) == 4 and len(spatial_scales) == 4
     require_cuda(rois, *feats)
-    feats = [f32c(f) for f in feats]
     rois = f32c(rois)
     R = rois.shape[0]
+    if layout == "auto":
+        # engine tensors: logical NCHW; if every level is stored channels_last use the NHWC kernel
+        # (coalesced channel vectors) and hand back a logical-NCHW view of the NHWC result
+        cl = all(f.dim() == 4 and f.permute(0, 2, 3, 1).is_contiguous() and not f.is_contiguous() for f in feats)
+        if cl:
+            out = fpn_roi_align([f.permute(0, 2, 3, 1) for f in feats], rois, pooled_height, pooled_width,
+                                spatial_scales, sampling_ratio, "nhwc", return_levels)
+            return (out[0].permute(0, 3, 1, 2), out[1]) if return_levels else out.permute(0, 3, 1, 2)
+        layout = "nchw"
+    feats = [f32c(f) for f in feats]
     if layout == "nchw":
         B, Cc = feats[0].shape[0], feats[0].shape[1]
         Hs = [f.shape[2] for f in feats]; Ws = [f.shape[3] for f in feats]
@@ -304,7 +397,7 @@ class DeformConvWithOffset(nn.Module):
                                deformable_groups=deformable_groups, bias=bias)
 
     def forward(self, x):
-        offset = conv2d(x, self.conv_offset.weight, self.conv_offset.bias, 1, 1, 1)
+        offset = conv2d(x, self.conv_offset.weight, self.conv_offset.bias, 1, 1, 1, out_format="nchw")
         return self.conv(x, offset)
 
 
@@ -338,7 +431,7 @@ class ModDeformConvWithOffsetMask(nn.Module):
                                   deformable_groups=deformable_groups, bias=bias)
 
     def forward(self, x):
-        om = conv2d(x, self.conv_offset_mask.weight, self.conv_offset_mask.bias, 1, 1, 1)
+        om = conv2d(x, self.conv_offset_mask.weight, self.conv_offset_mask.bias, 1, 1, 1, out_format="nchw")
         return self.conv(x, om)
 
 
@@ -381,7 +474,8 @@ class FPNRoIAlign(nn.Module):
         self.with_expand = with_expand
 
     def forward(self, feat, rois):
-        return fpn_roi_align(list(feat), rois, self.pooled_height, self.pooled_width, self.spatial_scale)
+        return fpn_roi_align(list(feat), rois, self.pooled_height, self.pooled_width, self.spatial_scale,
+                             layout="auto")
 
 
 # ------------------------------------------------------------------------------------------------
