@@ -355,6 +355,8 @@ def test_engine_forward_matches_cpu_path(dev):
     cfg = UPSNetConfig.cityscapes_r50()
     m_cpu = synthetic_model(cfg, depth=(1, 1, 1, 1), seed=3)
     m_gpu = synthetic_model(cfg, depth=(1, 1, 1, 1), seed=3, device=dev)
+    m_gpu.load_state_dict({k: v.to(dev) for k, v in m_cpu.state_dict().items()})   # identical weights by construction
+    m_cpu = m_cpu.to("cpu"); m_cpu.prepare(); m_gpu.prepare()
     Hh, Ww = 256, 384
     inp = synthetic_input(Hh, Ww, seed=4)
     with cpu_ops(), torch.no_grad():

@@ -228,6 +228,8 @@ def roi_align(features, rois, pooled_height, pooled_width, spatial_scale, sampli
         B, H, W, Cc = features.shape
         out = torch.empty((R, pooled_height, pooled_width, Cc), device=features.device, dtype=torch.float32)
         lay = _lib.LAYOUT_NHWC
+    if R == 0:
+        return out
     with torch.cuda.device(features.device), _Timed("roi_align", 1, {"bytes": 4.0 * out.numel()}, features.device):
         check(lib().upsnet_roi_align_forward(ptr(features), B, Cc, H, W, lay, ptr(rois), R, pooled_height,
                                              pooled_width, sampling_ratio, float(spatial_scale), ptr(out),

@@ -14,8 +14,12 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
     from upsnet_b200.model import resnet_upsnet, Bottleneck
     from upsnet_b200.operators import DeformConvWithOffset
     g = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
+    with torch.no_grad(), torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)          # module constructors draw from the global CPU generator
         m = resnet_upsnet(list(depth), cfg)
+        for prm in m.parameters():       # DeformConv creates its parameters on CUDA (like the reference):
+            if prm.is_cuda:              # re-draw them from the CPU generator so every build is identical
+                prm.copy_(torch.empty(prm.shape).uniform_(-0.05, 0.05, generator=g).to(prm.device))
         for mod in m.modules():
             if isinstance(mod, torch.nn.BatchNorm2d):
                 mod.weight.copy_(torch.empty_like(mod.weight).uniform_(0.5, 1.5, generator=g))
