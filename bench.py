@@ -266,5 +266,164 @@ def main():
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# --ops: per-operator table: new kernel vs the reference's own CUDA kernel
+# (oracle/_ref, when shipped) vs the CPU oracle, with achieved GB/s / TFLOP/s against the peaks.
+# ------------------------------------------------------------------------------------------------
+def run_ops(args):
+    import numpy as np
+    import torch
+    import upsnet_b200 as U
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    try:
+        ref = O.RefKernels()
+    except Exception:
+        ref = None
+
+    def gpu_ms(fn, iters=20, warm=3):
+        for _ in range(warm):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()                                   # L2 flush (256 MB > 126 MB L2)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / iters
+
+    def cpu_ms(fn, reps=3):
+        fn(); best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+
+    rows = []
+
+    def row(op, cfg, ms, by=None, fl=None, ref_ms=None, cpu=None, err=None):
+        r = {"op": op, "config": cfg, "b200_ms": round(ms, 5)}
+        if by is not None:
+            r["gbs"] = round(by / ms / 1e6, 1); r["frac_hbm"] = round(by / ms / 1e6 / pk["hbm_gbs"], 4)
+        if fl is not None:
+            r["tflops"] = round(fl / ms / 1e9, 2); r["frac_tensor"] = round(fl / ms / 1e9 / pk["tf_burst"], 4)
+        if ref_ms is not None:
+            r["ref_kernel_ms"] = round(ref_ms, 5)
+        if cpu is not None:
+            r["cpu_ms"] = round(cpu, 3); r["cpu_cores"] = os.cpu_count()
+        if err is not None:
+            r["max_abs_diff"] = float(err)
+        rows.append(r); print(json.dumps(r), flush=True)
+
+    rng = np.random.default_rng(0)
+    torch.manual_seed(0)
+
+    def rois_for(n, extent, smin, smax):
+        c = rng.uniform(0, extent, (n, 2)); s = np.exp(rng.uniform(np.log(smin), np.log(smax), (n, 2)))
+        return np.concatenate([np.zeros((n, 1)), np.clip(c - s / 2, 0, extent - 1), np.clip(c + s / 2, 0, extent - 1)], 1).astype(np.float32)
+
+    # ---- config 1: ROIAlign 1x256x256x256, 32 boxes ----
+    feat = torch.randn(1, 256, 256, 256, device=dev)
+    feat_nhwc = feat.permute(0, 2, 3, 1).contiguous()
+    r32 = rois_for(32, 1024, 16, 512); r32d = torch.from_numpy(r32).to(dev)
+    for ph in (7, 14):
+        want = O.roi_align(feat.cpu().numpy(), r32, ph, ph, 0.25)
+        cpu = cpu_ms(lambda: O.roi_align(feat.cpu().numpy(), r32, ph, ph, 0.25))
+        by = 4.0 * 32 * 256 * ph * ph * 2 + 20 * 32   # out + (<=) same amount of unique feature reads
+        got = U.roi_align(feat, r32d, ph, ph, 0.25)
+        rm = gpu_ms(lambda: ref.roi_align(feat, r32d, ph, ph, 0.25)) if ref else None
+        row("roi_align nchw", "1x256x256x256, 32 rois, %dx%d" % (ph, ph), gpu_ms(lambda: U.roi_align(feat, r32d, ph, ph, 0.25)),
+            by, None, rm, cpu, np.abs(got.cpu().numpy() - want).max())
+        row("roi_align nhwc", "1x256x256x256, 32 rois, %dx%d" % (ph, ph),
+            gpu_ms(lambda: U.roi_align(feat_nhwc, r32d, ph, ph, 0.25, layout="nhwc")), by)
+    # RCNN case: 1000 rois over the 4 FPN levels of a 1024x2048 image
+    feats = [torch.randn(1, 256, 256 >> l, 512 >> l, device=dev) for l in range(4)]
+    feats_cl = [f.permute(0, 2, 3, 1).contiguous() for f in feats]
+    r1k = rois_for(1000, 2048, 16, 600); r1k[:, 2::2] = np.clip(r1k[:, 2::2], 0, 1023); r1kd = torch.from_numpy(r1k).to(dev)
+    by = 4.0 * 1000 * 256 * 49 * 2
+    sc = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+    row("fpn_roi_align nchw", "P2..P5 of 1024x2048, 1000 rois, 7x7", gpu_ms(lambda: U.fpn_roi_align(feats, r1kd, 7, 7, sc)), by)
+    row("fpn_roi_align nhwc", "P2..P5 of 1024x2048, 1000 rois, 7x7",
+        gpu_ms(lambda: U.fpn_roi_align(feats_cl, r1kd, 7, 7, sc, layout="nhwc")), by)
+
+    # ---- NMS ----
+    def dets(n, extent):
+        c = rng.uniform(0, extent, (n, 2)); s = np.exp(rng.uniform(np.log(16), np.log(256), (n, 2)))
+        sc_ = np.sort((rng.permutation(n) + 1.0) / (n + 1))[::-1]
+        return np.concatenate([c - s / 2, c + s / 2, sc_[:, None]], 1).astype(np.float32)
+    for n, extent, thr in ((1000, 600, 0.7), (8000, 2048, 0.5)):
+        d = dets(n, extent); bx = torch.from_numpy(d[:, :4].copy()).to(dev)
+        seg = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        by = 20.0 * n + 8.0 * n * ((n + 63) // 64) / 2 + 4 * n
+        cpu = cpu_ms(lambda: O.nms(d, thr))
+        rm = None
+        if ref:
+            t0 = time.perf_counter(); ref.nms(d, thr); rm = (time.perf_counter() - t0) * 1e3
+        row("nms (device resident)", "N=%d thresh %.1f" % (n, thr), gpu_ms(lambda: U.nms_segmented(bx, seg, n, thr)), by, None, rm, cpu)
+    d5 = [dets(1000, 600) for _ in range(5)]
+    bx5 = torch.from_numpy(np.concatenate(d5)[:, :4].copy()).to(dev)
+    seg5 = torch.tensor([0, 1000, 2000, 3000, 4000, 5000], dtype=torch.int32, device=dev)
+    row("nms segmented", "5 RPN levels x 1000, one launch pair", gpu_ms(lambda: U.nms_segmented(bx5, seg5, 1000, 0.7)),
+        5 * (20.0 * 1000 + 8.0 * 1000 * 16 / 2 + 4000))
+
+    # ---- DCN: semantic-head layer 1 at P2 and the op-level v2 config ----
+    x = torch.randn(1, 256, 256, 512, device=dev)
+    w = torch.randn(128, 256, 3, 3, device=dev) / 48
+    b = torch.randn(128, device=dev)
+    off = torch.randn(1, 18, 256, 512, device=dev) * 2
+    fl = 2.0 * 256 * 512 * 128 * 256 * 9
+    by = 4.0 * (x.numel() + off.numel() + w.numel() + 128 * 256 * 512)
+    rm = gpu_ms(lambda: ref.deform_conv(x, off, w, b, pad=1), iters=5) if ref else None
+    base = U.deform_conv(x, off, w, b, 1, 1, 1, precision=0)
+    row("dcn v1 fp32 simt", "FCN L1@P2 256->128 3x3, 256x512", gpu_ms(lambda: U.deform_conv(x, off, w, b, 1, 1, 1, precision=0), iters=5), by, fl, rm)
+    for name, prec in (("bf16x3", 1), ("bf16", 2)):
+        got = U.deform_conv(x, off, w, b, 1, 1, 1, precision=prec)
+        row("dcn v1 tcgen05 " + name, "FCN L1@P2 256->128 3x3, 256x512",
+            gpu_ms(lambda: U.deform_conv(x, off, w, b, 1, 1, 1, precision=prec)), by, fl, None, None,
+            (got.float() - base).abs().max().item())
+    x2 = torch.randn(2, 256, 50, 84, device=dev); om = torch.randn(2, 27, 50, 84, device=dev)
+    m2 = U.ModulatedDeformConv(256, 256, 3, padding=1).to(dev)
+    fl2 = 2.0 * 2 * 50 * 84 * 256 * 256 * 9
+    for name in ("fp32", "bf16x3", "bf16"):
+        U.set_precision(name)
+        row("ModulatedDeformConv " + name, "x[2,256,50,84] offset_mask[2,27,50,84] w[256,256,3,3]", gpu_ms(lambda: m2(x2, om)), None, fl2)
+    U.set_precision("fp32")
+
+    # ---- dense conv: FPN output conv 3x3 256->256 at P2, and a res4 1x1 ----
+    wc = torch.randn(256, 256, 3, 3, device=dev) / 48
+    flc = 2.0 * 256 * 512 * 256 * 256 * 9
+    basec = U.conv2d(x, wc, None, 1, 1, 1, precision=0)
+    row("conv3x3 fp32 simt", "256->256 @256x512", gpu_ms(lambda: U.conv2d(x, wc, None, 1, 1, 1, precision=0), iters=5), None, flc)
+    xcl = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    for name, prec in (("bf16x3", 1), ("bf16", 2)):
+        got = U.conv2d(xcl, wc, None, 1, 1, 1, precision=prec)
+        row("conv3x3 tcgen05 " + name, "256->256 @256x512", gpu_ms(lambda: U.conv2d(xcl, wc, None, 1, 1, 1, precision=prec)),
+            None, flc, None, None, (got.float() - basec).abs().max().item())
+
+    # ---- config 5: panoptic-head sweep at 1024x2048 ----
+    fcn = (torch.randn(1, 19, H, W, device=dev) * 3)
+    for n in (100, 200, 500, 1000):
+        c = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1); s = np.exp(rng.uniform(np.log(16), np.log(512), (n, 2)))
+        bxs = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+        bxs[:, 0::2] = np.clip(bxs[:, 0::2], 0, W - 1); bxs[:, 1::2] = np.clip(bxs[:, 1::2], 0, H - 1)
+        prob = (0.6 + 0.4 * (rng.permutation(n) + 1) / (n + 1)).astype(np.float32)
+        ml = (rng.standard_normal((n, 1, 28, 28)) * 2).astype(np.float32)
+        cls = rng.integers(1, 9, n).astype(np.int64)
+        a = [torch.from_numpy(v).to(dev) for v in (bxs, prob, ml, cls)]
+        by = 4.0 * 19 * H * W + 8.0 * H * W + n * (4 * 784 + 24)
+        cpu = None
+        if n == 100:
+            fc = fcn[0].cpu().numpy()
+            cpu = cpu_ms(lambda: O.panoptic_head(fc, bxs, prob, ml, cls, 11), reps=2)
+        keep, _ = U.panoptic_fuse(fcn, a[0], a[1], a[2], a[3], 11)
+        row("panoptic_head", "19x1024x2048, n=%d (kept %d)" % (n, keep.numel()),
+            gpu_ms(lambda: U.panoptic_fuse(fcn, a[0], a[1], a[2], a[3], 11)), by, None, None, cpu)
+    print(json.dumps({"ops_table": rows, "peaks": pk}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--ops" in sys.argv:
+        run_ops(None)
+    else:
+        main()

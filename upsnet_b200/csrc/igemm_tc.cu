@@ -161,7 +161,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, i
 }
 
 template <bool DEFORM>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 igemm_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   // 1024-byte alignment of the stage buffers is required by SWIZZLE_128B
@@ -486,14 +486,24 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   const int bn_cap = p.x3 ? 128 : 256;
   if (BN > bn_cap) BN = (p.Cout_pad % bn_cap == 0) ? bn_cap : ((p.Cout_pad % 128 == 0) ? 128 : 64);
   p.BN = BN;
-  int stages = TC_MAX_STAGES;
-  TcSmem L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
-  const uint32_t budget = 200 * 1024;
-  while (stages > 2 && L.total + 1024 > budget) { --stages; L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0); }
-  if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  // Shared-memory budget: prefer a footprint that lets TWO CTAs share an SM (the kernel is not
+  // persistent, so co-residency is what overlaps one tile's epilogue with another's main loop);
+  // fall back to a single deep ring when two would leave fewer than 3 stages.
   const int num_kb = KHW * (p.Cin / TC_BK);
-  if (stages > num_kb) stages = num_kb < 2 ? 2 : num_kb;
-  L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
+  const int want = num_kb < 3 ? (num_kb < 2 ? 2 : num_kb) : 3;
+  auto fit = [&](uint32_t budget) {
+    int st = TC_MAX_STAGES;
+    if (st > num_kb) st = num_kb < 2 ? 2 : num_kb;
+    while (st > 2 && tc_smem_layout(deform, KHW, BN, st, p.x3 != 0).total + 1024 > budget) --st;
+    return st;
+  };
+  int stages = fit(112 * 1024);
+  TcSmem L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
+  if (stages < want || L.total + 1024 > 112 * 1024) {
+    stages = fit(200 * 1024);
+    L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
+  }
+  if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   p.stages = stages;
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
   if (Ptot <= 0) return 0;

@@ -449,6 +449,10 @@ class resnet_upsnet(nn.Module):
         keep = pan["keep_inds"]
         results.update({"fcn_outputs": pan["fcn_outputs"], "panoptic_cls_inds": pcls_idx[keep],
                         "panoptic_cls_probs": pcls_prob[keep], "panoptic_outputs": pan["panoptic_outputs"]})
+        if getattr(self, "keep_intermediates", False):   # parity tests: the exact inputs of the panoptic head
+            results["_intermediates"] = {"fcn_output": fcn_output["fcn_output"], "rois": rois, "cls_prob": cls_prob,
+                                         "bbox_pred": bbox_pred, "pmask_rois": pmask_rois, "pcls_prob": pcls_prob,
+                                         "pmask_score": mask_score, "pcls_idx": pcls_idx, "keep_inds": keep}
         return results
 
 
