@@ -15,7 +15,8 @@
 // * B (weights) is pre-packed once to bf16 [Cout_pad][tap][Cin] and copied by the same warps.
 // * One elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) per 16-column slice;
 //   tcgen05.commit releases the smem stage to the producers through an mbarrier; accumulators
-//   live in TMEM and are drained with tcgen05.ld (32x32b.x16) by all 8 producer warps.
+//   live in TMEM (two buffers) and are drained with tcgen05.ld (32x32b.x16) by 4 epilogue warps
+//   while the next tile's main loop is already running (persistent CTAs, static tile schedule).
 // * Precision modes: BF16 (one pass) and BF16X3 (x = hi + lo split of both operands, three
 //   MMAs: hi*hi + lo*hi + hi*lo; error ~2^-16 relative, i.e. fp32-grade results for the
 //   "fp32 logits within 1e-3" contract at 3x the tensor work).
@@ -31,7 +32,8 @@ namespace ups {
 constexpr int TC_BM = 128;         // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;          // bf16 elements per k-block row (= 128 bytes, one swizzle span)
 constexpr int TC_PRODUCERS = 256;  // 8 warps
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_EPILOGUE = 128;      // 4 warps (one per TMEM lane quadrant)
+constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 13 warps
 constexpr int TC_MAX_STAGES = 6;
 
 struct TcParams {
@@ -140,7 +142,7 @@ __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(_
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct TcSmem {
-  uint32_t bars;      // full[6], empty[6], accum (13 x 8 B) then tmem ptr
+  uint32_t bars;      // full[6], empty[6], tmem_full[2], tmem_empty[2] (16 x 8 B) then tmem ptr
   uint32_t rowbase;   // long long [128]
   uint32_t table;     // deform: float4 [KHW][128] + int4 [KHW][128]; dense: int [KHW][128]
   uint32_t stages;    // 1024-aligned
@@ -149,7 +151,7 @@ struct TcSmem {
 __host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, int stages, bool x3) {
   TcSmem s;
   s.bars = 0;
-  s.rowbase = 128;
+  s.rowbase = 256;
   s.table = s.rowbase + TC_BM * 8;
   const uint32_t tbytes = deform ? KHW * TC_BM * 32 : KHW * TC_BM * 4;
   s.stages = (uint32_t)((s.table + tbytes + 1023) / 1024 * 1024);
@@ -160,21 +162,32 @@ __host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, i
   return s;
 }
 
+// Named barrier among the producer warps only (ids 1.. ; id 0 is __syncthreads)
+__device__ __forceinline__ void producer_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
+}
+
+// Persistent, warp-specialised kernel.  Roles (13 warps):
+//   warps 0-3   epilogue: TMEM -> registers -> bias/residual/ReLU -> global (warp w owns TMEM lanes 32w..)
+//   warp  4     MMA issuer (one elected lane), owns TMEM alloc/dealloc and barrier init
+//   warps 5-12  producers: sample table + A gather + B copy into the smem ring
+// Pipelines: smem ring full[s]/empty[s] (producers <-> MMA) runs across tiles; two TMEM accumulator
+// buffers tmem_full[b]/tmem_empty[b] (MMA <-> epilogue) overlap tile i's epilogue with tile i+1's
+// main loop.  Tiles: id = blockIdx.x + it*gridDim.x, n-tile fastest (concurrent CTAs share the A rows in L2).
 template <bool DEFORM>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  // 1024-byte alignment of the stage buffers is required by SWIZZLE_128B
   const uint32_t raw = smem_u32(smem_dyn);
-  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B stage buffers need 1024-byte alignment
   uint8_t* sm = smem_dyn + (base - raw);
 
   const int KHW = p.kh * p.kw;
   const bool x3 = p.x3 != 0;
   const TcSmem L = tc_smem_layout(DEFORM, KHW, p.BN, p.stages, x3);
   const uint32_t bar_full = base + L.bars, bar_empty = bar_full + 8 * TC_MAX_STAGES;
-  const uint32_t bar_accum = bar_empty + 8 * TC_MAX_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + L.bars + 8 * (2 * TC_MAX_STAGES + 1));
+  const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + L.bars + 8 * (2 * TC_MAX_STAGES + 4));
   long long* rowbase = reinterpret_cast<long long*>(sm + L.rowbase);
   float4* tw = reinterpret_cast<float4*>(sm + L.table);
   int4* to = reinterpret_cast<int4*>(sm + L.table + (DEFORM ? KHW * TC_BM * 16 : 0));
@@ -183,253 +196,282 @@ igemm_tc_kernel(const TcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HoWo = p.Ho * p.Wo;
   const long long Ptot = (long long)p.N * HoWo;
-  const long long p0 = (long long)blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * p.BN;
   const int cchunks = p.Cin / TC_BK;
   const int num_kb = KHW * cchunks;
   const int Kp = KHW * p.Cin;
+  const int n_tiles = p.Cout_pad / p.BN;
+  const long long m_tiles = (Ptot + TC_BM - 1) / TC_BM;
+  const long long num_tiles = m_tiles * n_tiles;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * p.BN) tmem_cols <<= 1;
 
   // ---------------- one-time setup ----------------
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32);
         mbar_init(bar_empty + 8 * s, 1);
       }
-      mbar_init(bar_accum, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_tfull + 8 * b, 1);
+        mbar_init(bar_tempty + 8 * b, 4);   // one arrive per epilogue warp
+      }
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
-  }
-  for (int r = tid; r < TC_BM; r += TC_THREADS) {
-    const long long pg = p0 + r;
-    rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
-  }
-  // per-tile sample table (channel independent): one entry per (tap, pixel)
-  for (int e = tid; e < KHW * TC_BM; e += TC_THREADS) {
-    const int tap = e / TC_BM, r = e - tap * TC_BM;
-    const long long pg = p0 + r;
-    const int ki = tap / p.kw, kj = tap - ki * p.kw;
-    if (DEFORM) {
-      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-      int4 ov = make_int4(0, 0, 0, 0);
-      if (pg < Ptot) {
-        const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
-        const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-        const float* offp = p.offset + ((size_t)n * 2 * KHW + 2 * tap) * HoWo + pp;
-        const float oh = __ldg(offp), ow = __ldg(offp + HoWo);
-        const float h = (float)(ho * p.sh - p.ph + ki * p.dh) + oh;
-        const float w = (float)(wo * p.sw - p.pw + kj * p.dw) + ow;
-        if (h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {  // deform_conv_kernel.cu:229
-          const int hl = (int)floorf(h), wl = (int)floorf(w), hh = hl + 1, wh = wl + 1;
-          const float lh = h - hl, lw = w - wl, ch = 1.f - lh, cw = 1.f - lw;
-          const bool t_ok = hl >= 0, b_ok = hh <= p.H - 1, l_ok = wl >= 0, r_ok = wh <= p.W - 1;
-          float m = 1.f;
-          if (p.mask) m = __ldg(p.mask + ((size_t)n * KHW + tap) * HoWo + pp);
-          wv.x = (t_ok && l_ok) ? ch * cw * m : 0.f;
-          wv.y = (t_ok && r_ok) ? ch * lw * m : 0.f;
-          wv.z = (b_ok && l_ok) ? lh * cw * m : 0.f;
-          wv.w = (b_ok && r_ok) ? lh * lw * m : 0.f;
-          ov.x = (t_ok && l_ok) ? hl * p.W + wl : 0;
-          ov.y = (t_ok && r_ok) ? hl * p.W + wh : 0;
-          ov.z = (b_ok && l_ok) ? hh * p.W + wl : 0;
-          ov.w = (b_ok && r_ok) ? hh * p.W + wh : 0;
-        }
-      }
-      tw[e] = wv;
-      to[e] = ov;
-    } else {
-      int o = -1;
-      if (pg < Ptot) {
-        const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
-        const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-        const int hi = ho * p.sh - p.ph + ki * p.dh, wi = wo * p.sw - p.pw + kj * p.dw;
-        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) o = hi * p.W + wi;
-      }
-      ti[e] = o;
-    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 8) {
+  if (warp >= 5) {
     // =============================== PRODUCERS ===============================
-    const int j = tid & 7;         // 16-byte chunk (8 channels) inside the 128-byte row
-    const int r_first = tid >> 3;  // 32 rows per pass
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % p.stages, it = kb / p.stages;
-      mbar_wait(bar_empty + 8 * s, (uint32_t)((it & 1) ^ 1));
-      uint8_t* stage = sm + L.stages + (size_t)s * L.stage_bytes;
-      uint8_t* a_hi = stage;
-      uint8_t* b_hi = stage + L.a_bytes;
-      uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
-      uint8_t* b_lo = a_lo + L.a_bytes;
-      const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
-      // ---- A: gather 128 rows x 8 chunks ----
-#pragma unroll 2
-      for (int pass = 0; pass < TC_BM / 32; ++pass) {
-        const int r = r_first + pass * 32;
-        const long long rb = rowbase[r];
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = 0.f;
-        if (rb >= 0) {
-          const float* xb = p.x + rb + c0;
-          if (DEFORM) {
-            const float4 wv = tw[tap * TC_BM + r];
-            const int4 ov = to[tap * TC_BM + r];
-            const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin);
-            const float4* c01 = reinterpret_cast<const float4*>(xb + (size_t)ov.y * p.Cin);
-            const float4* c10 = reinterpret_cast<const float4*>(xb + (size_t)ov.z * p.Cin);
-            const float4* c11 = reinterpret_cast<const float4*>(xb + (size_t)ov.w * p.Cin);
-            const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
-            const float4 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
-            v[0] = wv.x * a0.x + wv.y * b0.x + wv.z * d0.x + wv.w * e0.x;
-            v[1] = wv.x * a0.y + wv.y * b0.y + wv.z * d0.y + wv.w * e0.y;
-            v[2] = wv.x * a0.z + wv.y * b0.z + wv.z * d0.z + wv.w * e0.z;
-            v[3] = wv.x * a0.w + wv.y * b0.w + wv.z * d0.w + wv.w * e0.w;
-            v[4] = wv.x * a1.x + wv.y * b1.x + wv.z * d1.x + wv.w * e1.x;
-            v[5] = wv.x * a1.y + wv.y * b1.y + wv.z * d1.y + wv.w * e1.y;
-            v[6] = wv.x * a1.z + wv.y * b1.z + wv.z * d1.z + wv.w * e1.z;
-            v[7] = wv.x * a1.w + wv.y * b1.w + wv.z * d1.w + wv.w * e1.w;
-          } else {
-            const int o = ti[tap * TC_BM + r];
-            if (o >= 0) {
-              const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)o * p.Cin);
-              const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1);
-              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-              v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    const int pt = tid - 5 * 32;   // 0..255
+    const int j = pt & 7;          // 16-byte chunk (8 channels) inside the 128-byte row
+    const int r_first = pt >> 3;   // 32 rows per pass
+    uint32_t g = 0;                // global k-block counter (ring position across tiles)
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long p0 = (tile / n_tiles) * TC_BM;
+      const int n0 = (int)(tile % n_tiles) * p.BN;
+      producer_bar_sync();   // every producer is done with the previous tile's table
+      for (int r = pt; r < TC_BM; r += TC_PRODUCERS) {
+        const long long pg = p0 + r;
+        rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
+      }
+      // per-tile sample table (channel independent): one entry per (tap, pixel)
+      for (int e = pt; e < KHW * TC_BM; e += TC_PRODUCERS) {
+        const int tap = e / TC_BM, r = e - tap * TC_BM;
+        const long long pg = p0 + r;
+        const int ki = tap / p.kw, kj = tap - ki * p.kw;
+        if (DEFORM) {
+          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+          int4 ov = make_int4(0, 0, 0, 0);
+          if (pg < Ptot) {
+            const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+            const float* offp = p.offset + ((size_t)n * 2 * KHW + 2 * tap) * HoWo + pp;
+            const float oh = __ldg(offp), ow = __ldg(offp + HoWo);
+            const float h = (float)(ho * p.sh - p.ph + ki * p.dh) + oh;
+            const float w = (float)(wo * p.sw - p.pw + kj * p.dw) + ow;
+            if (h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {  // deform_conv_kernel.cu:229
+              const int hl = (int)floorf(h), wl = (int)floorf(w), hh = hl + 1, wh = wl + 1;
+              const float lh = h - hl, lw = w - wl, ch = 1.f - lh, cw = 1.f - lw;
+              const bool t_ok = hl >= 0, b_ok = hh <= p.H - 1, l_ok = wl >= 0, r_ok = wh <= p.W - 1;
+              float m = 1.f;
+              if (p.mask) m = __ldg(p.mask + ((size_t)n * KHW + tap) * HoWo + pp);
+              wv.x = (t_ok && l_ok) ? ch * cw * m : 0.f;
+              wv.y = (t_ok && r_ok) ? ch * lw * m : 0.f;
+              wv.z = (b_ok && l_ok) ? lh * cw * m : 0.f;
+              wv.w = (b_ok && r_ok) ? lh * lw * m : 0.f;
+              ov.x = (t_ok && l_ok) ? hl * p.W + wl : 0;
+              ov.y = (t_ok && r_ok) ? hl * p.W + wh : 0;
+              ov.z = (b_ok && l_ok) ? hh * p.W + wl : 0;
+              ov.w = (b_ok && r_ok) ? hh * p.W + wh : 0;
             }
           }
-        }
-        const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-        uint4 hi;
-        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(a_hi + soff) = hi;
-        if (x3) {
-          uint4 lo;
-          lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-          lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-          lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-          lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-          *reinterpret_cast<uint4*>(a_lo + soff) = lo;
-        }
-      }
-      // ---- B: copy BN rows x 8 chunks of packed bf16 weights ----
-      for (int r = r_first; r < p.BN; r += 32) {
-        const size_t g = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
-        const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_hi + g));
-        if (x3) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_lo + g));
-      }
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-    }
-
-    // =============================== EPILOGUE ===============================
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int m = q * 32 + lane;
-    const long long pg = p0 + m;
-    const bool row_ok = pg < Ptot;
-    const int n_img = row_ok ? (int)(pg / HoWo) : 0;
-    const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
-    const int cols_half = p.BN / 2;
-    const bool vec_ptrs_ok = (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
-                             (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
-    for (int cb = 0; cb < cols_half; cb += 16) {
-      const int col = half * cols_half + cb;
-      uint32_t rr[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, rr);  // warp-collective
-      if (!row_ok) continue;
-      const int co0 = n0 + col;
-      if (p.out_nhwc) {
-        float* yo = p.y + (size_t)pg * p.Cout + co0;
-        const float* ro = p.residual ? p.residual + (size_t)pg * p.Cout + co0 : nullptr;
-        if (co0 + 15 < p.Cout && (p.Cout & 3) == 0 && vec_ptrs_ok) {
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            float4 o;
-            o.x = __uint_as_float(rr[g4 * 4 + 0]); o.y = __uint_as_float(rr[g4 * 4 + 1]);
-            o.z = __uint_as_float(rr[g4 * 4 + 2]); o.w = __uint_as_float(rr[g4 * 4 + 3]);
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g4 * 4));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (ro) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(ro + g4 * 4));
-              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-            }
-            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(yo + g4 * 4) = o;
-          }
+          tw[e] = wv;
+          to[e] = ov;
         } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (co0 + e >= p.Cout) break;
-            float o = __uint_as_float(rr[e]);
-            if (p.bias) o += __ldg(p.bias + co0 + e);
-            if (ro) o += __ldg(ro + e);
-            if (p.relu) o = fmaxf(o, 0.f);
-            yo[e] = o;
+          int o = -1;
+          if (pg < Ptot) {
+            const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+            const int hi = ho * p.sh - p.ph + ki * p.dh, wi = wo * p.sw - p.pw + kj * p.dw;
+            if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) o = hi * p.W + wi;
           }
-        }
-      } else {  // NCHW: for a fixed cout the 32 lanes of a warp write 32 consecutive pixels
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int co = co0 + e;
-          if (co >= p.Cout) break;
-          const size_t oidx = ((size_t)n_img * p.Cout + co) * HoWo + pp;
-          float o = __uint_as_float(rr[e]);
-          if (p.bias) o += __ldg(p.bias + co);
-          if (p.residual) o += __ldg(p.residual + oidx);
-          if (p.relu) o = fmaxf(o, 0.f);
-          p.y[oidx] = o;
+          ti[e] = o;
         }
       }
+      producer_bar_sync();   // table visible to all producers
+
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t s = g % (uint32_t)p.stages, it = g / (uint32_t)p.stages;
+        mbar_wait(bar_empty + 8 * s, (it & 1u) ^ 1u);
+        uint8_t* stage = sm + L.stages + (size_t)s * L.stage_bytes;
+        uint8_t* a_hi = stage;
+        uint8_t* b_hi = stage + L.a_bytes;
+        uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
+        uint8_t* b_lo = a_lo + L.a_bytes;
+        const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
+        // ---- A: gather 128 rows x 8 chunks ----
+#pragma unroll 2
+        for (int pass = 0; pass < TC_BM / 32; ++pass) {
+          const int r = r_first + pass * 32;
+          const long long rb = rowbase[r];
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = 0.f;
+          if (rb >= 0) {
+            const float* xb = p.x + rb + c0;
+            if (DEFORM) {
+              const float4 wv = tw[tap * TC_BM + r];
+              const int4 ov = to[tap * TC_BM + r];
+              const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin);
+              const float4* c01 = reinterpret_cast<const float4*>(xb + (size_t)ov.y * p.Cin);
+              const float4* c10 = reinterpret_cast<const float4*>(xb + (size_t)ov.z * p.Cin);
+              const float4* c11 = reinterpret_cast<const float4*>(xb + (size_t)ov.w * p.Cin);
+              const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
+              const float4 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
+              v[0] = wv.x * a0.x + wv.y * b0.x + wv.z * d0.x + wv.w * e0.x;
+              v[1] = wv.x * a0.y + wv.y * b0.y + wv.z * d0.y + wv.w * e0.y;
+              v[2] = wv.x * a0.z + wv.y * b0.z + wv.z * d0.z + wv.w * e0.z;
+              v[3] = wv.x * a0.w + wv.y * b0.w + wv.z * d0.w + wv.w * e0.w;
+              v[4] = wv.x * a1.x + wv.y * b1.x + wv.z * d1.x + wv.w * e1.x;
+              v[5] = wv.x * a1.y + wv.y * b1.y + wv.z * d1.y + wv.w * e1.y;
+              v[6] = wv.x * a1.z + wv.y * b1.z + wv.z * d1.z + wv.w * e1.z;
+              v[7] = wv.x * a1.w + wv.y * b1.w + wv.z * d1.w + wv.w * e1.w;
+            } else {
+              const int o = ti[tap * TC_BM + r];
+              if (o >= 0) {
+                const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)o * p.Cin);
+                const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1);
+                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+              }
+            }
+          }
+          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          uint4 hi;
+          hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+          hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+          if (x3) {
+            uint4 lo;
+            lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+            lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+            lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+            lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+            *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+          }
+        }
+        // ---- B: copy BN rows x 8 chunks of packed bf16 weights ----
+        for (int r = r_first; r < p.BN; r += 32) {
+          const size_t gi = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
+          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_hi + gi));
+          if (x3) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_lo + gi));
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      }
     }
-    tc_fence_before();
-  } else {
-    // =============================== MMA ISSUER (warp 8, lane 0) ===============================
+  } else if (warp == 4) {
+    // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TC_BM, p.BN);
       const uint32_t stage0 = base + L.stages;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages, it = kb / p.stages;
-        mbar_wait(bar_full + 8 * s, (uint32_t)(it & 1));
+      uint32_t g = 0, ti_local = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
+        const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = stage0 + (uint32_t)s * L.stage_bytes;
-        const uint32_t b_hi = a_hi + L.a_bytes;
-        const uint32_t a_lo = b_hi + L.b_bytes;
-        const uint32_t b_lo = a_lo + L.a_bytes;
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t s = g % (uint32_t)p.stages, it = g / (uint32_t)p.stages;
+          mbar_wait(bar_full + 8 * s, it & 1u);
+          tc_fence_after();
+          const uint32_t a_hi = stage0 + s * L.stage_bytes;
+          const uint32_t b_hi = a_hi + L.a_bytes;
+          const uint32_t a_lo = b_hi + L.b_bytes;
+          const uint32_t b_lo = a_lo + L.a_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 = 32 bytes inside the swizzle span
-          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-          if (x3) {
-            umma_bf16(tmem_base, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, first);
-            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
-            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, 1u);
-          } else {
-            umma_bf16(tmem_base, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, first);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 = 32 bytes inside the swizzle span
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            if (x3) {
+              umma_bf16(tmem_d, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, first);
+              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
+              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, 1u);
+            } else {
+              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, first);
+            }
           }
+          umma_commit(bar_empty + 8 * s);   // frees the stage once the MMAs above have read it
         }
-        umma_commit(bar_empty + 8 * s);  // frees the stage once the MMAs above have read it
+        umma_commit(bar_tfull + 8 * buf);   // accumulator complete -> epilogue
       }
-      umma_commit(bar_accum);            // accumulator complete -> epilogue
     }
     __syncwarp();
+  } else {
+    // =============================== EPILOGUE (warps 0-3) ===============================
+    const int q = warp;  // TMEM lane quadrant
+    const bool vec_ptrs_ok = (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
+                             (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
+    uint32_t ti_local = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
+      const long long p0 = (tile / n_tiles) * TC_BM;
+      const int n0 = (int)(tile % n_tiles) * p.BN;
+      const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+      mbar_wait(bar_tfull + 8 * buf, use & 1u);
+      tc_fence_after();
+      const int m = q * 32 + lane;
+      const long long pg = p0 + m;
+      const bool row_ok = pg < Ptot;
+      const int n_img = row_ok ? (int)(pg / HoWo) : 0;
+      const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
+      for (int col = 0; col < p.BN; col += 16) {
+        uint32_t rr[16];
+        tmem_ld16(trow + (uint32_t)col, rr);  // warp-collective
+        if (!row_ok) continue;
+        const int co0 = n0 + col;
+        if (co0 >= p.Cout) continue;
+        if (p.out_nhwc) {
+          float* yo = p.y + (size_t)pg * p.Cout + co0;
+          const float* ro = p.residual ? p.residual + (size_t)pg * p.Cout + co0 : nullptr;
+          if (co0 + 15 < p.Cout && (p.Cout & 3) == 0 && vec_ptrs_ok) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              float4 o;
+              o.x = __uint_as_float(rr[g4 * 4 + 0]); o.y = __uint_as_float(rr[g4 * 4 + 1]);
+              o.z = __uint_as_float(rr[g4 * 4 + 2]); o.w = __uint_as_float(rr[g4 * 4 + 3]);
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g4 * 4));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (ro) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(ro + g4 * 4));
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(yo + g4 * 4) = o;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (co0 + e >= p.Cout) break;
+              float o = __uint_as_float(rr[e]);
+              if (p.bias) o += __ldg(p.bias + co0 + e);
+              if (ro) o += __ldg(ro + e);
+              if (p.relu) o = fmaxf(o, 0.f);
+              yo[e] = o;
+            }
+          }
+        } else {  // NCHW: for a fixed cout the 32 lanes of a warp write 32 consecutive pixels
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int co = co0 + e;
+            if (co >= p.Cout) break;
+            const size_t oidx = ((size_t)n_img * p.Cout + co) * HoWo + pp;
+            float o = __uint_as_float(rr[e]);
+            if (p.bias) o += __ldg(p.bias + co);
+            if (p.residual) o += __ldg(p.residual + oidx);
+            if (p.relu) o = fmaxf(o, 0.f);
+            p.y[oidx] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);   // accumulator buffer may be overwritten
+    }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -486,30 +528,20 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   const int bn_cap = p.x3 ? 128 : 256;
   if (BN > bn_cap) BN = (p.Cout_pad % bn_cap == 0) ? bn_cap : ((p.Cout_pad % 128 == 0) ? 128 : 64);
   p.BN = BN;
-  // Shared-memory budget: prefer a footprint that lets TWO CTAs share an SM (the kernel is not
-  // persistent, so co-residency is what overlaps one tile's epilogue with another's main loop);
-  // fall back to a single deep ring when two would leave fewer than 3 stages.
+  // One persistent CTA per SM: give the smem ring everything that is left after the sample table.
   const int num_kb = KHW * (p.Cin / TC_BK);
-  const int want = num_kb < 3 ? (num_kb < 2 ? 2 : num_kb) : 3;
-  auto fit = [&](uint32_t budget) {
-    int st = TC_MAX_STAGES;
-    if (st > num_kb) st = num_kb < 2 ? 2 : num_kb;
-    while (st > 2 && tc_smem_layout(deform, KHW, BN, st, p.x3 != 0).total + 1024 > budget) --st;
-    return st;
-  };
-  int stages = fit(112 * 1024);
+  int stages = TC_MAX_STAGES;
   TcSmem L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
-  if (stages < want || L.total + 1024 > 112 * 1024) {
-    stages = fit(200 * 1024);
-    L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
-  }
+  while (stages > 2 && L.total + 1024 > 220 * 1024) { --stages; L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0); }
+  (void)num_kb;
   if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   p.stages = stages;
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
   if (Ptot <= 0) return 0;
-  const long long gx = (Ptot + TC_BM - 1) / TC_BM;
-  if (gx > 2147483647LL) return UPSNET_E_UNSUPPORTED;
-  dim3 grid((unsigned)gx, (unsigned)(p.Cout_pad / BN));
+  const long long num_tiles = ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN);
+  int dev = 0, sms = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
   const size_t smem = L.total + 1024;
   if (deform) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

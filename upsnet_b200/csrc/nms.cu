@@ -92,11 +92,14 @@ nms_sweep_kernel(const int* __restrict__ seg_offsets, int max_seg_len,
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long cur = removed[b], K = 0ULL;
-#pragma unroll 8
+      unsigned long long d[kNmsTile];
+#pragma unroll
+      for (int t = 0; t < kNmsTile; ++t) d[t] = diag[t];     // 64 independent LDS, then a pure ALU chain
+#pragma unroll
       for (int t = 0; t < kNmsTile; ++t) {
-        const unsigned long long d = diag[t];
         const bool take = (t < bsize) && !((cur >> t) & 1ULL);
-        if (take) { K |= 1ULL << t; cur |= d; }
+        K |= take ? (1ULL << t) : 0ULL;
+        cur |= take ? d[t] : 0ULL;
       }
       kept_word = K;
     }
@@ -107,14 +110,20 @@ nms_sweep_kernel(const int* __restrict__ seg_offsets, int max_seg_len,
       const int pos = base_cnt + __popcll(K & ((1ULL << threadIdx.x) - 1ULL));
       keep[pos] = b * kNmsTile + threadIdx.x;
     }
-    // OR the kept rows into the running removed words of the later blocks
+    // OR the kept rows into the running removed words of the later blocks.  Loads are issued in
+    // predicated batches of 8 so that they overlap (a data-dependent `while` over the set bits
+    // would serialise one L2 round trip per kept box).
     for (int j = b + 1 + threadIdx.x; j < cb; j += blockDim.x) {
       unsigned long long acc = removed[j];
-      unsigned long long kk = K;
-      while (kk) {
-        const int t = __ffsll((long long)kk) - 1;
-        kk &= kk - 1ULL;
-        acc |= seg_mask[(size_t)(b * kNmsTile + t) * max_cb + j];
+      const unsigned long long* col = seg_mask + (size_t)(b * kNmsTile) * max_cb + j;
+#pragma unroll 1
+      for (int t0 = 0; t0 < kNmsTile; t0 += 8) {
+        const unsigned int bits = (unsigned int)((K >> t0) & 0xffULL);
+        if (bits == 0) continue;
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ((bits >> u) & 1u) ? col[(size_t)(t0 + u) * max_cb] : 0ULL;
+        acc |= (v[0] | v[1]) | (v[2] | v[3]) | (v[4] | v[5]) | (v[6] | v[7]);
       }
       removed[j] = acc;
     }

@@ -76,15 +76,18 @@ def _nhwc(x):
     return xp if xp.is_contiguous() else xp.contiguous()
 
 
-_packed_cache = {}
+import weakref
+
+# keyed on the weight TENSOR OBJECT (weak): a data_ptr key would alias a freed weight whose storage the
+# caching allocator handed to a new tensor.  Entries die with their tensor; _version catches in-place updates.
+_packed_cache = weakref.WeakKeyDictionary()
 
 
 def _packed_weight(weight):
-    """bf16 hi/lo planes [Cout_pad][kh*kw][Cin] (upsnet_igemm_pack_weight), cached per weight version."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
-    hit = _packed_cache.get(key)
-    if hit is not None:
-        return hit
+    """bf16 hi/lo planes [Cout_pad][kh*kw][Cin] (upsnet_igemm_pack_weight), cached per weight tensor+version."""
+    hit = _packed_cache.get(weight)
+    if hit is not None and hit[0] == weight._version and hit[1].device == weight.device:
+        return hit[1]
     Cout, Cin, kh, kw = weight.shape
     nbytes = C.c_size_t(0)
     check(lib().upsnet_igemm_packed_weight_bytes(Cout, Cin, kh, kw, C.byref(nbytes)), "igemm_packed_weight_bytes")
@@ -94,9 +97,7 @@ def _packed_weight(weight):
         check(lib().upsnet_igemm_pack_weight(ptr(w), Cout, Cin, kh, kw, ptr(buf), stream_ptr(weight.device)),
               "igemm_pack_weight")
     STATS["launches"] += 1
-    if len(_packed_cache) > 4096:
-        _packed_cache.clear()
-    _packed_cache[key] = buf
+    _packed_cache[weight] = (weight._version, buf)
     return buf
 
 

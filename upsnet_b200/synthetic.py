@@ -7,7 +7,7 @@ import torch
 
 def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
     """Random-init resnet_upsnet per SURVEY.md section 8d config 2: reference initialisers, except
-    (a) offset convs get N(0, 0.5)-scaled weights so DCN offsets are non-zero (the reference zero-inits
+    (a) offset convs get non-zero weights/biases so DCN offsets are a few pixels (the reference zero-inits
     them, modules/deform_conv.py:72-73 -- zero offsets would hide DCN bugs), (b) BN statistics are
     randomised so folding is exercised, (c) the class / mask heads are biased so that several dozen
     detections survive score > 0.6 and reach the panoptic head."""
@@ -27,8 +27,11 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
                 mod.running_mean.copy_(torch.empty_like(mod.running_mean).normal_(0, 0.1, generator=g))
                 mod.running_var.copy_(torch.empty_like(mod.running_var).uniform_(0.5, 1.5, generator=g))
             elif isinstance(mod, DeformConvWithOffset):
+                # offsets of a few pixels, like a trained DCN: a per-tap constant (bias ~ N(0,1.5 px)) plus a
+                # small input-dependent part (activations here are O(100), hence the tiny weight scale)
                 w = mod.conv_offset.weight
-                w.copy_(torch.empty(w.shape).normal_(0, 0.5 / (w.shape[1] * 9) ** 0.5, generator=g).to(w.device))
+                w.copy_(torch.empty(w.shape).normal_(0, 0.01 / (w.shape[1] * 9) ** 0.5, generator=g).to(w.device))
+                mod.conv_offset.bias.copy_(torch.empty(mod.conv_offset.bias.shape).normal_(0, 1.5, generator=g))
                 cw = mod.conv.weight
                 cw.copy_(torch.empty(cw.shape).normal_(0, (2.0 / (cw.shape[1] * 9)) ** 0.5, generator=g).to(cw.device))
                 mod.conv.bias.zero_()
@@ -39,7 +42,8 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
                     w.copy_(torch.empty(w.shape).normal_(0, (2.0 / fan) ** 0.5, generator=g).to(w.device))
                 if mod.deformable:
                     w = mod.conv2_offset.weight
-                    w.copy_(torch.empty(w.shape).normal_(0, 0.5 / (w.shape[1] * 9) ** 0.5, generator=g))
+                    w.copy_(torch.empty(w.shape).normal_(0, 0.01 / (w.shape[1] * 9) ** 0.5, generator=g))
+                    mod.conv2_offset.bias.copy_(torch.empty(mod.conv2_offset.bias.shape).normal_(0, 1.5, generator=g))
                 if mod.downsample is not None:
                     w = mod.downsample[0].weight
                     w.copy_(torch.empty(w.shape).normal_(0, (1.0 / w.shape[1]) ** 0.5, generator=g))
