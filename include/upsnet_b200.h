@@ -132,13 +132,15 @@ int upsnet_igemm_forward(const float *x_nhwc, const float *offset, const float *
  * fcn [S,H,W] fp32 (fcn_output of one image); boxes [n,4] (mask_rois[:,1:]); cls_prob [n];
  * mask_logit [n,28,28] (logit of the predicted class); cls_idx int64 [n] (1-based thing class,
  * <= num_thing); num_stuff = S - num_thing.
+ * n is the (maximum) instance count known to the host; n_dev (optional, may be NULL) is a DEVICE int32 with
+ * the actual count <= n, so the call can be enqueued without knowing it (static-shape engine / CUDA graphs).
  * keep_out int64 [max(n,1)] original indices of kept instances in score order, k_out int32[1];
  * labels int64 [H,W] (255 = void); sem_labels int64 [H,W] or NULL (argmax_c fcn).
  */
 int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thing, size_t *bytes);
 int upsnet_panoptic_head(const float *fcn, int S, int H, int W, const float *boxes,
                          const float *cls_prob, const float *mask_logit, const int64_t *cls_idx,
-                         int n, int num_stuff, double fraction_threshold, int64_t *keep_out,
+                         int n, const int *n_dev, int num_stuff, double fraction_threshold, int64_t *keep_out,
                          int *k_out, int64_t *labels, int64_t *sem_labels, void *workspace,
                          size_t workspace_bytes, void *stream);
 

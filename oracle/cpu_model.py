@@ -89,14 +89,21 @@ def _nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
 
 
 def _panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                   want_sem=False):
-    r = O.panoptic_head(fcn_output[0].detach().numpy(), mask_rois.detach().numpy(), cls_prob.detach().numpy(),
-                        mask_logit.detach().numpy().reshape(-1, 28, 28), cls_idx.numpy(), num_stuff,
-                        fraction_threshold, want_sem=want_sem)
-    out = (torch.from_numpy(r[0]), torch.from_numpy(r[1])[None])
+                   want_sem=False, n_dev=None):
+    n = mask_rois.shape[0] if n_dev is None else max(min(int(n_dev.item()), mask_rois.shape[0]), 1)
+    r = O.panoptic_head(fcn_output[0].detach().contiguous().numpy(), mask_rois[:n].detach().contiguous().numpy(),
+                        cls_prob[:n].detach().numpy(), mask_logit[:n].detach().contiguous().numpy().reshape(-1, 28, 28),
+                        cls_idx[:n].numpy(), num_stuff, fraction_threshold, want_sem=want_sem)
+    keep = torch.from_numpy(r[0])
+    out = [keep, torch.from_numpy(r[1])[None]]
     if want_sem:
-        out = out + (torch.from_numpy(r[2])[None],)
-    return out
+        out.append(torch.from_numpy(r[2])[None])
+    if n_dev is not None:      # static-shape contract: padded keep + device-style count
+        pad = torch.zeros(mask_rois.shape[0], dtype=torch.int64)
+        pad[:keep.numel()] = keep
+        out[0] = pad
+        out.append(torch.tensor([keep.numel()], dtype=torch.int32))
+    return tuple(out)
 
 
 @contextlib.contextmanager

@@ -102,3 +102,20 @@ def test_end_to_end_forward_on_cpu(cfgname):
     num_stuff = cfg.num_seg_classes - cfg.num_classes + 1
     assert ((lab < num_stuff + k) | (lab == 255)).all()
     assert n >= 1  # ties at the max_det score threshold are all kept (mask_roi.py:110-113)
+
+
+def test_static_engine_equals_dynamic_path_on_cpu():
+    """The fixed-shape / device-count engine path must make exactly the decisions of the literal,
+    variable-length restatement of the reference glue (detection.MaskROI / ProposalGenerator)."""
+    from upsnet_b200.model import UPSNetConfig
+    m = synthetic_model(UPSNetConfig.cityscapes_r50(), depth=(1, 1, 1, 1), seed=5)
+    inp = synthetic_input(128, 192, seed=6)
+    with cpu_ops():
+        m.static_engine = True
+        a = m(inp)
+        m.static_engine = False
+        b = m(inp)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        assert torch.equal(a[k], b[k]) if a[k].dtype != torch.float32 else torch.allclose(a[k], b[k], atol=1e-4), k

@@ -45,7 +45,7 @@ def lib():
         L.upsnet_igemm_pack_weight.argtypes = [vp, i, i, i, i, vp, vp]
         L.upsnet_igemm_forward.argtypes = [vp] * 7 + [i] * 16 + [vp]
         L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
-        L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, d, vp, vp, vp, vp, vp, sz, vp]
+        L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, vp, i, d, vp, vp, vp, vp, vp, sz, vp]
         for name in dir(L):
             pass
         _lib = L

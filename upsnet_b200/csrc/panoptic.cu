@@ -97,7 +97,10 @@ __device__ __forceinline__ float blend(const float* __restrict__ S, int sx, floa
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
-                const int64_t* __restrict__ cls_idx, int n, int H, int W, PanWorkspace ws) {
+                const int64_t* __restrict__ cls_idx, int n_max, const int* __restrict__ n_dev, int H, int W,
+                PanWorkspace ws) {
+  const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;   // device-side instance count (static-shape engine)
+  if (threadIdx.x == 0) ws.meta[2] = n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float p = prob[i];
     int rank = 0;
@@ -127,8 +130,9 @@ pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
 
 // one CTA per thing class (blockIdx.x = class-1)
 __global__ void __launch_bounds__(1024)
-pan_removal_kernel(const float* __restrict__ mask_logit, int n, int H, int W,
+pan_removal_kernel(const float* __restrict__ mask_logit, int n_max, const int* __restrict__ n_dev, int H, int W,
                    double fraction_threshold, PanWorkspace ws) {
+  const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
   __shared__ float S[kMaskElems];
   __shared__ unsigned int s_sum, s_ovl;
   __shared__ int s_keep;
@@ -189,7 +193,9 @@ pan_removal_kernel(const float* __restrict__ mask_logit, int n, int H, int W,
 }
 
 __global__ void __launch_bounds__(32)
-pan_compact_kernel(int n, PanWorkspace ws, int64_t* __restrict__ keep_out, int* __restrict__ k_out) {
+pan_compact_kernel(int n_max, const int* __restrict__ n_dev, PanWorkspace ws, int64_t* __restrict__ keep_out,
+                   int* __restrict__ k_out) {
+  const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
   const int lane = threadIdx.x;
   int k = 0;
   for (int base = 0; base < n; base += 32) {
@@ -374,7 +380,7 @@ extern "C" int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thin
 
 extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const float* boxes,
                                     const float* cls_prob, const float* mask_logit,
-                                    const int64_t* cls_idx, int n, int num_stuff,
+                                    const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
                                     double fraction_threshold, int64_t* keep_out, int* k_out,
                                     int64_t* labels, int64_t* sem_labels, void* workspace,
                                     size_t workspace_bytes, void* stream) {
@@ -393,11 +399,11 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   const int Ww = ceil_div(W, 32);
   UPS_CUDA(cudaMemsetAsync(ws.occ, 0, (size_t)num_thing * H * Ww * sizeof(unsigned int), st));
   UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
-  pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, H, W, ws);
+  pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
-  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, H, W, fraction_threshold, ws);
+  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, n_dev, H, W, fraction_threshold, ws);
   UPS_CHECK_LAUNCH();
-  pan_compact_kernel<<<1, 32, 0, st>>>(n, ws, keep_out, k_out);
+  pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH));
   pan_fuse_kernel<<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels,

@@ -183,3 +183,132 @@ class MaskROI:
             sc, bx, cls = sc[sel], bx[sel], cls[sel]
         boxes = torch.cat([torch.zeros((bx.shape[0], 1), device=dev), bx], 1)
         return sc, boxes, cls.long()
+
+
+# ================================================================================================
+# Static-shape, synchronisation-free variants (the engine path).  Same decisions as the classes above
+# for every valid entry, but all outputs are padded to fixed sizes with a device-side count, so the
+# whole forward can run without a host round trip and be captured in a CUDA graph
+# (the reference synchronises >= 6 times per image, F8).
+# ================================================================================================
+NEG_INF = float("-inf")
+
+
+class StaticProposalGenerator(ProposalGenerator):
+    def _offsets(self, lens, dev):
+        key = ("offs", tuple(lens), str(dev))
+        if key not in self._anchors:
+            self._anchors[key] = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        return self._anchors[key]
+
+    def __call__(self, cls_probs, bbox_preds, im_info):
+        """-> rois [post,5] (invalid rows are all-zero), scores [post], valid [post] bool."""
+        assert self.min_size == 0, "static path assumes config.test.rpn_min_size == 0 (all shipped yamls)"
+        dev = cls_probs[0].device
+        im_h, im_w = float(im_info[0]), float(im_info[1])
+        boxes_l, scores_l, lens = [], [], []
+        for l in range(len(cls_probs)):
+            A = cls_probs[l].shape[1]
+            h, w = cls_probs[l].shape[-2:]
+            scores = cls_probs[l][0].permute(1, 2, 0).reshape(-1)
+            deltas = bbox_preds[l][0].reshape(A, 4, h, w).permute(2, 3, 0, 1).reshape(-1, 4)
+            k = min(self.pre, scores.numel()) if self.pre > 0 else scores.numel()
+            top_s, top_i = torch.topk(scores, k, sorted=True)
+            props = clip_boxes(bbox_transform(self.anchors(l, h, w, dev)[top_i], deltas[top_i]), im_h, im_w)
+            boxes_l.append(props); scores_l.append(top_s); lens.append(k)
+        boxes, scores = torch.cat(boxes_l), torch.cat(scores_l)
+        offs = self._offsets(lens, dev)
+        max_len = max(lens)
+        keep, cnt = nms_segmented(boxes, offs, max_len, self.thresh)
+        pos = torch.arange(max_len, device=dev)[None, :]
+        limit = cnt.clamp(max=self.post if self.post > 0 else max_len)[:, None]
+        valid = pos < limit
+        gidx = (keep.long() + offs[:-1, None].long()).clamp_(0, boxes.shape[0] - 1)   # rows >= cnt are garbage
+        sc = torch.where(valid, scores[gidx], torch.full_like(scores[gidx], NEG_INF))
+        k = min(self.post, sc.numel())
+        top_s, top_i = torch.topk(sc.reshape(-1), k, sorted=True)
+        ok = top_s > NEG_INF
+        sel = gidx.reshape(-1)[top_i]
+        rois = torch.cat([torch.zeros((k, 1), device=dev), boxes[sel]], 1) * ok[:, None]
+        return rois, torch.where(ok, top_s, torch.zeros_like(top_s)), ok
+
+
+def _compact(values_list, flag, cap, dev):
+    """Stable compaction of the rows where `flag` is set into `cap` slots (extra rows dropped).
+    Returns ([compacted tensors], count int32 device scalar)."""
+    n_all = flag.numel()
+    dest = torch.cumsum(flag.to(torch.int64), 0) - 1
+    count = flag.sum().clamp(max=cap).to(torch.int32)
+    slot = torch.where(flag & (dest < cap), dest, torch.full_like(dest, cap))     # cap = dump slot
+    outs = []
+    for v in values_list:
+        buf = torch.zeros((cap + 1,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+        buf.index_copy_(0, slot, v[:n_all]) if False else buf.scatter_(
+            0, slot.view(-1, *([1] * (v.dim() - 1))).expand_as(v), v)
+        outs.append(buf[:cap])
+    return outs, count
+
+
+class StaticMaskROI(MaskROI):
+    """MaskROI with fixed-size outputs: scores [cap], boxes [cap,5], cls [cap], n (int32 device scalar).
+    cap = top_n + slack (ties at the top-n score threshold are all kept by the reference)."""
+
+    def __init__(self, *a, slack=28, **kw):
+        super().__init__(*a, **kw)
+        self.cap = self.top_n + slack
+        self._const = {}
+
+    def _consts(self, R, dev):
+        key = (R, str(dev))
+        if key not in self._const:
+            Cm = self.num_classes - 1
+            cls_flat = torch.arange(1, self.num_classes, device=dev).repeat(R)
+            ridx_flat = torch.arange(R, device=dev).repeat_interleave(Cm)
+            self._const[key] = (cls_flat, ridx_flat)
+        return self._const[key]
+
+    def __call__(self, rois, roi_valid, bbox_delta, cls_prob, im_info):
+        dev = rois.device
+        C, R = self.num_classes, rois.shape[0]
+        Cm = C - 1
+        nseg = 1 if self.class_agnostic else Cm
+        # a softmax row has at most one entry above 0.5, so class-agnostic candidates <= R when thresh >= 0.5
+        M = R if (not self.class_agnostic or self.score_thresh >= 0.5) else R * Cm
+        cls_flat, ridx_flat = self._consts(R, dev)
+        proposal = clip_boxes(bbox_transform(rois[:, 1:], bbox_delta, self.weights), float(im_info[0]),
+                              float(im_info[1])).reshape(R, C, 4)
+        prob = cls_prob[:, 1:]
+        cand = ((prob > self.score_thresh) & roi_valid[:, None]).reshape(-1)
+        sc_all = torch.where(cand, prob.reshape(-1), torch.full_like(prob.reshape(-1), -1.0))
+        key = torch.where(cand, torch.zeros_like(cls_flat) if self.class_agnostic else cls_flat - 1,
+                          torch.full_like(cls_flat, nseg))
+        o1 = torch.sort(sc_all, descending=True, stable=True)[1]
+        o2 = torch.sort(key[o1], stable=True)[1]
+        order = o1[o2]
+        sc, cls, key = sc_all[order], cls_flat[order], key[order]
+        bx = proposal[ridx_flat[order], cls]
+        counts = (key[:, None] == torch.arange(nseg, device=dev)[None, :]).sum(0)
+        offs = torch.zeros(nseg + 1, dtype=torch.int32, device=dev)
+        offs[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        keep, cnt = nms_segmented(bx, offs, M, self.nms_thresh)
+        pos = torch.arange(M, device=dev)[None, :]
+        valid = (pos < cnt[:, None]).reshape(-1)
+        gidx = (keep.long() + offs[:-1, None].long()).clamp_(0, sc.numel() - 1).reshape(-1)
+        # 1st compaction: class-major, NMS order inside (mask_roi.py:96-104)
+        all_cap = min(nseg * M, 4096)
+        (kidx,), nk = _compact([gidx], valid, all_cap, dev)
+        live = torch.arange(all_cap, device=dev) < nk
+        ks = torch.where(live, sc[kidx], torch.full((all_cap,), NEG_INF, device=dev))
+        # global top-n: keep scores >= the top_n-th largest (mask_roi.py:106-121); fewer than top_n => keep all
+        kth = torch.topk(ks, min(self.top_n, all_cap), sorted=True)[0][-1] if self.top_n > 0 else NEG_INF
+        sel = live & (ks >= kth)
+        (oidx,), n_out = _compact([kidx], sel, self.cap, dev)
+        slot_live = torch.arange(self.cap, device=dev) < n_out
+        out_sc = torch.where(slot_live, sc[oidx], torch.zeros(self.cap, device=dev))
+        out_bx = torch.cat([torch.zeros((self.cap, 1), device=dev), bx[oidx]], 1) * slot_live[:, None]
+        out_cls = torch.where(slot_live, cls[oidx], torch.zeros_like(cls[oidx]))
+        # mask_roi.py:132-139: nothing survives -> one dummy detection (score 1, zero box, class 0)
+        empty = n_out == 0
+        out_sc[0] = torch.where(empty, 1.0, out_sc[0])
+        n_out = torch.where(empty, torch.ones_like(n_out), n_out)
+        return out_sc, out_bx, out_cls.long(), n_out

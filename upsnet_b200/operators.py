@@ -80,14 +80,14 @@ import weakref
 
 # keyed on the weight TENSOR OBJECT (weak): a data_ptr key would alias a freed weight whose storage the
 # caching allocator handed to a new tensor.  Entries die with their tensor; _version catches in-place updates.
-_packed_cache = weakref.WeakKeyDictionary()
+_packed_cache = {}   # id(tensor) -> (weakref to the tensor, version, packed buffer)
 
 
 def _packed_weight(weight):
     """bf16 hi/lo planes [Cout_pad][kh*kw][Cin] (upsnet_igemm_pack_weight), cached per weight tensor+version."""
-    hit = _packed_cache.get(weight)
-    if hit is not None and hit[0] == weight._version and hit[1].device == weight.device:
-        return hit[1]
+    hit = _packed_cache.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
+        return hit[2]
     Cout, Cin, kh, kw = weight.shape
     nbytes = C.c_size_t(0)
     check(lib().upsnet_igemm_packed_weight_bytes(Cout, Cin, kh, kw, C.byref(nbytes)), "igemm_packed_weight_bytes")
@@ -97,7 +97,8 @@ def _packed_weight(weight):
         check(lib().upsnet_igemm_pack_weight(ptr(w), Cout, Cin, kh, kw, ptr(buf), stream_ptr(weight.device)),
               "igemm_pack_weight")
     STATS["launches"] += 1
-    _packed_cache[weight] = (weight._version, buf)
+    wid = id(weight)
+    _packed_cache[wid] = (weakref.ref(weight, lambda _r, _k=wid: _packed_cache.pop(_k, None)), weight._version, buf)
     return buf
 
 
@@ -485,10 +486,12 @@ class FPNRoIAlign(nn.Module):
 # panoptic head
 # ------------------------------------------------------------------------------------------------
 def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                  want_sem=False):
+                  want_sem=False, n_dev=None):
     """Fused MaskRemoval + SegTerm + void/argmax (upsnet_panoptic_head).
     fcn_output [1,S,H,W]; mask_rois [n,4]; cls_prob [n]; mask_logit [n,1,28,28] or [n,28,28];
-    cls_idx int64 [n].  Returns (keep_inds int64 [k], panoptic_output int64 [1,H,W][, sem int64 [1,H,W]])."""
+    cls_idx int64 [n].  Returns (keep_inds int64 [k], panoptic_output int64 [1,H,W][, sem int64 [1,H,W]]).
+    With n_dev (int32 device scalar, actual count <= n) nothing is read back: keep_inds is the padded
+    [n] buffer and the device count k is returned as an extra last element (static-shape engine path)."""
     require_cuda(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx)
     assert fcn_output.dim() == 4 and fcn_output.shape[0] == 1, "only support batch size = 1"
     fcn = f32c(fcn_output)
@@ -502,15 +505,19 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     nbytes = C.c_size_t(0)
     check(lib().upsnet_panoptic_workspace_bytes(n, H, W, num_thing, C.byref(nbytes)), "panoptic_workspace_bytes")
     ws = _pan_ws.get(dev, nbytes.value)
-    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    if n_dev is not None:
+        assert n_dev.dtype == torch.int32 and n_dev.is_cuda
+    keep = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
     k = torch.empty((1,), dtype=torch.int32, device=dev)
     labels = torch.empty((1, H, W), dtype=torch.int64, device=dev)
     sem = torch.empty((1, H, W), dtype=torch.int64, device=dev) if want_sem else None
     work = {"bytes": 4.0 * S * H * W + 8.0 * H * W * (2 if want_sem else 1) + n * (4.0 * 784 + 24)}
     with torch.cuda.device(dev), _Timed("panoptic_head", 4, work, dev):
-        check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, num_stuff,
-                                         float(fraction_threshold), ptr(keep), ptr(k), ptr(labels), ptr(sem),
-                                         ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
+        check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, ptr(n_dev),
+                                         num_stuff, float(fraction_threshold), ptr(keep), ptr(k), ptr(labels),
+                                         ptr(sem), ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
+    if n_dev is not None:
+        return (keep, labels, sem, k) if want_sem else (keep, labels, k)
     keep = keep[:int(k.item())]
     return (keep, labels, sem) if want_sem else (keep, labels)
 

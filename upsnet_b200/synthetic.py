@@ -28,9 +28,9 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
                 mod.running_var.copy_(torch.empty_like(mod.running_var).uniform_(0.5, 1.5, generator=g))
             elif isinstance(mod, DeformConvWithOffset):
                 # offsets of a few pixels, like a trained DCN: a per-tap constant (bias ~ N(0,1.5 px)) plus a
-                # small input-dependent part (activations here are O(100), hence the tiny weight scale)
+                # small input-dependent part (FPN features are calibrated to RMS 1 below)
                 w = mod.conv_offset.weight
-                w.copy_(torch.empty(w.shape).normal_(0, 0.01 / (w.shape[1] * 9) ** 0.5, generator=g).to(w.device))
+                w.copy_(torch.empty(w.shape).normal_(0, 0.5 / (w.shape[1] * 9) ** 0.5, generator=g).to(w.device))
                 mod.conv_offset.bias.copy_(torch.empty(mod.conv_offset.bias.shape).normal_(0, 1.5, generator=g))
                 cw = mod.conv.weight
                 cw.copy_(torch.empty(cw.shape).normal_(0, (2.0 / (cw.shape[1] * 9)) ** 0.5, generator=g).to(cw.device))
@@ -58,9 +58,42 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
         m.rcnn.bbox_pred.weight.copy_(torch.empty_like(m.rcnn.bbox_pred.weight).normal_(0, 0.02, generator=g))
         m.mask_branch.mask_score.bias.fill_(0.2)
         m.fcn_head.score.weight.copy_(torch.empty_like(m.fcn_head.score.weight).normal_(0, 0.1, generator=g))
+        _calibrate_fpn_laterals(m, g)
     m = m.to(device)
     m.prepare()
     return m
+
+
+def _calibrate_fpn_laterals(m, g):
+    """Random-init residual stacks let activation scale drift (C5 was ~50x C2), which saturates the
+    softmax heads into exact ties and makes DCN offsets absurd.  One torch-only pass of the backbone over a
+    small random image measures the RMS of every FPN lateral output and rescales that lateral conv to
+    RMS 1, so P2..P6 -- and with them every head -- operate at O(1) like a trained network."""
+    import torch.nn.functional as F
+    bb = m.resnet_backbone
+    x = (torch.randn(1, 3, 96, 128, generator=g) * 50)
+    cpu = lambda t: t.detach().float().cpu()   # noqa: E731  (DeformConv parameters may live on CUDA)
+
+    def bn(t, b):
+        return F.batch_norm(t, cpu(b.running_mean), cpu(b.running_var), cpu(b.weight), cpu(b.bias), False, 0.0, b.eps)
+
+    def bott(b, t):
+        out = F.relu(bn(F.conv2d(t, cpu(b.conv1.weight), None, b.stride), b.bn1))
+        out = F.relu(bn(F.conv2d(out, cpu(b.conv2.weight), None, 1, b.dilation, b.dilation), b.bn2))   # offsets ignored
+        out = bn(F.conv2d(out, cpu(b.conv3.weight)), b.bn3)
+        res = t if b.downsample is None else bn(F.conv2d(t, cpu(b.downsample[0].weight), None, b.stride), b.downsample[1])
+        return F.relu(out + res)
+
+    t = F.max_pool2d(F.relu(bn(F.conv2d(x, cpu(bb.conv1.conv1.weight), None, 2, 3), bb.conv1.bn1)), 3, 2, 1)
+    feats = []
+    for blk in (bb.res2, bb.res3, bb.res4, bb.res5):
+        for b in blk.layers:
+            t = bott(b, t)
+        feats.append(t)
+    for name, f in zip(("fpn_p2_1x1", "fpn_p3_1x1", "fpn_p4_1x1", "fpn_p5_1x1"), feats):
+        conv = getattr(m.fpn, name)
+        rms = F.conv2d(f, cpu(conv.weight)).pow(2).mean().sqrt().item()
+        conv.weight.mul_(1.0 / max(rms, 1e-6))
 
 
 def synthetic_input(H=1024, W=2048, seed=0, device="cpu"):
