@@ -219,9 +219,11 @@ def main():
     ops.STATS["trace"] = []
     torch.cuda.synchronize()
     n_trace = min(3, args.steps)
+    graph_flag, model.use_cuda_graph = model.use_cuda_graph, False   # per-call events need eager launches
     for i in range(n_trace):
         step_resident(i)
     torch.cuda.synchronize()
+    model.use_cuda_graph = graph_flag
     trace, ops.STATS["trace"] = ops.STATS["trace"], None
     fam = {}
     for kind, a, b, work in trace:
@@ -233,13 +235,14 @@ def main():
     conv = {"ms": fam.get("conv2d", {"ms": 0})["ms"] + fam.get("dcn", {"ms": 0})["ms"],
             "flops": fam.get("conv2d", {"flops": 0})["flops"] + fam.get("dcn", {"flops": 0})["flops"],
             "calls": fam.get("conv2d", {"calls": 0})["calls"] + fam.get("dcn", {"calls": 0})["calls"]}
-    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    algo = sum(w.get("algo_flops", w.get("flops", 0.0)) for k_, _, _, w in trace if k_ in ("conv2d", "dcn"))
+    achieved = algo / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0   # ALGORITHMIC flops (x3 MMAs not counted)
     roofline = {"kernel": "igemm (conv2d + dcn tiles), precision=%s" % args.precision, "bound": "tensor",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + " (sustained bf16)",
                 "traffic": None, "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
                 "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
-                "flops_per_step": conv["flops"] / n_trace,
+                "flops_per_step": algo / n_trace, "mma_flops_per_step": conv["flops"] / n_trace,
                 "families_ms_per_step": {k: round(v["ms"] / n_trace, 4) for k, v in sorted(fam.items())}}
     if "panoptic_head" in fam:
         f = fam["panoptic_head"]
@@ -256,7 +259,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": "replicas x%d (one image per GPU, no collective)" % world,
                            "l2": "no flush: each step streams >1 GB of activations (>> 126 MB L2) and rotates %d images" % n_img,
-                           "weights": "random-init (upsnet_b200/synthetic.py), frozen BN folded"},
+                           "weights": "random-init (upsnet_b200/synthetic.py), frozen BN folded",
+                           "engine": "static shapes, device-side counts, CUDA graph replay=%s" % bool(model.use_cuda_graph)},
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -235,13 +235,14 @@ int launch_igemm_simt(const ConvParams& p, cudaStream_t stream) {
   const long long gx = (Ptot + TN - 1) / TN;
   if (gx > 2147483647LL) return UPSNET_E_UNSUPPORTED;
   dim3 grid((unsigned)gx, (unsigned)ceil_div(p.Cout, TM));
-  if (deform) {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    igemm_simt_kernel<true><<<grid, NT, smem, stream>>>(p);
-  } else {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    igemm_simt_kernel<false><<<grid, NT, smem, stream>>>(p);
+  static bool configured = false;   // once per process (not per launch: CUDA-graph capture)
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
+  if (deform) igemm_simt_kernel<true><<<grid, NT, smem, stream>>>(p);
+  else igemm_simt_kernel<false><<<grid, NT, smem, stream>>>(p);
   UPS_CHECK_LAUNCH();
   return 0;
 }

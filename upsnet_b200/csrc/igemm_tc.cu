@@ -539,17 +539,23 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
   if (Ptot <= 0) return 0;
   const long long num_tiles = ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN);
-  int dev = 0, sms = kNumSMs;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms = v > 0 ? v : kNumSMs;
+  }
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
   const size_t smem = L.total + 1024;
-  if (deform) {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    igemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
-  } else {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    igemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
+  // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
+  static bool configured = false;
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
+  if (deform) igemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
+  else igemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
   UPS_CHECK_LAUNCH();
   return 0;
 }
