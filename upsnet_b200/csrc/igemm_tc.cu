@@ -31,9 +31,11 @@ namespace ups {
 
 constexpr int TC_BM = 128;         // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;          // bf16 elements per k-block row (= 128 bytes, one swizzle span)
-constexpr int TC_PRODUCERS = 256;  // 8 warps
+constexpr int TC_GROUP = 256;       // producer threads that fill one smem stage together (8 warps)
+constexpr int TC_GROUPS = 2;        // producer groups work on alternate k-blocks (two stages in flight)
+constexpr int TC_PRODUCERS = TC_GROUP * TC_GROUPS;  // 16 warps
 constexpr int TC_EPILOGUE = 128;      // 4 warps (one per TMEM lane quadrant)
-constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 13 warps
+constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 21 warps
 constexpr int TC_MAX_STAGES = 6;
 
 struct TcParams {
@@ -117,6 +119,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
 // bits [0,14), LBO [16,30) (unused for swizzled K-major), SBO>>4 = 1024>>4 in [32,46) (8 rows of
 // 128 B), version 1 in [46,48), layout type SWIZZLE_128B (=2) in [61,64).
@@ -167,10 +175,11 @@ __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
 }
 
-// Persistent, warp-specialised kernel.  Roles (13 warps):
+// Persistent, warp-specialised kernel.  Roles (21 warps):
 //   warps 0-3   epilogue: TMEM -> registers -> bias/residual/ReLU -> global (warp w owns TMEM lanes 32w..)
 //   warp  4     MMA issuer (one elected lane), owns TMEM alloc/dealloc and barrier init
-//   warps 5-12  producers: sample table + A gather + B copy into the smem ring
+//   warps 5-20  producers, two groups of 8 warps filling alternate k-blocks (two smem stages in flight):
+//               sample table, B via cp.async, A gather (loads issued first, then bf16 conversion)
 // Pipelines: smem ring full[s]/empty[s] (producers <-> MMA) runs across tiles; two TMEM accumulator
 // buffers tmem_full[b]/tmem_empty[b] (MMA <-> epilogue) overlap tile i's epilogue with tile i+1's
 // main loop.  Tiles: id = blockIdx.x + it*gridDim.x, n-tile fastest (concurrent CTAs share the A rows in L2).
@@ -209,7 +218,7 @@ igemm_tc_kernel(const TcParams p) {
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
-        mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32);
+        mbar_init(bar_full + 8 * s, TC_GROUP / 32);
         mbar_init(bar_empty + 8 * s, 1);
       }
       for (int b = 0; b < 2; ++b) {
@@ -228,10 +237,12 @@ igemm_tc_kernel(const TcParams p) {
 
   if (warp >= 5) {
     // =============================== PRODUCERS ===============================
-    const int pt = tid - 5 * 32;   // 0..255
-    const int j = pt & 7;          // 16-byte chunk (8 channels) inside the 128-byte row
-    const int r_first = pt >> 3;   // 32 rows per pass
-    uint32_t g = 0;                // global k-block counter (ring position across tiles)
+    const int pt = tid - 5 * 32;          // 0..511
+    const int group = pt / TC_GROUP;      // which alternate k-blocks this thread fills
+    const int gt = pt - group * TC_GROUP; // 0..255 inside the group
+    const int j = gt & 7;                 // 16-byte chunk (8 channels) inside the 128-byte row
+    const int r_first = gt >> 3;          // 32 rows per pass
+    uint32_t g0 = 0;                      // ring position of this tile's first k-block
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long p0 = (tile / n_tiles) * TC_BM;
       const int n0 = (int)(tile % n_tiles) * p.BN;
@@ -286,7 +297,8 @@ igemm_tc_kernel(const TcParams p) {
       }
       producer_bar_sync();   // table visible to all producers
 
-      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+      for (int kb = (int)((uint32_t)(group - (int)g0) & 1u); kb < num_kb; kb += TC_GROUPS) {  // ring parity == group
+        const uint32_t g = g0 + (uint32_t)kb;
         const uint32_t s = g % (uint32_t)p.stages, it = g / (uint32_t)p.stages;
         mbar_wait(bar_empty + 8 * s, (it & 1u) ^ 1u);
         uint8_t* stage = sm + L.stages + (size_t)s * L.stage_bytes;
@@ -295,17 +307,60 @@ igemm_tc_kernel(const TcParams p) {
         uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
         uint8_t* b_lo = a_lo + L.a_bytes;
         const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
+        // ---- B: BN rows x 8 chunks of packed bf16 weights, cp.async straight into the swizzled stage
+        //      (no registers, overlaps the A gather below) ----
+        for (int r = r_first; r < p.BN; r += 32) {
+          const size_t gi = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
+          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          cp_async16(smem_u32(b_hi + soff), p.w_hi + gi);
+          if (x3) cp_async16(smem_u32(b_lo + soff), p.w_lo + gi);
+        }
+        cp_async_commit();
         // ---- A: gather 128 rows x 8 chunks ----
-#pragma unroll 2
-        for (int pass = 0; pass < TC_BM / 32; ++pass) {
-          const int r = r_first + pass * 32;
-          const long long rb = rowbase[r];
-          float v[8];
+        if (!DEFORM) {
+          // dense: issue all eight 16-byte loads of this thread first (memory-level parallelism), then convert
+          float4 q0[TC_BM / 32], q1[TC_BM / 32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = 0.f;
-          if (rb >= 0) {
-            const float* xb = p.x + rb + c0;
-            if (DEFORM) {
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowbase[r];
+            const int o = ti[tap * TC_BM + r];
+            q0[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q1[pass] = q0[pass];
+            if (rb >= 0 && o >= 0) {
+              const float4* c00 = reinterpret_cast<const float4*>(p.x + rb + c0 + (size_t)o * p.Cin);
+              q0[pass] = __ldg(c00);
+              q1[pass] = __ldg(c00 + 1);
+            }
+          }
+#pragma unroll
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            const float v[8] = {q0[pass].x, q0[pass].y, q0[pass].z, q0[pass].w, q1[pass].x, q1[pass].y, q1[pass].z, q1[pass].w};
+            uint4 hi;
+            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+            if (x3) {
+              uint4 lo;
+              lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+              lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+              lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+              lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+              *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowbase[r];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (rb >= 0) {
+              const float* xb = p.x + rb + c0;
               const float4 wv = tw[tap * TC_BM + r];
               const int4 ov = to[tap * TC_BM + r];
               const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin);
@@ -322,41 +377,28 @@ igemm_tc_kernel(const TcParams p) {
               v[5] = wv.x * a1.y + wv.y * b1.y + wv.z * d1.y + wv.w * e1.y;
               v[6] = wv.x * a1.z + wv.y * b1.z + wv.z * d1.z + wv.w * e1.z;
               v[7] = wv.x * a1.w + wv.y * b1.w + wv.z * d1.w + wv.w * e1.w;
-            } else {
-              const int o = ti[tap * TC_BM + r];
-              if (o >= 0) {
-                const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)o * p.Cin);
-                const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1);
-                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-                v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-              }
+            }
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            uint4 hi;
+            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+            if (x3) {
+              uint4 lo;
+              lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+              lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+              lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+              lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+              *reinterpret_cast<uint4*>(a_lo + soff) = lo;
             }
           }
-          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          uint4 hi;
-          hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-          hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(a_hi + soff) = hi;
-          if (x3) {
-            uint4 lo;
-            lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-            lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-            lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-            lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-            *reinterpret_cast<uint4*>(a_lo + soff) = lo;
-          }
         }
-        // ---- B: copy BN rows x 8 chunks of packed bf16 weights ----
-        for (int r = r_first; r < p.BN; r += 32) {
-          const size_t gi = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
-          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(b_hi + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_hi + gi));
-          if (x3) *reinterpret_cast<uint4*>(b_lo + soff) = __ldg(reinterpret_cast<const uint4*>(p.w_lo + gi));
-        }
+        cp_async_wait_all();
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
+      g0 += (uint32_t)num_kb;
     }
   } else if (warp == 4) {
     // =============================== MMA ISSUER ===============================
