@@ -144,6 +144,15 @@ int upsnet_panoptic_head(const float *fcn, int S, int H, int W, const float *box
                          int *k_out, int64_t *labels, int64_t *sem_labels, void *workspace,
                          size_t workspace_bytes, void *stream);
 
+/* MaskRemoval alone (API parity with operators/modules/mask_removal.py:29-93): score-ordered overlap
+ * pruning; keep_out / k_out as above; mask_energy (optional, may be NULL) float [n,H,W]: planes 0..k-1
+ * receive the pasted, resized logits of the kept instances (zeros elsewhere), as the reference returns
+ * them.  Workspace size: upsnet_panoptic_workspace_bytes. */
+int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *mask_logit,
+                        const int64_t *cls_idx, int n, const int *n_dev, int H, int W, int num_thing,
+                        double fraction_threshold, int64_t *keep_out, int *k_out, float *mask_energy,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

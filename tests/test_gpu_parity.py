@@ -388,3 +388,23 @@ def test_engine_forward_matches_cpu_path(dev):
     assert np.array_equal(out_gpu["fcn_outputs"][0].cpu().numpy(), ws)
     assert out_gpu["panoptic_outputs"].dtype == torch.int64 and out_gpu["panoptic_outputs"].shape == (1, Hh, Ww)
     assert out_gpu["pred_boxes"].shape[1] == 5 and out_gpu["mask_probs"].shape[1:] == (9, 28, 28)
+
+
+def test_mask_removal_and_segterm_modules_match_reference_composition(dev):
+    """The stand-alone MaskRemoval / SegTerm modules (reference signatures) composed exactly like
+    models/resnet_upsnet.py:223-240 in plain torch must reproduce the fused head bit for bit."""
+    import upsnet_b200 as U
+    fcn, b, prob, ml, cls = pan_case(20, 96, 128, seed=31)
+    fcn_t = t(fcn[None], dev); b_t = t(b, dev); cls_t = t(cls, dev)
+    keep, energy = U.MaskRemoval(0.3)(b_t, t(prob, dev), t(ml[:, None], dev), cls_t, (96, 128))
+    rois5 = torch.cat([torch.zeros(len(keep), 1, device=dev), b_t[keep]], 1)
+    seg_logits, seg_inst = U.SegTerm(19, num_classes=9)(cls_t[keep], fcn_t, rois5 * 4.0)
+    void = fcn_t[:, 11:].max(dim=1, keepdim=True)[0] - seg_inst.max(dim=1, keepdim=True)[0]
+    logits = torch.cat([seg_logits, seg_inst + energy, void], dim=1)
+    out = logits.max(dim=1)[1]
+    out[out == logits.shape[1] - 1] = 255
+    wk, wl = O.panoptic_head(fcn, b, prob, ml, cls, 11)
+    assert keep.cpu().tolist() == wk.tolist()
+    assert np.array_equal(out[0].cpu().numpy(), wl)
+    fk, fl = run_pan(dev, fcn, b, prob, ml, cls)
+    assert fk.cpu().tolist() == wk.tolist() and np.array_equal(fl[0].cpu().numpy(), wl)

@@ -3,10 +3,12 @@ behind the reference's own operator API.  All compute lives in libupsnet_b200.so
 include/upsnet_b200.h); this package is the thin PyTorch-facing host layer."""
 from .operators import (DeformConv, DeformConvWithOffset, ModDeformConv, ModDeformConvWithOffsetMask,  # noqa: F401
                         ModulatedDeformConv, RoIAlign, ROIAlign, RoIAlignFunction, FPNRoIAlign, PanopticHead,
+                        MaskRemoval, SegTerm,
                         conv2d, linear, deform_conv, roi_align, fpn_roi_align, nms, nms_segmented, gpu_nms,
                         gpu_nms_wrapper, panoptic_fuse, set_precision)
 
 __all__ = ["DeformConv", "DeformConvWithOffset", "ModDeformConv", "ModDeformConvWithOffsetMask",
            "ModulatedDeformConv", "RoIAlign", "ROIAlign", "RoIAlignFunction", "FPNRoIAlign", "PanopticHead",
+           "MaskRemoval", "SegTerm",
            "conv2d", "linear", "deform_conv", "roi_align", "fpn_roi_align", "nms", "nms_segmented", "gpu_nms",
            "gpu_nms_wrapper", "panoptic_fuse", "set_precision"]

@@ -46,8 +46,7 @@ def lib():
         L.upsnet_igemm_forward.argtypes = [vp] * 7 + [i] * 16 + [vp]
         L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
         L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, vp, i, d, vp, vp, vp, vp, vp, sz, vp]
-        for name in dir(L):
-            pass
+        L.upsnet_mask_removal.argtypes = [vp, vp, vp, vp, i, vp, i, i, i, d, vp, vp, vp, vp, sz, vp]
         _lib = L
     return _lib
 
@@ -56,7 +55,7 @@ EXPORTED_SYMBOLS = [
     "upsnet_version", "upsnet_roi_align_forward", "upsnet_roi_align_fpn_forward",
     "upsnet_nms_workspace_bytes", "upsnet_nms_segmented", "upsnet_nms_host", "upsnet_dcn_forward",
     "upsnet_conv2d_forward", "upsnet_igemm_packed_weight_bytes", "upsnet_igemm_pack_weight",
-    "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head",
+    "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head", "upsnet_mask_removal",
 ]
 
 

@@ -26,6 +26,7 @@ namespace ups {
 
 constexpr int kMaskS = 28;
 constexpr int kMaskElems = kMaskS * kMaskS;
+constexpr int kMaxList = 2048;   // max instances per call (per-tile / per-class uint16 lists)
 
 // per-instance integer geometry, SoA with stride n (indexed by ORIGINAL instance id)
 struct PanGeom {
@@ -128,51 +129,103 @@ pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
   }
 }
 
-// one CTA per thing class (blockIdx.x = class-1)
+// One CTA per thing class (blockIdx.x = class-1): the keep decision of an instance depends only on the
+// earlier kept instances of the SAME class, so classes run concurrently and each CTA walks its class's
+// instances in score order.  Per instance: thread-per-word (32 consecutive pixels of one row): the
+// occupancy word is requested first, the 32 mask bits are evaluated while it is in flight, popc gives
+// |mask| and |mask & occupied|; the next instance's 28x28 logit is prefetched with cp.async meanwhile.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(1024)
 pan_removal_kernel(const float* __restrict__ mask_logit, int n_max, const int* __restrict__ n_dev, int H, int W,
                    double fraction_threshold, PanWorkspace ws) {
   const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
-  __shared__ float S[kMaskElems];
+  __shared__ float S[2][kMaskElems];
+  __shared__ unsigned short list[kMaxList];   // ranks (score order) of this class's instances
   __shared__ unsigned int s_sum, s_ovl;
-  __shared__ int s_keep;
+  __shared__ int s_keep, s_cnt;
+  __shared__ int s_warp_cnt[32];
   const int c = blockIdx.x;  // 0-based class
   const int Ww = ceil_div(W, 32);
   unsigned int* occ = ws.occ + (size_t)c * H * Ww;
   unsigned int* scr = ws.scratch + (size_t)c * H * Ww;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const bool dummy_single = (n == 1 && ws.g.cls[0] == 0);  // mask_removal.py:55-57
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (n == 1 && ws.g.cls[0] == 0) return;  // MaskROI's dummy detection: mask_removal.py:55-57
 
-  for (int r = 0; r < n; ++r) {
+  // ---- ordered list of the ranks that belong to this class ----
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    const bool mine = r < n && ws.g.cls[ws.order[r]] - 1 == c;
+    const unsigned int m = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = s_cnt;
+    for (int w2 = 0; w2 < warp; ++w2) off += s_warp_cnt[w2];
+    if (mine) list[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) tot += s_warp_cnt[w2];
+      s_cnt += tot;
+    }
+    __syncthreads();
+  }
+  const int cnt = s_cnt;
+  if (cnt == 0) return;
+  for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x)
+    cp_async4(&S[0][t], mask_logit + (size_t)ws.order[list[0]] * kMaskElems + t);
+  cp_async_wait_all_();
+  __syncthreads();
+
+  for (int li = 0; li < cnt; ++li) {
+    const int r = list[li];
     const int i = ws.order[r];
-    if (ws.g.cls[i] - 1 != c || dummy_single) continue;  // uniform across the CTA
+    const float* Sm = S[li & 1];
+    if (li + 1 < cnt)   // prefetch the next instance's logits into the other buffer
+      for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x)
+        cp_async4(&S[(li + 1) & 1][t], mask_logit + (size_t)ws.order[list[li + 1]] * kMaskElems + t);
+    if (threadIdx.x == 0) { s_sum = 0; s_ovl = 0; }
     const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], w = ws.g.w[i], h = ws.g.h[i];
     const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
-    __syncthreads();  // previous instance fully retired (S, counters, occ updates)
-    for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x) S[t] = mask_logit[(size_t)i * kMaskElems + t];
-    if (threadIdx.x == 0) { s_sum = 0; s_ovl = 0; }
-    __syncthreads();
     const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;  // word columns [wx0, wx1)
     const int nwc = max(wx1 - wx0, 0), rows = max(y1 - y0, 0);
     unsigned int my_sum = 0, my_ovl = 0;
-    for (int item = warp; item < nwc * rows; item += nwarps) {
+    for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {
       const int wy = y0 + item / nwc, wc = wx0 + item % nwc;
-      const int x = wc * 32 + lane;
-      bool bit = false;
-      const int dx = x - bx0, dy = wy - by0;
-      if (x >= x0 && x < x1 && dx >= 0 && dx < w && dy >= 0 && dy < h) {
-        int sx, sy; float fx, fy;
-        coef_x(dx, w, sx, fx);
+      const size_t o = (size_t)wy * Ww + wc;
+      const unsigned int occ_w = occ[o];            // in flight while the 32 bits are evaluated
+      unsigned int word = 0;
+      const int dy = wy - by0;
+      if (dy >= 0 && dy < h) {
+        int sy; float fy;
         coef_y(dy, h, sy, fy);
-        bit = blend(S, sx, fx, sy, fy) > 0.f;
+        const int xa = max(wc * 32, x0), xb = min(wc * 32 + 32, x1);
+        for (int x = xa; x < xb; ++x) {
+          const int dx = x - bx0;
+          if (dx >= 0 && dx < w) {
+            int sx; float fx;
+            coef_x(dx, w, sx, fx);
+            if (blend(Sm, sx, fx, sy, fy) > 0.f) word |= 1u << (x & 31);
+          }
+        }
       }
-      const unsigned int word = __ballot_sync(0xffffffffu, bit);
-      if (lane == 0) {
-        scr[(size_t)wy * Ww + wc] = word;
-        my_sum += __popc(word);
-        my_ovl += __popc(word & occ[(size_t)wy * Ww + wc]);
-      }
+      scr[o] = word;
+      my_sum += __popc(word);
+      my_ovl += __popc(word & occ_w);
     }
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      my_sum += __shfl_xor_sync(0xffffffffu, my_sum, sh);
+      my_ovl += __shfl_xor_sync(0xffffffffu, my_ovl, sh);
+    }
+    __syncthreads();   // counters zeroed
     if (lane == 0 && (my_sum | my_ovl)) { atomicAdd(&s_sum, my_sum); atomicAdd(&s_ovl, my_ovl); }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -183,12 +236,13 @@ pan_removal_kernel(const float* __restrict__ mask_logit, int n_max, const int* _
       ws.kept_flag[r] = drop ? 0 : 1;
     }
     __syncthreads();
-    if (s_keep) {
-      for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {
+    if (s_keep)
+      for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {   // same items this thread wrote
         const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
         occ[o] |= scr[o];
       }
-    }
+    cp_async_wait_all_();
+    __syncthreads();   // occupancy + next logits visible to the whole CTA
   }
 }
 
@@ -221,7 +275,7 @@ pan_compact_kernel(int n_max, const int* __restrict__ n_dev, PanWorkspace ws, in
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kTileW = 128, kTileH = 8, kFuseThreads = 256, kMaxList = 2048;
+constexpr int kTileW = 128, kTileH = 8, kFuseThreads = 256;
 
 struct Best { float v; int i; };
 __device__ __forceinline__ void feed(Best& b, float v, int i) { if (v > b.v) { b.v = v; b.i = i; } }
@@ -370,7 +424,62 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
   }
 }
 
+// Materialises MaskRemoval's second output, mask_energy [k,H,W] (mask_removal.py:86): the resized logit
+// inside the paste window, 0 elsewhere.  API-parity path only (the fused head never builds these planes).
+__global__ void __launch_bounds__(256)
+pan_paste_kernel(const float* __restrict__ mask_logit, int H, int W, PanWorkspace ws, float* __restrict__ energy) {
+  const int k = ws.meta[0], zero_mask = ws.meta[1];
+  const int j = blockIdx.y;
+  if (j >= k) return;
+  const int i = ws.kept_list[j];
+  const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], bw = ws.g.w[i], bh = ws.g.h[i];
+  const int gx0 = ws.g.gx0[i], gx1 = ws.g.gx1[i], gy0 = ws.g.gy0[i], gy1 = ws.g.gy1[i];
+  const float* Sm = mask_logit + (size_t)i * kMaskElems;
+  const size_t HW = (size_t)H * W;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+    float v = 0.f;
+    const int dx = x - bx0, dy = y - by0;
+    if (!zero_mask && x >= gx0 && x < gx1 && y >= gy0 && y < gy1 && dx >= 0 && dx < bw && dy >= 0 && dy < bh) {
+      int sx, sy; float fx, fy;
+      coef_x(dx, bw, sx, fx);
+      coef_y(dy, bh, sy, fy);
+      v = blend(Sm, sx, fx, sy, fy);
+    }
+    energy[(size_t)j * HW + p] = v;
+  }
+}
+
 }  // namespace ups
+
+extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, const float* mask_logit,
+                                   const int64_t* cls_idx, int n, const int* n_dev, int H, int W, int num_thing,
+                                   double fraction_threshold, int64_t* keep_out, int* k_out, float* mask_energy,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace ups;
+  if (!boxes || !cls_prob || !mask_logit || !cls_idx || !keep_out || !k_out || !workspace) return UPSNET_E_BADARG;
+  if (n < 1 || H <= 0 || W <= 0 || num_thing <= 0) return UPSNET_E_BADARG;
+  if (n > kMaxList) return UPSNET_E_UNSUPPORTED;
+  PanWorkspace ws;
+  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace);
+  if (workspace_bytes < need) return UPSNET_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ww = ceil_div(W, 32);
+  UPS_CUDA(cudaMemsetAsync(ws.occ, 0, (size_t)num_thing * H * Ww * sizeof(unsigned int), st));
+  UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
+  pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
+  UPS_CHECK_LAUNCH();
+  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, n_dev, H, W, fraction_threshold, ws);
+  UPS_CHECK_LAUNCH();
+  pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
+  UPS_CHECK_LAUNCH();
+  if (mask_energy) {
+    dim3 grid((unsigned)min((size_t)kNumSMs * 8, ((size_t)H * W + 255) / 256), (unsigned)n);
+    pan_paste_kernel<<<grid, 256, 0, st>>>(mask_logit, H, W, ws, mask_energy);
+    UPS_CHECK_LAUNCH();
+  }
+  return 0;
+}
 
 extern "C" int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thing, size_t* bytes) {
   if (!bytes || n < 0 || H <= 0 || W <= 0 || num_thing <= 0) return UPSNET_E_BADARG;

@@ -522,6 +522,67 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     return (keep, labels, sem) if want_sem else (keep, labels)
 
 
+class MaskRemoval(nn.Module):
+    """operators/modules/mask_removal.py:23-93, same signature and return values:
+    forward(mask_rois[n,4], cls_prob[n], mask_prob[n,1,28,28], cls_idx[n], im_shape) ->
+    (keep_inds LongTensor [k], mask_energy [1,k,H,W]).  Runs the device kernels of the fused head and, for
+    API parity, materialises mask_energy (the fused PanopticHead never does)."""
+
+    def __init__(self, fraction_threshold=0.3):
+        super().__init__()
+        self.fraction_threshold = fraction_threshold
+
+    def forward(self, mask_rois, cls_prob, mask_prob, cls_idx, im_shape):
+        require_cuda(mask_rois, cls_prob, mask_prob, cls_idx)
+        boxes, prob, ml = f32c(mask_rois), f32c(cls_prob).reshape(-1), f32c(mask_prob)
+        cls = cls_idx.to(torch.int64).contiguous()
+        n, (H, W) = boxes.shape[0], (int(im_shape[0]), int(im_shape[1]))
+        dev = boxes.device
+        num_thing = max(int(cls.max().item()), 1)          # mask_image planes: np.max(cls_idx) (host read, as the reference)
+        nbytes = C.c_size_t(0)
+        check(lib().upsnet_panoptic_workspace_bytes(n, H, W, num_thing, C.byref(nbytes)), "panoptic_workspace_bytes")
+        ws = _pan_ws.get(dev, nbytes.value)
+        keep = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
+        k = torch.empty((1,), dtype=torch.int32, device=dev)
+        energy = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _Timed("mask_removal", 4, {"bytes": 4.0 * n * H * W}, dev):
+            check(lib().upsnet_mask_removal(ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, None, H, W, num_thing,
+                                            float(self.fraction_threshold), ptr(keep), ptr(k), ptr(energy), ptr(ws),
+                                            ws.numel(), stream_ptr(dev)), "mask_removal")
+        kk = int(k.item())
+        return keep[:kk], energy[:kk].unsqueeze(0)
+
+
+class SegTerm(nn.Module):
+    """operators/modules/unary_logits.py:69-105: (stuff logits view, per-instance boxed copy of the instance's
+    thing-class logit).  Pure tensor slicing on the device, same integer conventions as the reference
+    (int() truncation, numpy half-to-even round, python-slice clamping).  API parity only: the fused
+    PanopticHead evaluates the same windows inside pan_fuse without building [1,k,H,W]."""
+
+    def __init__(self, num_seg_classes, box_scale=1 / 4.0, class_mapping=None, thresh=0.3, num_classes=None):
+        super().__init__()
+        num_classes = num_classes if num_classes is not None else 9
+        self.class_mapping = dict(zip(range(1, num_classes), range(num_seg_classes - num_classes + 1, num_seg_classes))) \
+            if class_mapping is None else class_mapping
+        self.num_seg_classes, self.num_inst_classes, self.box_scale = num_seg_classes, len(self.class_mapping), box_scale
+
+    def forward(self, cls_indices, seg_score, boxes):
+        assert seg_score.shape[0] == 1, "only support batch size = 1"
+        cls_np = cls_indices.detach().cpu().numpy()
+        seg_energy = seg_score[[0], :-self.num_inst_classes, :, :]
+        b = boxes.detach().cpu().numpy()[:, 1:] * self.box_scale
+        if cls_np.size == 0:
+            return seg_energy, torch.ones_like(seg_energy[[0], [0], :, :]).view(1, 1, seg_energy.shape[2], seg_energy.shape[3]) * -10
+        inst = torch.zeros((1, cls_np.shape[0], seg_score.shape[2], seg_score.shape[3]), device=seg_score.device)
+        for i in range(cls_np.shape[0]):
+            if cls_np[i] == 0:
+                continue
+            y0, y1 = int(b[i][1]), int(b[i][3].round() + 1)
+            x0, x1 = int(b[i][0]), int(b[i][2].round() + 1)
+            inst[0, i, y0:y1, x0:x1] = seg_score[0, self.class_mapping[int(cls_np[i])], y0:y1, x0:x1]
+        return seg_energy, inst
+
+
 class PanopticHead(nn.Module):
     """The parameter-free panoptic head of models/resnet_upsnet.py:217-247 as one module (the
     reference has no such class: SURVEY.md F1).  forward takes what lines 220-227 consume."""
