@@ -318,78 +318,69 @@ igemm_tc_kernel(const TcParams p) {
         cp_async_commit();
         // ---- A: gather 128 rows x 8 chunks ----
         if (!DEFORM) {
-          // dense: issue all eight 16-byte loads of this thread first (memory-level parallelism), then convert
-          float4 q0[TC_BM / 32], q1[TC_BM / 32];
+          // dense: a row's 64 fp32 channels (256 B) are read by 16 consecutive lanes, 16 B each, so every
+          // warp-wide LDG.128 covers two fully used 256-byte spans; all eight loads of a thread are
+          // issued before the first conversion (memory-level parallelism); each lane then stores 4 bf16
+          // (8 B) into its half of the swizzled 16-byte chunk.
+          const int l16 = gt & 15;            // 4-channel group inside the 64-channel row
+          const int rr0 = gt >> 4;            // 16 rows per pass
+          const int cg = c0 - j * 8 + l16 * 4;  // first channel of this lane's group
+          float4 qv[TC_BM / 16];
 #pragma unroll
-          for (int pass = 0; pass < TC_BM / 32; ++pass) {
-            const int r = r_first + pass * 32;
+          for (int pass = 0; pass < TC_BM / 16; ++pass) {
+            const int r = rr0 + pass * 16;
             const long long rb = rowbase[r];
             const int o = ti[tap * TC_BM + r];
-            q0[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-            q1[pass] = q0[pass];
-            if (rb >= 0 && o >= 0) {
-              const float4* c00 = reinterpret_cast<const float4*>(p.x + rb + c0 + (size_t)o * p.Cin);
-              q0[pass] = __ldg(c00);
-              q1[pass] = __ldg(c00 + 1);
-            }
+            qv[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rb >= 0 && o >= 0) qv[pass] = __ldg(reinterpret_cast<const float4*>(p.x + rb + cg + (size_t)o * p.Cin));
           }
 #pragma unroll
-          for (int pass = 0; pass < TC_BM / 32; ++pass) {
-            const int r = r_first + pass * 32;
-            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-            const float v[8] = {q0[pass].x, q0[pass].y, q0[pass].z, q0[pass].w, q1[pass].x, q1[pass].y, q1[pass].z, q1[pass].w};
-            uint4 hi;
-            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+          for (int pass = 0; pass < TC_BM / 16; ++pass) {
+            const int r = rr0 + pass * 16;
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)(((l16 >> 1) ^ (r & 7)) << 4) + (uint32_t)((l16 & 1) << 3);
+            uint2 hi;
+            hi.x = pack_bf16x2(qv[pass].x, qv[pass].y); hi.y = pack_bf16x2(qv[pass].z, qv[pass].w);
+            *reinterpret_cast<uint2*>(a_hi + soff) = hi;
             if (x3) {
-              uint4 lo;
-              lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-              lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-              lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-              lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-              *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+              uint2 lo;
+              lo.x = pack_bf16x2(qv[pass].x - bf16_round(qv[pass].x), qv[pass].y - bf16_round(qv[pass].y));
+              lo.y = pack_bf16x2(qv[pass].z - bf16_round(qv[pass].z), qv[pass].w - bf16_round(qv[pass].w));
+              *reinterpret_cast<uint2*>(a_lo + soff) = lo;
             }
           }
         } else {
+          // deformable: same coalesced lane mapping; per (row, 4-channel group) four 16-byte corner reads,
+          // blended in fp32 with the tile's sample table (weights already carry validity and the v2 mask).
+          const int l16 = gt & 15;
+          const int rr0 = gt >> 4;
+          const int cg = c0 - j * 8 + l16 * 4;
 #pragma unroll 2
-          for (int pass = 0; pass < TC_BM / 32; ++pass) {
-            const int r = r_first + pass * 32;
+          for (int pass = 0; pass < TC_BM / 16; ++pass) {
+            const int r = rr0 + pass * 16;
             const long long rb = rowbase[r];
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rb >= 0) {
-              const float* xb = p.x + rb + c0;
+              const float* xb = p.x + rb + cg;
               const float4 wv = tw[tap * TC_BM + r];
               const int4 ov = to[tap * TC_BM + r];
-              const float4* c00 = reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin);
-              const float4* c01 = reinterpret_cast<const float4*>(xb + (size_t)ov.y * p.Cin);
-              const float4* c10 = reinterpret_cast<const float4*>(xb + (size_t)ov.z * p.Cin);
-              const float4* c11 = reinterpret_cast<const float4*>(xb + (size_t)ov.w * p.Cin);
-              const float4 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
-              const float4 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
-              v[0] = wv.x * a0.x + wv.y * b0.x + wv.z * d0.x + wv.w * e0.x;
-              v[1] = wv.x * a0.y + wv.y * b0.y + wv.z * d0.y + wv.w * e0.y;
-              v[2] = wv.x * a0.z + wv.y * b0.z + wv.z * d0.z + wv.w * e0.z;
-              v[3] = wv.x * a0.w + wv.y * b0.w + wv.z * d0.w + wv.w * e0.w;
-              v[4] = wv.x * a1.x + wv.y * b1.x + wv.z * d1.x + wv.w * e1.x;
-              v[5] = wv.x * a1.y + wv.y * b1.y + wv.z * d1.y + wv.w * e1.y;
-              v[6] = wv.x * a1.z + wv.y * b1.z + wv.z * d1.z + wv.w * e1.z;
-              v[7] = wv.x * a1.w + wv.y * b1.w + wv.z * d1.w + wv.w * e1.w;
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)ov.y * p.Cin));
+              const float4 d0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)ov.z * p.Cin));
+              const float4 e0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)ov.w * p.Cin));
+              v.x = wv.x * a0.x + wv.y * b0.x + wv.z * d0.x + wv.w * e0.x;
+              v.y = wv.x * a0.y + wv.y * b0.y + wv.z * d0.y + wv.w * e0.y;
+              v.z = wv.x * a0.z + wv.y * b0.z + wv.z * d0.z + wv.w * e0.z;
+              v.w = wv.x * a0.w + wv.y * b0.w + wv.z * d0.w + wv.w * e0.w;
             }
-            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-            uint4 hi;
-            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)(((l16 >> 1) ^ (r & 7)) << 4) + (uint32_t)((l16 & 1) << 3);
+            uint2 hi;
+            hi.x = pack_bf16x2(v.x, v.y); hi.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(a_hi + soff) = hi;
             if (x3) {
-              uint4 lo;
-              lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
-              lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
-              lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
-              lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
-              *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+              uint2 lo;
+              lo.x = pack_bf16x2(v.x - bf16_round(v.x), v.y - bf16_round(v.y));
+              lo.y = pack_bf16x2(v.z - bf16_round(v.z), v.w - bf16_round(v.w));
+              *reinterpret_cast<uint2*>(a_lo + soff) = lo;
             }
           }
         }
