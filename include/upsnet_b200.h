@@ -26,6 +26,9 @@ extern "C" {
 #define UPSNET_LAYOUT_NCHW 0
 #define UPSNET_LAYOUT_NHWC 1
 
+#define UPSNET_DTYPE_F32 0
+#define UPSNET_DTYPE_BF16 1
+
 /* epilogue flags for the convolution entry points */
 #define UPSNET_EPI_RELU 1
 
@@ -43,20 +46,21 @@ int upsnet_version(int *n_sm);
  *           -> operators/src/roi_align_kernel.cu:351 roi_align_forward_gpu_kernel_launcher
  * feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC) fp32; rois [R,5] = (batch,x1,y1,x2,y2);
  * out [R,C,PH,PW] (NCHW) or [R,PH,PW,C] (NHWC) -- same layout flag as feat.
+ * dtype: UPSNET_DTYPE_F32, or UPSNET_DTYPE_BF16 (NHWC only: bf16 features in, bf16 out, fp32 accumulation).
  */
-int upsnet_roi_align_forward(const float *feat, int B, int C, int H, int W, int layout,
+int upsnet_roi_align_forward(const void *feat, int B, int C, int H, int W, int layout, int dtype,
                              const float *rois, int R, int PH, int PW, int sampling_ratio,
-                             float spatial_scale, float *out, void *stream);
+                             float spatial_scale, void *out, void *stream);
 
 /* FPN ROIAlign: level assignment + 4 pyramid levels + un-permute in ONE launch.
  * replaces: operators/modules/fpn_roi_align.py:32-62 FPNRoIAlign.forward (host bucketing,
  *           4 launches, cat, index_select).  feats[l] has spatial size (Hs[l],Ws[l]) and
  *           scale scales[l]; level(roi) = clip(floor(2+log2(sqrt(w*h)/224+1e-6)),0,3).
  * levels_out (optional, may be NULL): int32 [R] chosen level per roi. */
-int upsnet_roi_align_fpn_forward(const float *const feats[4], const int Hs[4], const int Ws[4],
-                                 const float scales[4], int B, int C, int layout,
+int upsnet_roi_align_fpn_forward(const void *const feats[4], const int Hs[4], const int Ws[4],
+                                 const float scales[4], int B, int C, int layout, int dtype,
                                  const float *rois, int R, int PH, int PW, int sampling_ratio,
-                                 float *out, int *levels_out, void *stream);
+                                 void *out, int *levels_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * NMS (IoU with the legacy +1 box area, suppress when IoU > thresh).
@@ -108,7 +112,9 @@ int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias
 /* ---------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolution / deformable convolution (engine entry point).
  * Same arithmetic contract as upsnet_conv2d_forward / upsnet_dcn_forward, but
- *   - x is NHWC fp32 [N,H,W,Cin] (Cin % 64 == 0), y / residual are NHWC or NCHW (out_layout),
+ *   - x is NHWC [N,H,W,Cin] (Cin % 64 == 0) stored as fp32 or bf16 (x_dtype); y and residual are NHWC or
+ *     NCHW (out_layout) stored as fp32 or bf16 (y_dtype); bf16 activations are copied by cp.async straight
+ *     into the tensor-core layout (UPSNET_PREC_BF16 only: the hi/lo split needs fp32 activations),
  *   - weights are pre-packed once with upsnet_igemm_pack_weight (bf16 hi/lo planes,
  *     [Cout_pad][kh*kw][Cin]); `packed` must hold upsnet_igemm_packed_weight_bytes bytes,
  *   - offset [N,2*kh*kw,Ho,Wo] / mask [N,kh*kw,Ho,Wo] stay NCHW (reference layout), NULL for a
@@ -119,11 +125,11 @@ int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias
 int upsnet_igemm_packed_weight_bytes(int Cout, int Cin, int kh, int kw, size_t *bytes);
 int upsnet_igemm_pack_weight(const float *weight, int Cout, int Cin, int kh, int kw, void *packed,
                              void *stream);
-int upsnet_igemm_forward(const float *x_nhwc, const float *offset, const float *mask,
-                         const void *packed, const float *bias, const float *residual, float *y,
+int upsnet_igemm_forward(const void *x_nhwc, const float *offset, const float *mask,
+                         const void *packed, const float *bias, const void *residual, void *y,
                          int N, int H, int W, int Cin, int Cout, int kh, int kw, int stride_h,
                          int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int out_layout,
-                         int epi_flags, int precision, void *stream);
+                         int x_dtype, int y_dtype, int epi_flags, int precision, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Parameter-free panoptic head, fused: MaskRemoval + SegTerm + void/concat/argmax.

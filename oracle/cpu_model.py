@@ -17,14 +17,14 @@ from . import oracle as O
 
 
 def _conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-            out_format=None):
+            out_format=None, out_dtype=None):
     y = F.conv2d(x.float(), weight.float(), None if bias is None else bias.float(), stride, padding, dilation)
     if residual is not None:
         y = y + residual
     return F.relu(y) if relu else y
 
 
-def _linear(x, weight, bias=None, relu=False, precision=None):
+def _linear(x, weight, bias=None, relu=False, precision=None, out_dtype=None):
     y = F.linear(x, weight, bias)
     return F.relu(y) if relu else y
 
@@ -34,7 +34,7 @@ def _pair(v):
 
 
 def _deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1, mask=None,
-                 relu=False, precision=None, out_format=None):
+                 relu=False, precision=None, out_format=None, out_dtype=None):
     """Reference structure (functions/deform_conv.py:44-57): per image, deformable im2col (C oracle,
     OpenMP) into a column buffer, then torch.mm on the host cores, then bias."""
     s, p, d = _pair(stride)[0], _pair(padding)[0], _pair(dilation)[0]

@@ -124,3 +124,107 @@ def test_engine_forward_tc_precisions(dev):
     for name in ("bf16x3", "bf16"):
         agree = (outs[name][1]["fcn_outputs"] == outs["fp32"][1]["fcn_outputs"]).float().mean().item()
         assert agree > (0.999 if name == "bf16x3" else 0.97), (name, agree)
+
+
+# ------------------------------- bf16 activation storage ------------------------------------------
+def _bf16_exact(a):
+    """Round to bf16-representable fp32 values: with such inputs the tensor-core products are exact, so the
+    bf16-storage path can be checked tightly (only the fp32 accumulation order and the bf16 OUTPUT rounding
+    remain)."""
+    return torch.from_numpy(np.ascontiguousarray(a)).bfloat16().float().numpy()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, Cin=64, Cout=64, H=16, W=16, k=1, stride=1, pad=0, dil=1),
+    dict(N=1, Cin=256, Cout=128, H=20, W=28, k=3, stride=1, pad=1, dil=1),
+    dict(N=2, Cin=128, Cout=256, H=15, W=17, k=3, stride=1, pad=1, dil=1),
+    dict(N=1, Cin=256, Cout=512, H=16, W=20, k=1, stride=2, pad=0, dil=1),
+    dict(N=1, Cin=64, Cout=18, H=24, W=24, k=3, stride=1, pad=1, dil=1),
+    dict(N=50, Cin=1024, Cout=45, H=1, W=1, k=1, stride=1, pad=0, dil=1),
+])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("out_format", ["nhwc", "nchw"])
+def test_tc_conv2d_bf16_activations(dev, cfg, out_dtype, out_format):
+    import upsnet_b200 as U
+    rng = np.random.default_rng(8)
+    x, w, b = _case(rng, cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"], cfg["k"])
+    x, w = _bf16_exact(x), _bf16_exact(w)
+    want = O.conv2d(x, w, b, cfg["stride"], cfg["pad"], cfg["dil"])
+    res = _bf16_exact(rng.standard_normal(want.shape).astype(np.float32))
+    xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    got = U.conv2d(xb, t(w, dev), t(b, dev), cfg["stride"], cfg["pad"], cfg["dil"], precision=BF16,
+                   out_format=out_format, out_dtype=out_dtype)
+    assert got.dtype == out_dtype and got.shape == want.shape
+    tol = 1e-4 + (2.0 ** -8) * np.abs(want).max() if out_dtype == torch.bfloat16 else 1e-4
+    assert np.abs(got.float().cpu().numpy() - want).max() < tol
+    got2 = U.conv2d(xb, t(w, dev), t(b, dev), cfg["stride"], cfg["pad"], cfg["dil"], residual=t(res, dev).to(out_dtype),
+                    relu=True, precision=BF16, out_format=out_format, out_dtype=out_dtype)
+    want2 = np.maximum(want + res, 0)
+    tol2 = 1e-4 + (2.0 ** -8) * np.abs(want2).max() if out_dtype == torch.bfloat16 else 1e-4
+    assert np.abs(got2.float().cpu().numpy() - want2).max() < tol2
+
+
+@pytest.mark.parametrize("modulated", [False, True])
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, Cin=64, Cout=64, H=16, W=16, stride=1, pad=1, dil=1),
+    dict(N=1, Cin=256, Cout=128, H=32, W=48, stride=1, pad=1, dil=1),
+    dict(N=2, Cin=128, Cout=128, H=25, W=42, stride=1, pad=1, dil=1),
+    dict(N=1, Cin=64, Cout=64, H=20, W=20, stride=1, pad=2, dil=2),
+])
+def test_tc_dcn_bf16_activations(dev, cfg, modulated):
+    """bf16 features in, fp32 out: the blended sample is rounded to bf16 before the MMA (2^-9 relative per
+    element), hence the bf16-level bound; offsets / masks stay fp32."""
+    import upsnet_b200 as U
+    rng = np.random.default_rng(9)
+    N, Cin, Cout, H, W = cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"]
+    Ho = O.conv_out(H, cfg["pad"], cfg["dil"], 3, cfg["stride"]); Wo = O.conv_out(W, cfg["pad"], cfg["dil"], 3, cfg["stride"])
+    x, w, b = _case(rng, N, Cin, Cout, H, W, 3)
+    x, w = _bf16_exact(x), _bf16_exact(w)
+    off = (rng.standard_normal((N, 18, Ho, Wo)) * 2.5).astype(np.float32)
+    mask = rng.uniform(0, 2, (N, 9, Ho, Wo)).astype(np.float32) if modulated else None
+    want = O.deform_conv(x, off, w, b, mask, cfg["stride"], cfg["pad"], cfg["dil"], 1)
+    xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    got = U.deform_conv(xb, t(off, dev), t(w, dev), t(b, dev), cfg["stride"], cfg["pad"], cfg["dil"], 1,
+                        mask=None if mask is None else t(mask, dev), precision=BF16, out_dtype=torch.float32)
+    assert np.abs(got.float().cpu().numpy() - want).max() < TOL[BF16]
+
+
+def test_fpn_roi_align_bf16_nhwc(dev):
+    import upsnet_b200 as U
+    rng = np.random.default_rng(10)
+    feats = [_bf16_exact(rng.standard_normal((1, 64, 64 >> l, 96 >> l)).astype(np.float32)) for l in range(4)]
+    c = rng.uniform(0, 256, (200, 2)); s = np.exp(rng.uniform(np.log(8), np.log(400), (200, 2)))
+    rois = np.concatenate([np.zeros((200, 1)), np.clip(c - s / 2, 0, 383), np.clip(c + s / 2, 0, 383)], 1).astype(np.float32)
+    want = O.fpn_roi_align(feats, rois, 7, 7)
+    fd = [t(f, dev).bfloat16().permute(0, 2, 3, 1).contiguous() for f in feats]
+    got = U.fpn_roi_align(fd, t(rois, dev), 7, 7, [1 / 4., 1 / 8., 1 / 16., 1 / 32.], layout="nhwc")
+    assert got.dtype == torch.bfloat16
+    err = np.abs(got.float().permute(0, 3, 1, 2).cpu().numpy() - want).max()
+    assert err < 1e-4 + (2.0 ** -8) * np.abs(want).max(), err
+
+
+def test_engine_bf16_activation_stream(dev):
+    """Whole engine with bf16-stored activations (the speed configuration) vs the same engine with fp32
+    storage and the same single-pass bf16 MMAs: storage adds one bf16 rounding per layer."""
+    import upsnet_b200 as U
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    m = synthetic_model(UPSNetConfig.cityscapes_r50(), depth=(1, 1, 1, 1), seed=3, device=dev)
+    m.keep_intermediates = True
+    inp = synthetic_input(256, 384, seed=4, device=dev)
+    outs = {}
+    try:
+        for name, act in (("fp32", False), ("bf16", False), ("bf16", True)):
+            U.set_precision(name, bf16_activations=act)
+            with torch.no_grad():
+                outs[(name, act)] = m(inp)
+    finally:
+        U.set_precision("fp32")
+    ref = outs[("fp32", False)]["_intermediates"]["fcn_output"]
+    scale = max(1.0, float(ref.abs().max()))
+    e_mma = (outs[("bf16", False)]["_intermediates"]["fcn_output"] - ref).abs().max().item() / scale
+    e_act = (outs[("bf16", True)]["_intermediates"]["fcn_output"] - ref).abs().max().item() / scale
+    assert e_mma < 6e-2 and e_act < 8e-2, (e_mma, e_act)
+    agree = (outs[("bf16", True)]["fcn_outputs"] == outs[("fp32", False)]["fcn_outputs"]).float().mean().item()
+    assert agree > 0.95, agree
+    assert outs[("bf16", True)]["panoptic_outputs"].dtype == torch.int64

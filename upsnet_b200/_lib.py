@@ -33,9 +33,9 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, i, f, d, sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
         L.upsnet_version.argtypes = [C.POINTER(i)]
-        L.upsnet_roi_align_forward.argtypes = [vp, i, i, i, i, i, vp, i, i, i, i, f, vp, vp]
+        L.upsnet_roi_align_forward.argtypes = [vp, i, i, i, i, i, i, vp, i, i, i, i, f, vp, vp]
         L.upsnet_roi_align_fpn_forward.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(f),
-                                                   i, i, i, vp, i, i, i, i, vp, vp, vp]
+                                                   i, i, i, i, vp, i, i, i, i, vp, vp, vp]
         L.upsnet_nms_workspace_bytes.argtypes = [i, i, C.POINTER(sz)]
         L.upsnet_nms_segmented.argtypes = [vp, vp, i, i, f, vp, vp, vp, sz, vp]
         L.upsnet_nms_host.argtypes = [vp, vp, vp, i, i, f, i]
@@ -43,7 +43,7 @@ def lib():
         L.upsnet_conv2d_forward.argtypes = [vp] * 5 + [i] * 15 + [vp]
         L.upsnet_igemm_packed_weight_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
         L.upsnet_igemm_pack_weight.argtypes = [vp, i, i, i, i, vp, vp]
-        L.upsnet_igemm_forward.argtypes = [vp] * 7 + [i] * 16 + [vp]
+        L.upsnet_igemm_forward.argtypes = [vp] * 7 + [i] * 18 + [vp]
         L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
         L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, vp, i, d, vp, vp, vp, vp, vp, sz, vp]
         L.upsnet_mask_removal.argtypes = [vp, vp, vp, vp, i, vp, i, i, i, d, vp, vp, vp, vp, sz, vp]

@@ -12,11 +12,12 @@ struct ConvParams {
 int launch_igemm_simt(const ConvParams& p, cudaStream_t stream);
 
 struct TcParams {
-  const float* x; const float* offset; const float* mask;
+  const void* x; const float* offset; const float* mask;
   const uint16_t* w_hi; const uint16_t* w_lo;
-  const float* bias; const float* residual; float* y;
+  const float* bias; const void* residual; void* y;
   int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
   int relu, out_nhwc, BN, stages, x3;
+  int x_bf16, y_bf16;
 };
 size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
 int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream);
@@ -98,12 +99,12 @@ extern "C" int upsnet_igemm_pack_weight(const float* weight, int Cout, int Cin, 
   return ups::tc_pack_weight(weight, Cout, Cin, kh, kw, packed, (cudaStream_t)stream);
 }
 
-extern "C" int upsnet_igemm_forward(const float* x_nhwc, const float* offset, const float* mask,
-                                    const void* packed, const float* bias, const float* residual,
-                                    float* y, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+extern "C" int upsnet_igemm_forward(const void* x_nhwc, const float* offset, const float* mask,
+                                    const void* packed, const float* bias, const void* residual,
+                                    void* y, int N, int H, int W, int Cin, int Cout, int kh, int kw,
                                     int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
-                                    int dil_w, int out_layout, int epi_flags, int precision,
-                                    void* stream) {
+                                    int dil_w, int out_layout, int x_dtype, int y_dtype, int epi_flags,
+                                    int precision, void* stream) {
   if (!x_nhwc || !packed || !y) return UPSNET_E_BADARG;
   if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride_h <= 0 ||
       stride_w <= 0 || pad_h < 0 || pad_w < 0 || dil_h <= 0 || dil_w <= 0)
@@ -122,5 +123,10 @@ extern "C" int upsnet_igemm_forward(const float* x_nhwc, const float* offset, co
   p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
   p.out_nhwc = out_layout == UPSNET_LAYOUT_NHWC;
   p.x3 = precision == UPSNET_PREC_BF16X3;
+  if ((x_dtype != UPSNET_DTYPE_F32 && x_dtype != UPSNET_DTYPE_BF16) || (y_dtype != UPSNET_DTYPE_F32 && y_dtype != UPSNET_DTYPE_BF16))
+    return UPSNET_E_BADARG;
+  p.x_bf16 = x_dtype == UPSNET_DTYPE_BF16;
+  p.y_bf16 = y_dtype == UPSNET_DTYPE_BF16;
+  if (p.x_bf16 && p.x3) return UPSNET_E_UNSUPPORTED;
   return ups::launch_igemm_tc(p, packed, (cudaStream_t)stream);
 }

@@ -39,14 +39,15 @@ constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 21 warps
 constexpr int TC_MAX_STAGES = 6;
 
 struct TcParams {
-  const float* x;        // NHWC fp32 [N,H,W,Cin]
+  const void* x;         // NHWC [N,H,W,Cin], fp32 or bf16 (x_bf16)
   const float* offset;   // NCHW fp32 [N,2*KHW,Ho,Wo] or null
   const float* mask;     // NCHW fp32 [N,KHW,Ho,Wo] or null
   const uint16_t* w_hi;  // bf16 [Cout_pad][KHW*Cin]
   const uint16_t* w_lo;  // bf16 residual plane (BF16X3) or null
-  const float* bias; const float* residual; float* y;
+  const float* bias; const void* residual; void* y;   // residual / y: fp32 or bf16 (y_bf16)
   int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
   int relu, out_nhwc, BN, stages, x3;
+  int x_bf16, y_bf16;    // activation storage: 0 = fp32, 1 = bf16 (x / y+residual)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -122,6 +123,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -183,7 +187,7 @@ __device__ __forceinline__ void producer_bar_sync() {
 // Pipelines: smem ring full[s]/empty[s] (producers <-> MMA) runs across tiles; two TMEM accumulator
 // buffers tmem_full[b]/tmem_empty[b] (MMA <-> epilogue) overlap tile i's epilogue with tile i+1's
 // main loop.  Tiles: id = blockIdx.x + it*gridDim.x, n-tile fastest (concurrent CTAs share the A rows in L2).
-template <bool DEFORM>
+template <bool DEFORM, bool XBF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -317,7 +321,22 @@ igemm_tc_kernel(const TcParams p) {
         }
         cp_async_commit();
         // ---- A: gather 128 rows x 8 chunks ----
-        if (!DEFORM) {
+        if (!DEFORM && XBF16) {
+          // dense, bf16 activations: the 128-byte row IS the smem row -> cp.async 16 B per (row, chunk)
+          // straight into the swizzled stage (zero-fill for padding / out-of-range rows), no registers.
+          const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
+#pragma unroll
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowbase[r];
+            const int o = ti[tap * TC_BM + r];
+            const bool ok = rb >= 0 && o >= 0;
+            const __nv_bfloat16* src = ok ? xh + rb + c0 + (size_t)o * p.Cin : xh;
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            cp_async16_zfill(smem_u32(a_hi + soff), src, ok ? 16u : 0u);
+          }
+        } else if (!DEFORM) {
+          const float* xf = reinterpret_cast<const float*>(p.x);
           // dense: a row's 64 fp32 channels (256 B) are read by 16 consecutive lanes, 16 B each, so every
           // warp-wide LDG.128 covers two fully used 256-byte spans; all eight loads of a thread are
           // issued before the first conversion (memory-level parallelism); each lane then stores 4 bf16
@@ -332,7 +351,7 @@ igemm_tc_kernel(const TcParams p) {
             const long long rb = rowbase[r];
             const int o = ti[tap * TC_BM + r];
             qv[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rb >= 0 && o >= 0) qv[pass] = __ldg(reinterpret_cast<const float4*>(p.x + rb + cg + (size_t)o * p.Cin));
+            if (rb >= 0 && o >= 0) qv[pass] = __ldg(reinterpret_cast<const float4*>(xf + rb + cg + (size_t)o * p.Cin));
           }
 #pragma unroll
           for (int pass = 0; pass < TC_BM / 16; ++pass) {
@@ -348,7 +367,43 @@ igemm_tc_kernel(const TcParams p) {
               *reinterpret_cast<uint2*>(a_lo + soff) = lo;
             }
           }
+        } else if (XBF16) {
+          // deformable, bf16 activations: 8 lanes x 16 B cover a row's 64 channels; four corner reads of
+          // 8 bf16 each, blended in fp32 (sample table), repacked to bf16.
+          const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
+#pragma unroll 2
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowbase[r];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (rb >= 0) {
+              const __nv_bfloat16* xb = xh + rb + c0;
+              const float4 wv = tw[tap * TC_BM + r];
+              const int4 ov = to[tap * TC_BM + r];
+              const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.x * p.Cin));
+              const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.y * p.Cin));
+              const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.z * p.Cin));
+              const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.w * p.Cin));
+              const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w}, bw[4] = {b0.x, b0.y, b0.z, b0.w};
+              const uint32_t dw[4] = {d0.x, d0.y, d0.z, d0.w}, ew[4] = {e0.x, e0.y, e0.z, e0.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {   // bf16 -> fp32 is a 16-bit shift
+                v[2 * q] = wv.x * __uint_as_float(aw[q] << 16) + wv.y * __uint_as_float(bw[q] << 16) +
+                           wv.z * __uint_as_float(dw[q] << 16) + wv.w * __uint_as_float(ew[q] << 16);
+                v[2 * q + 1] = wv.x * __uint_as_float(aw[q] & 0xffff0000u) + wv.y * __uint_as_float(bw[q] & 0xffff0000u) +
+                               wv.z * __uint_as_float(dw[q] & 0xffff0000u) + wv.w * __uint_as_float(ew[q] & 0xffff0000u);
+              }
+            }
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            uint4 hi;
+            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+          }
         } else {
+          const float* xf = reinterpret_cast<const float*>(p.x);
           // deformable: same coalesced lane mapping; per (row, 4-channel group) four 16-byte corner reads,
           // blended in fp32 with the tile's sample table (weights already carry validity and the v2 mask).
           const int l16 = gt & 15;
@@ -360,7 +415,7 @@ igemm_tc_kernel(const TcParams p) {
             const long long rb = rowbase[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rb >= 0) {
-              const float* xb = p.x + rb + cg;
+              const float* xb = xf + rb + cg;
               const float4 wv = tw[tap * TC_BM + r];
               const int4 ov = to[tap * TC_BM + r];
               const float4 a0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)ov.x * p.Cin));
@@ -384,6 +439,7 @@ igemm_tc_kernel(const TcParams p) {
             }
           }
         }
+        cp_async_commit();
         cp_async_wait_all();
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -431,8 +487,7 @@ igemm_tc_kernel(const TcParams p) {
   } else {
     // =============================== EPILOGUE (warps 0-3) ===============================
     const int q = warp;  // TMEM lane quadrant
-    const bool vec_ptrs_ok = (!p.bias || (((uintptr_t)p.bias) & 15) == 0) &&
-                             (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
+    const bool vec_ptrs_ok = (((uintptr_t)p.y) & 15) == 0 && (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
     uint32_t ti_local = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
       const long long p0 = (tile / n_tiles) * TC_BM;
@@ -452,35 +507,73 @@ igemm_tc_kernel(const TcParams p) {
         if (!row_ok) continue;
         const int co0 = n0 + col;
         if (co0 >= p.Cout) continue;
-        if (p.out_nhwc) {
-          float* yo = p.y + (size_t)pg * p.Cout + co0;
-          const float* ro = p.residual ? p.residual + (size_t)pg * p.Cout + co0 : nullptr;
-          if (co0 + 15 < p.Cout && (p.Cout & 3) == 0 && vec_ptrs_ok) {
+        float o16[16];
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              float4 o;
-              o.x = __uint_as_float(rr[g4 * 4 + 0]); o.y = __uint_as_float(rr[g4 * 4 + 1]);
-              o.z = __uint_as_float(rr[g4 * 4 + 2]); o.w = __uint_as_float(rr[g4 * 4 + 3]);
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + g4 * 4));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
+        for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(rr[e]);
+        if (p.bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) if (co0 + e < p.Cout) o16[e] += __ldg(p.bias + co0 + e);
+        }
+        if (p.out_nhwc) {
+          const size_t oidx = (size_t)pg * p.Cout + co0;
+          const bool full = (co0 + 15 < p.Cout) && ((p.Cout & 7) == 0) && vec_ptrs_ok;
+          if (p.y_bf16) {
+            __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + oidx;
+            const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + oidx : nullptr;
+            if (full) {
               if (ro) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(ro + g4 * 4));
-                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  o16[2 * q] += __uint_as_float(rw[q] << 16);
+                  o16[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                }
               }
-              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(yo + g4 * 4) = o;
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o16[e] = fmaxf(o16[e], 0.f);
+              }
+              uint4 w0, w1;
+              w0.x = pack_bf16x2(o16[0], o16[1]); w0.y = pack_bf16x2(o16[2], o16[3]);
+              w0.z = pack_bf16x2(o16[4], o16[5]); w0.w = pack_bf16x2(o16[6], o16[7]);
+              w1.x = pack_bf16x2(o16[8], o16[9]); w1.y = pack_bf16x2(o16[10], o16[11]);
+              w1.z = pack_bf16x2(o16[12], o16[13]); w1.w = pack_bf16x2(o16[14], o16[15]);
+              reinterpret_cast<uint4*>(yo)[0] = w0;
+              reinterpret_cast<uint4*>(yo)[1] = w1;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (co0 + e >= p.Cout) break;
+                float o = o16[e];
+                if (ro) o += __bfloat162float(ro[e]);
+                if (p.relu) o = fmaxf(o, 0.f);
+                yo[e] = __float2bfloat16_rn(o);
+              }
             }
           } else {
+            float* yo = reinterpret_cast<float*>(p.y) + oidx;
+            const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + oidx : nullptr;
+            if (full) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (co0 + e >= p.Cout) break;
-              float o = __uint_as_float(rr[e]);
-              if (p.bias) o += __ldg(p.bias + co0 + e);
-              if (ro) o += __ldg(ro + e);
-              if (p.relu) o = fmaxf(o, 0.f);
-              yo[e] = o;
+              for (int g4 = 0; g4 < 4; ++g4) {
+                float4 o = make_float4(o16[g4 * 4], o16[g4 * 4 + 1], o16[g4 * 4 + 2], o16[g4 * 4 + 3]);
+                if (ro) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(ro + g4 * 4));
+                  o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                }
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(yo + g4 * 4) = o;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (co0 + e >= p.Cout) break;
+                float o = o16[e];
+                if (ro) o += __ldg(ro + e);
+                if (p.relu) o = fmaxf(o, 0.f);
+                yo[e] = o;
+              }
             }
           }
         } else {  // NCHW: for a fixed cout the 32 lanes of a warp write 32 consecutive pixels
@@ -489,11 +582,16 @@ igemm_tc_kernel(const TcParams p) {
             const int co = co0 + e;
             if (co >= p.Cout) break;
             const size_t oidx = ((size_t)n_img * p.Cout + co) * HoWo + pp;
-            float o = __uint_as_float(rr[e]);
-            if (p.bias) o += __ldg(p.bias + co);
-            if (p.residual) o += __ldg(p.residual + oidx);
-            if (p.relu) o = fmaxf(o, 0.f);
-            p.y[oidx] = o;
+            float o = o16[e];
+            if (p.y_bf16) {
+              if (p.residual) o += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[oidx]);
+              if (p.relu) o = fmaxf(o, 0.f);
+              reinterpret_cast<__nv_bfloat16*>(p.y)[oidx] = __float2bfloat16_rn(o);
+            } else {
+              if (p.residual) o += __ldg(reinterpret_cast<const float*>(p.residual) + oidx);
+              if (p.relu) o = fmaxf(o, 0.f);
+              reinterpret_cast<float*>(p.y)[oidx] = o;
+            }
           }
         }
       }
@@ -583,12 +681,20 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
   static bool configured = false;
   if (!configured) {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  if (deform) igemm_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
-  else igemm_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
+  if (p.x_bf16) {
+    if (p.x3) return UPSNET_E_UNSUPPORTED;   // the hi/lo split needs fp32 activations
+    if (deform) igemm_tc_kernel<true, true><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(p);
+  } else {
+    if (deform) igemm_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(p);
+  }
   UPS_CHECK_LAUNCH();
   return 0;
 }

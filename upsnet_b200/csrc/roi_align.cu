@@ -10,12 +10,14 @@
 //   NHWC  (engine layout): one CTA per (roi, ph), lanes over channels -> every bilinear tap is
 //         one contiguous C*4-byte read and every output write is coalesced.
 // HBM-bound gather: algorithmic bytes = 4*R*C*PH*PW (write) + unique feature reads.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ups {
 
 struct FpnFeats {
-  const float* p[4];
+  const void* p[4];   // fp32, or bf16 for the NHWC engine layout
   int H[4], W[4];
   float scale[4];
   int nlevels;  // 1 => plain RoIAlign (level 0 always)
@@ -83,7 +85,7 @@ roi_align_nchw_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, 
     const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
     const float bsh = rh / (float)PH, bsw = rw / (float)PW;
     const int gh = sr > 0 ? sr : (int)ceilf(rh / PH), gw = sr > 0 ? sr : (int)ceilf(rw / PW);
-    const float* d = f.p[lv] + ((size_t)b * C + c) * H * W;
+    const float* d = reinterpret_cast<const float*>(f.p[lv]) + ((size_t)b * C + c) * H * W;
     float acc = 0.f;
     for (int iy = 0; iy < gh; ++iy) {
       const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
@@ -118,7 +120,7 @@ roi_align_nhwc_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, 
   const float bsh = rh / (float)PH, bsw = rw / (float)PW;
   const int gh = sr > 0 ? sr : (int)ceilf(rh / PH), gw = sr > 0 ? sr : (int)ceilf(rw / PW);
   const float inv_count_div = (float)(gh * gw);
-  const float* base = f.p[lv] + (size_t)b * H * W * C;
+  const float* base = reinterpret_cast<const float*>(f.p[lv]) + (size_t)b * H * W * C;
   for (int c = threadIdx.x * VEC; c < C; c += blockDim.x * VEC) {
     for (int pw = 0; pw < PW; ++pw) {
       float acc[VEC];
@@ -159,11 +161,71 @@ roi_align_nhwc_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, 
   }
 }
 
-static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, const float* rois, int R,
-                            int PH, int PW, int sr, float* out, int* levels_out,
+// NHWC, bf16 features in / bf16 out (engine layout when activations are stored as bf16): lanes over channel
+// quads (8-byte loads), fp32 accumulation, same sample arithmetic.
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_bf16_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, int PH, int PW, int sr,
+                           __nv_bfloat16* __restrict__ out, int* __restrict__ levels_out) {
+  const int n = blockIdx.x / PH, ph = blockIdx.x % PH;
+  const float* r = rois + (size_t)n * 5;
+  const int b = (int)roundf(r[0]);
+  const float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+  const int lv = f.nlevels > 1 ? fpn_level_of(rx1, ry1, rx2, ry2) : 0;
+  if (levels_out && ph == 0 && threadIdx.x == 0) levels_out[n] = lv;
+  const int H = f.H[lv], W = f.W[lv];
+  const float sc = f.scale[lv];
+  const float rsw = rx1 * sc, rsh = ry1 * sc, rew = rx2 * sc, reh = ry2 * sc;
+  const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
+  const float bsh = rh / (float)PH, bsw = rw / (float)PW;
+  const int gh = sr > 0 ? sr : (int)ceilf(rh / PH), gw = sr > 0 ? sr : (int)ceilf(rw / PW);
+  const float cnt = (float)(gh * gw);
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(f.p[lv]) + (size_t)b * H * W * C;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    for (int pw = 0; pw < PW; ++pw) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int iy = 0; iy < gh; ++iy) {
+        const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          const float x = rsw + pw * bsw + (float)(ix + .5f) * bsw / (float)gw;
+          const SamplePos s = roi_sample(H, W, y, x);
+          const uint2 v00 = __ldg(reinterpret_cast<const uint2*>(base + (size_t)s.o00 * C + c));
+          const uint2 v01 = __ldg(reinterpret_cast<const uint2*>(base + (size_t)s.o01 * C + c));
+          const uint2 v10 = __ldg(reinterpret_cast<const uint2*>(base + (size_t)s.o10 * C + c));
+          const uint2 v11 = __ldg(reinterpret_cast<const uint2*>(base + (size_t)s.o11 * C + c));
+          const uint32_t a[2] = {v00.x, v00.y}, bq[2] = {v01.x, v01.y}, d[2] = {v10.x, v10.y}, e[2] = {v11.x, v11.y};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            acc[2 * q] += (s.w00 * __uint_as_float(a[q] << 16) + s.w01 * __uint_as_float(bq[q] << 16) +
+                           s.w10 * __uint_as_float(d[q] << 16) + s.w11 * __uint_as_float(e[q] << 16));
+            acc[2 * q + 1] += (s.w00 * __uint_as_float(a[q] & 0xffff0000u) + s.w01 * __uint_as_float(bq[q] & 0xffff0000u) +
+                               s.w10 * __uint_as_float(d[q] & 0xffff0000u) + s.w11 * __uint_as_float(e[q] & 0xffff0000u));
+          }
+        }
+      }
+      __nv_bfloat162 o0 = __floats2bfloat162_rn(acc[0] / cnt, acc[1] / cnt), o1 = __floats2bfloat162_rn(acc[2] / cnt, acc[3] / cnt);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&o0); w.y = *reinterpret_cast<uint32_t*>(&o1);
+      *reinterpret_cast<uint2*>(out + (((size_t)n * PH + ph) * PW + pw) * C + c) = w;
+    }
+  }
+}
+
+static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, int dtype, const float* rois, int R,
+                            int PH, int PW, int sr, void* out_v, int* levels_out,
                             cudaStream_t stream) {
   if (R < 0 || C <= 0 || PH <= 0 || PW <= 0 || B <= 0) return UPSNET_E_BADARG;
   if (R == 0) return 0;
+  if (dtype == UPSNET_DTYPE_BF16) {
+    if (layout != UPSNET_LAYOUT_NHWC || (C & 3)) return UPSNET_E_UNSUPPORTED;
+    for (int l = 0; l < f.nlevels; ++l) if (((uintptr_t)f.p[l]) & 7) return UPSNET_E_BADARG;
+    if (((uintptr_t)out_v) & 7) return UPSNET_E_BADARG;
+    const int threads = C / 4 < 32 ? 32 : (C / 4 > 256 ? 256 : (C / 4 + 31) / 32 * 32);
+    roi_align_nhwc_bf16_kernel<<<R * PH, threads, 0, stream>>>(f, C, rois, R, PH, PW, sr, (__nv_bfloat16*)out_v, levels_out);
+    UPS_CHECK_LAUNCH();
+    return 0;
+  }
+  if (dtype != UPSNET_DTYPE_F32) return UPSNET_E_BADARG;
+  float* out = reinterpret_cast<float*>(out_v);
   if (layout == UPSNET_LAYOUT_NCHW) {
     const long long total = (long long)R * C * PH * PW;
     long long blocks = (total + 255) / 256;
@@ -192,21 +254,21 @@ static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, const f
 
 }  // namespace ups
 
-extern "C" int upsnet_roi_align_forward(const float* feat, int B, int C, int H, int W, int layout,
+extern "C" int upsnet_roi_align_forward(const void* feat, int B, int C, int H, int W, int layout, int dtype,
                                         const float* rois, int R, int PH, int PW,
-                                        int sampling_ratio, float spatial_scale, float* out,
+                                        int sampling_ratio, float spatial_scale, void* out,
                                         void* stream) {
   if (!feat || !out || (!rois && R > 0)) return UPSNET_E_BADARG;
   ups::FpnFeats f{};
   f.p[0] = feat; f.H[0] = H; f.W[0] = W; f.scale[0] = spatial_scale; f.nlevels = 1;
-  return ups::launch_roi_align(f, B, C, layout, rois, R, PH, PW, sampling_ratio, out, nullptr,
+  return ups::launch_roi_align(f, B, C, layout, dtype, rois, R, PH, PW, sampling_ratio, out, nullptr,
                                (cudaStream_t)stream);
 }
 
-extern "C" int upsnet_roi_align_fpn_forward(const float* const feats[4], const int Hs[4],
+extern "C" int upsnet_roi_align_fpn_forward(const void* const feats[4], const int Hs[4],
                                             const int Ws[4], const float scales[4], int B, int C,
-                                            int layout, const float* rois, int R, int PH, int PW,
-                                            int sampling_ratio, float* out, int* levels_out,
+                                            int layout, int dtype, const float* rois, int R, int PH, int PW,
+                                            int sampling_ratio, void* out, int* levels_out,
                                             void* stream) {
   if (!feats || !Hs || !Ws || !scales || !out || (!rois && R > 0)) return UPSNET_E_BADARG;
   ups::FpnFeats f{};
@@ -215,6 +277,6 @@ extern "C" int upsnet_roi_align_fpn_forward(const float* const feats[4], const i
     f.p[l] = feats[l]; f.H[l] = Hs[l]; f.W[l] = Ws[l]; f.scale[l] = scales[l];
   }
   f.nlevels = 4;
-  return ups::launch_roi_align(f, B, C, layout, rois, R, PH, PW, sampling_ratio, out, levels_out,
+  return ups::launch_roi_align(f, B, C, layout, dtype, rois, R, PH, PW, sampling_ratio, out, levels_out,
                                (cudaStream_t)stream);
 }

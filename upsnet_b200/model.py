@@ -202,8 +202,8 @@ class FPN(nn.Module):
     def forward(self, res2, res3, res4, res5):
         p5_1x1 = self._c(self.fpn_p5_1x1, res5)
         if hasattr(self, "fpn_gap"):
-            gap = ops.linear(res5.mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias)
-            p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1)
+            gap = ops.linear(res5.float().mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias)
+            p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1).to(p5_1x1.dtype)
         up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")  # noqa: E731
         p4_plus = self._c(self.fpn_p4_1x1, res4, residual=up(p5_1x1))   # lateral + top-down fused
         p3_plus = self._c(self.fpn_p3_1x1, res3, residual=up(p4_plus))
@@ -238,6 +238,7 @@ class RPN(nn.Module):
         c = self.conv_proposal[0]
         t = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
         both = ops.conv2d(t, self._f[0], self._f[1], out_format="nchw")
+        both = both.float()
         cls_score, bbox_pred = both[:, :self.num_anchors], both[:, self.num_anchors:]
         return cls_score, bbox_pred, torch.sigmoid(cls_score)
 
@@ -272,7 +273,7 @@ class RCNN(nn.Module):
         x = pool.reshape(pool.size(0), -1)
         fc6 = ops.linear(x, self.fc6[0].weight, self.fc6[0].bias, relu=True)
         fc7 = ops.linear(fc6, self.fc7[0].weight, self.fc7[0].bias, relu=True)
-        both = ops.linear(fc7, self._f[0], self._f[1])
+        both = ops.linear(fc7, self._f[0], self._f[1], out_dtype=torch.float32).float()
         return {"cls_score": both[:, :self.num_classes].contiguous(),
                 "bbox_pred": both[:, self.num_classes:].contiguous(), "fc_feat": fc7}
 
@@ -438,16 +439,16 @@ class resnet_upsnet(nn.Module):
             rpn_cls_prob.append(prob)
             rpn_bbox_pred.append(bbox)
         rois, _, roi_valid = self.pyramid_proposal_static(rpn_cls_prob, rpn_bbox_pred, im_info)
-        fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"]
+        fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
         feats = [p2, p3, p4, p5]
         rcnn_output = self.rcnn(feats, rois)
-        cls_prob = F.softmax(rcnn_output["cls_score"], dim=1)
-        bbox_pred = rcnn_output["bbox_pred"]
+        cls_prob = F.softmax(rcnn_output["cls_score"].float(), dim=1)
+        bbox_pred = rcnn_output["bbox_pred"].float()
         s1, b1, c1, n1 = self.mask_roi_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
-        mask_prob = torch.sigmoid(self.mask_branch(feats, b1))
+        mask_prob = torch.sigmoid(self.mask_branch(feats, b1).float())
         s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
         ms = self.cfg.mask_size
-        mask_score = self.mask_branch(feats, b2).gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
+        mask_score = self.mask_branch(feats, b2).float().gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
         keep, labels, sem, k = ops.panoptic_fuse(fcn_output, b2[:, 1:], s2, mask_score, c2, self.panoptic_head.num_stuff,
                                                  self.panoptic_head.fraction_threshold, want_sem=True,
                                                  n_dev=n2.reshape(1))
@@ -459,7 +460,7 @@ class resnet_upsnet(nn.Module):
     def _run_static(self, x, im_info):
         if not (self.use_cuda_graph and x.is_cuda):
             return self._forward_static(x, im_info), None
-        key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], tuple(float(v) for v in im_info))
+        key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], ops.ACT_BF16["on"], tuple(float(v) for v in im_info))
         ent = self._graphs.get(key)
         if ent is None:
             static_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)

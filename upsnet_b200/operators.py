@@ -29,11 +29,15 @@ from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
 
 # default arithmetic of the convolution tiles; switched by upsnet_b200.set_precision()
 _PRECISION = {"conv": _lib.PREC_FP32_SIMT}
+ACT_BF16 = {"on": False}   # engine switch: store activations as bf16 (precision 'bf16' only)
 
 
-def set_precision(name):
-    """'fp32' (CUDA-core fp32 tiles), 'bf16x3' or 'bf16' (tcgen05 tiles)."""
+def set_precision(name, bf16_activations=None):
+    """'fp32' (CUDA-core fp32 tiles), 'bf16x3' or 'bf16' (tcgen05 tiles).  With 'bf16' the engine also stores
+    the NHWC activation stream as bf16 (halves HBM traffic; the gather becomes a cp.async copy) unless
+    bf16_activations=False."""
     _PRECISION["conv"] = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.PREC_BF16}[name]
+    ACT_BF16["on"] = (name == "bf16") if bf16_activations is None else (bool(bf16_activations) and name == "bf16")
 
 
 # launch accounting (bench.py reports gpu_launches) and optional per-call CUDA-event timing of the
@@ -106,31 +110,42 @@ def _tc_ok(Cin, kh, kw, dg):
     return Cin % 64 == 0 and dg == 1 and kh * kw <= 49
 
 
-def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format):
-    """upsnet_igemm_forward: x logical NCHW (any memory format), result logical NCHW whose storage is
-    NHWC (channels_last view, the engine layout) unless out_format == 'nchw'."""
+def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format,
+              out_dtype=None):
+    """upsnet_igemm_forward: x logical NCHW (any memory format; fp32 or bf16), result logical NCHW whose
+    storage is NHWC (channels_last view, the engine layout) unless out_format == 'nchw'.
+    Output dtype: bf16 when the engine stores bf16 activations (ACT_BF16) and the result stays in the
+    NHWC activation stream; fp32 for plane-wise (NCHW) head outputs or when asked via out_dtype."""
     sh, sw = stride; ph, pw = padding; dh, dw = dilation
     N, Cin, H, W = x.shape
     Cout, _, kh, kw = weight.shape
     Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
-    xs = _nhwc(x if x.dtype == torch.float32 else x.float())
-    packed = _packed_weight(weight)
     nhwc_out = out_format != "nchw"
+    if prec == _lib.PREC_BF16X3 and x.dtype != torch.float32:
+        x = x.float()                                      # the hi/lo split needs fp32 activations
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if out_dtype is None:
+        out_dtype = torch.bfloat16 if (ACT_BF16["on"] and prec == _lib.PREC_BF16 and nhwc_out) else torch.float32
+    xs = _nhwc(x)
+    packed = _packed_weight(weight)
     if nhwc_out:
-        store = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+        store = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=out_dtype)
         y = store.permute(0, 3, 1, 2)
-        res = None if residual is None else _nhwc(residual.float())
+        res = None if residual is None else _nhwc(residual.to(out_dtype))
     else:
-        store = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+        store = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=out_dtype)
         y = store
-        res = None if residual is None else f32c(residual)
+        res = None if residual is None else residual.to(out_dtype).contiguous()
     work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * (3 if prec == _lib.PREC_BF16X3 else 1),
             "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
-            "bytes": 4.0 * (x.numel() + weight.numel() + store.numel() * (2 if residual is not None else 1))}
+            "bytes": float(x.numel() * x.element_size() + 4 * weight.numel() +
+                           store.numel() * store.element_size() * (2 if residual is not None else 1))}
     with torch.cuda.device(x.device), _Timed(kind, 1, work, x.device):
         check(lib().upsnet_igemm_forward(ptr(xs), ptr(offset), ptr(mask), ptr(packed), ptr(bias), ptr(res),
                                          ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
                                          _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW,
+                                         1 if xs.dtype == torch.bfloat16 else 0, 1 if out_dtype == torch.bfloat16 else 0,
                                          _lib.EPI_RELU if relu else 0, prec, stream_ptr(x.device)), kind)
     return y
 
@@ -139,14 +154,14 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
 # functional layer
 # ------------------------------------------------------------------------------------------------
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-           out_format=None):
+           out_format=None, out_dtype=None):
     """Dense conv + fused bias / residual / ReLU epilogue.  fp32 precision -> upsnet_conv2d_forward
     (NCHW CUDA-core tiles); bf16x3 / bf16 -> upsnet_igemm_forward (tcgen05 tiles, NHWC storage)."""
     require_cuda(x, weight, bias, residual)
     prec = _PRECISION["conv"] if precision is None else precision
     if prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], 1):
         return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
-                         _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format)
+                         _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype)
     x, weight = f32c(x), f32c(weight)
     bias = None if bias is None else f32c(bias)
     residual = None if residual is None else f32c(residual)
@@ -168,16 +183,30 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
     return y
 
 
-def linear(x, weight, bias=None, relu=False, precision=None):
+def linear(x, weight, bias=None, relu=False, precision=None, out_dtype=None):
     """y = x @ weight.T + bias as a 1x1 convolution over N 'images' of 1x1 pixels."""
     N, K = x.shape
-    y = conv2d(x.reshape(N, K, 1, 1), weight.reshape(weight.shape[0], K, 1, 1), bias, relu=relu,
-               precision=precision)
+    y = conv2d(x.reshape(N, K, 1, 1), _as_1x1(weight), bias, relu=relu, precision=precision, out_dtype=out_dtype)
     return y.reshape(N, weight.shape[0])
 
 
+_view_cache = {}
+
+
+def _as_1x1(weight):
+    """[Cout,K] -> [Cout,K,1,1] view, cached per weight tensor so the packed-weight cache (keyed on tensor
+    identity) hits on every call."""
+    hit = _view_cache.get(id(weight))
+    if hit is not None and hit[0]() is weight:
+        return hit[1]
+    v = weight.reshape(weight.shape[0], weight.shape[1], 1, 1)
+    wid = id(weight)
+    _view_cache[wid] = (weakref.ref(weight, lambda _r, _k=wid: _view_cache.pop(_k, None)), v)
+    return v
+
+
 def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1, deformable_groups=1,
-                mask=None, relu=False, precision=None, out_format=None):
+                mask=None, relu=False, precision=None, out_format=None, out_dtype=None):
     """DeformConvFunction.forward (functions/deform_conv.py:26-57); with `mask` (already 2*sigmoid)
     ModDeformConvFunction.forward (functions/mod_deform_conv.py:25-59).  One fused launch."""
     require_cuda(data, offset, weight, bias, mask)
@@ -195,7 +224,7 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
         if mask is not None:
             assert tuple(mask.shape) == (N, kh * kw, Ho, Wo), mask.shape
         return _igemm_tc("dcn", data, offset, mask, weight, bias, None, (sh, sw), (ph, pw), (dh, dw), relu, prec,
-                         out_format)
+                         out_format, out_dtype)
     data, weight = f32c(data), f32c(weight)
     N, Cin, H, W = data.shape
     Cout, Cin_w, kh, kw = weight.shape
@@ -233,7 +262,7 @@ def roi_align(features, rois, pooled_height, pooled_width, spatial_scale, sampli
     if R == 0:
         return out
     with torch.cuda.device(features.device), _Timed("roi_align", 1, {"bytes": 4.0 * out.numel()}, features.device):
-        check(lib().upsnet_roi_align_forward(ptr(features), B, Cc, H, W, lay, ptr(rois), R, pooled_height,
+        check(lib().upsnet_roi_align_forward(ptr(features), B, Cc, H, W, lay, 0, ptr(rois), R, pooled_height,
                                              pooled_width, sampling_ratio, float(spatial_scale), ptr(out),
                                              stream_ptr(features.device)), "roi_align")
     return out
@@ -255,7 +284,9 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
                                 spatial_scales, sampling_ratio, "nhwc", return_levels)
             return (out[0].permute(0, 3, 1, 2), out[1]) if return_levels else out.permute(0, 3, 1, 2)
         layout = "nchw"
-    feats = [f32c(f) for f in feats]
+    bf16 = layout == "nhwc" and all(f.dtype == torch.bfloat16 for f in feats)
+    feats = [f.contiguous() for f in feats] if bf16 else [f32c(f) for f in feats]
+    odt = torch.bfloat16 if bf16 else torch.float32
     if layout == "nchw":
         B, Cc = feats[0].shape[0], feats[0].shape[1]
         Hs = [f.shape[2] for f in feats]; Ws = [f.shape[3] for f in feats]
@@ -264,14 +295,14 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
     else:
         B, Cc = feats[0].shape[0], feats[0].shape[3]
         Hs = [f.shape[1] for f in feats]; Ws = [f.shape[2] for f in feats]
-        out = torch.empty((R, pooled_height, pooled_width, Cc), device=rois.device, dtype=torch.float32)
+        out = torch.empty((R, pooled_height, pooled_width, Cc), device=rois.device, dtype=odt)
         lay = _lib.LAYOUT_NHWC
     levels = torch.empty((R,), device=rois.device, dtype=torch.int32) if return_levels else None
     fp = (C.c_void_p * 4)(*[f.data_ptr() for f in feats])
     hs = (C.c_int * 4)(*Hs); ws = (C.c_int * 4)(*Ws)
     sc = (C.c_float * 4)(*[float(s) for s in spatial_scales])
     with torch.cuda.device(rois.device), _Timed("roi_align_fpn", 1, {"bytes": 4.0 * out.numel()}, rois.device):
-        check(lib().upsnet_roi_align_fpn_forward(fp, hs, ws, sc, B, Cc, lay, ptr(rois), R, pooled_height,
+        check(lib().upsnet_roi_align_fpn_forward(fp, hs, ws, sc, B, Cc, lay, 1 if bf16 else 0, ptr(rois), R, pooled_height,
                                                  pooled_width, sampling_ratio, ptr(out), ptr(levels),
                                                  stream_ptr(rois.device)), "fpn_roi_align")
     return (out, levels) if return_levels else out
