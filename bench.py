@@ -231,6 +231,18 @@ def main():
         f["ms"] += a.elapsed_time(b); f["calls"] += 1
         f["flops"] += work.get("flops", 0.0); f["bytes"] += work.get("bytes", 0.0)
     pk = peaks()
+    layer_path = os.environ.get("UPSNET_LAYER_TABLE")
+    if layer_path and rank == 0:      # per-layer table of the conv family (eager trace, CUDA events per call)
+        per = {}
+        for kind, a, b, work in trace:
+            if "shape" in work:
+                e = per.setdefault((kind, work["shape"]), [0, 0.0, work["algo_flops"], work["bytes"]])
+                e[0] += 1; e[1] += a.elapsed_time(b)
+        with open(layer_path, "w") as fh:
+            fh.write("| kernel | layer shape | calls/step | ms/call | TFLOP/s | GB/s |\n|---|---|---:|---:|---:|---:|\n")
+            for (kind, shape), (cnt, ms_, fl, by) in sorted(per.items(), key=lambda kv: -kv[1][1]):
+                mc = ms_ / cnt
+                fh.write("| %s | %s | %.1f | %.4f | %.1f | %.0f |\n" % (kind, shape, cnt / n_trace, mc, fl / mc / 1e9, by / mc / 1e6))
     tot_ms = sum(f["ms"] for f in fam.values())
     conv = {"ms": fam.get("conv2d", {"ms": 0})["ms"] + fam.get("dcn", {"ms": 0})["ms"],
             "flops": fam.get("conv2d", {"flops": 0})["flops"] + fam.get("dcn", {"flops": 0})["flops"],

@@ -31,6 +31,7 @@ extern "C" {
 
 /* epilogue flags for the convolution entry points */
 #define UPSNET_EPI_RELU 1
+#define UPSNET_EPI_RES_UP2 2 /* upsnet_igemm_forward only: residual is [N,Ho/2,Wo/2,Cout], read with nearest 2x upsampling */
 
 /* precision of the tensor-core convolution path */
 #define UPSNET_PREC_FP32_SIMT 0 /* fp32 FFMA tiles (exact-order-free fp32)            */

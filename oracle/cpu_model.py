@@ -17,10 +17,10 @@ from . import oracle as O
 
 
 def _conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-            out_format=None, out_dtype=None):
+            out_format=None, out_dtype=None, residual_up2=False):
     y = F.conv2d(x.float(), weight.float(), None if bias is None else bias.float(), stride, padding, dilation)
     if residual is not None:
-        y = y + residual
+        y = y + (F.interpolate(residual, scale_factor=2, mode="nearest") if residual_up2 else residual)
     return F.relu(y) if relu else y
 
 

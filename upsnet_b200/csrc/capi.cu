@@ -18,6 +18,7 @@ struct TcParams {
   int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
   int relu, out_nhwc, BN, stages, x3;
   int x_bf16, y_bf16;
+  int res_up2;
 };
 size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
 int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream);
@@ -122,6 +123,8 @@ extern "C" int upsnet_igemm_forward(const void* x_nhwc, const float* offset, con
   if (p.Ho <= 0 || p.Wo <= 0) return UPSNET_E_BADARG;
   p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
   p.out_nhwc = out_layout == UPSNET_LAYOUT_NHWC;
+  p.res_up2 = (epi_flags & UPSNET_EPI_RES_UP2) ? 1 : 0;
+  if (p.res_up2 && (!residual || !p.out_nhwc || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_BADARG;
   p.x3 = precision == UPSNET_PREC_BF16X3;
   if ((x_dtype != UPSNET_DTYPE_F32 && x_dtype != UPSNET_DTYPE_BF16) || (y_dtype != UPSNET_DTYPE_F32 && y_dtype != UPSNET_DTYPE_BF16))
     return UPSNET_E_BADARG;

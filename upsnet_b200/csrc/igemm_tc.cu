@@ -48,6 +48,7 @@ struct TcParams {
   int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
   int relu, out_nhwc, BN, stages, x3;
   int x_bf16, y_bf16;    // activation storage: 0 = fp32, 1 = bf16 (x / y+residual)
+  int res_up2;           // residual is a half-resolution NHWC map read with nearest-neighbour 2x upsampling
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -516,10 +517,17 @@ igemm_tc_kernel(const TcParams p) {
         }
         if (p.out_nhwc) {
           const size_t oidx = (size_t)pg * p.Cout + co0;
+          // FPN top-down path (models/fpn.py:88-93): lateral conv + nearest-2x-upsampled coarser map, fused:
+          // the residual is indexed at (ho/2, wo/2) of the half-resolution tensor instead of being materialised.
+          size_t ridx = oidx;
+          if (p.res_up2) {
+            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+            ridx = (((size_t)n_img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + co0;
+          }
           const bool full = (co0 + 15 < p.Cout) && ((p.Cout & 7) == 0) && vec_ptrs_ok;
           if (p.y_bf16) {
             __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + oidx;
-            const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + oidx : nullptr;
+            const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx : nullptr;
             if (full) {
               if (ro) {
                 const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
@@ -553,7 +561,7 @@ igemm_tc_kernel(const TcParams p) {
             }
           } else {
             float* yo = reinterpret_cast<float*>(p.y) + oidx;
-            const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + oidx : nullptr;
+            const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + ridx : nullptr;
             if (full) {
 #pragma unroll
               for (int g4 = 0; g4 < 4; ++g4) {

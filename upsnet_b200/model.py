@@ -196,18 +196,18 @@ class FPN(nn.Module):
                 m.bias.data.zero_()
 
     @staticmethod
-    def _c(m, x, residual=None, padding=0):
-        return ops.conv2d(x, m.weight, m.bias, padding=padding, residual=residual)
+    def _c(m, x, residual=None, padding=0, up2=False):
+        return ops.conv2d(x, m.weight, m.bias, padding=padding, residual=residual, residual_up2=up2)
 
     def forward(self, res2, res3, res4, res5):
         p5_1x1 = self._c(self.fpn_p5_1x1, res5)
         if hasattr(self, "fpn_gap"):
             gap = ops.linear(res5.float().mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias)
             p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1).to(p5_1x1.dtype)
-        up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")  # noqa: E731
-        p4_plus = self._c(self.fpn_p4_1x1, res4, residual=up(p5_1x1))   # lateral + top-down fused
-        p3_plus = self._c(self.fpn_p3_1x1, res3, residual=up(p4_plus))
-        p2_plus = self._c(self.fpn_p2_1x1, res2, residual=up(p3_plus))
+        # lateral 1x1 + nearest-2x-upsampled coarser level, fused into the conv epilogue (no upsampled tensor)
+        p4_plus = self._c(self.fpn_p4_1x1, res4, residual=p5_1x1, up2=True)
+        p3_plus = self._c(self.fpn_p3_1x1, res3, residual=p4_plus, up2=True)
+        p2_plus = self._c(self.fpn_p2_1x1, res2, residual=p3_plus, up2=True)
         p5 = self._c(self.fpn_p5, p5_1x1, padding=1)
         p4 = self._c(self.fpn_p4, p4_plus, padding=1)
         p3 = self._c(self.fpn_p3, p3_plus, padding=1)
@@ -358,9 +358,29 @@ class FCNHead(nn.Module):
         self.score = nn.Conv2d(512, num_classes, 1)
         nn.init.normal_(self.score.weight.data, 0, 0.01)
         self.score.bias.data.zero_()
+        self.fuse_score = True   # inference: score each level at its own resolution (see forward)
+        self._f = None
+
+    def prepare(self):
+        w = self.score.weight.detach()
+        self._f = [w[:, 128 * l:128 * (l + 1)].contiguous() for l in range(4)]
 
     def forward(self, p2, p3, p4, p5):
         p2, p3, p4, p5 = (self.fcn_subnet(p) for p in (p2, p3, p4, p5))
+        if self.fuse_score and self._f is not None:
+            # models/fcn.py:94-101 computes score(cat(p2, up2(p3), up4(p4), up8(p5))).  The 1x1 score conv and the
+            # bilinear upsampling are both linear and act on different axes, so they commute:
+            #   score = W2*p2 + up2(W3*p3) + up4(W4*p4) + up8(W5*p5) + b
+            # -- identical up to fp32 reassociation, and the three 128-channel upsampled maps plus the
+            # 512-channel concat (0.5 GB of traffic at 1024x2048) are never built.
+            score = ops.conv2d(p2, self._f[0], self.score.bias, out_format="nchw").float()
+            for l, feat in enumerate((p3, p4, p5), start=1):
+                s_l = ops.conv2d(feat, self._f[l], None, out_format="nchw").float()
+                score = score + F.interpolate(s_l, None, 2 ** l, mode="bilinear", align_corners=False)
+            ret = {"fcn_score": score}
+            if self.upsample_rate != 1:
+                ret["fcn_output"] = F.interpolate(score, None, self.upsample_rate, mode="bilinear", align_corners=False)
+            return ret
         p3 = F.interpolate(p3, None, 2, mode="bilinear", align_corners=False)
         p4 = F.interpolate(p4, None, 4, mode="bilinear", align_corners=False)
         p5 = F.interpolate(p5, None, 8, mode="bilinear", align_corners=False)

@@ -111,7 +111,7 @@ def _tc_ok(Cin, kh, kw, dg):
 
 
 def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format,
-              out_dtype=None):
+              out_dtype=None, residual_up2=False):
     """upsnet_igemm_forward: x logical NCHW (any memory format; fp32 or bf16), result logical NCHW whose
     storage is NHWC (channels_last view, the engine layout) unless out_format == 'nchw'.
     Output dtype: bf16 when the engine stores bf16 activations (ACT_BF16) and the result stays in the
@@ -139,6 +139,8 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
         res = None if residual is None else residual.to(out_dtype).contiguous()
     work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * (3 if prec == _lib.PREC_BF16X3 else 1),
             "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "shape": "N%d %dx%d Cin%d->Cout%d k%d s%d %s->%s%s" % (N, H, W, Cin, Cout, kh, sh, str(xs.dtype)[6:] if False else str(x.dtype)[6:],
+                                                              str(out_dtype)[6:], " +res" if residual is not None else ""),
             "bytes": float(x.numel() * x.element_size() + 4 * weight.numel() +
                            store.numel() * store.element_size() * (2 if residual is not None else 1))}
     with torch.cuda.device(x.device), _Timed(kind, 1, work, x.device):
@@ -146,7 +148,8 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
                                          ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
                                          _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW,
                                          1 if xs.dtype == torch.bfloat16 else 0, 1 if out_dtype == torch.bfloat16 else 0,
-                                         _lib.EPI_RELU if relu else 0, prec, stream_ptr(x.device)), kind)
+                                         (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if residual_up2 else 0),
+                                         prec, stream_ptr(x.device)), kind)
     return y
 
 
@@ -154,14 +157,19 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
 # functional layer
 # ------------------------------------------------------------------------------------------------
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-           out_format=None, out_dtype=None):
+           out_format=None, out_dtype=None, residual_up2=False):
     """Dense conv + fused bias / residual / ReLU epilogue.  fp32 precision -> upsnet_conv2d_forward
     (NCHW CUDA-core tiles); bf16x3 / bf16 -> upsnet_igemm_forward (tcgen05 tiles, NHWC storage)."""
     require_cuda(x, weight, bias, residual)
     prec = _PRECISION["conv"] if precision is None else precision
     if prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], 1):
+        if residual_up2 and out_format == "nchw":
+            residual, residual_up2 = torch.nn.functional.interpolate(residual, scale_factor=2, mode="nearest"), False
         return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
-                         _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype)
+                         _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype,
+                         residual_up2)
+    if residual_up2:   # CUDA-core path: materialise the nearest-neighbour upsampling (models/fpn.py:33-34)
+        residual = torch.nn.functional.interpolate(residual, scale_factor=2, mode="nearest")
     x, weight = f32c(x), f32c(weight)
     bias = None if bias is None else f32c(bias)
     residual = None if residual is None else f32c(residual)
