@@ -228,3 +228,30 @@ def test_engine_bf16_activation_stream(dev):
     agree = (outs[("bf16", True)]["fcn_outputs"] == outs[("fp32", False)]["fcn_outputs"]).float().mean().item()
     assert agree > 0.95, agree
     assert outs[("bf16", True)]["panoptic_outputs"].dtype == torch.int64
+
+
+def test_engine_coco_r101_dcn_config_tc(dev):
+    """BASELINE config 3 shape family (81 / 133 classes, DCN bottlenecks in res3..res5, fpn_gap, 3 semantic-head
+    layers) on the tensor-core path vs the fp32 CUDA-core path, reduced depth / resolution."""
+    import upsnet_b200 as U
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    cfg = UPSNetConfig.coco_r101_dcn()
+    m = synthetic_model(cfg, depth=(1, 2, 2, 1), seed=7, device=dev)
+    m.keep_intermediates = True
+    inp = synthetic_input(224, 320, seed=8, device=dev)
+    outs = {}
+    try:
+        for name in ("fp32", "bf16x3"):
+            U.set_precision(name)
+            with torch.no_grad():
+                outs[name] = m(inp)
+    finally:
+        U.set_precision("fp32")
+    a, b = outs["fp32"]["_intermediates"]["fcn_output"], outs["bf16x3"]["_intermediates"]["fcn_output"]
+    assert a.shape == (1, 133, 224, 320)
+    assert (a - b).abs().max() <= 2e-3 * max(1.0, float(a.abs().max()))
+    assert (outs["fp32"]["fcn_outputs"] == outs["bf16x3"]["fcn_outputs"]).float().mean().item() > 0.995
+    lab = outs["bf16x3"]["panoptic_outputs"]
+    k = outs["bf16x3"]["panoptic_cls_inds"].numel()
+    assert ((lab < 53 + k) | (lab == 255)).all()

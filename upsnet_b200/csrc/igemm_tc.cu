@@ -34,7 +34,8 @@ constexpr int TC_BK = 64;          // bf16 elements per k-block row (= 128 bytes
 constexpr int TC_GROUP = 256;       // producer threads that fill one smem stage together (8 warps)
 constexpr int TC_GROUPS = 2;        // producer groups work on alternate k-blocks (two stages in flight)
 constexpr int TC_PRODUCERS = TC_GROUP * TC_GROUPS;  // 16 warps
-constexpr int TC_EPILOGUE = 128;      // 4 warps (one per TMEM lane quadrant)
+constexpr int TC_EPILOGUE = 128;      // 4 warps: TMEM lane quadrant = warp & 3 (x TC_EPI_SPLIT column slices)
+constexpr int TC_EPI_SPLIT = TC_EPILOGUE / 128;
 constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 21 warps
 constexpr int TC_MAX_STAGES = 6;
 
@@ -111,6 +112,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -181,7 +191,7 @@ __device__ __forceinline__ void producer_bar_sync() {
 }
 
 // Persistent, warp-specialised kernel.  Roles (21 warps):
-//   warps 0-3   epilogue: TMEM -> registers -> bias/residual/ReLU -> global (warp w owns TMEM lanes 32w..)
+//   warps 0-3   epilogue: TMEM -> registers -> bias/residual/ReLU -> global (TMEM lane quadrant = warp)
 //   warp  4     MMA issuer (one elected lane), owns TMEM alloc/dealloc and barrier init
 //   warps 5-20  producers, two groups of 8 warps filling alternate k-blocks (two smem stages in flight):
 //               sample table, B via cp.async, A gather (loads issued first, then bf16 conversion)
@@ -220,7 +230,7 @@ igemm_tc_kernel(const TcParams p) {
   while ((int)tmem_cols < 2 * p.BN) tmem_cols <<= 1;
 
   // ---------------- one-time setup ----------------
-  if (warp == 4) {
+  if (warp == TC_EPILOGUE / 32) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(bar_full + 8 * s, TC_GROUP / 32);
@@ -228,7 +238,7 @@ igemm_tc_kernel(const TcParams p) {
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull + 8 * b, 1);
-        mbar_init(bar_tempty + 8 * b, 4);   // one arrive per epilogue warp
+        mbar_init(bar_tempty + 8 * b, TC_EPILOGUE / 32);   // one arrive per epilogue warp
       }
       fence_mbar_init();
     }
@@ -240,9 +250,9 @@ igemm_tc_kernel(const TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp >= 5) {
+  if (warp > TC_EPILOGUE / 32) {
     // =============================== PRODUCERS ===============================
-    const int pt = tid - 5 * 32;          // 0..511
+    const int pt = tid - (TC_EPILOGUE + 32);  // 0..511
     const int group = pt / TC_GROUP;      // which alternate k-blocks this thread fills
     const int gt = pt - group * TC_GROUP; // 0..255 inside the group
     const int j = gt & 7;                 // 16-byte chunk (8 channels) inside the 128-byte row
@@ -448,7 +458,7 @@ igemm_tc_kernel(const TcParams p) {
       }
       g0 += (uint32_t)num_kb;
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_EPILOGUE / 32) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TC_BM, p.BN);
@@ -487,7 +497,8 @@ igemm_tc_kernel(const TcParams p) {
     __syncwarp();
   } else {
     // =============================== EPILOGUE (warps 0-3) ===============================
-    const int q = warp;  // TMEM lane quadrant
+    const int q = warp & 3;        // TMEM lane quadrant
+    const int half = warp >> 2;    // which slice of the BN accumulator columns (TC_EPI_SPLIT slices)
     const bool vec_ptrs_ok = (((uintptr_t)p.y) & 15) == 0 && (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
     uint32_t ti_local = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
@@ -502,9 +513,38 @@ igemm_tc_kernel(const TcParams p) {
       const int n_img = row_ok ? (int)(pg / HoWo) : 0;
       const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
-      for (int col = 0; col < p.BN; col += 16) {
-        uint32_t rr[16];
-        tmem_ld16(trow + (uint32_t)col, rr);  // warp-collective
+      const int col_begin = half * (p.BN / TC_EPI_SPLIT), col_end = col_begin + p.BN / TC_EPI_SPLIT;
+      for (int colb = col_begin; colb < col_end; colb += 32) {
+        // two 16-column chunks per TMEM wait; the residual of both chunks is requested BEFORE the wait so that
+        // its global-memory latency overlaps the TMEM read (the epilogue is latency-, not bandwidth-bound)
+        const bool two = colb + 16 < col_end;
+        uint32_t rr2[2][16];
+        tmem_ld16_issue(trow + (uint32_t)colb, rr2[0]);          // warp-collective
+        if (two) tmem_ld16_issue(trow + (uint32_t)colb + 16u, rr2[1]);
+        uint4 pre[2][2];
+        bool has_pre[2] = {false, false};
+        if (row_ok && p.residual && p.out_nhwc && p.y_bf16 && ((p.Cout & 7) == 0) && vec_ptrs_ok) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int co0p = n0 + colb + c * 16;
+            if ((c == 0 || two) && co0p + 15 < p.Cout) {
+              size_t ridx = (size_t)pg * p.Cout + co0p;
+              if (p.res_up2) {
+                const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+                ridx = (((size_t)n_img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + co0p;
+              }
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx);
+              pre[c][0] = __ldg(rp); pre[c][1] = __ldg(rp + 1);
+              has_pre[c] = true;
+            }
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+       for (int c = 0; c < 2; ++c) {
+        if (c == 1 && !two) break;
+        const uint32_t* rr = rr2[c];
+        const int col = colb + c * 16;
         if (!row_ok) continue;
         const int co0 = n0 + col;
         if (co0 >= p.Cout) continue;
@@ -530,7 +570,8 @@ igemm_tc_kernel(const TcParams p) {
             const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx : nullptr;
             if (full) {
               if (ro) {
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
+                const uint4 r0 = has_pre[c] ? pre[c][0] : __ldg(reinterpret_cast<const uint4*>(ro));
+                const uint4 r1 = has_pre[c] ? pre[c][1] : __ldg(reinterpret_cast<const uint4*>(ro) + 1);
                 const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -602,6 +643,7 @@ igemm_tc_kernel(const TcParams p) {
             }
           }
         }
+       }
       }
       tc_fence_before();
       __syncwarp();
@@ -610,7 +652,7 @@ igemm_tc_kernel(const TcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EPILOGUE / 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -666,6 +708,10 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   int BN = p.Cout_pad;
   const int bn_cap = p.x3 ? 128 : 256;
   if (BN > bn_cap) BN = (p.Cout_pad % bn_cap == 0) ? bn_cap : ((p.Cout_pad % 128 == 0) ? 128 : 64);
+  {  // few output tiles (FC layers, coarse pyramid levels): narrower N tiles so that every SM gets work
+    const long long mt = ((long long)p.N * p.Ho * p.Wo + TC_BM - 1) / TC_BM;
+    while (BN > 64 && (BN % 32) == 0 && mt * (p.Cout_pad / BN) < kNumSMs && p.Cout_pad % (BN / 2) == 0 && ((BN / 2) % 32) == 0) BN /= 2;
+  }
   p.BN = BN;
   // One persistent CTA per SM: give the smem ring everything that is left after the sample table.
   const int num_kb = KHW * (p.Cin / TC_BK);
