@@ -113,7 +113,8 @@ int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias
 /* ---------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolution / deformable convolution (engine entry point).
  * Same arithmetic contract as upsnet_conv2d_forward / upsnet_dcn_forward, but
- *   - x is NHWC [N,H,W,Cin] (Cin % 64 == 0) stored as fp32 or bf16 (x_dtype); y and residual are NHWC or
+ *   - x is NHWC [N,H,W,Cin] (Cin % 64 == 0) stored as fp32 or bf16 (x_dtype) -- or, for a tiny Cin <= 8 (the
+ *     RGB stem), the fp32 NCHW image itself: K = kh*kw*Cin is flattened and zero-padded to a multiple of 64; y and residual are NHWC or
  *     NCHW (out_layout) stored as fp32 or bf16 (y_dtype); bf16 activations are copied by cp.async straight
  *     into the tensor-core layout (UPSNET_PREC_BF16 only: the hi/lo split needs fp32 activations),
  *   - weights are pre-packed once with upsnet_igemm_pack_weight (bf16 hi/lo planes,

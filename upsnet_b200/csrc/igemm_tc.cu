@@ -198,9 +198,13 @@ __device__ __forceinline__ void producer_bar_sync() {
 // Pipelines: smem ring full[s]/empty[s] (producers <-> MMA) runs across tiles; two TMEM accumulator
 // buffers tmem_full[b]/tmem_empty[b] (MMA <-> epilogue) overlap tile i's epilogue with tile i+1's
 // main loop.  Tiles: id = blockIdx.x + it*gridDim.x, n-tile fastest (concurrent CTAs share the A rows in L2).
-template <bool DEFORM, bool XBF16>
+// MODE: 0 = dense (Cin % 64 == 0, NHWC), 1 = deformable, 2 = tiny Cin (stem: NCHW fp32 image, K = kh*kw*Cin
+// flattened and zero-padded to a multiple of 64, element-wise gather through a per-k table)
+template <int MODE, bool XBF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_tc_kernel(const TcParams p) {
+  constexpr bool DEFORM = MODE == 1;
+  constexpr bool SMALLC = MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B stage buffers need 1024-byte alignment
@@ -208,7 +212,7 @@ igemm_tc_kernel(const TcParams p) {
 
   const int KHW = p.kh * p.kw;
   const bool x3 = p.x3 != 0;
-  const TcSmem L = tc_smem_layout(DEFORM, KHW, p.BN, p.stages, x3);
+  const TcSmem L = tc_smem_layout(DEFORM, SMALLC ? 2 : KHW, p.BN, p.stages, x3);
   const uint32_t bar_full = base + L.bars, bar_empty = bar_full + 8 * TC_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + L.bars + 8 * (2 * TC_MAX_STAGES + 4));
@@ -220,9 +224,10 @@ igemm_tc_kernel(const TcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HoWo = p.Ho * p.Wo;
   const long long Ptot = (long long)p.N * HoWo;
-  const int cchunks = p.Cin / TC_BK;
-  const int num_kb = KHW * cchunks;
-  const int Kp = KHW * p.Cin;
+  const int cchunks = SMALLC ? 1 : p.Cin / TC_BK;
+  const int Kreal = KHW * p.Cin;
+  const int Kp = (Kreal + TC_BK - 1) / TC_BK * TC_BK;      // == Kreal unless SMALLC
+  const int num_kb = Kp / TC_BK;
   const int n_tiles = p.Cout_pad / p.BN;
   const long long m_tiles = (Ptot + TC_BM - 1) / TC_BM;
   const long long num_tiles = m_tiles * n_tiles;
@@ -245,6 +250,17 @@ igemm_tc_kernel(const TcParams p) {
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
+  if (SMALLC) {   // per-k table: k -> (dy, dx, channel) packed, -1 for the zero padding of K
+    for (int k = tid; k < Kp; k += TC_THREADS) {
+      int v = -1;
+      if (k < Kreal) {
+        const int tap = k / p.Cin, c = k - tap * p.Cin;
+        const int ki = tap / p.kw, kj = tap - ki * p.kw;
+        v = ((ki * p.dh) << 16) | ((kj * p.dw) << 8) | c;
+      }
+      ti[k] = v;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -264,10 +280,20 @@ igemm_tc_kernel(const TcParams p) {
       producer_bar_sync();   // every producer is done with the previous tile's table
       for (int r = pt; r < TC_BM; r += TC_PRODUCERS) {
         const long long pg = p0 + r;
-        rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
+        if (SMALLC) {   // (image, top-left input row/col of the receptive field), 20 bits each, biased by 2^19
+          long long v = -1;
+          if (pg < Ptot) {
+            const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+            v = ((long long)n << 40) | ((long long)(ho * p.sh - p.ph + (1 << 19)) << 20) | (long long)(wo * p.sw - p.pw + (1 << 19));
+          }
+          rowbase[r] = v;
+        } else {
+          rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
+        }
       }
       // per-tile sample table (channel independent): one entry per (tap, pixel)
-      for (int e = pt; e < KHW * TC_BM; e += TC_PRODUCERS) {
+      for (int e = pt; e < (SMALLC ? 0 : KHW * TC_BM); e += TC_PRODUCERS) {
         const int tap = e / TC_BM, r = e - tap * TC_BM;
         const long long pg = p0 + r;
         const int ki = tap / p.kw, kj = tap - ki * p.kw;
@@ -332,7 +358,43 @@ igemm_tc_kernel(const TcParams p) {
         }
         cp_async_commit();
         // ---- A: gather 128 rows x 8 chunks ----
-        if (!DEFORM && XBF16) {
+        if (SMALLC) {
+          // tiny Cin (stem): every k of the flattened (ky,kx,c) axis is an independent scalar read of the NCHW image
+          const float* xf = reinterpret_cast<const float*>(p.x);
+#pragma unroll 1
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowbase[r];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (rb >= 0) {
+              const int n = (int)(rb >> 40), h0 = (int)((rb >> 20) & 0xfffff) - (1 << 19), w0 = (int)(rb & 0xfffff) - (1 << 19);
+              const float* xn = xf + (size_t)n * p.Cin * p.H * p.W;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int e = ti[kb * TC_BK + j * 8 + q];
+                if (e >= 0) {
+                  const int hi = h0 + (e >> 16), wi = w0 + ((e >> 8) & 0xff), c = e & 0xff;
+                  if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[q] = __ldg(xn + ((size_t)c * p.H + hi) * p.W + wi);
+                }
+              }
+            }
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            uint4 hi4;
+            hi4.x = pack_bf16x2(v[0], v[1]); hi4.y = pack_bf16x2(v[2], v[3]);
+            hi4.z = pack_bf16x2(v[4], v[5]); hi4.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a_hi + soff) = hi4;
+            if (x3) {
+              uint4 lo;
+              lo.x = pack_bf16x2(v[0] - bf16_round(v[0]), v[1] - bf16_round(v[1]));
+              lo.y = pack_bf16x2(v[2] - bf16_round(v[2]), v[3] - bf16_round(v[3]));
+              lo.z = pack_bf16x2(v[4] - bf16_round(v[4]), v[5] - bf16_round(v[5]));
+              lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
+              *reinterpret_cast<uint4*>(a_lo + soff) = lo;
+            }
+          }
+        } else if (!DEFORM && XBF16) {
           // dense, bf16 activations: the 128-byte row IS the smem row -> cp.async 16 B per (row, chunk)
           // straight into the swizzled stage (zero-fill for padding / out-of-range rows), no registers.
           const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
@@ -513,38 +575,9 @@ igemm_tc_kernel(const TcParams p) {
       const int n_img = row_ok ? (int)(pg / HoWo) : 0;
       const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
-      const int col_begin = half * (p.BN / TC_EPI_SPLIT), col_end = col_begin + p.BN / TC_EPI_SPLIT;
-      for (int colb = col_begin; colb < col_end; colb += 32) {
-        // two 16-column chunks per TMEM wait; the residual of both chunks is requested BEFORE the wait so that
-        // its global-memory latency overlaps the TMEM read (the epilogue is latency-, not bandwidth-bound)
-        const bool two = colb + 16 < col_end;
-        uint32_t rr2[2][16];
-        tmem_ld16_issue(trow + (uint32_t)colb, rr2[0]);          // warp-collective
-        if (two) tmem_ld16_issue(trow + (uint32_t)colb + 16u, rr2[1]);
-        uint4 pre[2][2];
-        bool has_pre[2] = {false, false};
-        if (row_ok && p.residual && p.out_nhwc && p.y_bf16 && ((p.Cout & 7) == 0) && vec_ptrs_ok) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int co0p = n0 + colb + c * 16;
-            if ((c == 0 || two) && co0p + 15 < p.Cout) {
-              size_t ridx = (size_t)pg * p.Cout + co0p;
-              if (p.res_up2) {
-                const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-                ridx = (((size_t)n_img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + co0p;
-              }
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx);
-              pre[c][0] = __ldg(rp); pre[c][1] = __ldg(rp + 1);
-              has_pre[c] = true;
-            }
-          }
-        }
-        tmem_ld_wait();
-#pragma unroll
-       for (int c = 0; c < 2; ++c) {
-        if (c == 1 && !two) break;
-        const uint32_t* rr = rr2[c];
-        const int col = colb + c * 16;
+      for (int col = 0; col < p.BN; col += 16) {
+        uint32_t rr[16];
+        tmem_ld16(trow + (uint32_t)col, rr);  // warp-collective
         if (!row_ok) continue;
         const int co0 = n0 + col;
         if (co0 >= p.Cout) continue;
@@ -570,8 +603,7 @@ igemm_tc_kernel(const TcParams p) {
             const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx : nullptr;
             if (full) {
               if (ro) {
-                const uint4 r0 = has_pre[c] ? pre[c][0] : __ldg(reinterpret_cast<const uint4*>(ro));
-                const uint4 r1 = has_pre[c] ? pre[c][1] : __ldg(reinterpret_cast<const uint4*>(ro) + 1);
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
                 const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -643,7 +675,6 @@ igemm_tc_kernel(const TcParams p) {
             }
           }
         }
-       }
       }
       tc_fence_before();
       __syncwarp();
@@ -661,14 +692,14 @@ igemm_tc_kernel(const TcParams p) {
 // ----------------------------------------------------------------------------------------------
 // weight pre-pack: fp32 [Cout,Cin,kh,kw] -> bf16 hi / lo planes [Cout_pad][KHW*Cin], k = tap*Cin + c
 // ----------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int Cout_pad,
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KHW, int Cout_pad, int Kp,
                                    uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  const size_t total = (size_t)Cout_pad * KHW * Cin;
+  const size_t total = (size_t)Cout_pad * Kp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % ((size_t)KHW * Cin));
-    const int co = (int)(i / ((size_t)KHW * Cin));
+    const int kk = (int)(i % (size_t)Kp);
+    const int co = (int)(i / (size_t)Kp);
     const int tap = kk / Cin, c = kk - tap * Cin;
-    const float v = co < Cout ? w[((size_t)co * Cin + c) * KHW + tap] : 0.f;
+    const float v = (co < Cout && kk < KHW * Cin) ? w[((size_t)co * Cin + c) * KHW + tap] : 0.f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
     hi[i] = *reinterpret_cast<const uint16_t*>(&h);
@@ -677,24 +708,28 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 }
 
 static int tc_cout_pad(int Cout) { return Cout <= 32 ? 32 : (Cout + 63) / 64 * 64; }
+static int tc_kp(int Cin, int KHW) { return (KHW * Cin + TC_BK - 1) / TC_BK * TC_BK; }
 
 size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw) {
-  return (size_t)2 * tc_cout_pad(Cout) * kh * kw * Cin * sizeof(uint16_t);
+  return (size_t)2 * tc_cout_pad(Cout) * tc_kp(Cin, kh * kw) * sizeof(uint16_t);
 }
 
 int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream) {
-  const int Cout_pad = tc_cout_pad(Cout), KHW = kh * kw;
+  const int Cout_pad = tc_cout_pad(Cout), KHW = kh * kw, Kp = tc_kp(Cin, KHW);
   uint16_t* hi = reinterpret_cast<uint16_t*>(packed);
-  uint16_t* lo = hi + (size_t)Cout_pad * KHW * Cin;
-  const size_t total = (size_t)Cout_pad * KHW * Cin;
+  uint16_t* lo = hi + (size_t)Cout_pad * Kp;
+  const size_t total = (size_t)Cout_pad * Kp;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, KHW, Cout_pad, hi, lo);
+  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, KHW, Cout_pad, Kp, hi, lo);
   UPS_CHECK_LAUNCH();
   return 0;
 }
 
-bool tc_supported(int Cin, int kh, int kw, int dg) { return (Cin % TC_BK) == 0 && dg == 1 && kh * kw <= 49; }
+// Cin % 64 == 0 (NHWC gather / cp.async), or a tiny Cin <= 8 (the RGB stem: NCHW fp32 input, flattened K)
+bool tc_supported(int Cin, int kh, int kw, int dg) {
+  return ((Cin % TC_BK) == 0 || Cin <= 8) && dg == 1 && kh * kw <= 49 && kh <= 15 && kw <= 15;
+}
 
 int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   const int KHW = p.kh * p.kw;
@@ -702,8 +737,10 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   if ((((uintptr_t)p.x) & 15) || (((uintptr_t)packed) & 15) || (((uintptr_t)p.y) & 15)) return UPSNET_E_BADARG;
   p.Cout_pad = tc_cout_pad(p.Cout);
   p.w_hi = reinterpret_cast<const uint16_t*>(packed);
-  p.w_lo = p.w_hi + (size_t)p.Cout_pad * KHW * p.Cin;
+  p.w_lo = p.w_hi + (size_t)p.Cout_pad * tc_kp(p.Cin, KHW);
   const bool deform = p.offset != nullptr;
+  const bool smallc = (p.Cin % TC_BK) != 0;
+  if (smallc && (deform || p.x_bf16 || p.dh * (p.kh - 1) > 255 || p.dw * (p.kw - 1) > 255)) return UPSNET_E_UNSUPPORTED;
   // tile N: as wide as possible (each gathered A tile is reused by BN couts)
   int BN = p.Cout_pad;
   const int bn_cap = p.x3 ? 128 : 256;
@@ -714,11 +751,10 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   }
   p.BN = BN;
   // One persistent CTA per SM: give the smem ring everything that is left after the sample table.
-  const int num_kb = KHW * (p.Cin / TC_BK);
+  const int khw_l = smallc ? 2 : KHW;   // table region: [KHW][128] entries, or the 1 KB per-k table of the stem mode
   int stages = TC_MAX_STAGES;
-  TcSmem L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0);
-  while (stages > 2 && L.total + 1024 > 220 * 1024) { --stages; L = tc_smem_layout(deform, KHW, BN, stages, p.x3 != 0); }
-  (void)num_kb;
+  TcSmem L = tc_smem_layout(deform, khw_l, BN, stages, p.x3 != 0);
+  while (stages > 2 && L.total + 1024 > 220 * 1024) { --stages; L = tc_smem_layout(deform, khw_l, BN, stages, p.x3 != 0); }
   if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   p.stages = stages;
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
@@ -735,19 +771,22 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
   static bool configured = false;
   if (!configured) {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  if (p.x_bf16) {
+  if (smallc) {
+    igemm_tc_kernel<2, false><<<grid, TC_THREADS, smem, stream>>>(p);
+  } else if (p.x_bf16) {
     if (p.x3) return UPSNET_E_UNSUPPORTED;   // the hi/lo split needs fp32 activations
-    if (deform) igemm_tc_kernel<true, true><<<grid, TC_THREADS, smem, stream>>>(p);
-    else igemm_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(p);
+    if (deform) igemm_tc_kernel<1, true><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<0, true><<<grid, TC_THREADS, smem, stream>>>(p);
   } else {
-    if (deform) igemm_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(p);
-    else igemm_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    if (deform) igemm_tc_kernel<1, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<0, false><<<grid, TC_THREADS, smem, stream>>>(p);
   }
   UPS_CHECK_LAUNCH();
   return 0;

@@ -106,8 +106,8 @@ def _packed_weight(weight):
     return buf
 
 
-def _tc_ok(Cin, kh, kw, dg):
-    return Cin % 64 == 0 and dg == 1 and kh * kw <= 49
+def _tc_ok(Cin, kh, kw, dg, deform=False):
+    return (Cin % 64 == 0 or (Cin <= 8 and not deform)) and dg == 1 and kh * kw <= 49
 
 
 def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format,
@@ -127,7 +127,7 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
         x = x.float()
     if out_dtype is None:
         out_dtype = torch.bfloat16 if (ACT_BF16["on"] and prec == _lib.PREC_BF16 and nhwc_out) else torch.float32
-    xs = _nhwc(x)
+    xs = f32c(x) if Cin % 64 else _nhwc(x)      # tiny-Cin (stem) mode reads the NCHW fp32 image directly
     packed = _packed_weight(weight)
     if nhwc_out:
         store = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=out_dtype)
@@ -219,7 +219,7 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
     ModDeformConvFunction.forward (functions/mod_deform_conv.py:25-59).  One fused launch."""
     require_cuda(data, offset, weight, bias, mask)
     prec = _PRECISION["conv"] if precision is None else precision
-    use_tc = prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], deformable_groups)
+    use_tc = prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], deformable_groups, True)
     offset = f32c(offset)
     bias = None if bias is None else f32c(bias)
     mask = None if mask is None else f32c(mask)
