@@ -175,7 +175,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, i
   TcSmem s;
   s.bars = 0;
   s.rowbase = 256;
-  s.table = s.rowbase + TC_BM * 8;
+  s.table = s.rowbase + 2 * TC_BM * 8;   // two row-info buffers
   const uint32_t tbytes = deform ? KHW * TC_BM * 32 : KHW * TC_BM * 4;
   s.stages = (uint32_t)((s.table + tbytes + 1023) / 1024 * 1024);
   s.a_bytes = TC_BM * 128;
@@ -274,30 +274,32 @@ igemm_tc_kernel(const TcParams p) {
     const int j = gt & 7;                 // 16-byte chunk (8 channels) inside the 128-byte row
     const int r_first = gt >> 3;          // 32 rows per pass
     uint32_t g0 = 0;                      // ring position of this tile's first k-block
+    uint32_t tile_it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long p0 = (tile / n_tiles) * TC_BM;
       const int n0 = (int)(tile % n_tiles) * p.BN;
-      producer_bar_sync();   // every producer is done with the previous tile's table
+      // Per-tile row info (image, top-left input coordinate of the receptive field) is double-buffered, so ONE
+      // producer barrier per tile suffices for the dense / stem modes; the deformable sample table is a single
+      // buffer and needs the extra barrier before it is overwritten.
+      long long* rowinfo = rowbase + (tile_it & 1) * TC_BM;
+      if (DEFORM) producer_bar_sync();   // every producer is done with the previous tile's sample table
       for (int r = pt; r < TC_BM; r += TC_PRODUCERS) {
         const long long pg = p0 + r;
-        if (SMALLC) {   // (image, top-left input row/col of the receptive field), 20 bits each, biased by 2^19
-          long long v = -1;
-          if (pg < Ptot) {
-            const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
-            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-            v = ((long long)n << 40) | ((long long)(ho * p.sh - p.ph + (1 << 19)) << 20) | (long long)(wo * p.sw - p.pw + (1 << 19));
-          }
-          rowbase[r] = v;
-        } else {
-          rowbase[r] = pg < Ptot ? (long long)(pg / HoWo) * p.H * p.W * (long long)p.Cin : -1;
+        long long v = -1;
+        if (pg < Ptot) {
+          const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
+          const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+          if (DEFORM) v = (long long)n * p.H * p.W * (long long)p.Cin;
+          else v = ((long long)n << 40) | ((long long)(ho * p.sh - p.ph + (1 << 19)) << 20) | (long long)(wo * p.sw - p.pw + (1 << 19));
         }
+        rowinfo[r] = v;
       }
-      // per-tile sample table (channel independent): one entry per (tap, pixel)
-      for (int e = pt; e < (SMALLC ? 0 : KHW * TC_BM); e += TC_PRODUCERS) {
+      // deformable: per-tile sample table (channel independent), one entry per (tap, pixel)
+      for (int e = pt; e < (DEFORM ? KHW * TC_BM : 0); e += TC_PRODUCERS) {
         const int tap = e / TC_BM, r = e - tap * TC_BM;
         const long long pg = p0 + r;
         const int ki = tap / p.kw, kj = tap - ki * p.kw;
-        if (DEFORM) {
+        {
           float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
           int4 ov = make_int4(0, 0, 0, 0);
           if (pg < Ptot) {
@@ -325,18 +327,10 @@ igemm_tc_kernel(const TcParams p) {
           }
           tw[e] = wv;
           to[e] = ov;
-        } else {
-          int o = -1;
-          if (pg < Ptot) {
-            const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
-            const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-            const int hi = ho * p.sh - p.ph + ki * p.dh, wi = wo * p.sw - p.pw + kj * p.dw;
-            if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) o = hi * p.W + wi;
-          }
-          ti[e] = o;
         }
       }
-      producer_bar_sync();   // table visible to all producers
+      producer_bar_sync();   // row info (and sample table) visible to all producers
+      ++tile_it;
 
       for (int kb = (int)((uint32_t)(group - (int)g0) & 1u); kb < num_kb; kb += TC_GROUPS) {  // ring parity == group
         const uint32_t g = g0 + (uint32_t)kb;
@@ -348,6 +342,7 @@ igemm_tc_kernel(const TcParams p) {
         uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
         uint8_t* b_lo = a_lo + L.a_bytes;
         const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
+        const int tki = tap / p.kw, tdy = tki * p.dh, tdx = (tap - tki * p.kw) * p.dw;   // dense: tap displacement
         // ---- B: BN rows x 8 chunks of packed bf16 weights, cp.async straight into the swizzled stage
         //      (no registers, overlaps the A gather below) ----
         for (int r = r_first; r < p.BN; r += 32) {
@@ -364,7 +359,7 @@ igemm_tc_kernel(const TcParams p) {
 #pragma unroll 1
           for (int pass = 0; pass < TC_BM / 32; ++pass) {
             const int r = r_first + pass * 32;
-            const long long rb = rowbase[r];
+            const long long rb = rowinfo[r];
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = 0.f;
@@ -401,10 +396,10 @@ igemm_tc_kernel(const TcParams p) {
 #pragma unroll
           for (int pass = 0; pass < TC_BM / 32; ++pass) {
             const int r = r_first + pass * 32;
-            const long long rb = rowbase[r];
-            const int o = ti[tap * TC_BM + r];
-            const bool ok = rb >= 0 && o >= 0;
-            const __nv_bfloat16* src = ok ? xh + rb + c0 + (size_t)o * p.Cin : xh;
+            const long long rb = rowinfo[r];
+            const int hi = (int)((rb >> 20) & 0xfffff) - (1 << 19) + tdy, wi = (int)(rb & 0xfffff) - (1 << 19) + tdx;
+            const bool ok = rb >= 0 && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const __nv_bfloat16* src = ok ? xh + (((size_t)(rb >> 40) * p.H + hi) * p.W + wi) * p.Cin + c0 : xh;
             const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
             cp_async16_zfill(smem_u32(a_hi + soff), src, ok ? 16u : 0u);
           }
@@ -421,10 +416,11 @@ igemm_tc_kernel(const TcParams p) {
 #pragma unroll
           for (int pass = 0; pass < TC_BM / 16; ++pass) {
             const int r = rr0 + pass * 16;
-            const long long rb = rowbase[r];
-            const int o = ti[tap * TC_BM + r];
+            const long long rb = rowinfo[r];
+            const int hi = (int)((rb >> 20) & 0xfffff) - (1 << 19) + tdy, wi = (int)(rb & 0xfffff) - (1 << 19) + tdx;
             qv[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rb >= 0 && o >= 0) qv[pass] = __ldg(reinterpret_cast<const float4*>(xf + rb + cg + (size_t)o * p.Cin));
+            if (rb >= 0 && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
+              qv[pass] = __ldg(reinterpret_cast<const float4*>(xf + (((size_t)(rb >> 40) * p.H + hi) * p.W + wi) * p.Cin + cg));
           }
 #pragma unroll
           for (int pass = 0; pass < TC_BM / 16; ++pass) {
@@ -447,7 +443,7 @@ igemm_tc_kernel(const TcParams p) {
 #pragma unroll 2
           for (int pass = 0; pass < TC_BM / 32; ++pass) {
             const int r = r_first + pass * 32;
-            const long long rb = rowbase[r];
+            const long long rb = rowinfo[r];
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = 0.f;
@@ -485,7 +481,7 @@ igemm_tc_kernel(const TcParams p) {
 #pragma unroll 2
           for (int pass = 0; pass < TC_BM / 16; ++pass) {
             const int r = rr0 + pass * 16;
-            const long long rb = rowbase[r];
+            const long long rb = rowinfo[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (rb >= 0) {
               const float* xb = xf + rb + cg;
