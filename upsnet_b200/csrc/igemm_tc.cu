@@ -571,9 +571,34 @@ igemm_tc_kernel(const TcParams p) {
       const int n_img = row_ok ? (int)(pg / HoWo) : 0;
       const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
+      // Residual (bf16 NHWC fast path) is software-pipelined one 16-column chunk ahead: its global-memory
+      // latency (~1 us) would otherwise be paid 16 times per tile, serially, by every epilogue thread.
+      const bool pre_ok = row_ok && p.residual && p.out_nhwc && p.y_bf16 && ((p.Cout & 7) == 0) && vec_ptrs_ok;
+      size_t rrow = 0;   // element index of this row's residual at column n0
+      if (pre_ok) {
+        rrow = (size_t)pg * p.Cout + n0;
+        if (p.res_up2) {
+          const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
+          rrow = (((size_t)n_img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + n0;
+        }
+      }
+      uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0;
+      bool nx_has = false;
+      if (pre_ok && n0 + 15 < p.Cout) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow);
+        nx0 = __ldg(rp); nx1 = __ldg(rp + 1); nx_has = true;
+      }
       for (int col = 0; col < p.BN; col += 16) {
         uint32_t rr[16];
-        tmem_ld16(trow + (uint32_t)col, rr);  // warp-collective
+        tmem_ld16_issue(trow + (uint32_t)col, rr);  // warp-collective
+        const uint4 cu0 = nx0, cu1 = nx1;
+        const bool cu_has = nx_has;
+        nx_has = false;
+        if (pre_ok && col + 16 < p.BN && n0 + col + 31 < p.Cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow + col + 16);
+          nx0 = __ldg(rp); nx1 = __ldg(rp + 1); nx_has = true;
+        }
+        tmem_ld_wait();
         if (!row_ok) continue;
         const int co0 = n0 + col;
         if (co0 >= p.Cout) continue;
@@ -599,7 +624,8 @@ igemm_tc_kernel(const TcParams p) {
             const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx : nullptr;
             if (full) {
               if (ro) {
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
+                const uint4 r0 = cu_has ? cu0 : __ldg(reinterpret_cast<const uint4*>(ro));
+                const uint4 r1 = cu_has ? cu1 : __ldg(reinterpret_cast<const uint4*>(ro) + 1);
                 const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {

@@ -267,11 +267,19 @@ class RCNN(nn.Module):
     def prepare(self):
         self._f = (torch.cat([self.cls_score.weight, self.bbox_pred.weight]).detach().contiguous(),
                    torch.cat([self.cls_score.bias, self.bbox_pred.bias]).detach().contiguous())
+        # fc6 consumes the flattened (c, ph, pw) roi feature; the engine's ROIAlign writes (ph, pw, c) (NHWC), so
+        # keep a column-permuted copy of the weight instead of transposing 1000x12544 activations every image
+        w6 = self.fc6[0].weight.detach()
+        ps = self.pool_size
+        self._w6_nhwc = w6.view(w6.shape[0], -1, ps, ps).permute(0, 2, 3, 1).reshape(w6.shape[0], -1).contiguous()
 
     def forward(self, feat, rois):
         pool = self.roi_pooling(feat, rois)
-        x = pool.reshape(pool.size(0), -1)
-        fc6 = ops.linear(x, self.fc6[0].weight, self.fc6[0].bias, relu=True)
+        nhwc = pool.permute(0, 2, 3, 1)
+        if self._f is not None and nhwc.is_contiguous() and not pool.is_contiguous():
+            fc6 = ops.linear(nhwc.reshape(pool.size(0), -1), self._w6_nhwc, self.fc6[0].bias, relu=True)
+        else:
+            fc6 = ops.linear(pool.reshape(pool.size(0), -1), self.fc6[0].weight, self.fc6[0].bias, relu=True)
         fc7 = ops.linear(fc6, self.fc7[0].weight, self.fc7[0].bias, relu=True)
         both = ops.linear(fc7, self._f[0], self._f[1], out_dtype=torch.float32).float()
         return {"cls_score": both[:, :self.num_classes].contiguous(),
