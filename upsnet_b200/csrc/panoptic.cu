@@ -338,23 +338,37 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
   float thing_max[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) { best[q].v = -INFINITY; best[q].i = 0; sem[q].v = -INFINITY; sem[q].i = 0; thing_max[q] = -INFINITY; }
-  for (int c = 0; c < S; ++c) {
-    float v[4];
-    if (vec) {
-      const float4 t = __ldg((const float4*)(fcn + (size_t)c * HW + p));
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
+  // channels in batches of 4: the four 16-byte loads of a batch are issued before the first compare
+  // (memory-level parallelism: this kernel is the HBM-bound one, 4*S*H*W bytes stream through here once)
+  for (int cb = 0; cb < S; cb += 4) {
+    float vv[4][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = q < npx ? __ldg(fcn + (size_t)c * HW + p + q) : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const int c = cb + u;
+      if (c < S) {
+        if (vec) {
+          const float4 t = __ldg((const float4*)(fcn + (size_t)c * HW + p));
+          vv[u][0] = t.x; vv[u][1] = t.y; vv[u][2] = t.z; vv[u][3] = t.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) vv[u][q] = q < npx ? __ldg(fcn + (size_t)c * HW + p + q) : 0.f;
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (c == 0) { best[q].v = v[q]; sem[q].v = v[q]; }
-      else {
-        if (c < num_stuff) feed(best[q], v[q], c);
-        feed(sem[q], v[q], c);
+    for (int u = 0; u < 4; ++u) {
+      const int c = cb + u;
+      if (c >= S) break;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float v = vv[u][q];
+        if (c == 0) { best[q].v = v; sem[q].v = v; }
+        else {
+          if (c < num_stuff) feed(best[q], v, c);
+          feed(sem[q], v, c);
+        }
+        if (c >= num_stuff) thing_max[q] = (c == num_stuff) ? v : fmaxf(thing_max[q], v);
       }
-      if (c >= num_stuff) thing_max[q] = (c == num_stuff) ? v[q] : fmaxf(thing_max[q], v[q]);
     }
   }
   // ---- instances, ascending kept index; unlisted instances contribute the value 0 at u0 ----
