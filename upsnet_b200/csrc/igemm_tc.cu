@@ -36,6 +36,7 @@ constexpr int TC_GROUPS = 2;        // producer groups work on alternate k-block
 constexpr int TC_PRODUCERS = TC_GROUP * TC_GROUPS;  // 16 warps
 constexpr int TC_EPILOGUE = 128;      // 4 warps: TMEM lane quadrant = warp & 3 (x TC_EPI_SPLIT column slices)
 constexpr int TC_EPI_SPLIT = TC_EPILOGUE / 128;
+constexpr int TC_EPI_PITCH = 36;      // floats per staged row: 32 columns + 4 pad (16-byte aligned, conflict-free)
 constexpr int TC_THREADS = TC_EPILOGUE + 32 + TC_PRODUCERS;  // 21 warps
 constexpr int TC_MAX_STAGES = 6;
 
@@ -167,6 +168,7 @@ __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(_
 struct TcSmem {
   uint32_t bars;      // full[6], empty[6], tmem_full[2], tmem_empty[2] (16 x 8 B) then tmem ptr
   uint32_t rowbase;   // long long [128]
+  uint32_t epi;       // epilogue staging: 4 warps x 32 rows x 36 floats (coalesced NHWC stores)
   uint32_t table;     // deform: float4 [KHW][128] + int4 [KHW][128]; dense: int [KHW][128]
   uint32_t stages;    // 1024-aligned
   uint32_t a_bytes, b_bytes, stage_bytes, total;
@@ -175,7 +177,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(bool deform, int KHW, int BN, i
   TcSmem s;
   s.bars = 0;
   s.rowbase = 256;
-  s.table = s.rowbase + 2 * TC_BM * 8;   // two row-info buffers
+  s.epi = s.rowbase + 2 * TC_BM * 8;     // two row-info buffers, then the epilogue staging area
+  s.table = s.epi + (TC_EPILOGUE / 32) * 32 * TC_EPI_PITCH * 4;
   const uint32_t tbytes = deform ? KHW * TC_BM * 32 : KHW * TC_BM * 4;
   s.stages = (uint32_t)((s.table + tbytes + 1023) / 1024 * 1024);
   s.a_bytes = TC_BM * 128;
@@ -571,6 +574,88 @@ igemm_tc_kernel(const TcParams p) {
       const int n_img = row_ok ? (int)(pg / HoWo) : 0;
       const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
+      if (p.out_nhwc && (p.Cout & 7) == 0 && vec_ptrs_ok) {
+        // ---- NHWC: stage 32 rows x 32 columns (fp32, +bias) per warp in shared memory, then write them out
+        //      row-wise: 4 (bf16) or 8 (fp32) lanes cover one row's 64 / 128 contiguous bytes, so every store
+        //      -- and every residual read -- is made of fully used 32-byte sectors instead of one 16-byte
+        //      fragment per 512-byte-strided row. ----
+        float* st = reinterpret_cast<float*>(sm + L.epi) + (size_t)warp * 32 * TC_EPI_PITCH;
+        const int lpr = p.y_bf16 ? 4 : 8;              // lanes per row in the write-out phase
+        const int rpi = 32 / lpr;                       // rows per iteration
+        const int sub = lane % lpr, rsub = lane / lpr;
+        for (int cb = 0; cb < p.BN; cb += 32) {
+          if (n0 + cb >= p.Cout) break;                 // zero-padded weight rows beyond Cout
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t rr[16];
+            tmem_ld16(trow + (uint32_t)(cb + c * 16), rr);   // warp-collective
+            const int co0 = n0 + cb + c * 16;
+            float4* dst = reinterpret_cast<float4*>(st + lane * TC_EPI_PITCH + c * 16);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              float4 o = make_float4(__uint_as_float(rr[g4 * 4]), __uint_as_float(rr[g4 * 4 + 1]),
+                                     __uint_as_float(rr[g4 * 4 + 2]), __uint_as_float(rr[g4 * 4 + 3]));
+              if (p.bias && co0 + g4 * 4 + 3 < p.Cout) {
+                o.x += __ldg(p.bias + co0 + g4 * 4); o.y += __ldg(p.bias + co0 + g4 * 4 + 1);
+                o.z += __ldg(p.bias + co0 + g4 * 4 + 2); o.w += __ldg(p.bias + co0 + g4 * 4 + 3);
+              }
+              dst[g4] = o;
+            }
+          }
+          __syncwarp();
+          const int ce = p.y_bf16 ? sub * 8 : sub * 4;   // first staged column of this lane
+          const int co = n0 + cb + ce;
+          if (co < p.Cout) {
+            for (int it = 0; it < lpr; ++it) {
+              const int row = it * rpi + rsub;
+              const long long pgr = p0 + q * 32 + row;
+              if (pgr >= Ptot) continue;
+              size_t ridx = (size_t)pgr * p.Cout + co;
+              if (p.residual && p.res_up2) {
+                const int ni = (int)(pgr / HoWo), ppr = (int)(pgr - (long long)ni * HoWo);
+                const int ho = ppr / p.Wo, wo = ppr - ho * p.Wo;
+                ridx = (((size_t)ni * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + co;
+              }
+              const float* src = st + row * TC_EPI_PITCH + ce;
+              if (p.y_bf16) {
+                const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+                float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (p.residual) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx));
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    o[2 * e] += __uint_as_float(rw[e] << 16);
+                    o[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                uint4 w;
+                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+                w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)pgr * p.Cout + co) = w;
+              } else {
+                float4 o = *reinterpret_cast<const float4*>(src);
+                if (p.residual) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + ridx));
+                  o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                }
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (size_t)pgr * p.Cout + co) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
+      // ---- legacy per-lane path (NCHW outputs, odd channel counts) ----
       // Residual (bf16 NHWC fast path) is software-pipelined one 16-column chunk ahead: its global-memory
       // latency (~1 us) would otherwise be paid 16 times per tile, serially, by every epilogue thread.
       const bool pre_ok = row_ok && p.residual && p.out_nhwc && p.y_bf16 && ((p.Cout & 7) == 0) && vec_ptrs_ok;
