@@ -140,6 +140,7 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 in
 // bits [0,14), LBO [16,30) (unused for swizzled K-major), SBO>>4 = 1024>>4 in [32,46) (8 rows of
@@ -278,6 +279,10 @@ igemm_tc_kernel(const TcParams p) {
     const int r_first = gt >> 3;          // 32 rows per pass
     uint32_t g0 = 0;                      // ring position of this tile's first k-block
     uint32_t tile_it = 0;
+    // bf16 dense mode: both operands travel by cp.async, so the producer keeps ONE k-block outstanding and
+    // signals the previous one only after issuing the next (two k-blocks of loads in flight per group).
+    const bool deferred = (MODE == 0) && XBF16 && p.stages >= 3;
+    int pend_s = -1;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long p0 = (tile / n_tiles) * TC_BM;
       const int n0 = (int)(tile % n_tiles) * p.BN;
@@ -512,12 +517,28 @@ igemm_tc_kernel(const TcParams p) {
           }
         }
         cp_async_commit();
-        cp_async_wait_all();
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        if (deferred) {
+          if (pend_s >= 0) {
+            cp_async_wait_but2();   // everything except this k-block's two commit groups has landed
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * pend_s);
+          }
+          pend_s = (int)s;
+        } else {
+          cp_async_wait_all();
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
       }
       g0 += (uint32_t)num_kb;
+    }
+    if (pend_s >= 0) {
+      cp_async_wait_all();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * pend_s);
     }
   } else if (warp == TC_EPILOGUE / 32) {
     // =============================== MMA ISSUER ===============================
@@ -656,34 +677,9 @@ igemm_tc_kernel(const TcParams p) {
         continue;
       }
       // ---- legacy per-lane path (NCHW outputs, odd channel counts) ----
-      // Residual (bf16 NHWC fast path) is software-pipelined one 16-column chunk ahead: its global-memory
-      // latency (~1 us) would otherwise be paid 16 times per tile, serially, by every epilogue thread.
-      const bool pre_ok = row_ok && p.residual && p.out_nhwc && p.y_bf16 && ((p.Cout & 7) == 0) && vec_ptrs_ok;
-      size_t rrow = 0;   // element index of this row's residual at column n0
-      if (pre_ok) {
-        rrow = (size_t)pg * p.Cout + n0;
-        if (p.res_up2) {
-          const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-          rrow = (((size_t)n_img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + n0;
-        }
-      }
-      uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0;
-      bool nx_has = false;
-      if (pre_ok && n0 + 15 < p.Cout) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow);
-        nx0 = __ldg(rp); nx1 = __ldg(rp + 1); nx_has = true;
-      }
       for (int col = 0; col < p.BN; col += 16) {
         uint32_t rr[16];
-        tmem_ld16_issue(trow + (uint32_t)col, rr);  // warp-collective
-        const uint4 cu0 = nx0, cu1 = nx1;
-        const bool cu_has = nx_has;
-        nx_has = false;
-        if (pre_ok && col + 16 < p.BN && n0 + col + 31 < p.Cout) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow + col + 16);
-          nx0 = __ldg(rp); nx1 = __ldg(rp + 1); nx_has = true;
-        }
-        tmem_ld_wait();
+        tmem_ld16(trow + (uint32_t)col, rr);  // warp-collective
         if (!row_ok) continue;
         const int co0 = n0 + col;
         if (co0 >= p.Cout) continue;
@@ -709,8 +705,7 @@ igemm_tc_kernel(const TcParams p) {
             const __nv_bfloat16* ro = p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx : nullptr;
             if (full) {
               if (ro) {
-                const uint4 r0 = cu_has ? cu0 : __ldg(reinterpret_cast<const uint4*>(ro));
-                const uint4 r1 = cu_has ? cu1 : __ldg(reinterpret_cast<const uint4*>(ro) + 1);
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(ro)), r1 = __ldg(reinterpret_cast<const uint4*>(ro) + 1);
                 const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
