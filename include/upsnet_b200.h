@@ -32,6 +32,7 @@ extern "C" {
 /* epilogue flags for the convolution entry points */
 #define UPSNET_EPI_RELU 1
 #define UPSNET_EPI_RES_UP2 2 /* upsnet_igemm_forward only: residual is [N,Ho/2,Wo/2,Cout], read with nearest 2x upsampling */
+#define UPSNET_EPI_NO_TMA 4  /* upsnet_igemm_forward only: use the cp.async gather kernel even where the TMA-fed one qualifies */
 
 /* precision of the tensor-core convolution path */
 #define UPSNET_PREC_FP32_SIMT 0 /* fp32 FFMA tiles (exact-order-free fp32)            */

@@ -275,3 +275,51 @@ def test_tc_tiny_cin_stem_mode(dev, cfg, prec):
     assert got.shape == want.shape
     err = np.abs(got.float().cpu().numpy() - want).max()
     assert err < TOL[prec], err
+
+
+# ------------------------------- TMA-fed kernel (igemm_tma.cu) ------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, Cin=64, Cout=64, H=16, W=16, k=1, pad=0, dil=1),        # BN=64: both epilogue halves share one slab
+    dict(N=1, Cin=256, Cout=64, H=40, W=72, k=1, pad=0, dil=1),       # 4 k-blocks, 16x8 boxes
+    dict(N=1, Cin=64, Cout=256, H=64, W=96, k=1, pad=0, dil=1),       # res2-style expansion (BN=128 with residual)
+    dict(N=1, Cin=128, Cout=256, H=160, W=160, k=3, pad=1, dil=1),    # >= 148 m-tiles: BN=256, two slabs per half
+    dict(N=2, Cin=128, Cout=128, H=15, W=17, k=3, pad=1, dil=1),      # ragged boxes clipped by the TMA store
+    dict(N=20, Cin=256, Cout=256, H=14, W=14, k=3, pad=1, dil=1),     # mask-head shape: boxes span several images
+    dict(N=300, Cin=1024, Cout=1024, H=1, W=1, k=1, pad=0, dil=1),    # fully connected: 128 "images" per box
+    dict(N=1, Cin=128, Cout=192, H=14, W=30, k=3, pad=2, dil=2),      # dilation, Cout = 3 x 64
+    dict(N=3, Cin=64, Cout=128, H=7, W=7, k=7, pad=3, dil=1),         # 49 taps (ring wraps many times)
+])
+def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as OPS
+    rng = np.random.default_rng(21)
+    x, w, b = _case(rng, cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"], cfg["k"])
+    x, w = _bf16_exact(x), _bf16_exact(w)
+    want = O.conv2d(x, w, b, 1, cfg["pad"], cfg["dil"])
+    res = _bf16_exact(rng.standard_normal(want.shape).astype(np.float32))
+    xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    rb = t(res, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = {}
+    for tma in (True, False):
+        OPS.USE_TMA["on"] = tma
+        try:
+            y0 = U.conv2d(xb, t(w, dev), t(b, dev), 1, cfg["pad"], cfg["dil"], precision=BF16, out_format="nhwc",
+                          out_dtype=torch.bfloat16)
+            y1 = U.conv2d(xb, t(w, dev), t(b, dev), 1, cfg["pad"], cfg["dil"], residual=rb, relu=True, precision=BF16,
+                          out_format="nhwc", out_dtype=torch.bfloat16)
+            y2 = U.conv2d(xb, t(w, dev), None, 1, cfg["pad"], cfg["dil"], relu=True, precision=BF16, out_format="nhwc",
+                          out_dtype=torch.bfloat16)
+        finally:
+            OPS.USE_TMA["on"] = True
+        torch.cuda.synchronize()
+        outs[tma] = (y0, y1, y2)
+    y0, y1, y2 = outs[True]
+    tol = 1e-4 + (2.0 ** -8) * np.abs(want).max()
+    assert np.abs(y0.float().cpu().numpy() - want).max() < tol
+    want1 = np.maximum(want + res, 0)
+    assert np.abs(y1.float().cpu().numpy() - want1).max() < 1e-4 + (2.0 ** -8) * np.abs(want1).max()
+    want2 = np.maximum(want - b[None, :, None, None], 0)
+    assert np.abs(y2.float().cpu().numpy() - want2).max() < tol
+    # same MMA sequence and epilogue arithmetic as the gather kernel -> identical bf16 outputs
+    for a, g in zip(outs[True], outs[False]):
+        assert torch.equal(a, g)

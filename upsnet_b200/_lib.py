@@ -16,6 +16,7 @@ _lib = None
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 EPI_RELU = 1
 EPI_RES_UP2 = 2
+EPI_NO_TMA = 4
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 
 _ERR = {-1: "bad argument", -2: "unsupported configuration", -3: "workspace too small"}

@@ -2,6 +2,7 @@
 // between the fp32 CUDA-core tiles (igemm_simt.cu) and the tcgen05 tensor-core tiles
 // (igemm_tc.cu).  See include/upsnet_b200.h for the contract of every symbol.
 #include "common.cuh"
+#include "tc_params.cuh"
 
 namespace ups {
 struct ConvParams {
@@ -11,19 +12,6 @@ struct ConvParams {
 };
 int launch_igemm_simt(const ConvParams& p, cudaStream_t stream);
 
-struct TcParams {
-  const void* x; const float* offset; const float* mask;
-  const uint16_t* w_hi; const uint16_t* w_lo;
-  const float* bias; const void* residual; void* y;
-  int N, H, W, Cin, Cout, Cout_pad, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
-  int relu, out_nhwc, BN, stages, x3;
-  int x_bf16, y_bf16;
-  int res_up2;
-};
-size_t tc_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
-int tc_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, void* packed, cudaStream_t stream);
-bool tc_supported(int Cin, int kh, int kw, int dg);
-int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream);
 }  // namespace ups
 
 extern "C" int upsnet_version(int* n_sm) {
@@ -124,6 +112,7 @@ extern "C" int upsnet_igemm_forward(const void* x_nhwc, const float* offset, con
   p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
   p.out_nhwc = out_layout == UPSNET_LAYOUT_NHWC;
   p.res_up2 = (epi_flags & UPSNET_EPI_RES_UP2) ? 1 : 0;
+  p.no_tma = (epi_flags & UPSNET_EPI_NO_TMA) ? 1 : 0;
   if (p.res_up2 && (!residual || !p.out_nhwc || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_BADARG;
   p.x3 = precision == UPSNET_PREC_BF16X3;
   if ((x_dtype != UPSNET_DTYPE_F32 && x_dtype != UPSNET_DTYPE_BF16) || (y_dtype != UPSNET_DTYPE_F32 && y_dtype != UPSNET_DTYPE_BF16))

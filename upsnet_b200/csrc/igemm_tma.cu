@@ -1,0 +1,436 @@
+// igemm_tma.cu -- TMA-fed tcgen05 implicit-GEMM convolution for sm_100a (dense, stride 1, bf16 NHWC in / out).
+//
+// The layers that dominate the UPSNet backbone / FPN / RPN / mask head / FC path (1x1 and 3x3, stride 1,
+// Cin % 64 == 0, Cout % 64 == 0; reference: models/resnet.py, models/fpn.py, models/rcnn.py) need no gather
+// arithmetic at all once the activations are NHWC bf16: a tile of output pixels is a bw x bh x bn BOX of the
+// 4-D tensor (C, W, H, N), and filter tap (ki, kj) of that tile is the SAME box shifted by (kj*dil - pad,
+// ki*dil - pad) with out-of-range pixels reading zero.  That is exactly one tiled-mode TMA load per k-block:
+//
+//   A[<=128 pixels x 64 ch]  cp.async.bulk.tensor.4d  box (64, bw, bh, bn) at (c0, w0 + kj*dw - pw, h0 + ki*dh - ph, n0)
+//   B[BN couts x 64 k]       cp.async.bulk.tensor.2d  box (64, BN) of the packed weights [Cout][tap*Cin + c]
+//   D[128 x BN] fp32 in TMEM (two buffers)  +=  A * B^T     tcgen05.mma kind::f16, one elected thread
+//   epilogue (8 warps, thread = accumulator row): tcgen05.ld -> +bias (+residual slab, TMA-prefetched) -> ReLU
+//            -> bf16 -> SWIZZLE_128B slab in smem -> cp.async.bulk.tensor.4d store (clips the box at the borders)
+//
+// Both operands land in the K-major SWIZZLE_128B layout the UMMA descriptors expect (the TMA swizzle mode and
+// the smem descriptor's layout type are the same permutation), so no thread touches the operands: 3 service
+// warps (TMA loads, MMA issue, residual loads) + 8 epilogue warps per persistent CTA, one CTA per SM.
+// Roofline: tensor pipe for the 3x3 layers (2*P*Cout*Cin*9 flop), HBM for the 1x1 (+residual) layers
+// (x + residual + y bytes); per-SM L2->smem operand traffic is (128 + BN) * 128 B per k-block.
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is resolved at run time (no libcuda link dependency)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_params.cuh"
+
+namespace ups {
+
+constexpr int TM_EPI_WARPS = 8;
+constexpr int TM_WARP_TMA = 8, TM_WARP_MMA = 9, TM_WARP_RES = 10;
+constexpr int TM_THREADS = 11 * 32;
+constexpr int TM_MAX_STAGES = 8;
+constexpr int TM_SLAB_BYTES = 128 * 128;   // 128 rows x 64 bf16
+
+struct TmaGeom {
+  const float* bias;
+  int N, Ho, Wo, Cout, Cin;
+  int kw, KHW, ph, pw, dh, dw;
+  int bw, bh, bn;                       // M-tile box: pixels along W, along H, images (bw*bh*bn <= 128)
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int BN, stages, relu, has_res;
+};
+
+// ---- PTX: TMA (bulk tensor) copies ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct TmaSmem {
+  uint32_t stages, out, res, a_bytes, b_bytes, stage_bytes, total;
+};
+__host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res) {
+  TmaSmem s;
+  s.a_bytes = 128 * 128;
+  s.b_bytes = (uint32_t)BN * 128;
+  s.stage_bytes = s.a_bytes + s.b_bytes;
+  s.stages = 1024;                                           // barriers live in the first KB
+  s.out = s.stages + s.stage_bytes * (uint32_t)stages;
+  const uint32_t out_slabs = BN == 64 ? 1 : 2;               // one output slab per epilogue group
+  s.res = s.out + out_slabs * TM_SLAB_BYTES;
+  s.total = s.res + (has_res ? (uint32_t)(BN / 64) * TM_SLAB_BYTES : 0u);
+  return s;
+}
+
+// Roles (11 warps): warps 0-7 epilogue (TMEM lane quadrant = warp & 3; column half = warp >> 2), warp 8 TMA
+// operand loads, warp 9 MMA issue + TMEM ownership, warp 10 residual-slab loads.
+// Barriers: full[s]/empty[s] smem ring (TMA <-> MMA), tfull[b]/tempty[b] TMEM buffers (MMA <-> epilogue),
+// rfull/rempty residual slabs (TMA <-> epilogue).
+__global__ void __launch_bounds__(TM_THREADS, 1)
+igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r, const TmaGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_dyn + (base - raw);
+  const TmaSmem L = tma_smem_layout(g.BN, g.stages, g.has_res != 0);
+  const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 6));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cchunks = g.Cin / 64;
+  const int num_kb = g.KHW * cchunks;
+  const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  const long long num_tiles = m_tiles * g.n_tiles;
+  const uint32_t box_bytes = (uint32_t)(g.bw * g.bh * g.bn) * 128u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * g.BN) tmem_cols <<= 1;
+
+  if (warp == TM_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_tfull + 8 * b, 1);
+        mbar_init(bar_tempty + 8 * b, TM_EPI_WARPS);
+      }
+      mbar_init(bar_rfull, 1);
+      mbar_init(bar_rempty, TM_EPI_WARPS);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+  } else if (warp == TM_WARP_TMA && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_y);
+    if (g.has_res) prefetch_tmap(&tm_r);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == TM_WARP_TMA) {
+    // =============================== OPERAND LOADS ===============================
+    if (lane == 0) {
+      uint32_t gk = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % g.n_tiles);
+        const long long mt = tile / g.n_tiles;
+        const int w0 = (int)(mt % g.tiles_w) * g.bw;
+        const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+        const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+        const int n0 = nt * g.BN;
+        int tap = 0, cc = 0, ki = 0, kj = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
+          const uint32_t s = gk % (uint32_t)g.stages, it = gk / (uint32_t)g.stages;
+          mbar_wait(bar_empty + 8 * s, (it & 1u) ^ 1u);
+          const uint32_t a_dst = base + L.stages + s * L.stage_bytes;
+          mbar_arrive_expect_tx(bar_full + 8 * s, box_bytes + L.b_bytes);
+          tma_load_4d(a_dst, &tm_x, bar_full + 8 * s, cc * 64, w0 - g.pw + kj * g.dw, h0 - g.ph + ki * g.dh, i0);
+          tma_load_2d(a_dst + L.a_bytes, &tm_w, bar_full + 8 * s, kb * 64, n0);
+          if (++cc == cchunks) {
+            cc = 0; ++tap;
+            if (++kj == g.kw) { kj = 0; ++ki; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_WARP_MMA) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, g.BN);
+      uint32_t gk = 0, ti_local = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
+        const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
+          const uint32_t s = gk % (uint32_t)g.stages, it = gk / (uint32_t)g.stages;
+          mbar_wait(bar_full + 8 * s, it & 1u);
+          tc_fence_after();
+          const uint32_t a = base + L.stages + s * L.stage_bytes;
+          const uint32_t b = a + L.a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_d, umma_desc(a + k * 32), umma_desc(b + k * 32), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_WARP_RES) {
+    // =============================== RESIDUAL LOADS ===============================
+    if (lane == 0 && g.has_res) {
+      uint32_t ti_local = 0;
+      const int slabs = g.BN / 64;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
+        const int nt = (int)(tile % g.n_tiles);
+        const long long mt = tile / g.n_tiles;
+        const int w0 = (int)(mt % g.tiles_w) * g.bw;
+        const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+        const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+        mbar_wait(bar_rempty, (ti_local & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_rfull, box_bytes * (uint32_t)slabs);
+        for (int s = 0; s < slabs; ++s)
+          tma_load_4d(base + L.res + s * TM_SLAB_BYTES, &tm_r, bar_rfull, nt * g.BN + s * 64, w0, h0, i0);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE (warps 0-7) ===============================
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int units = g.BN / 32;                       // 32-column units of the accumulator
+    const int upw = units >= 4 ? units / 2 : 1;        // units per half (BN = 64: one each)
+    const int bar_id = g.BN == 64 ? 1 : 1 + half;
+    const int bar_cnt = g.BN == 64 ? 256 : 128;
+    const bool leader = (g.BN == 64 ? warp == 0 : q == 0) && lane == 0;
+    const uint32_t out_slab = base + L.out + (g.BN == 64 ? 0u : (uint32_t)half * TM_SLAB_BYTES);
+    const uint32_t sw_row = (uint32_t)row * 128u;
+    const uint32_t rx = (uint32_t)(row & 7);
+    uint32_t ti_local = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
+      const int nt = (int)(tile % g.n_tiles);
+      const long long mt = tile / g.n_tiles;
+      const int w0 = (int)(mt % g.tiles_w) * g.bw;
+      const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+      const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+      const int n0 = nt * g.BN;
+      const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+      mbar_wait(bar_tfull + 8 * buf, use & 1u);
+      tc_fence_after();
+      if (g.has_res) mbar_wait(bar_rfull, ti_local & 1u);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      for (int ui = 0; ui < upw; ++ui) {
+        const int u = half * upw + ui;
+        const int slab = u >> 1;
+        const uint32_t jb = (uint32_t)(u & 1) * 4u;     // first 16-byte chunk of this unit inside the slab row
+        uint32_t v0[16], v1[16];
+        tmem_ld16_issue(trow + (uint32_t)(u * 32), v0);
+        tmem_ld16_issue(trow + (uint32_t)(u * 32 + 16), v1);
+        if ((u & 1) == 0 || g.BN == 64) {
+          // the output slab is about to be overwritten: its previous TMA store must have finished reading it
+          if (leader) bulk_wait_read0();
+          named_bar_sync(bar_id, bar_cnt);
+        }
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { o[e] = __uint_as_float(v0[e]); o[16 + e] = __uint_as_float(v1[e]); }
+        if (g.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + u * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 b4 = __ldg(bp + e);
+            o[4 * e] += b4.x; o[4 * e + 1] += b4.y; o[4 * e + 2] += b4.z; o[4 * e + 3] += b4.w;
+          }
+        }
+        if (g.has_res) {
+          const uint32_t rs = base + L.res + (uint32_t)slab * TM_SLAB_BYTES + sw_row;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 rv = lds128(rs + (((jb + c) ^ rx) << 4));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[c * 8 + 2 * e] += __uint_as_float(rw[e] << 16);
+              o[c * 8 + 2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+            }
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = fmaxf(o[e], 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 w;
+          w.x = pack_bf16x2(o[c * 8], o[c * 8 + 1]); w.y = pack_bf16x2(o[c * 8 + 2], o[c * 8 + 3]);
+          w.z = pack_bf16x2(o[c * 8 + 4], o[c * 8 + 5]); w.w = pack_bf16x2(o[c * 8 + 6], o[c * 8 + 7]);
+          sts128(out_slab + sw_row + (((jb + c) ^ rx) << 4), w);
+        }
+        if ((u & 1) == 1 || g.BN == 64) {
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA store
+          named_bar_sync(bar_id, bar_cnt);
+          if (leader) {
+            tma_store_4d(&tm_y, out_slab, n0 + slab * 64, w0, h0, i0);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_tempty + 8 * buf);
+        if (g.has_res) mbar_arrive(bar_rempty);
+      }
+    }
+    if (leader) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TM_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tensor maps, tile geometry, launch
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+    tried = true;
+  }
+  return fn;
+}
+
+// bf16 tensor, innermost dimension first; box[0] = 64 elements = one 128-byte swizzle span
+static bool encode_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                        const cuuint32_t* box) {
+  cuuint64_t strides[4];
+  cuuint64_t acc = 2;
+  for (int i = 0; i + 1 < rank; ++i) { acc *= dims[i]; strides[i] = acc; }
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Output-pixel box (bw, bh, bn) with bw*bh*bn <= 128: fewest tiles, then smallest input halo, then widest rows.
+static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, int* bw_o, int* bh_o, int* bn_o) {
+  long long best_tiles = -1, best_halo = 0;
+  int bbw = 1, bbh = 1, bbn = 1;
+  const int wmax = Wo < 128 ? Wo : 128;
+  for (int bw = 1; bw <= wmax; ++bw) {
+    if (Wo > 32 && (bw & (bw - 1))) continue;     // large maps: power-of-two widths only (keeps the search tiny)
+    const int hmax = (128 / bw) < Ho ? (128 / bw) : Ho;
+    for (int bh = 1; bh <= hmax; ++bh) {
+      int bn = 128 / (bw * bh);
+      if (bn > N) bn = N;
+      if (bn < 1) continue;
+      const long long tiles = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((N + bn - 1) / bn);
+      const long long halo = (long long)(bw + (kw - 1) * dw) * (bh + (kh - 1) * dh) * bn;
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && (halo < best_halo || (halo == best_halo && bw > bbw)))) {
+        best_tiles = tiles; best_halo = halo; bbw = bw; bbh = bh; bbn = bn;
+      }
+    }
+  }
+  *bw_o = bbw; *bh_o = bbh; *bn_o = bbn;
+}
+
+int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream) {
+  if (p.no_tma || p.offset || p.x3 || !p.x_bf16 || !p.y_bf16 || !p.out_nhwc || p.res_up2) return UPSNET_E_UNSUPPORTED;
+  if (p.sh != 1 || p.sw != 1 || (p.Cin % 64) || (p.Cout % 64) || p.kh * p.kw > 49) return UPSNET_E_UNSUPPORTED;
+  if ((((uintptr_t)p.x) & 15) || (((uintptr_t)p.y) & 15) || (((uintptr_t)packed) & 15) || (p.residual && (((uintptr_t)p.residual) & 15)))
+    return UPSNET_E_UNSUPPORTED;
+  if (p.bias && (((uintptr_t)p.bias) & 15)) return UPSNET_E_UNSUPPORTED;
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return UPSNET_E_UNSUPPORTED;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms = v > 0 ? v : kNumSMs;
+  }
+  TmaGeom g{};
+  g.bias = p.bias;
+  g.N = p.N; g.Ho = p.Ho; g.Wo = p.Wo; g.Cout = p.Cout; g.Cin = p.Cin;
+  g.kw = p.kw; g.KHW = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.dh = p.dh; g.dw = p.dw;
+  g.relu = p.relu; g.has_res = p.residual ? 1 : 0;
+  tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, &g.bw, &g.bh, &g.bn);
+  g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
+  g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
+  g.tiles_n = (p.N + g.bn - 1) / g.bn;
+  const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  int BN = (p.Cout % 256 == 0 && !g.has_res) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
+  while (BN > 64 && m_tiles * (p.Cout / BN) < sms) BN /= 2;
+  g.BN = BN;
+  g.n_tiles = p.Cout / BN;
+  int stages = TM_MAX_STAGES;
+  TmaSmem L = tma_smem_layout(BN, stages, g.has_res != 0);
+  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0); }
+  if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  g.stages = stages;
+
+  const int Kp = g.KHW * p.Cin;
+  CUtensorMap tm_x, tm_w, tm_y, tm_r;
+  {
+    const cuuint64_t dx[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    const cuuint64_t dy[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+    const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)p.Cout};
+    const cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
+    const cuuint32_t boxw[2] = {64, (cuuint32_t)BN};
+    if (!encode_bf16(enc, &tm_x, p.x, 4, dx, box)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_w, packed, 2, dwt, boxw)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_y, p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_r, p.residual ? p.residual : p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
+  }
+  const long long num_tiles = m_tiles * g.n_tiles;
+  if (num_tiles <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
+  igemm_tma_kernel<<<grid, TM_THREADS, L.total + 1024, stream>>>(tm_x, tm_w, tm_y, tm_r, g);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ups

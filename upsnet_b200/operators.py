@@ -30,6 +30,7 @@ from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
 # default arithmetic of the convolution tiles; switched by upsnet_b200.set_precision()
 _PRECISION = {"conv": _lib.PREC_FP32_SIMT}
 ACT_BF16 = {"on": False}   # engine switch: store activations as bf16 (precision 'bf16' only)
+USE_TMA = {"on": True}     # False forces the cp.async gather kernel where the TMA-fed one would qualify (A/B tests)
 
 
 def set_precision(name, bf16_activations=None):
@@ -148,7 +149,8 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
                                          ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
                                          _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW,
                                          1 if xs.dtype == torch.bfloat16 else 0, 1 if out_dtype == torch.bfloat16 else 0,
-                                         (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if residual_up2 else 0),
+                                         (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if residual_up2 else 0) |
+                                         (0 if USE_TMA["on"] else _lib.EPI_NO_TMA),
                                          prec, stream_ptr(x.device)), kind)
     return y
 
