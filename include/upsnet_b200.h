@@ -162,6 +162,38 @@ int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *
                         double fraction_threshold, int64_t *keep_out, int *k_out, float *mask_energy,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Detection glue, fused (device-resident; nothing returns to the host).
+ *
+ * upsnet_rpn_decode: anchors + deltas -> clipped proposal boxes for the pre-NMS top-k of every pyramid level.
+ * replaces: operators/functions/pyramid_proposal.py:83-131 (shifted anchors, bbox_transform, clip_boxes;
+ *           bbox/bbox_transform.py:290-330,45-60) for the selected indices.
+ * deltas[l] fp32 [4A,h_l,w_l] (RPN head output, channel a*4+c); top_idx[l] int64 [k_l] flat (y,x,a) indices
+ * (device); k/hs/ws/strides host arrays [L]; base_anchors float64 [L,A,4] on the device (generate_anchors);
+ * boxes_out fp32 [sum k_l, 4] in level order. */
+int upsnet_rpn_decode(const float *const *deltas, const long long *const *top_idx, const int *k,
+                      const int *hs, const int *ws, const int *strides, const double *base_anchors,
+                      int L, int A, float im_h, float im_w, float *boxes_out, void *stream);
+
+/* upsnet_maskroi_prepare: candidate selection (prob > score_thresh, roi valid), ordering (class segment
+ * ascending -- one segment when class_agnostic --, score descending, roi-major index ascending) and box decode
+ * (weights, clip) in one launch.  replaces: operators/modules/mask_roi.py:36-95 up to the per-class NMS.
+ * rois [R,5]; roi_valid uint8 [R]; bbox_delta [R,4C]; cls_prob [R,C]; R*(C-1) <= 8192.
+ * sc_out/cls_out/bx_out [R*(C-1)] (/[.,4]): candidates first, in NMS input order (others: score -1);
+ * offs_out int32 [nseg+1]: segment offsets for upsnet_nms_segmented. */
+int upsnet_maskroi_prepare(const float *rois, const unsigned char *roi_valid, const float *bbox_delta,
+                           const float *cls_prob, int R, int C, int class_agnostic, float score_thresh,
+                           const float weights[4], float im_h, float im_w, float *sc_out, int *cls_out,
+                           float *bx_out, int *offs_out, void *stream);
+
+/* upsnet_maskroi_finish: NMS survivors (class-major) -> keep scores >= the top_n-th largest -> `cap` output
+ * slots (score, (0,x1,y1,x2,y2), class) + device count; no survivor -> one dummy detection (score 1, zero box,
+ * class 0).  replaces: operators/modules/mask_roi.py:96-139.  keep/keep_cnt/seg_offsets as produced by
+ * upsnet_nms_segmented on bx; nseg <= 128. */
+int upsnet_maskroi_finish(const int *keep, const int *keep_cnt, const int *seg_offsets, const float *sc,
+                          const int *cls, const float *bx, int nseg, int max_seg_len, int top_n, int cap,
+                          float *out_sc, float *out_bx, long long *out_cls, int *n_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,6 +288,8 @@ def test_tc_tiny_cin_stem_mode(dev, cfg, prec):
     dict(N=300, Cin=1024, Cout=1024, H=1, W=1, k=1, pad=0, dil=1),    # fully connected: 128 "images" per box
     dict(N=1, Cin=128, Cout=192, H=14, W=30, k=3, pad=2, dil=2),      # dilation, Cout = 3 x 64
     dict(N=3, Cin=64, Cout=128, H=7, W=7, k=7, pad=3, dil=1),         # 49 taps (ring wraps many times)
+    dict(N=2, Cin=256, Cout=512, H=17, W=21, k=1, pad=0, dil=1, stride=2),   # down-sampling 1x1: strided view
+    dict(N=1, Cin=128, Cout=64, H=64, W=64, k=1, pad=0, dil=1, stride=2),
 ])
 def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
     import upsnet_b200 as U
@@ -295,7 +297,8 @@ def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
     rng = np.random.default_rng(21)
     x, w, b = _case(rng, cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"], cfg["k"])
     x, w = _bf16_exact(x), _bf16_exact(w)
-    want = O.conv2d(x, w, b, 1, cfg["pad"], cfg["dil"])
+    st = cfg.get("stride", 1)
+    want = O.conv2d(x, w, b, st, cfg["pad"], cfg["dil"])
     res = _bf16_exact(rng.standard_normal(want.shape).astype(np.float32))
     xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
     rb = t(res, dev).bfloat16().contiguous(memory_format=torch.channels_last)
@@ -303,11 +306,11 @@ def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
     for tma in (True, False):
         OPS.USE_TMA["on"] = tma
         try:
-            y0 = U.conv2d(xb, t(w, dev), t(b, dev), 1, cfg["pad"], cfg["dil"], precision=BF16, out_format="nhwc",
+            y0 = U.conv2d(xb, t(w, dev), t(b, dev), st, cfg["pad"], cfg["dil"], precision=BF16, out_format="nhwc",
                           out_dtype=torch.bfloat16)
-            y1 = U.conv2d(xb, t(w, dev), t(b, dev), 1, cfg["pad"], cfg["dil"], residual=rb, relu=True, precision=BF16,
+            y1 = U.conv2d(xb, t(w, dev), t(b, dev), st, cfg["pad"], cfg["dil"], residual=rb, relu=True, precision=BF16,
                           out_format="nhwc", out_dtype=torch.bfloat16)
-            y2 = U.conv2d(xb, t(w, dev), None, 1, cfg["pad"], cfg["dil"], relu=True, precision=BF16, out_format="nhwc",
+            y2 = U.conv2d(xb, t(w, dev), None, st, cfg["pad"], cfg["dil"], relu=True, precision=BF16, out_format="nhwc",
                           out_dtype=torch.bfloat16)
         finally:
             OPS.USE_TMA["on"] = True
@@ -323,3 +326,29 @@ def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
     # same MMA sequence and epilogue arithmetic as the gather kernel -> identical bf16 outputs
     for a, g in zip(outs[True], outs[False]):
         assert torch.equal(a, g)
+
+
+@pytest.mark.parametrize("cfg", [dict(N=1, Cin=256, Cout=256, H=32, W=48), dict(N=2, Cin=512, Cout=128, H=18, W=22),
+                                 dict(N=1, Cin=64, Cout=64, H=64, W=160)])
+def test_tma_fpn_lateral_residual_up2(dev, cfg):
+    """FPN top-down merge (models/fpn.py:88-93): lateral 1x1 conv + nearest-2x up-sampled coarser map, fused."""
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as OPS
+    rng = np.random.default_rng(23)
+    x, w, b = _case(rng, cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"], 1)
+    x, w = _bf16_exact(x), _bf16_exact(w)
+    coarse = _bf16_exact(rng.standard_normal((cfg["N"], cfg["Cout"], cfg["H"] // 2, cfg["W"] // 2)).astype(np.float32))
+    want = O.conv2d(x, w, b, 1, 0, 1) + np.repeat(np.repeat(coarse, 2, axis=2), 2, axis=3)
+    xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    cb = t(coarse, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for tma in (True, False):
+        OPS.USE_TMA["on"] = tma
+        try:
+            outs.append(U.conv2d(xb, t(w, dev), t(b, dev), 1, 0, 1, residual=cb, residual_up2=True, precision=BF16,
+                                 out_format="nhwc", out_dtype=torch.bfloat16))
+        finally:
+            OPS.USE_TMA["on"] = True
+    torch.cuda.synchronize()
+    assert np.abs(outs[0].float().cpu().numpy() - want).max() < 1e-4 + (2.0 ** -8) * np.abs(want).max()
+    assert torch.equal(outs[0], outs[1])

@@ -49,6 +49,10 @@ def lib():
         L.upsnet_panoptic_workspace_bytes.argtypes = [i, i, i, i, C.POINTER(sz)]
         L.upsnet_panoptic_head.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, vp, i, d, vp, vp, vp, vp, vp, sz, vp]
         L.upsnet_mask_removal.argtypes = [vp, vp, vp, vp, i, vp, i, i, i, d, vp, vp, vp, vp, sz, vp]
+        L.upsnet_rpn_decode.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                        C.POINTER(i), vp, i, i, f, f, vp, vp]
+        L.upsnet_maskroi_prepare.argtypes = [vp, vp, vp, vp, i, i, i, f, C.POINTER(f), f, f, vp, vp, vp, vp, vp]
+        L.upsnet_maskroi_finish.argtypes = [vp] * 6 + [i] * 4 + [vp] * 5
         _lib = L
     return _lib
 
@@ -58,6 +62,7 @@ EXPORTED_SYMBOLS = [
     "upsnet_nms_workspace_bytes", "upsnet_nms_segmented", "upsnet_nms_host", "upsnet_dcn_forward",
     "upsnet_conv2d_forward", "upsnet_igemm_packed_weight_bytes", "upsnet_igemm_pack_weight",
     "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head", "upsnet_mask_removal",
+    "upsnet_rpn_decode", "upsnet_maskroi_prepare", "upsnet_maskroi_finish",
 ]
 
 

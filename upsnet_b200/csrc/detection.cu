@@ -1,0 +1,338 @@
+// detection.cu -- fused device-side detection glue between the hot kernels: RPN box decode for the pre-NMS
+// top-k of every pyramid level, and the two halves of MaskROI (candidate selection + ordering + decode before
+// the segmented NMS, global top-n + compaction after it).
+//
+// The reference does this on the HOST in numpy (operators/functions/pyramid_proposal.py:83-131,
+// operators/modules/mask_roi.py:36-146, bbox/bbox_transform.py:290-330,45-60); the engine's first GPU version
+// restated it with ~30 elementwise / sort / scatter torch launches per call, which made ~600 tiny launches per
+// image.  Each kernel here replaces one such cluster with a single launch and keeps the arithmetic order of
+// the reference's float32 formulas (separately rounded mul/add: no FMA contraction), so the decoded boxes --
+// and therefore every NMS decision -- are the ones the torch restatement (still used on CPU tensors and as the
+// test oracle for these kernels) produces.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace ups {
+
+// bbox/bbox_transform.py:290-330 for one (box, delta) pair; weights divide the deltas; clip to the image.
+__device__ __forceinline__ float4 decode_clip(float x1, float y1, float x2, float y2, float dx, float dy, float dw, float dh,
+                                              float xform_clip, float im_h, float im_w) {
+  const float w = __fadd_rn(__fsub_rn(x2, x1), 1.0f), h = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+  const float cx = __fadd_rn(x1, __fmul_rn(0.5f, w)), cy = __fadd_rn(y1, __fmul_rn(0.5f, h));
+  dw = fminf(dw, xform_clip);
+  dh = fminf(dh, xform_clip);
+  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  float4 o;
+  o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o.z = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+  o.w = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), 1.0f);
+  const float mx = __fsub_rn(im_w, 1.0f), my = __fsub_rn(im_h, 1.0f);
+  o.x = fminf(fmaxf(o.x, 0.f), mx);
+  o.y = fminf(fmaxf(o.y, 0.f), my);
+  o.z = fminf(fmaxf(o.z, 0.f), mx);
+  o.w = fminf(fmaxf(o.w, 0.f), my);
+  return o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// RPN decode
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxLevels = 8;
+struct RpnDecodeParams {
+  const float* deltas[kMaxLevels];       // [4A, h, w] fp32 (channel = a*4 + c)
+  const long long* idx[kMaxLevels];      // [k] flat indices in (y, x, a) order
+  int k[kMaxLevels], h[kMaxLevels], w[kMaxLevels], stride[kMaxLevels], start[kMaxLevels + 1];
+  const double* base;                    // [L, A, 4] generate_anchors() of every level (float64, like the reference)
+  int L, A;
+  float im_h, im_w, xform_clip;
+  float* out;                            // [sum k, 4]
+};
+
+__global__ void rpn_decode_kernel(const RpnDecodeParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.start[p.L]) return;
+  int l = 0;
+  while (l + 1 < p.L && t >= p.start[l + 1]) ++l;
+  const long long i = p.idx[l][t - p.start[l]];
+  const int a = (int)(i % p.A);
+  const long long pix = i / p.A;
+  const int x = (int)(pix % p.w[l]), y = (int)(pix / p.w[l]);
+  // anchors = float32(base(float64) + shift) (pyramid_proposal.py:83-100, bbox_transform.py:298)
+  const double sx = (double)(x * p.stride[l]), sy = (double)(y * p.stride[l]);
+  const double* b = p.base + ((size_t)l * p.A + a) * 4;
+  const float x1 = (float)(b[0] + sx), y1 = (float)(b[1] + sy), x2 = (float)(b[2] + sx), y2 = (float)(b[3] + sy);
+  const size_t hw = (size_t)p.h[l] * p.w[l];
+  const float* d = p.deltas[l] + (size_t)a * 4 * hw + (size_t)y * p.w[l] + x;
+  const float4 o = decode_clip(x1, y1, x2, y2, __ldg(d), __ldg(d + hw), __ldg(d + 2 * hw), __ldg(d + 3 * hw), p.xform_clip,
+                               p.im_h, p.im_w);
+  reinterpret_cast<float4*>(p.out)[t] = o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// MaskROI, part 1: candidates -> (segment asc, score desc, index asc) order -> decoded boxes + segment offsets
+// ----------------------------------------------------------------------------------------------
+constexpr int kSortN = 8192;
+constexpr int kMrThreads = 1024;
+
+__global__ void __launch_bounds__(kMrThreads, 1)
+maskroi_prepare_kernel(const float* __restrict__ rois, const uint8_t* __restrict__ roi_valid,
+                       const float* __restrict__ bbox_delta, const float* __restrict__ cls_prob, int R, int C,
+                       int class_agnostic, float score_thresh, float wx, float wy, float ww, float wh, float xform_clip,
+                       float im_h, float im_w, float* __restrict__ sc_out, int* __restrict__ cls_out,
+                       float* __restrict__ bx_out, int* __restrict__ offs_out) {
+  extern __shared__ unsigned long long keys[];   // kSortN
+  __shared__ int seg_cnt[130];
+  const int Cm = C - 1, n = R * Cm;
+  const int nseg = class_agnostic ? 1 : Cm;
+  const int tid = threadIdx.x;
+  for (int s = tid; s <= nseg; s += kMrThreads) seg_cnt[s] = 0;
+  __syncthreads();
+  for (int i = tid; i < kSortN; i += kMrThreads) {
+    unsigned long long key = ~0ull;
+    if (i < n) {
+      const int r = i / Cm, c = i - r * Cm;
+      const float pr = __ldg(cls_prob + (size_t)r * C + c + 1);
+      const bool cand = pr > score_thresh && roi_valid[r] != 0;
+      const int seg = cand ? (class_agnostic ? 0 : c) : nseg;
+      // descending score: prob > thresh >= 0 is a positive float, whose bit pattern is monotonic
+      const unsigned inv = cand ? 0xffffffffu - __float_as_uint(pr) : 0u;
+      key = ((unsigned long long)seg << 45) | ((unsigned long long)inv << 13) | (unsigned long long)i;
+      atomicAdd(&seg_cnt[seg], 1);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort, ascending
+  for (int k = 2; k <= kSortN; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < kSortN / 2; t += kMrThreads) {
+        const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < nseg; ++s) { offs_out[s] = acc; acc += seg_cnt[s]; }
+    offs_out[nseg] = acc;
+    seg_cnt[nseg + 1] = acc;
+  }
+  __syncthreads();
+  const int n_cand = seg_cnt[nseg + 1];
+  for (int pidx = tid; pidx < n; pidx += kMrThreads) {
+    float sc = -1.0f;
+    int cls = 0;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pidx < n_cand) {
+      const int i = (int)(keys[pidx] & 0x1fffull);
+      const int r = i / Cm, c = i - r * Cm;
+      cls = c + 1;
+      sc = __ldg(cls_prob + (size_t)r * C + cls);
+      const float* ro = rois + (size_t)r * 5 + 1;
+      const float* d = bbox_delta + (size_t)r * 4 * C + 4 * cls;
+      bx = decode_clip(ro[0], ro[1], ro[2], ro[3], __fdiv_rn(d[0], wx), __fdiv_rn(d[1], wy), __fdiv_rn(d[2], ww),
+                       __fdiv_rn(d[3], wh), xform_clip, im_h, im_w);
+    }
+    sc_out[pidx] = sc;
+    cls_out[pidx] = cls;
+    reinterpret_cast<float4*>(bx_out)[pidx] = bx;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// MaskROI, part 2: NMS survivors (class-major) -> global top-n score threshold -> compaction into `cap` slots
+// ----------------------------------------------------------------------------------------------
+constexpr int kAllCap = 4096;
+
+__device__ __forceinline__ unsigned orderable(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// exclusive block scan of one int per thread (1024 threads); returns the prefix, total in *total
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;   // inclusive
+  }
+  __syncthreads();
+  const int base = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[31];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(kMrThreads, 1)
+maskroi_finish_kernel(const int* __restrict__ keep, const int* __restrict__ cnt, const int* __restrict__ offs,
+                      const float* __restrict__ sc, const int* __restrict__ cls, const float* __restrict__ bx, int nseg,
+                      int M, int top_n, int cap, float* __restrict__ out_sc, float* __restrict__ out_bx,
+                      long long* __restrict__ out_cls, int* __restrict__ n_out) {
+  __shared__ int gidx[kAllCap];
+  __shared__ unsigned key[kAllCap];
+  __shared__ int seg_base[130];
+  __shared__ int hist[256];
+  __shared__ int warp_sums[32];
+  __shared__ unsigned sel_prefix;
+  __shared__ int sel_k;
+  const int tid = threadIdx.x;
+  const int all_cap = min(nseg * M, kAllCap);
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < nseg; ++s) { seg_base[s] = acc; acc += min(max(cnt[s], 0), M); }
+    seg_base[nseg] = acc;
+  }
+  __syncthreads();
+  const int nk = min(seg_base[nseg], all_cap);
+  // class-major list of survivors (mask_roi.py:96-104), NMS (descending score) order inside a class
+  for (int s = 0; s < nseg; ++s) {
+    const int b = seg_base[s], c = seg_base[s + 1] - b, o = offs[s];
+    for (int j = tid; j < c; j += kMrThreads)
+      if (b + j < all_cap) {
+        const int g = keep[(size_t)s * M + j] + o;
+        gidx[b + j] = g;
+        key[b + j] = orderable(sc[g]);
+      }
+  }
+  __syncthreads();
+  // k-th largest score (mask_roi.py:106-121): 4-pass radix select over the order-preserving keys
+  const int K = min(top_n, all_cap);
+  unsigned kth = 0u;            // keep everything
+  if (top_n > 0 && nk >= K) {
+    if (tid == 0) { sel_prefix = 0u; sel_k = K; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int b = tid; b < 256; b += kMrThreads) hist[b] = 0;
+      __syncthreads();
+      const unsigned pref = sel_prefix;
+      for (int i = tid; i < nk; i += kMrThreads)
+        if ((key[i] & pmask) == pref) atomicAdd(&hist[(key[i] >> shift) & 255u], 1);
+      __syncthreads();
+      if (tid == 0) {
+        int need = sel_k, b = 255;
+        for (; b > 0; --b) {
+          if (hist[b] >= need) break;
+          need -= hist[b];
+        }
+        sel_k = need;
+        sel_prefix = pref | ((unsigned)b << shift);
+      }
+      __syncthreads();
+    }
+    kth = sel_prefix;
+  }
+  // ordered compaction of {score >= kth} into the output slots
+  constexpr int PER = kAllCap / kMrThreads;
+  int flags[PER], mine = 0;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int i = tid * PER + e;
+    flags[e] = (i < nk && key[i] >= kth) ? 1 : 0;
+    mine += flags[e];
+  }
+  int total = 0;
+  int dst = block_scan_excl(mine, warp_sums, &total);
+  const int n_sel = min(total, cap);
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    if (flags[e]) {
+      if (dst < cap) {
+        const int g = gidx[tid * PER + e];
+        out_sc[dst] = sc[g];
+        out_cls[dst] = (long long)cls[g];
+        out_bx[(size_t)dst * 5] = 0.f;
+        const float4 b4 = reinterpret_cast<const float4*>(bx)[g];
+        out_bx[(size_t)dst * 5 + 1] = b4.x; out_bx[(size_t)dst * 5 + 2] = b4.y;
+        out_bx[(size_t)dst * 5 + 3] = b4.z; out_bx[(size_t)dst * 5 + 4] = b4.w;
+      }
+      ++dst;
+    }
+  }
+  for (int sidx = n_sel + tid; sidx < cap; sidx += kMrThreads) {
+    out_sc[sidx] = (sidx == 0) ? 1.0f : 0.f;     // mask_roi.py:132-139: nothing survives -> one dummy detection
+    out_cls[sidx] = 0;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) out_bx[(size_t)sidx * 5 + e] = 0.f;
+  }
+  if (tid == 0) *n_out = n_sel == 0 ? 1 : n_sel;
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_rpn_decode(const float* const* deltas, const long long* const* top_idx, const int* k, const int* hs,
+                                 const int* ws, const int* strides, const double* base_anchors, int L, int A, float im_h,
+                                 float im_w, float* boxes_out, void* stream) {
+  if (!deltas || !top_idx || !k || !hs || !ws || !strides || !base_anchors || !boxes_out) return UPSNET_E_BADARG;
+  if (L <= 0 || L > ups::kMaxLevels || A <= 0) return UPSNET_E_BADARG;
+  ups::RpnDecodeParams p{};
+  int acc = 0;
+  for (int l = 0; l < L; ++l) {
+    if (k[l] < 0 || hs[l] <= 0 || ws[l] <= 0 || (k[l] > 0 && (!deltas[l] || !top_idx[l]))) return UPSNET_E_BADARG;
+    p.deltas[l] = deltas[l]; p.idx[l] = top_idx[l];
+    p.k[l] = k[l]; p.h[l] = hs[l]; p.w[l] = ws[l]; p.stride[l] = strides[l];
+    p.start[l] = acc;
+    acc += k[l];
+  }
+  p.start[L] = acc;
+  p.base = base_anchors; p.L = L; p.A = A; p.im_h = im_h; p.im_w = im_w;
+  p.xform_clip = (float)4.135166556742356;   // log(1000 / 16), bbox_transform.py
+  p.out = boxes_out;
+  if (acc == 0) return 0;
+  ups::rpn_decode_kernel<<<(acc + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int upsnet_maskroi_prepare(const float* rois, const unsigned char* roi_valid, const float* bbox_delta,
+                                      const float* cls_prob, int R, int C, int class_agnostic, float score_thresh,
+                                      const float weights[4], float im_h, float im_w, float* sc_out, int* cls_out,
+                                      float* bx_out, int* offs_out, void* stream) {
+  if (!rois || !roi_valid || !bbox_delta || !cls_prob || !weights || !sc_out || !cls_out || !bx_out || !offs_out)
+    return UPSNET_E_BADARG;
+  if (R <= 0 || C < 2) return UPSNET_E_BADARG;
+  if ((long long)R * (C - 1) > ups::kSortN || C - 1 > 128 || score_thresh < 0.f) return UPSNET_E_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(ups::maskroi_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ups::kSortN * 8));
+    configured = true;
+  }
+  ups::maskroi_prepare_kernel<<<1, ups::kMrThreads, ups::kSortN * 8, (cudaStream_t)stream>>>(
+      rois, roi_valid, bbox_delta, cls_prob, R, C, class_agnostic, score_thresh, weights[0], weights[1], weights[2],
+      weights[3], (float)4.135166556742356, im_h, im_w, sc_out, cls_out, bx_out, offs_out);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int upsnet_maskroi_finish(const int* keep, const int* keep_cnt, const int* seg_offsets, const float* sc,
+                                     const int* cls, const float* bx, int nseg, int max_seg_len, int top_n, int cap,
+                                     float* out_sc, float* out_bx, long long* out_cls, int* n_out, void* stream) {
+  if (!keep || !keep_cnt || !seg_offsets || !sc || !cls || !bx || !out_sc || !out_bx || !out_cls || !n_out)
+    return UPSNET_E_BADARG;
+  if (nseg <= 0 || nseg > 128 || max_seg_len <= 0 || cap <= 0 || top_n < 0) return UPSNET_E_BADARG;
+  ups::maskroi_finish_kernel<<<1, ups::kMrThreads, 0, (cudaStream_t)stream>>>(
+      keep, keep_cnt, seg_offsets, sc, cls, bx, nseg, max_seg_len, top_n, cap, out_sc, out_bx, out_cls, n_out);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -39,6 +39,7 @@ struct TmaGeom {
   int bw, bh, bn;                       // M-tile box: pixels along W, along H, images (bw*bh*bn <= 128)
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int BN, stages, relu, has_res;
+  int res_up2;                          // residual = half-resolution map, nearest 2x up-sampling (FPN top-down)
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -211,9 +212,11 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
         const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
         mbar_wait(bar_rempty, (ti_local & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_rfull, box_bytes * (uint32_t)slabs);
+        // res_up2: the box of the half-resolution map that covers this tile is (bw/2, bh/2) at (w0/2, h0/2)
+        mbar_arrive_expect_tx(bar_rfull, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs);
         for (int s = 0; s < slabs; ++s)
-          tma_load_4d(base + L.res + s * TM_SLAB_BYTES, &tm_r, bar_rfull, nt * g.BN + s * 64, w0, h0, i0);
+          tma_load_4d(base + L.res + s * TM_SLAB_BYTES, &tm_r, bar_rfull, nt * g.BN + s * 64, w0 >> g.res_up2,
+                      h0 >> g.res_up2, i0);
       }
     }
     __syncwarp();
@@ -229,6 +232,12 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t out_slab = base + L.out + (g.BN == 64 ? 0u : (uint32_t)half * TM_SLAB_BYTES);
     const uint32_t sw_row = (uint32_t)row * 128u;
     const uint32_t rx = (uint32_t)(row & 7);
+    int rrow = row;                                    // row of the residual slab this accumulator row reads
+    if (g.res_up2) {
+      const int w = row % g.bw, h = (row / g.bw) % g.bh, n = row / (g.bw * g.bh);
+      rrow = (w >> 1) + (g.bw >> 1) * ((h >> 1) + (g.bh >> 1) * n);
+    }
+    const uint32_t rs_row = (uint32_t)rrow * 128u, rrx = (uint32_t)(rrow & 7);
     uint32_t ti_local = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
       const int nt = (int)(tile % g.n_tiles);
@@ -267,10 +276,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         if (g.has_res) {
-          const uint32_t rs = base + L.res + (uint32_t)slab * TM_SLAB_BYTES + sw_row;
+          const uint32_t rs = base + L.res + (uint32_t)slab * TM_SLAB_BYTES + rs_row;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint4 rv = lds128(rs + (((jb + c) ^ rx) << 4));
+            const uint4 rv = lds128(rs + (((jb + c) ^ rrx) << 4));
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -341,10 +350,10 @@ static EncodeTiledFn tma_encoder() {
 
 // bf16 tensor, innermost dimension first; box[0] = 64 elements = one 128-byte swizzle span
 static bool encode_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
-                        const cuuint32_t* box) {
+                        const cuuint32_t* box, const cuuint64_t* byte_strides = nullptr) {
   cuuint64_t strides[4];
   cuuint64_t acc = 2;
-  for (int i = 0; i + 1 < rank; ++i) { acc *= dims[i]; strides[i] = acc; }
+  for (int i = 0; i + 1 < rank; ++i) { acc *= dims[i]; strides[i] = byte_strides ? byte_strides[i] : acc; }
   const cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -352,14 +361,16 @@ static bool encode_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int
 }
 
 // Output-pixel box (bw, bh, bn) with bw*bh*bn <= 128: fewest tiles, then smallest input halo, then widest rows.
-static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, int* bw_o, int* bh_o, int* bn_o) {
+static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, bool even, int* bw_o, int* bh_o, int* bn_o) {
   long long best_tiles = -1, best_halo = 0;
   int bbw = 1, bbh = 1, bbn = 1;
   const int wmax = Wo < 128 ? Wo : 128;
   for (int bw = 1; bw <= wmax; ++bw) {
     if (Wo > 32 && (bw & (bw - 1))) continue;     // large maps: power-of-two widths only (keeps the search tiny)
+    if (even && (bw & 1)) continue;
     const int hmax = (128 / bw) < Ho ? (128 / bw) : Ho;
     for (int bh = 1; bh <= hmax; ++bh) {
+      if (even && (bh & 1)) continue;
       int bn = 128 / (bw * bh);
       if (bn > N) bn = N;
       if (bn < 1) continue;
@@ -374,8 +385,13 @@ static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, 
 }
 
 int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream) {
-  if (p.no_tma || p.offset || p.x3 || !p.x_bf16 || !p.y_bf16 || !p.out_nhwc || p.res_up2) return UPSNET_E_UNSUPPORTED;
-  if (p.sh != 1 || p.sw != 1 || (p.Cin % 64) || (p.Cout % 64) || p.kh * p.kw > 49) return UPSNET_E_UNSUPPORTED;
+  if (p.no_tma || p.offset || p.x3 || !p.x_bf16 || !p.y_bf16 || !p.out_nhwc) return UPSNET_E_UNSUPPORTED;
+  if (p.res_up2 && (!p.residual || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_UNSUPPORTED;
+  // stride > 1 only for 1x1 / pad 0 (the ResNet down-sampling convs): the input is then addressed through a
+  // strided VIEW (every sh-th row, sw-th pixel) and the layer is a stride-1 1x1 convolution of that view
+  const bool strided = p.sh != 1 || p.sw != 1;
+  if (strided && (p.kh != 1 || p.kw != 1 || p.ph != 0 || p.pw != 0)) return UPSNET_E_UNSUPPORTED;
+  if ((p.Cin % 64) || (p.Cout % 64) || p.kh * p.kw > 49) return UPSNET_E_UNSUPPORTED;
   if ((((uintptr_t)p.x) & 15) || (((uintptr_t)p.y) & 15) || (((uintptr_t)packed) & 15) || (p.residual && (((uintptr_t)p.residual) & 15)))
     return UPSNET_E_UNSUPPORTED;
   if (p.bias && (((uintptr_t)p.bias) & 15)) return UPSNET_E_UNSUPPORTED;
@@ -391,8 +407,8 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.bias = p.bias;
   g.N = p.N; g.Ho = p.Ho; g.Wo = p.Wo; g.Cout = p.Cout; g.Cin = p.Cin;
   g.kw = p.kw; g.KHW = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.dh = p.dh; g.dw = p.dw;
-  g.relu = p.relu; g.has_res = p.residual ? 1 : 0;
-  tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, &g.bw, &g.bh, &g.bn);
+  g.relu = p.relu; g.has_res = p.residual ? 1 : 0; g.res_up2 = p.res_up2 ? 1 : 0;
+  tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, g.res_up2 != 0, &g.bw, &g.bh, &g.bn);
   g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
   g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
   g.tiles_n = (p.N + g.bn - 1) / g.bn;
@@ -410,15 +426,23 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   const int Kp = g.KHW * p.Cin;
   CUtensorMap tm_x, tm_w, tm_y, tm_r;
   {
-    const cuuint64_t dx[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    const cuuint64_t dx[4] = {(cuuint64_t)p.Cin, (cuuint64_t)(strided ? p.Wo : p.W), (cuuint64_t)(strided ? p.Ho : p.H),
+                              (cuuint64_t)p.N};
+    const cuuint64_t sx[3] = {(cuuint64_t)p.sw * p.Cin * 2, (cuuint64_t)p.sh * p.W * p.Cin * 2, (cuuint64_t)p.H * p.W * p.Cin * 2};
     const cuuint64_t dy[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
     const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)p.Cout};
     const cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
     const cuuint32_t boxw[2] = {64, (cuuint32_t)BN};
-    if (!encode_bf16(enc, &tm_x, p.x, 4, dx, box)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_x, p.x, 4, dx, box, sx)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_w, packed, 2, dwt, boxw)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_y, p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
-    if (!encode_bf16(enc, &tm_r, p.residual ? p.residual : p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
+    if (g.res_up2) {
+      const cuuint64_t dr[4] = {(cuuint64_t)p.Cout, (cuuint64_t)(p.Wo / 2), (cuuint64_t)(p.Ho / 2), (cuuint64_t)p.N};
+      const cuuint32_t boxr[4] = {64, (cuuint32_t)(g.bw / 2), (cuuint32_t)(g.bh / 2), (cuuint32_t)g.bn};
+      if (!encode_bf16(enc, &tm_r, p.residual, 4, dr, boxr)) return UPSNET_E_UNSUPPORTED;
+    } else if (!encode_bf16(enc, &tm_r, p.residual ? p.residual : p.y, 4, dy, box)) {
+      return UPSNET_E_UNSUPPORTED;
+    }
   }
   const long long num_tiles = m_tiles * g.n_tiles;
   if (num_tiles <= 0) return 0;

@@ -16,7 +16,10 @@ import math
 import numpy as np
 import torch
 
+from . import operators as _ops
 from .operators import nms_segmented
+
+FUSED = {"on": True}   # CUDA tensors: fused decode / MaskROI kernels (detection.cu); False = torch restatement
 
 BBOX_XFORM_CLIP = math.log(1000. / 16.)
 
@@ -195,6 +198,14 @@ NEG_INF = float("-inf")
 
 
 class StaticProposalGenerator(ProposalGenerator):
+    def _base_anchors(self, L, dev):
+        key = ("base", L, str(dev))
+        if key not in self._anchors:
+            base = np.stack([generate_anchors(self.feat_stride[l], np.array(self.scales) * self.feat_stride[l], self.ratios)
+                             for l in range(L)])
+            self._anchors[key] = torch.from_numpy(np.ascontiguousarray(base, dtype=np.float64)).to(dev)
+        return self._anchors[key]
+
     def _offsets(self, lens, dev):
         key = ("offs", tuple(lens), str(dev))
         if key not in self._anchors:
@@ -206,17 +217,25 @@ class StaticProposalGenerator(ProposalGenerator):
         assert self.min_size == 0, "static path assumes config.test.rpn_min_size == 0 (all shipped yamls)"
         dev = cls_probs[0].device
         im_h, im_w = float(im_info[0]), float(im_info[1])
-        boxes_l, scores_l, lens = [], [], []
+        boxes_l, scores_l, lens, idx_l = [], [], [], []
+        fused = FUSED["on"] and dev.type == "cuda"
         for l in range(len(cls_probs)):
             A = cls_probs[l].shape[1]
             h, w = cls_probs[l].shape[-2:]
             scores = cls_probs[l][0].permute(1, 2, 0).reshape(-1)
-            deltas = bbox_preds[l][0].reshape(A, 4, h, w).permute(2, 3, 0, 1).reshape(-1, 4)
             k = min(self.pre, scores.numel()) if self.pre > 0 else scores.numel()
             top_s, top_i = torch.topk(scores, k, sorted=True)
-            props = clip_boxes(bbox_transform(self.anchors(l, h, w, dev)[top_i], deltas[top_i]), im_h, im_w)
-            boxes_l.append(props); scores_l.append(top_s); lens.append(k)
-        boxes, scores = torch.cat(boxes_l), torch.cat(scores_l)
+            scores_l.append(top_s); lens.append(k); idx_l.append(top_i)
+            if not fused:
+                deltas = bbox_preds[l][0].reshape(A, 4, h, w).permute(2, 3, 0, 1).reshape(-1, 4)
+                boxes_l.append(clip_boxes(bbox_transform(self.anchors(l, h, w, dev)[top_i], deltas[top_i]), im_h, im_w))
+        if fused:   # one launch: shifted anchors + bbox_transform + clip for the top-k of every level
+            boxes = _ops.rpn_decode([b[0] for b in bbox_preds], idx_l, [c.shape[-2:] for c in cls_probs],
+                                    self.feat_stride[:len(cls_probs)], self._base_anchors(len(cls_probs), dev),
+                                    cls_probs[0].shape[1], im_h, im_w)
+        else:
+            boxes = torch.cat(boxes_l)
+        scores = torch.cat(scores_l)
         offs = self._offsets(lens, dev)
         max_len = max(lens)
         keep, cnt = nms_segmented(boxes, offs, max_len, self.thresh)
@@ -274,6 +293,11 @@ class StaticMaskROI(MaskROI):
         nseg = 1 if self.class_agnostic else Cm
         # a softmax row has at most one entry above 0.5, so class-agnostic candidates <= R when thresh >= 0.5
         M = R if (not self.class_agnostic or self.score_thresh >= 0.5) else R * Cm
+        if FUSED["on"] and dev.type == "cuda" and R * Cm <= 8192 and Cm <= 128:
+            sc, cls, bx, offs = _ops.maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, self.class_agnostic,
+                                                     self.score_thresh, self.weights, float(im_info[0]), float(im_info[1]))
+            keep, cnt = nms_segmented(bx, offs, M, self.nms_thresh)
+            return _ops.maskroi_finish(keep, cnt, offs, sc, cls, bx, self.top_n, self.cap)
         cls_flat, ridx_flat = self._consts(R, dev)
         proposal = clip_boxes(bbox_transform(rois[:, 1:], bbox_delta, self.weights), float(im_info[0]),
                               float(im_info[1])).reshape(R, C, 4)

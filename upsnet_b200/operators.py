@@ -359,6 +359,66 @@ def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
     return keep, cnt
 
 
+def rpn_decode(bbox_preds, top_idx, shapes, strides, base_anchors, A, im_h, im_w):
+    """Fused anchors + bbox_transform + clip_boxes for the pre-NMS top-k of every level (one launch).
+    bbox_preds[l] fp32 [4A,h,w] (contiguous), top_idx[l] int64 [k_l] flat (y,x,a) indices, base_anchors float64
+    [L,A,4] on the device.  -> boxes [sum k_l, 4]."""
+    L = len(bbox_preds)
+    dev = bbox_preds[0].device
+    require_cuda(*bbox_preds, *top_idx, base_anchors)
+    assert base_anchors.dtype == torch.float64 and base_anchors.is_contiguous()
+    bbox_preds = [f32c(b) for b in bbox_preds]
+    top_idx = [t.contiguous() for t in top_idx]
+    assert all(t.dtype == torch.int64 for t in top_idx)
+    ks = [int(t.numel()) for t in top_idx]
+    out = torch.empty((sum(ks), 4), dtype=torch.float32, device=dev)
+    vp, ci = C.c_void_p, C.c_int
+    with torch.cuda.device(dev), _Timed("rpn_decode", 1, {"bytes": 56.0 * sum(ks)}, dev):
+        check(lib().upsnet_rpn_decode((vp * L)(*[b.data_ptr() for b in bbox_preds]), (vp * L)(*[t.data_ptr() for t in top_idx]),
+                                      (ci * L)(*ks), (ci * L)(*[int(s[0]) for s in shapes]), (ci * L)(*[int(s[1]) for s in shapes]),
+                                      (ci * L)(*[int(s) for s in strides]), ptr(base_anchors), L, int(A), float(im_h), float(im_w),
+                                      ptr(out), stream_ptr(dev)), "rpn_decode")
+    return out
+
+
+def maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, class_agnostic, score_thresh, weights, im_h, im_w):
+    """Fused MaskROI front half -> (sc [n], cls int32 [n], bx [n,4], offs int32 [nseg+1]), n = R*(C-1):
+    candidates first in (segment, score desc, index) order, decoded and clipped."""
+    require_cuda(rois, roi_valid, bbox_delta, cls_prob)
+    rois, bbox_delta, cls_prob = f32c(rois), f32c(bbox_delta), f32c(cls_prob)
+    assert roi_valid.dtype == torch.bool and roi_valid.is_contiguous()
+    R, Cn = cls_prob.shape
+    n = R * (Cn - 1)
+    dev = rois.device
+    nseg = 1 if class_agnostic else Cn - 1
+    sc = torch.empty((n,), dtype=torch.float32, device=dev)
+    cls = torch.empty((n,), dtype=torch.int32, device=dev)
+    bx = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    offs = torch.empty((nseg + 1,), dtype=torch.int32, device=dev)
+    w4 = (C.c_float * 4)(*[float(w) for w in weights])
+    with torch.cuda.device(dev), _Timed("maskroi", 1, {"bytes": 4.0 * (rois.numel() + bbox_delta.numel() + cls_prob.numel())}, dev):
+        check(lib().upsnet_maskroi_prepare(ptr(rois), ptr(roi_valid), ptr(bbox_delta), ptr(cls_prob), R, Cn,
+                                           1 if class_agnostic else 0, float(score_thresh), w4, float(im_h), float(im_w),
+                                           ptr(sc), ptr(cls), ptr(bx), ptr(offs), stream_ptr(dev)), "maskroi_prepare")
+    return sc, cls, bx, offs
+
+
+def maskroi_finish(keep, cnt, offs, sc, cls, bx, top_n, cap):
+    """Fused MaskROI back half -> (scores [cap], boxes [cap,5], cls int64 [cap], n int32 device scalar)."""
+    require_cuda(keep, cnt, offs, sc, cls, bx)
+    dev = sc.device
+    nseg, M = keep.shape
+    out_sc = torch.empty((cap,), dtype=torch.float32, device=dev)
+    out_bx = torch.empty((cap, 5), dtype=torch.float32, device=dev)
+    out_cls = torch.empty((cap,), dtype=torch.int64, device=dev)
+    n_out = torch.empty((), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _Timed("maskroi", 1, {"bytes": 32.0 * cap}, dev):
+        check(lib().upsnet_maskroi_finish(ptr(keep), ptr(cnt), ptr(offs), ptr(sc), ptr(cls), ptr(bx), nseg, M, int(top_n),
+                                          int(cap), ptr(out_sc), ptr(out_bx), ptr(out_cls), ptr(n_out), stream_ptr(dev)),
+              "maskroi_finish")
+    return out_sc, out_bx, out_cls, n_out
+
+
 def nms(boxes, scores, thresh):
     """Device API: boxes [N,4], scores [N] (CUDA) -> int64 indices of kept boxes, descending score
     (== order[keep] of nms/gpu_nms.pyx:32-38).  One D2H of the count only."""
