@@ -1,7 +1,12 @@
 """Prints the device-side result sizes (detections, panoptic candidates, kept instances) of the synthetic bench
 workload -- they decide how much of the static-capacity mask branch / panoptic head is live work."""
+import os
+import sys
+
 import torch
-import upsnet_b200 as U
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import upsnet_b200 as U  # noqa: E402
 from upsnet_b200.synthetic import synthetic_input, synthetic_model
 
 U.set_precision("bf16")

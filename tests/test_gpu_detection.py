@@ -74,5 +74,7 @@ def test_maskroi_fused_matches_torch_glue(dev, cfg):
     assert int(n1) == n and n >= 1
     assert c1.dtype == c0.dtype and torch.equal(c1[:n], c0[:n])
     assert torch.equal(s1[:n], s0[:n])
-    assert torch.equal(b1[:n], b0[:n])
+    # boxes: the kernel divides the deltas by the regression weights like the reference's numpy (true division);
+    # torch's CUDA `tensor / python_scalar` multiplies by the rounded reciprocal -> last-bit differences
+    assert (b1[:n] - b0[:n]).abs().max().item() < 1e-3
     assert float(s1[n:].abs().sum()) == 0.0 and float(b1[n:].abs().sum()) == 0.0
