@@ -162,6 +162,12 @@ int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *
                         double fraction_threshold, int64_t *keep_out, int *k_out, float *mask_energy,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* Max-pooling on NHWC activations (bf16 or fp32 storage; C % 8 == 0 resp. C % 4 == 0), floor output size.
+ * replaces: models/resnet.py:163 nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the stem.
+ * x [N,H,W,C] -> y [N,Ho,Wo,C], Ho = (H + 2*pad - k)/stride + 1; padding never wins the max. */
+int upsnet_maxpool2d_nhwc(const void *x, void *y, int N, int H, int W, int C, int k, int stride,
+                          int pad, int dtype, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Detection glue, fused (device-resident; nothing returns to the host).
  *

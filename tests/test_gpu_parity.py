@@ -408,3 +408,16 @@ def test_mask_removal_and_segterm_modules_match_reference_composition(dev):
     assert np.array_equal(out[0].cpu().numpy(), wl)
     fk, fl = run_pan(dev, fcn, b, prob, ml, cls)
     assert fk.cpu().tolist() == wk.tolist() and np.array_equal(fl[0].cpu().numpy(), wl)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(1, 64, 62, 90), (2, 8, 17, 5), (1, 64, 128, 256)])
+def test_maxpool_nhwc_matches_torch(dev, dtype, shape):
+    """Stem max-pool (models/resnet.py:163) on NHWC storage: exact (max of the same values)."""
+    import upsnet_b200 as U
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(shape, generator=g).to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    got = U.operators.max_pool2d(x, 3, 2, 1)
+    want = torch.nn.functional.max_pool2d(x.float(), 3, 2, 1)
+    assert got.dtype == dtype and got.shape == want.shape
+    assert torch.equal(got.float(), want)

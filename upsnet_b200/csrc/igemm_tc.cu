@@ -228,12 +228,18 @@ igemm_tc_kernel(const TcParams p) {
         uint8_t* b_hi = stage + L.a_bytes;
         uint8_t* a_lo = stage + L.a_bytes + L.b_bytes;
         uint8_t* b_lo = a_lo + L.a_bytes;
-        const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * TC_BK + j * 8;
+        // k-block order: dense = tap-major (matches the packed weight columns); deformable = CHANNEL-CHUNK-major, so
+        // that the nine taps x four bilinear corners of one 64-channel chunk -- which revisit the same few hundred
+        // 128-byte lines of the input -- run back to back and hit in L1 instead of going to L2 36 times.
+        const int tap = DEFORM ? kb % KHW : kb / cchunks;
+        const int cck = DEFORM ? kb / KHW : kb - tap * cchunks;
+        const int c0 = cck * TC_BK + j * 8;
+        const size_t kcol = (size_t)tap * p.Cin + (size_t)cck * TC_BK;   // == kb * 64 for the dense modes
         const int tki = tap / p.kw, tdy = tki * p.dh, tdx = (tap - tki * p.kw) * p.dw;   // dense: tap displacement
         // ---- B: BN rows x 8 chunks of packed bf16 weights, cp.async straight into the swizzled stage
         //      (no registers, overlaps the A gather below) ----
         for (int r = r_first; r < p.BN; r += 32) {
-          const size_t gi = (size_t)(n0 + r) * Kp + (size_t)kb * TC_BK + j * 8;
+          const size_t gi = (size_t)(n0 + r) * Kp + (SMALLC ? (size_t)kb * TC_BK : kcol) + j * 8;
           const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
           cp_async16(smem_u32(b_hi + soff), p.w_hi + gi);
           if (x3) cp_async16(smem_u32(b_lo + soff), p.w_lo + gi);
@@ -737,7 +743,8 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   p.BN = BN;
   // One persistent CTA per SM: give the smem ring everything that is left after the sample table.
   const int khw_l = smallc ? 2 : KHW;   // table region: [KHW][128] entries, or the 1 KB per-k table of the stem mode
-  int stages = TC_MAX_STAGES;
+  // deformable: a short ring leaves ~100 KB of the SM's 256 KB as L1 for the corner gathers (see the producer)
+  int stages = deform ? 3 : TC_MAX_STAGES;
   TcSmem L = tc_smem_layout(deform, khw_l, BN, stages, p.x3 != 0);
   while (stages > 2 && L.total + 1024 > 220 * 1024) { --stages; L = tc_smem_layout(deform, khw_l, BN, stages, p.x3 != 0); }
   if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
@@ -761,6 +768,9 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // deformable instantiations: prefer the smallest shared-memory carve-out that fits, the rest of the 256 KB is L1
+    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
     configured = true;
   }
   if (smallc) {

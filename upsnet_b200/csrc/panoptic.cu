@@ -8,10 +8,11 @@
 //
 // Kernels
 //   pan_prep     1 CTA : rank instances by score (counting rank, stable), integer geometry.
-//   pan_removal  1 CTA per thing class: serial over that class's instances in score order,
-//                parallel over the pixels of the paste window; class occupancy kept as a
-//                1-bit/pixel plane; warp ballots build 32-pixel words, popc gives |mask| and
-//                |mask & occupied|.
+//   pan_bits     whole GPU: the resized-logit > 0 bit mask of EVERY instance (no dependence on the keep
+//                decisions), packed 32 pixels / word over the instance's paste window, + |mask| by popc.
+//   pan_decide   1 CTA per thing class: serial over that class's instances in score order -- the only
+//                inherently sequential part (mask_removal.py:66-86) -- now just popc(bits & occupied) over
+//                the window words, the float64 ratio test, and occupied |= bits for the kept ones.
 //   pan_compact  1 CTA : kept list in score order (ballot prefix sums), k==0 fallback.
 //   pan_fuse     CTA per 128x8 pixel tile: bins the kept instances against the tile, then every
 //                thread streams the S semantic logits of 4 consecutive pixels (float4, coalesced)
@@ -27,6 +28,8 @@ namespace ups {
 constexpr int kMaskS = 28;
 constexpr int kMaskElems = kMaskS * kMaskS;
 constexpr int kMaxList = 2048;   // max instances per call (per-tile / per-class uint16 lists)
+constexpr int kMaxRounds = 64;
+constexpr long long kBitsBudget = 16ll << 20;   // words (64 MB) of instance bit windows resident at a time
 
 // per-instance integer geometry, SoA with stride n (indexed by ORIGINAL instance id)
 struct PanGeom {
@@ -43,7 +46,12 @@ struct PanWorkspace {
   int* meta;        // [4]  k, zero_mask, ...
   PanGeom g;
   unsigned int* occ;      // [num_thing][H][Ww]  occupancy bit planes
-  unsigned int* scratch;  // [num_thing][H][Ww]  candidate mask words of the current instance
+  long long* off;         // [n]  by rank: word offset of the instance's bit window (exclusive scan of window sizes)
+  int* msum;              // [n]  by rank: |mask| (popc over the window)
+  int* round_lo;          // [kMaxRounds + 1]  first rank of every bit-buffer round (ranks of a round are contiguous)
+  unsigned int* bits;     // [budget + H*Ww]  bit windows of the instances of the current round
+  long long budget;       // words per round
+  int rounds;
 };
 
 static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorkspace* ws,
@@ -56,7 +64,17 @@ static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorksp
   const size_t o_geom = take(sizeof(int) * nn * 13);
   const int Ww = ceil_div(W, 32);
   const size_t plane = (size_t)num_thing * H * Ww * sizeof(unsigned int);
-  const size_t o_occ = take(plane), o_scr = take(plane);
+  const size_t o_occ = take(plane);
+  const size_t o_off = take(sizeof(long long) * nn), o_msum = take(sizeof(int) * nn);
+  const size_t o_round = take(sizeof(int) * (kMaxRounds + 1));
+  // bit windows: every instance needs at most one full plane (H*Ww words).  All of them are resident when they
+  // fit the budget, otherwise the instances are processed in rounds of consecutive ranks.
+  const long long win = (long long)H * Ww, all = win * nn;
+  long long budget = all < kBitsBudget ? all : kBitsBudget;
+  if ((all + budget - 1) / budget > kMaxRounds) budget = (all + kMaxRounds - 1) / kMaxRounds;
+  if (budget < win) budget = win;
+  const int rounds = (int)((all + budget - 1) / budget);
+  const size_t o_bits = take(sizeof(unsigned int) * (size_t)(budget + win));
   if (ws) {
     ws->order = (int*)(base + o_order); ws->kept_flag = (int*)(base + o_flag);
     ws->kept_list = (int*)(base + o_list); ws->meta = (int*)(base + o_meta);
@@ -65,7 +83,9 @@ static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorksp
     ws->g.gx0 = g + 4 * nn; ws->g.gy0 = g + 5 * nn; ws->g.gx1 = g + 6 * nn; ws->g.gy1 = g + 7 * nn;
     ws->g.sx0 = g + 8 * nn; ws->g.sy0 = g + 9 * nn; ws->g.sx1 = g + 10 * nn; ws->g.sy1 = g + 11 * nn;
     ws->g.cls = g + 12 * nn;
-    ws->occ = (unsigned int*)(base + o_occ); ws->scratch = (unsigned int*)(base + o_scr);
+    ws->occ = (unsigned int*)(base + o_occ);
+    ws->off = (long long*)(base + o_off); ws->msum = (int*)(base + o_msum); ws->round_lo = (int*)(base + o_round);
+    ws->bits = (unsigned int*)(base + o_bits); ws->budget = budget; ws->rounds = rounds;
   }
   return off;
 }
@@ -127,13 +147,55 @@ pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
     ws.g.sx0[i] = sx0; ws.g.sy0[i] = sy0; ws.g.sx1[i] = sx1; ws.g.sy1[i] = sy1;
     ws.g.cls[i] = c;
   }
+  // ---- bit-window sizes by rank -> exclusive scan -> word offsets and round boundaries ----
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  for (int q = threadIdx.x; q <= kMaxRounds; q += blockDim.x) ws.round_lo[q] = n;
+  __syncthreads();   // order[] and the geometry are complete
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    long long sz = 0;
+    if (r < n) {
+      const int i = ws.order[r];
+      const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
+      sz = (long long)max(((x1 + 31) >> 5) - (x0 >> 5), 0) * max(y1 - y0, 0);
+    }
+    long long x = sz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const long long start = s_carry + (warp ? s_warp[warp - 1] : 0) + x - sz;
+    if (r < n) {
+      ws.off[r] = start;
+      ws.msum[r] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += s_warp[31];
+    __syncthreads();
+  }
+  // round boundaries: rank r opens round q when it is the first rank whose start offset falls in [q*budget, ...)
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int rq = (int)(ws.off[r] / ws.budget);
+    if (r == 0 || (int)(ws.off[r - 1] / ws.budget) != rq) ws.round_lo[rq] = r;
+  }
 }
 
-// One CTA per thing class (blockIdx.x = class-1): the keep decision of an instance depends only on the
-// earlier kept instances of the SAME class, so classes run concurrently and each CTA walks its class's
-// instances in score order.  Per instance: thread-per-word (32 consecutive pixels of one row): the
-// occupancy word is requested first, the 32 mask bits are evaluated while it is in flight, popc gives
-// |mask| and |mask & occupied|; the next instance's 28x28 logit is prefetched with cp.async meanwhile.
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
@@ -141,28 +203,92 @@ __device__ __forceinline__ void cp_async_wait_all_() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(1024)
-pan_removal_kernel(const float* __restrict__ mask_logit, int n_max, const int* __restrict__ n_dev, int H, int W,
-                   double fraction_threshold, PanWorkspace ws) {
+// The mask bits of every instance of round `rq`: grid (kBitsChunks, n_max), CTA = (chunk of the window rows x words,
+// rank).  The column coefficients of the 28 -> w resize (float64 scale, oracle resize_coef_x) are computed once per
+// CTA into shared memory instead of once per pixel.
+constexpr int kBitsChunks = 8, kBitsThreads = 256, kColCap = 2048;
+__global__ void __launch_bounds__(kBitsThreads)
+pan_bits_kernel(const float* __restrict__ mask_logit, int n_max, const int* __restrict__ n_dev, int rq, PanWorkspace ws) {
   const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
-  __shared__ float S[2][kMaskElems];
-  __shared__ unsigned short list[kMaxList];   // ranks (score order) of this class's instances
-  __shared__ unsigned int s_sum, s_ovl;
-  __shared__ int s_keep, s_cnt;
+  const int r = blockIdx.y;
+  if (r >= n || r < ws.round_lo[rq] || r >= ws.round_lo[rq + 1]) return;
+  if (n == 1 && ws.g.cls[0] == 0) return;   // MaskROI's dummy detection
+  __shared__ float S[kMaskElems];
+  __shared__ float s_fx[kColCap];
+  __shared__ unsigned char s_sx[kColCap];
+  const int i = ws.order[r];
+  const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], w = ws.g.w[i], h = ws.g.h[i];
+  const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
+  const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;
+  const int nwc = max(wx1 - wx0, 0), rows = max(y1 - y0, 0);
+  const int items = nwc * rows;
+  const int per = (items + kBitsChunks - 1) / kBitsChunks;
+  const int it0 = blockIdx.x * per, it1 = min(it0 + per, items);
+  if (it0 >= it1) return;
+  for (int t = threadIdx.x; t < kMaskElems; t += kBitsThreads) S[t] = __ldg(mask_logit + (size_t)i * kMaskElems + t);
+  const int ncol = x1 - x0;
+  const bool tab = ncol <= kColCap;
+  if (tab)
+    for (int t = threadIdx.x; t < ncol; t += kBitsThreads) {
+      const int dx = x0 + t - bx0;
+      int sx = 0; float fx = 0.f;
+      if (dx >= 0 && dx < w) coef_x(dx, w, sx, fx);
+      s_sx[t] = (unsigned char)sx; s_fx[t] = fx;
+    }
+  __syncthreads();
+  unsigned int* bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
+  unsigned int my_sum = 0;
+  for (int item = it0 + threadIdx.x; item < it1; item += kBitsThreads) {
+    const int wy = y0 + item / nwc, wc = wx0 + item % nwc;
+    unsigned int word = 0;
+    const int dy = wy - by0;
+    if (dy >= 0 && dy < h) {
+      int sy; float fy;
+      coef_y(dy, h, sy, fy);
+      const int xa = max(wc * 32, x0), xb = min(wc * 32 + 32, x1);
+      for (int x = xa; x < xb; ++x) {
+        const int dx = x - bx0;
+        if (dx >= 0 && dx < w) {
+          int sx; float fx;
+          if (tab) { sx = s_sx[x - x0]; fx = s_fx[x - x0]; } else coef_x(dx, w, sx, fx);
+          if (blend(S, sx, fx, sy, fy) > 0.f) word |= 1u << (x & 31);
+        }
+      }
+    }
+    bits[item] = word;
+    my_sum += __popc(word);
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) my_sum += __shfl_xor_sync(0xffffffffu, my_sum, sh);
+  if ((threadIdx.x & 31) == 0 && my_sum) atomicAdd(&ws.msum[r], (int)my_sum);
+}
+
+// One CTA per thing class (blockIdx.x = class-1): the keep decision of an instance depends only on the earlier
+// kept instances of the SAME class, so classes run concurrently and each CTA walks its class's instances of the
+// round in score order: |mask & occupied| by popc over the precomputed window words, the float64 ratio test
+// (mask_removal.py:82), occupied |= mask for the kept ones.
+__global__ void __launch_bounds__(1024)
+pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double fraction_threshold, int rq,
+                  PanWorkspace ws) {
+  const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
+  __shared__ unsigned short list[kMaxList];   // ranks (score order) of this class's instances in this round
+  __shared__ unsigned int s_ovl[2];
+  __shared__ int s_cnt;
   __shared__ int s_warp_cnt[32];
   const int c = blockIdx.x;  // 0-based class
   const int Ww = ceil_div(W, 32);
   unsigned int* occ = ws.occ + (size_t)c * H * Ww;
-  unsigned int* scr = ws.scratch + (size_t)c * H * Ww;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (n == 1 && ws.g.cls[0] == 0) return;  // MaskROI's dummy detection: mask_removal.py:55-57
+  const int r_lo = ws.round_lo[rq], r_hi = min(ws.round_lo[rq + 1], n);
+  if (r_lo >= r_hi) return;
 
   // ---- ordered list of the ranks that belong to this class ----
-  if (threadIdx.x == 0) s_cnt = 0;
+  if (threadIdx.x == 0) { s_cnt = 0; s_ovl[0] = 0; s_ovl[1] = 0; }
   __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
+  for (int base = r_lo; base < r_hi; base += blockDim.x) {
     const int r = base + threadIdx.x;
-    const bool mine = r < n && ws.g.cls[ws.order[r]] - 1 == c;
+    const bool mine = r < r_hi && ws.g.cls[ws.order[r]] - 1 == c;
     const unsigned int m = __ballot_sync(0xffffffffu, mine);
     if (lane == 0) s_warp_cnt[warp] = __popc(m);
     __syncthreads();
@@ -178,71 +304,35 @@ pan_removal_kernel(const float* __restrict__ mask_logit, int n_max, const int* _
     __syncthreads();
   }
   const int cnt = s_cnt;
-  if (cnt == 0) return;
-  for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x)
-    cp_async4(&S[0][t], mask_logit + (size_t)ws.order[list[0]] * kMaskElems + t);
-  cp_async_wait_all_();
-  __syncthreads();
-
   for (int li = 0; li < cnt; ++li) {
     const int r = list[li];
     const int i = ws.order[r];
-    const float* Sm = S[li & 1];
-    if (li + 1 < cnt)   // prefetch the next instance's logits into the other buffer
-      for (int t = threadIdx.x; t < kMaskElems; t += blockDim.x)
-        cp_async4(&S[(li + 1) & 1][t], mask_logit + (size_t)ws.order[list[li + 1]] * kMaskElems + t);
-    if (threadIdx.x == 0) { s_sum = 0; s_ovl = 0; }
-    const int bx0 = ws.g.bx0[i], by0 = ws.g.by0[i], w = ws.g.w[i], h = ws.g.h[i];
     const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
-    const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;  // word columns [wx0, wx1)
-    const int nwc = max(wx1 - wx0, 0), rows = max(y1 - y0, 0);
-    unsigned int my_sum = 0, my_ovl = 0;
-    for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {
-      const int wy = y0 + item / nwc, wc = wx0 + item % nwc;
-      const size_t o = (size_t)wy * Ww + wc;
-      const unsigned int occ_w = occ[o];            // in flight while the 32 bits are evaluated
-      unsigned int word = 0;
-      const int dy = wy - by0;
-      if (dy >= 0 && dy < h) {
-        int sy; float fy;
-        coef_y(dy, h, sy, fy);
-        const int xa = max(wc * 32, x0), xb = min(wc * 32 + 32, x1);
-        for (int x = xa; x < xb; ++x) {
-          const int dx = x - bx0;
-          if (dx >= 0 && dx < w) {
-            int sx; float fx;
-            coef_x(dx, w, sx, fx);
-            if (blend(Sm, sx, fx, sy, fy) > 0.f) word |= 1u << (x & 31);
-          }
-        }
-      }
-      scr[o] = word;
-      my_sum += __popc(word);
-      my_ovl += __popc(word & occ_w);
+    const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;
+    const int nwc = max(wx1 - wx0, 0), items = nwc * max(y1 - y0, 0);
+    const unsigned int* bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
+    unsigned int my_ovl = 0;
+    for (int item = threadIdx.x; item < items; item += blockDim.x) {
+      const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
+      my_ovl += __popc(bits[item] & occ[o]);
     }
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) {
-      my_sum += __shfl_xor_sync(0xffffffffu, my_sum, sh);
-      my_ovl += __shfl_xor_sync(0xffffffffu, my_ovl, sh);
-    }
-    __syncthreads();   // counters zeroed
-    if (lane == 0 && (my_sum | my_ovl)) { atomicAdd(&s_sum, my_sum); atomicAdd(&s_ovl, my_ovl); }
+    for (int sh = 16; sh > 0; sh >>= 1) my_ovl += __shfl_xor_sync(0xffffffffu, my_ovl, sh);
+    if (lane == 0 && my_ovl) atomicAdd(&s_ovl[li & 1], my_ovl);
     __syncthreads();
+    const unsigned int ms = (unsigned int)ws.msum[r], ov = s_ovl[li & 1];
+    // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
+    const bool drop = (ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold);
     if (threadIdx.x == 0) {
-      const unsigned int ms = s_sum, ov = s_ovl;
-      // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
-      const bool drop = (ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold);
-      s_keep = drop ? 0 : 1;
       ws.kept_flag[r] = drop ? 0 : 1;
+      s_ovl[(li + 1) & 1] = 0;            // the other counter is idle until the next instance's barrier
     }
-    __syncthreads();
-    if (s_keep)
-      for (int item = threadIdx.x; item < nwc * rows; item += blockDim.x) {   // same items this thread wrote
+    if (!drop)
+      for (int item = threadIdx.x; item < items; item += blockDim.x) {
         const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-        occ[o] |= scr[o];
+        occ[o] |= bits[item];
       }
-    cp_async_wait_all_();
-    __syncthreads();   // occupancy + next logits visible to the whole CTA
+    __syncthreads();   // occupancy visible to the whole CTA before the next instance reads it
   }
 }
 
@@ -483,8 +573,12 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
   UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
-  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, n_dev, H, W, fraction_threshold, ws);
-  UPS_CHECK_LAUNCH();
+  for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
+    pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
+    UPS_CHECK_LAUNCH();
+    pan_decide_kernel<<<num_thing, 1024, 0, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    UPS_CHECK_LAUNCH();
+  }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   if (mask_energy) {
@@ -524,8 +618,12 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
-  pan_removal_kernel<<<num_thing, 1024, 0, st>>>(mask_logit, n, n_dev, H, W, fraction_threshold, ws);
-  UPS_CHECK_LAUNCH();
+  for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
+    pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
+    UPS_CHECK_LAUNCH();
+    pan_decide_kernel<<<num_thing, 1024, 0, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    UPS_CHECK_LAUNCH();
+  }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH));

@@ -1,0 +1,71 @@
+// pool.cu -- k x k / stride s max-pooling on NHWC activations (the ResNet stem's 3x3/2 pool, models/resnet.py:163
+// `self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)`), bf16 or fp32 storage.
+// One thread = one output pixel x 8 (bf16) / 4 (fp32) channels: k*k 16-byte reads, one 16-byte write; the
+// overlapping windows are served by L1/L2, HBM sees the input once (roofline: HBM, in + out bytes).
+#include <cuda_bf16.h>
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace ups {
+
+template <bool BF16>
+__global__ void maxpool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV,
+                                    int Ho, int Wo, int k, int s, int pad) {
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    long long pix = t / CV;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+    const int h0 = ho * s - pad, w0 = wo * s - pad;
+    uint4 best;
+    if (BF16) best = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);     // -inf pairs
+    else best = make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u);
+    for (int i = 0; i < k; ++i) {
+      const int h = h0 + i;
+      if (h < 0 || h >= H) continue;
+      for (int j = 0; j < k; ++j) {
+        const int w = w0 + j;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(x + (((size_t)n * H + h) * W + w) * CV + cv);
+        if (BF16) {
+          __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&best);
+          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) b[e] = __hmax2(b[e], a[e]);
+        } else {
+          float* b = reinterpret_cast<float*>(&best);
+          const float* a = reinterpret_cast<const float*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) b[e] = fmaxf(b[e], a[e]);
+        }
+      }
+    }
+    y[t] = best;
+  }
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_maxpool2d_nhwc(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad,
+                                     int dtype, void* stream) {
+  if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0 || 2 * pad > k) return UPSNET_E_BADARG;
+  const int vec = dtype == UPSNET_DTYPE_BF16 ? 8 : 4;
+  if (dtype != UPSNET_DTYPE_BF16 && dtype != UPSNET_DTYPE_F32) return UPSNET_E_BADARG;
+  if (C % vec || (((uintptr_t)x) & 15) || (((uintptr_t)y) & 15)) return UPSNET_E_UNSUPPORTED;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
+  const long long total = (long long)N * Ho * Wo * (C / vec);
+  long long blocks = (total + 255) / 256;
+  if (blocks > ups::kNumSMs * 32) blocks = ups::kNumSMs * 32;
+  if (dtype == UPSNET_DTYPE_BF16)
+    ups::maxpool_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, N, H, W, C / vec, Ho, Wo, k, stride, pad);
+  else
+    ups::maxpool_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, N, H, W, C / vec, Ho, Wo, k, stride, pad);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -131,7 +131,7 @@ class Stem(nn.Module):
 
     def forward(self, x):
         x = ops.conv2d(x, self._f[0], self._f[1], stride=2, padding=3, relu=True)
-        return F.max_pool2d(x, 3, 2, 1)
+        return ops.max_pool2d(x, 3, 2, 1)
 
 
 class ResBlock(nn.Module):
@@ -317,8 +317,19 @@ class MaskBranch(nn.Module):
             c = getattr(self, "mask_conv%d" % i)[0]
             x = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
         w1, b1, cout = self._f
-        y = ops.conv2d(x, w1, b1, relu=True)                 # [n, 4*Cout, h, w]
+        y = ops.conv2d(x, w1, b1, relu=True)                 # [n, 4*Cout, h, w], channels ordered (a, b, co)
         n, _, h, w = y.shape
+        if y.is_contiguous(memory_format=torch.channels_last) and y.dim() == 4:
+            # The pixel shuffle only permutes pixels and mask_score is a 1x1 conv, so they commute: score the four
+            # (a, b) channel groups in place -- the NHWC storage [n,h,w,(a,b,co)] IS an NHWC tensor of 4w "pixels" per
+            # row with Cout channels (a free view) -- and shuffle the num_classes-channel logits instead of the
+            # 256-channel feature map (two 50 MB permute copies per call in the first version).
+            yv = y.permute(0, 2, 3, 1).reshape(n, h, w * 4, cout).permute(0, 3, 1, 2)
+            z = ops.conv2d(yv, self.mask_score.weight, self.mask_score.bias, out_format="nhwc",
+                           out_dtype=torch.float32)                                               # [n, K, h, 4w]
+            K = z.shape[1]
+            z = z.permute(0, 2, 3, 1).reshape(n, h, w, 2, 2, K)                                    # (i, j, a, b, k)
+            return z.permute(0, 5, 1, 3, 2, 4).reshape(n, K, 2 * h, 2 * w)
         y = y.reshape(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, cout, 2 * h, 2 * w)
         return ops.conv2d(y, self.mask_score.weight, self.mask_score.bias, out_format="nchw")
 

@@ -278,6 +278,23 @@ def roi_align(features, rois, pooled_height, pooled_width, spatial_scale, sampli
     return out
 
 
+def max_pool2d(x, kernel_size, stride, padding):
+    """nn.MaxPool2d on the engine's activation stream (models/resnet.py:163).  x is a logical NCHW tensor; the
+    kernel works on NHWC storage (channels_last tensors are used as they are) in bf16 or fp32."""
+    require_cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    N, Cc, H, W = x.shape
+    xs = _nhwc(x)
+    Ho = (H + 2 * padding - kernel_size) // stride + 1
+    Wo = (W + 2 * padding - kernel_size) // stride + 1
+    store = torch.empty((N, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device), _Timed("maxpool", 1, {"bytes": float((xs.numel() + store.numel()) * x.element_size())}, x.device):
+        check(lib().upsnet_maxpool2d_nhwc(ptr(xs), ptr(store), N, H, W, Cc, kernel_size, stride, padding,
+                                          1 if x.dtype == torch.bfloat16 else 0, stream_ptr(x.device)), "maxpool2d")
+    return store.permute(0, 3, 1, 2)
+
+
 def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, sampling_ratio=2, layout="nchw",
                   return_levels=False):
     """FPNRoIAlign.forward in one launch (level assignment on device, output already in roi order)."""
@@ -613,7 +630,7 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     labels = torch.empty((1, H, W), dtype=torch.int64, device=dev)
     sem = torch.empty((1, H, W), dtype=torch.int64, device=dev) if want_sem else None
     work = {"bytes": 4.0 * S * H * W + 8.0 * H * W * (2 if want_sem else 1) + n * (4.0 * 784 + 24)}
-    with torch.cuda.device(dev), _Timed("panoptic_head", 4, work, dev):
+    with torch.cuda.device(dev), _Timed("panoptic_head", 5, work, dev):
         check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, ptr(n_dev),
                                          num_stuff, float(fraction_threshold), ptr(keep), ptr(k), ptr(labels),
                                          ptr(sem), ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
@@ -646,7 +663,7 @@ class MaskRemoval(nn.Module):
         keep = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
         k = torch.empty((1,), dtype=torch.int32, device=dev)
         energy = torch.empty((n, H, W), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev), _Timed("mask_removal", 4, {"bytes": 4.0 * n * H * W}, dev):
+        with torch.cuda.device(dev), _Timed("mask_removal", 5, {"bytes": 4.0 * n * H * W}, dev):
             check(lib().upsnet_mask_removal(ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, None, H, W, num_thing,
                                             float(self.fraction_threshold), ptr(keep), ptr(k), ptr(energy), ptr(ws),
                                             ws.numel(), stream_ptr(dev)), "mask_removal")
