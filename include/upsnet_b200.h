@@ -181,6 +181,16 @@ int upsnet_rpn_decode(const float *const *deltas, const long long *const *top_id
                       const int *hs, const int *ws, const int *strides, const double *base_anchors,
                       int L, int A, float im_h, float im_w, float *boxes_out, void *stream);
 
+/* upsnet_rpn_topk: the pre_nms_top_n best anchors of every pyramid level, sorted by descending score, one call.
+ * replaces: operators/functions/pyramid_proposal.py:104-118 (per-level argsort(-scores)[:pre_nms_top_n]).
+ * probs[l] fp32 [A,h_l,w_l] (device); k_l = min(pre_nms_top_n, A*h_l*w_l) <= 2048; out_scores fp32 / out_idx int64
+ * [sum k_l]: level after level, flat (y,x,a) indices as the reference's transposed score vector uses; equal
+ * scores are ordered by ascending index.  Workspace: upsnet_rpn_topk_workspace_bytes(L). */
+int upsnet_rpn_topk_workspace_bytes(int L, size_t *bytes);
+int upsnet_rpn_topk(const float *const *probs, const int *hs, const int *ws, int L, int A,
+                    int pre_nms_top_n, float *out_scores, long long *out_idx, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 /* upsnet_maskroi_prepare: candidate selection (prob > score_thresh, roi valid), ordering (class segment
  * ascending -- one segment when class_agnostic --, score descending, roi-major index ascending) and box decode
  * (weights, clip) in one launch.  replaces: operators/modules/mask_roi.py:36-95 up to the per-class NMS.

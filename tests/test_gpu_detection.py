@@ -33,7 +33,9 @@ def test_rpn_decode_fused_matches_torch_glue(dev, seed):
     gen = StaticProposalGenerator(pre_nms_top_n=300, post_nms_top_n=200)
     A = 3
     shapes = [(48, 80), (24, 40), (12, 20), (6, 10), (3, 5)]
-    probs = [torch.rand(1, A, h, w, generator=g).to(dev) for h, w in shapes]
+    # distinct scores: the order of equal scores is unspecified in torch.topk (and in the reference's argsort)
+    probs = [((torch.randperm(A * h * w, generator=g).float() + 0.5) / (A * h * w)).reshape(1, A, h, w).to(dev)
+             for h, w in shapes]
     # large deltas exercise the exp clamp and the image clip
     deltas = [(torch.randn(1, 4 * A, h, w, generator=g) * (0.5 + 2.0 * (i == 1))).to(dev) for i, (h, w) in enumerate(shapes)]
     im_info = np.array([190.0, 317.0, 1.0], np.float32)
@@ -78,3 +80,30 @@ def test_maskroi_fused_matches_torch_glue(dev, cfg):
     # torch's CUDA `tensor / python_scalar` multiplies by the rounded reciprocal -> last-bit differences
     assert (b1[:n] - b0[:n]).abs().max().item() < 1e-3
     assert float(s1[n:].abs().sum()) == 0.0 and float(b1[n:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("quant", [0, 64, 3])
+def test_rpn_topk_matches_stable_sort(dev, quant):
+    """Radix-select top-k of every level == the first k of a stable descending sort of the (y,x,a)-ordered scores,
+    also with massive ties (quantised / saturated scores)."""
+    from upsnet_b200 import operators as OPS
+    g = torch.Generator(device="cpu").manual_seed(11 + quant)
+    A = 3
+    shapes = [(96, 160), (48, 80), (24, 40), (12, 20), (6, 10)]
+    probs = []
+    for h, w in shapes:
+        pr = torch.sigmoid(torch.randn(A, h, w, generator=g) * 4)
+        if quant:
+            pr = torch.round(pr * quant) / quant
+        probs.append(pr.to(dev))
+    for pre in (1000, 300, 2048):
+        sc, idx, ks = OPS.rpn_topk(probs, A, pre)
+        torch.cuda.synchronize()
+        o = 0
+        for pr, k in zip(probs, ks):
+            flat = pr.permute(1, 2, 0).reshape(-1)
+            assert k == min(pre, flat.numel())
+            want_s, want_i = torch.sort(flat, descending=True, stable=True)
+            assert torch.equal(idx[o:o + k], want_i[:k])
+            assert torch.equal(sc[o:o + k], want_s[:k])
+            o += k

@@ -336,3 +336,209 @@ extern "C" int upsnet_maskroi_finish(const int* keep, const int* keep_cnt, const
   UPS_CHECK_LAUNCH();
   return 0;
 }
+
+// ----------------------------------------------------------------------------------------------
+// RPN pre-NMS top-k for all pyramid levels (pyramid_proposal.py:104-118: argsort(-scores)[:pre_nms_top_n]).
+//
+// Exact radix select on the 54-bit key  (orderable(score) << 22) | (2^22-1 - flat_index):  all keys are
+// distinct, so "the k largest" is a unique set and ties in the score resolve to the lowest (y,x,a) index --
+// a valid instance of the reference's unspecified tie order.  Five digit passes (11+11+10 score bits, 11+11
+// index bits): every CTA histograms its slice of the level in shared memory, the LAST CTA of a level to
+// finish (ticket) scans the 2048 bins, fixes the digit and re-arms the counters, so a pass is one launch for
+// all levels.  Then one gather of the keys >= k-th key and one single-CTA bitonic sort per level.
+// ----------------------------------------------------------------------------------------------
+namespace ups {
+
+constexpr int kTkBins = 2048, kTkThreads = 512, kTkItems = 16, kTkMaxK = 2048, kTkIdxBits = 22;
+
+struct TopkLevel {
+  const float* prob;      // [A, h, w]
+  int hw, L, k, blocks;   // L = A*hw elements, k = min(pre_nms_top_n, L)
+  int out_start;          // offset of this level in the concatenated outputs
+};
+struct TopkParams {
+  TopkLevel lv[kMaxLevels];
+  int nlev, A;
+  unsigned int* hist;            // [nlev][kTkBins]
+  unsigned int* ticket;          // [nlev]
+  unsigned long long* prefix;    // [nlev]  key bits fixed so far
+  int* need;                     // [nlev]  how many of the k are still to be found inside the current prefix
+  unsigned int* fill;            // [nlev]  gather cursor
+  unsigned long long* keys;      // [nlev][kTkMaxK]
+  float* out_scores; long long* out_idx;
+};
+
+__device__ __forceinline__ unsigned long long topk_key(float s, unsigned int flat) {
+  return ((unsigned long long)orderable(s) << kTkIdxBits) | (unsigned long long)((1u << kTkIdxBits) - 1u - flat);
+}
+// element e of the [A,h,w] array -> flat (y,x,a) index
+__device__ __forceinline__ unsigned int topk_flat(int e, int hw, int A) {
+  const int a = e / hw, pix = e - a * hw;
+  return (unsigned int)(pix * A + a);
+}
+
+// pass over digit [shift, shift+bits): mask_hi selects the already fixed (higher) bits
+__global__ void __launch_bounds__(kTkThreads)
+topk_pass_kernel(const TopkParams p, int shift, int bits, int first) {
+  const int l = blockIdx.y;
+  const TopkLevel lv = p.lv[l];
+  if ((int)blockIdx.x >= lv.blocks) return;
+  __shared__ unsigned int sh[kTkBins];
+  __shared__ int s_last;
+  for (int b = threadIdx.x; b < kTkBins; b += kTkThreads) sh[b] = 0;
+  __syncthreads();
+  const unsigned long long fixed = first ? 0ull : p.prefix[l];
+  const unsigned long long mask_hi = first ? 0ull : (~0ull << (shift + bits));
+  const unsigned int dmask = (1u << bits) - 1u;
+  const int e0 = blockIdx.x * (kTkThreads * kTkItems);
+#pragma unroll 4
+  for (int it = 0; it < kTkItems; ++it) {
+    const int e = e0 + it * kTkThreads + threadIdx.x;
+    if (e < lv.L) {
+      const unsigned long long key = topk_key(__ldg(lv.prob + e), topk_flat(e, lv.hw, p.A));
+      if ((key & mask_hi) == fixed) atomicAdd(&sh[(unsigned int)(key >> shift) & dmask], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned int* gh = p.hist + (size_t)l * kTkBins;
+  for (int b = threadIdx.x; b < kTkBins; b += kTkThreads)
+    if (sh[b]) atomicAdd(&gh[b], sh[b]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.ticket[l], 1u) == (unsigned int)(lv.blocks - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA of this level: find the digit that contains the need-th largest key ----
+  __threadfence();
+  for (int b = threadIdx.x; b < kTkBins; b += kTkThreads) { sh[b] = __ldcg(&gh[b]); gh[b] = 0; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp scan from the top bin downwards, 64 bins per lane
+    const int lane = threadIdx.x;
+    const int need = first ? lv.k : p.need[l];
+    const int per = kTkBins / 32;
+    unsigned int mine = 0;
+    for (int b = 0; b < per; ++b) mine += sh[kTkBins - 1 - (lane * per + b)];
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const unsigned int excl = incl - mine;
+    const bool here = excl < (unsigned int)need && incl >= (unsigned int)need;
+    if (here) {
+      unsigned int acc = excl;
+      int d = 0;
+      for (int b = 0; b < per; ++b) {
+        const int bin = kTkBins - 1 - (lane * per + b);
+        if (acc + sh[bin] >= (unsigned int)need) { d = bin; break; }
+        acc += sh[bin];
+      }
+      p.need[l] = need - (int)acc;
+      p.prefix[l] = fixed | ((unsigned long long)d << shift);
+    }
+    if (lane == 0) { p.ticket[l] = 0; p.fill[l] = 0; }
+  }
+}
+
+__global__ void __launch_bounds__(kTkThreads)
+topk_gather_kernel(const TopkParams p) {
+  const int l = blockIdx.y;
+  const TopkLevel lv = p.lv[l];
+  if ((int)blockIdx.x >= lv.blocks) return;
+  const unsigned long long kth = p.prefix[l];
+  const int e0 = blockIdx.x * (kTkThreads * kTkItems);
+  for (int it = 0; it < kTkItems; ++it) {
+    const int e = e0 + it * kTkThreads + threadIdx.x;
+    if (e < lv.L) {
+      const unsigned long long key = topk_key(__ldg(lv.prob + e), topk_flat(e, lv.hw, p.A));
+      if (key >= kth) {
+        const unsigned int pos = atomicAdd(&p.fill[l], 1u);
+        if (pos < (unsigned int)kTkMaxK) p.keys[(size_t)l * kTkMaxK + pos] = key;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+topk_sort_kernel(const TopkParams p) {
+  const int l = blockIdx.x;
+  const TopkLevel lv = p.lv[l];
+  __shared__ unsigned long long sk[kTkMaxK];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kTkMaxK; i += 1024) sk[i] = i < lv.k ? p.keys[(size_t)l * kTkMaxK + i] : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= kTkMaxK; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int t = tid;   // kTkMaxK / 2 == 1024 pairs
+      const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+      const unsigned long long a = sk[lo], b = sk[hi];
+      const bool desc = (lo & k) == 0;
+      if ((a < b) == desc) { sk[lo] = b; sk[hi] = a; }
+      __syncthreads();
+    }
+  for (int i = tid; i < lv.k; i += 1024) {
+    const unsigned long long key = sk[i];
+    const unsigned int o = (unsigned int)(key >> kTkIdxBits);
+    const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;   // inverse of orderable()
+    p.out_scores[lv.out_start + i] = __uint_as_float(u);
+    p.out_idx[lv.out_start + i] = (long long)((1u << kTkIdxBits) - 1u - (unsigned int)(key & ((1u << kTkIdxBits) - 1u)));
+  }
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_rpn_topk_workspace_bytes(int L, size_t* bytes) {
+  if (!bytes || L <= 0 || L > ups::kMaxLevels) return UPSNET_E_BADARG;
+  *bytes = (size_t)L * (ups::kTkBins * 4 + 4 + 8 + 4 + 4 + 4 + (size_t)ups::kTkMaxK * 8) + 256;
+  return 0;
+}
+
+extern "C" int upsnet_rpn_topk(const float* const* probs, const int* hs, const int* ws, int L, int A, int pre_nms_top_n,
+                               float* out_scores, long long* out_idx, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  using namespace ups;
+  if (!probs || !hs || !ws || !out_scores || !out_idx || !workspace) return UPSNET_E_BADARG;
+  if (L <= 0 || L > kMaxLevels || A <= 0 || pre_nms_top_n <= 0) return UPSNET_E_BADARG;
+  if (pre_nms_top_n > kTkMaxK) return UPSNET_E_UNSUPPORTED;
+  size_t need_bytes = 0;
+  upsnet_rpn_topk_workspace_bytes(L, &need_bytes);
+  if (workspace_bytes < need_bytes) return UPSNET_E_WORKSPACE;
+  TopkParams p{};
+  char* base = (char*)workspace;
+  p.hist = (unsigned int*)base; base += (size_t)L * kTkBins * 4;
+  p.keys = (unsigned long long*)base; base += (size_t)L * kTkMaxK * 8;
+  p.prefix = (unsigned long long*)base; base += (size_t)L * 8;
+  p.ticket = (unsigned int*)base; base += (size_t)L * 4;
+  p.need = (int*)base; base += (size_t)L * 4;
+  p.fill = (unsigned int*)base; base += (size_t)L * 4;
+  p.nlev = L; p.A = A; p.out_scores = out_scores; p.out_idx = out_idx;
+  int acc = 0, max_blocks = 0;
+  for (int l = 0; l < L; ++l) {
+    if (!probs[l] || hs[l] <= 0 || ws[l] <= 0) return UPSNET_E_BADARG;
+    const long long Ll = (long long)A * hs[l] * ws[l];
+    if (Ll >= (1ll << kTkIdxBits)) return UPSNET_E_UNSUPPORTED;
+    p.lv[l].prob = probs[l]; p.lv[l].hw = hs[l] * ws[l]; p.lv[l].L = (int)Ll;
+    p.lv[l].k = (int)(Ll < pre_nms_top_n ? Ll : pre_nms_top_n);
+    p.lv[l].blocks = (int)((Ll + kTkThreads * kTkItems - 1) / (kTkThreads * kTkItems));
+    p.lv[l].out_start = acc;
+    acc += p.lv[l].k;
+    if (p.lv[l].blocks > max_blocks) max_blocks = p.lv[l].blocks;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // histograms + tickets start at zero (every pass re-arms them for the next one)
+  UPS_CUDA(cudaMemsetAsync(p.hist, 0, (size_t)L * kTkBins * 4, st));
+  UPS_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)L * 4, st));
+  const dim3 grid((unsigned)max_blocks, (unsigned)L);
+  const int shifts[5] = {43, 32, 22, 11, 0}, nbits[5] = {11, 11, 10, 11, 11};
+  for (int ps = 0; ps < 5; ++ps) {
+    topk_pass_kernel<<<grid, kTkThreads, 0, st>>>(p, shifts[ps], nbits[ps], ps == 0 ? 1 : 0);
+    UPS_CHECK_LAUNCH();
+  }
+  topk_gather_kernel<<<grid, kTkThreads, 0, st>>>(p);
+  UPS_CHECK_LAUNCH();
+  topk_sort_kernel<<<L, 1024, 0, st>>>(p);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -219,6 +219,15 @@ class StaticProposalGenerator(ProposalGenerator):
         im_h, im_w = float(im_info[0]), float(im_info[1])
         boxes_l, scores_l, lens, idx_l = [], [], [], []
         fused = FUSED["on"] and dev.type == "cuda"
+        if fused and 0 < self.pre <= 2048 and all(c.shape[0] == 1 and c.numel() < (1 << 22) for c in cls_probs):
+            # one radix-select + sort for all levels, then one decode launch
+            A = cls_probs[0].shape[1]
+            scores, top_i, lens = _ops.rpn_topk([c[0] for c in cls_probs], A, self.pre)
+            starts = np.concatenate([[0], np.cumsum(lens)])
+            idx_l = [top_i[starts[l]:starts[l + 1]] for l in range(len(lens))]
+            boxes = _ops.rpn_decode([b[0] for b in bbox_preds], idx_l, [c.shape[-2:] for c in cls_probs],
+                                    self.feat_stride[:len(cls_probs)], self._base_anchors(len(cls_probs), dev), A, im_h, im_w)
+            return self._after_topk(boxes, scores, lens, dev)
         for l in range(len(cls_probs)):
             A = cls_probs[l].shape[1]
             h, w = cls_probs[l].shape[-2:]
@@ -236,6 +245,9 @@ class StaticProposalGenerator(ProposalGenerator):
         else:
             boxes = torch.cat(boxes_l)
         scores = torch.cat(scores_l)
+        return self._after_topk(boxes, scores, lens, dev)
+
+    def _after_topk(self, boxes, scores, lens, dev):
         offs = self._offsets(lens, dev)
         max_len = max(lens)
         keep, cnt = nms_segmented(boxes, offs, max_len, self.thresh)

@@ -398,6 +398,33 @@ def rpn_decode(bbox_preds, top_idx, shapes, strides, base_anchors, A, im_h, im_w
     return out
 
 
+_topk_ws = None
+
+
+def rpn_topk(probs, A, pre_nms_top_n):
+    """Top pre_nms_top_n anchors of every level in one call.  probs[l] fp32 [A,h,w] -> (scores [sum k_l], flat (y,x,a)
+    indices int64 [sum k_l], [k_l]): sorted by descending score, ties by ascending index."""
+    global _topk_ws
+    L = len(probs)
+    dev = probs[0].device
+    require_cuda(*probs)
+    probs = [f32c(pr) for pr in probs]
+    ks = [min(int(pre_nms_top_n), int(pr.numel())) for pr in probs]
+    out_s = torch.empty((sum(ks),), dtype=torch.float32, device=dev)
+    out_i = torch.empty((sum(ks),), dtype=torch.int64, device=dev)
+    if _topk_ws is None:
+        _topk_ws = _Workspace()
+    nbytes = C.c_size_t(0)
+    check(lib().upsnet_rpn_topk_workspace_bytes(L, C.byref(nbytes)), "rpn_topk_workspace_bytes")
+    ws = _topk_ws.get(dev, nbytes.value)
+    vp, ci = C.c_void_p, C.c_int
+    with torch.cuda.device(dev), _Timed("rpn_topk", 7, {"bytes": 4.0 * 6 * sum(pr.numel() for pr in probs)}, dev):
+        check(lib().upsnet_rpn_topk((vp * L)(*[pr.data_ptr() for pr in probs]), (ci * L)(*[int(pr.shape[-2]) for pr in probs]),
+                                    (ci * L)(*[int(pr.shape[-1]) for pr in probs]), L, int(A), int(pre_nms_top_n),
+                                    ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), stream_ptr(dev)), "rpn_topk")
+    return out_s, out_i, ks
+
+
 def maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, class_agnostic, score_thresh, weights, im_h, im_w):
     """Fused MaskROI front half -> (sc [n], cls int32 [n], bx [n,4], offs int32 [nseg+1]), n = R*(C-1):
     candidates first in (segment, score desc, index) order, decoded and clipped."""
