@@ -352,3 +352,38 @@ def test_tma_fpn_lateral_residual_up2(dev, cfg):
     torch.cuda.synchronize()
     assert np.abs(outs[0].float().cpu().numpy() - want).max() < 1e-4 + (2.0 ** -8) * np.abs(want).max()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=1, Cin=256, Cout=18, H=40, W=56, k=3, pad=1, fmt="nchw", dt=torch.float32),     # DCN offset conv
+    dict(N=1, Cin=256, Cout=15, H=33, W=47, k=1, pad=0, fmt="nchw", dt=torch.float32),     # RPN cls+bbox head
+    dict(N=9, Cin=256, Cout=9, H=28, W=28, k=1, pad=0, fmt="nhwc", dt=torch.float32),      # mask logits
+    dict(N=300, Cin=1024, Cout=45, H=1, W=1, k=1, pad=0, fmt="nchw", dt=torch.float32),    # cls + bbox FC
+    dict(N=1, Cin=128, Cout=19, H=24, W=40, k=1, pad=0, fmt="nhwc", dt=torch.bfloat16),    # semantic score
+    dict(N=2, Cin=64, Cout=100, H=12, W=20, k=3, pad=1, fmt="nchw", dt=torch.bfloat16),    # Cout_pad 128, NCHW bf16
+])
+def test_tma_direct_store_epilogue(dev, cfg):
+    """Small / odd Cout and fp32 or NCHW outputs: TMA-fed main loop + per-thread stores; identical to the gather kernel."""
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as OPS
+    rng = np.random.default_rng(31)
+    x, w, b = _case(rng, cfg["N"], cfg["Cin"], cfg["Cout"], cfg["H"], cfg["W"], cfg["k"])
+    x, w = _bf16_exact(x), _bf16_exact(w)
+    want = O.conv2d(x, w, b, 1, cfg["pad"], 1)
+    xb = t(x, dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for tma in (True, False):
+        OPS.USE_TMA["on"] = tma
+        try:
+            outs.append((U.conv2d(xb, t(w, dev), t(b, dev), 1, cfg["pad"], 1, precision=BF16, out_format=cfg["fmt"], out_dtype=cfg["dt"]),
+                         U.conv2d(xb, t(w, dev), None, 1, cfg["pad"], 1, relu=True, precision=BF16, out_format=cfg["fmt"],
+                                  out_dtype=cfg["dt"])))
+        finally:
+            OPS.USE_TMA["on"] = True
+    torch.cuda.synchronize()
+    tol = 1e-4 + ((2.0 ** -8) * np.abs(want).max() if cfg["dt"] == torch.bfloat16 else 0.0)
+    assert outs[0][0].dtype == cfg["dt"] and outs[0][0].shape == want.shape
+    assert np.abs(outs[0][0].float().cpu().numpy() - want).max() < tol
+    assert np.abs(outs[0][1].float().cpu().numpy() - np.maximum(want - b[None, :, None, None], 0)).max() < tol
+    for a, g in zip(outs[0], outs[1]):
+        assert torch.equal(a, g)

@@ -40,6 +40,9 @@ struct TmaGeom {
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int BN, stages, relu, has_res;
   int res_up2;                          // residual = half-resolution map, nearest 2x up-sampling (FPN top-down)
+  // direct-store epilogue (small / odd Cout, fp32 or NCHW outputs: offset convs, RPN / score / mask-logit heads)
+  int direct, y_bf16, out_nhwc;
+  void* y;
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -251,6 +254,36 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       tc_fence_after();
       if (g.has_res) mbar_wait(bar_rfull, ti_local & 1u);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      if (g.direct) {
+        // thread = accumulator row = one output pixel of the box; the two halves split the columns
+        const int wq = row % g.bw, hq = (row / g.bw) % g.bh, nq = row / (g.bw * g.bh);
+        const int wo = w0 + wq, ho = h0 + hq, ni = i0 + nq;
+        const bool ok = nq < g.bn && wo < g.Wo && ho < g.Ho && ni < g.N;
+        const size_t HoWo = (size_t)g.Ho * g.Wo;
+        const size_t pix = ((size_t)ni * g.Ho + ho) * g.Wo + wo;
+        const int cbeg = half * (g.BN / 2), cend = cbeg + g.BN / 2;
+        for (int cb = cbeg; cb < cend; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + (uint32_t)cb, v);         // warp-collective
+          const int co0 = n0 + cb;
+          if (!ok || co0 >= g.Cout) continue;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int co = co0 + e;
+            if (co >= g.Cout) break;
+            float o = __uint_as_float(v[e]);
+            if (g.bias) o += __ldg(g.bias + co);
+            if (g.relu) o = fmaxf(o, 0.f);
+            const size_t oi = g.out_nhwc ? pix * g.Cout + co : ((size_t)ni * g.Cout + co) * HoWo + (size_t)ho * g.Wo + wo;
+            if (g.y_bf16) reinterpret_cast<__nv_bfloat16*>(g.y)[oi] = __float2bfloat16_rn(o);
+            else reinterpret_cast<float*>(g.y)[oi] = o;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
       for (int ui = 0; ui < upw; ++ui) {
         const int u = half * upw + ui;
         const int slab = u >> 1;
@@ -385,13 +418,17 @@ static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, 
 }
 
 int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream) {
-  if (p.no_tma || p.offset || p.x3 || !p.x_bf16 || !p.y_bf16 || !p.out_nhwc) return UPSNET_E_UNSUPPORTED;
+  if (p.no_tma || p.offset || p.x3 || !p.x_bf16) return UPSNET_E_UNSUPPORTED;
+  // slab epilogue (TMA store): bf16 NHWC output with Cout % 64 == 0; everything else without a residual goes
+  // through the direct-store epilogue (small heads: Cout 9..45, fp32 planes)
+  const bool direct = !p.y_bf16 || !p.out_nhwc || (p.Cout % 64) != 0;
+  if (direct && (p.residual || p.Cout > 256)) return UPSNET_E_UNSUPPORTED;
   if (p.res_up2 && (!p.residual || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_UNSUPPORTED;
   // stride > 1 only for 1x1 / pad 0 (the ResNet down-sampling convs): the input is then addressed through a
   // strided VIEW (every sh-th row, sw-th pixel) and the layer is a stride-1 1x1 convolution of that view
   const bool strided = p.sh != 1 || p.sw != 1;
   if (strided && (p.kh != 1 || p.kw != 1 || p.ph != 0 || p.pw != 0)) return UPSNET_E_UNSUPPORTED;
-  if ((p.Cin % 64) || (p.Cout % 64) || p.kh * p.kw > 49) return UPSNET_E_UNSUPPORTED;
+  if ((p.Cin % 64) || (!direct && (p.Cout % 64)) || p.kh * p.kw > 49) return UPSNET_E_UNSUPPORTED;
   if ((((uintptr_t)p.x) & 15) || (((uintptr_t)p.y) & 15) || (((uintptr_t)packed) & 15) || (p.residual && (((uintptr_t)p.residual) & 15)))
     return UPSNET_E_UNSUPPORTED;
   if (p.bias && (((uintptr_t)p.bias) & 15)) return UPSNET_E_UNSUPPORTED;
@@ -413,10 +450,12 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
   g.tiles_n = (p.N + g.bn - 1) / g.bn;
   const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
-  int BN = (p.Cout % 256 == 0 && !g.has_res) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
-  while (BN > 64 && m_tiles * (p.Cout / BN) < sms) BN /= 2;
+  const int Cout_pad = p.Cout <= 32 ? 32 : (p.Cout + 63) / 64 * 64;      // rows of the packed weight planes (tc_cout_pad)
+  int BN = (Cout_pad % 256 == 0 && !g.has_res) ? 256 : ((Cout_pad % 128 == 0) ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
+  while (BN > 64 && m_tiles * (Cout_pad / BN) < sms) BN /= 2;
   g.BN = BN;
-  g.n_tiles = p.Cout / BN;
+  g.n_tiles = Cout_pad / BN;
+  g.direct = direct ? 1 : 0; g.y_bf16 = p.y_bf16; g.out_nhwc = p.out_nhwc; g.y = p.y;
   int stages = TM_MAX_STAGES;
   TmaSmem L = tma_smem_layout(BN, stages, g.has_res != 0);
   while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0); }
@@ -430,11 +469,15 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
                               (cuuint64_t)p.N};
     const cuuint64_t sx[3] = {(cuuint64_t)p.sw * p.Cin * 2, (cuuint64_t)p.sh * p.W * p.Cin * 2, (cuuint64_t)p.H * p.W * p.Cin * 2};
     const cuuint64_t dy[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
-    const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)p.Cout};
+    const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)Cout_pad};
     const cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
     const cuuint32_t boxw[2] = {64, (cuuint32_t)BN};
     if (!encode_bf16(enc, &tm_x, p.x, 4, dx, box, sx)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_w, packed, 2, dwt, boxw)) return UPSNET_E_UNSUPPORTED;
+    if (direct) {   // no TMA store / residual in the direct-store epilogue: the two maps are placeholders
+      tm_y = tm_x;
+      tm_r = tm_x;
+    } else {
     if (!encode_bf16(enc, &tm_y, p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
     if (g.res_up2) {
       const cuuint64_t dr[4] = {(cuuint64_t)p.Cout, (cuuint64_t)(p.Wo / 2), (cuuint64_t)(p.Ho / 2), (cuuint64_t)p.N};
@@ -442,6 +485,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
       if (!encode_bf16(enc, &tm_r, p.residual, 4, dr, boxr)) return UPSNET_E_UNSUPPORTED;
     } else if (!encode_bf16(enc, &tm_r, p.residual ? p.residual : p.y, 4, dy, box)) {
       return UPSNET_E_UNSUPPORTED;
+    }
     }
   }
   const long long num_tiles = m_tiles * g.n_tiles;
