@@ -88,27 +88,31 @@ maskroi_prepare_kernel(const float* __restrict__ rois, const uint8_t* __restrict
   const int Cm = C - 1, n = R * Cm;
   const int nseg = class_agnostic ? 1 : Cm;
   const int tid = threadIdx.x;
+  __shared__ int s_ncand;
   for (int s = tid; s <= nseg; s += kMrThreads) seg_cnt[s] = 0;
+  if (tid == 0) s_ncand = 0;
   __syncthreads();
-  for (int i = tid; i < kSortN; i += kMrThreads) {
-    unsigned long long key = ~0ull;
-    if (i < n) {
-      const int r = i / Cm, c = i - r * Cm;
-      const float pr = __ldg(cls_prob + (size_t)r * C + c + 1);
-      const bool cand = pr > score_thresh && roi_valid[r] != 0;
-      const int seg = cand ? (class_agnostic ? 0 : c) : nseg;
+  // keys of the CANDIDATES only (their final order is fixed by the sort, so the append order is irrelevant)
+  for (int i = tid; i < n; i += kMrThreads) {
+    const int r = i / Cm, c = i - r * Cm;
+    const float pr = __ldg(cls_prob + (size_t)r * C + c + 1);
+    if (pr > score_thresh && roi_valid[r] != 0) {
+      const int seg = class_agnostic ? 0 : c;
       // descending score: prob > thresh >= 0 is a positive float, whose bit pattern is monotonic
-      const unsigned inv = cand ? 0xffffffffu - __float_as_uint(pr) : 0u;
-      key = ((unsigned long long)seg << 45) | ((unsigned long long)inv << 13) | (unsigned long long)i;
+      const unsigned inv = 0xffffffffu - __float_as_uint(pr);
+      keys[atomicAdd(&s_ncand, 1)] = ((unsigned long long)seg << 45) | ((unsigned long long)inv << 13) | (unsigned long long)i;
       atomicAdd(&seg_cnt[seg], 1);
     }
-    keys[i] = key;
   }
   __syncthreads();
-  // bitonic sort, ascending
-  for (int k = 2; k <= kSortN; k <<= 1) {
+  int sortN = 64;
+  while (sortN < s_ncand) sortN <<= 1;
+  for (int i = s_ncand + tid; i < sortN; i += kMrThreads) keys[i] = ~0ull;
+  __syncthreads();
+  // bitonic sort, ascending, over the next power of two >= the candidate count
+  for (int k = 2; k <= sortN; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < kSortN / 2; t += kMrThreads) {
+      for (int t = tid; t < sortN / 2; t += kMrThreads) {
         const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
         const unsigned long long a = keys[lo], b = keys[hi];
         const bool up = (lo & k) == 0;

@@ -429,34 +429,36 @@ igemm_tc_kernel(const TcParams p) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TC_BM, p.BN);
-      const uint32_t stage0 = base + L.stages;
-      uint32_t g = 0, ti_local = 0;
+      // descriptors: constant high word (SBO 1024 B, version 1, SWIZZLE_128B) + running low word (address >> 4);
+      // ring position / phase are running counters (no division on this single thread's per-k-block path)
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4;
+      const uint32_t a16 = L.a_bytes >> 4, b16 = L.b_bytes >> 4;
+      uint32_t s = 0, ph = 0, a_hi = a_lo0, ti_local = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const uint32_t s = g % (uint32_t)p.stages, it = g / (uint32_t)p.stages;
-          mbar_wait(bar_full + 8 * s, it & 1u);
+        uint32_t acc = 0u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a_hi = stage0 + s * L.stage_bytes;
-          const uint32_t b_hi = a_hi + L.a_bytes;
-          const uint32_t a_lo = b_hi + L.b_bytes;
-          const uint32_t b_lo = a_lo + L.a_bytes;
+          const uint32_t b_hi = a_hi + a16, a_lo = b_hi + b16, b_lo = a_lo + a16;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint32_t koff = (uint32_t)k * 32u;  // 16 bf16 = 32 bytes inside the swizzle span
-            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          for (uint32_t k = 0; k < TC_BK / 16; ++k) {       // 16 bf16 = 32 bytes = 2 descriptor units
             if (x3) {
-              umma_bf16(tmem_d, umma_desc(a_lo + koff), umma_desc(b_hi + koff), idesc, first);
-              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_lo + koff), idesc, 1u);
-              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_lo + 2 * k, b_hi + 2 * k, desc_hi, idesc, acc);
+              umma_bf16_lohi(tmem_d, a_hi + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_hi + 2 * k, b_hi + 2 * k, desc_hi, idesc, 1u);
             } else {
-              umma_bf16(tmem_d, umma_desc(a_hi + koff), umma_desc(b_hi + koff), idesc, first);
+              umma_bf16_lohi(tmem_d, a_hi + 2 * k, b_hi + 2 * k, desc_hi, idesc, acc);
             }
+            acc = 1u;
           }
           umma_commit(bar_empty + 8 * s);   // frees the stage once the MMAs above have read it
+          a_hi += stage16;
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; a_hi = a_lo0; }
         }
         umma_commit(bar_tfull + 8 * buf);   // accumulator complete -> epilogue
       }

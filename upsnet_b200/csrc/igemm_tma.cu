@@ -154,7 +154,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == TM_WARP_TMA) {
     // =============================== OPERAND LOADS ===============================
     if (lane == 0) {
-      uint32_t gk = 0;
+      // ring position / phase are running counters: no division on the per-k-block path of this single thread
+      uint32_t s = 0, ph = 0;
+      uint32_t a_dst = base + L.stages;
+      const uint32_t tx_bytes = box_bytes + L.b_bytes;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % g.n_tiles);
         const long long mt = tile / g.n_tiles;
@@ -162,18 +165,20 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
         const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
         const int n0 = nt * g.BN;
-        int tap = 0, cc = 0, ki = 0, kj = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
-          const uint32_t s = gk % (uint32_t)g.stages, it = gk / (uint32_t)g.stages;
-          mbar_wait(bar_empty + 8 * s, (it & 1u) ^ 1u);
-          const uint32_t a_dst = base + L.stages + s * L.stage_bytes;
-          mbar_arrive_expect_tx(bar_full + 8 * s, box_bytes + L.b_bytes);
-          tma_load_4d(a_dst, &tm_x, bar_full + 8 * s, cc * 64, w0 - g.pw + kj * g.dw, h0 - g.ph + ki * g.dh, i0);
-          tma_load_2d(a_dst + L.a_bytes, &tm_w, bar_full + 8 * s, kb * 64, n0);
+        int cc = 0, kj = 0;
+        int cw = w0 - g.pw, ch = h0 - g.ph;         // box origin of the current tap
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t bf = bar_full + 8 * s;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bf, tx_bytes);
+          tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
+          tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, n0);
           if (++cc == cchunks) {
-            cc = 0; ++tap;
-            if (++kj == g.kw) { kj = 0; ++ki; }
+            cc = 0; cw += g.dw;
+            if (++kj == g.kw) { kj = 0; cw = w0 - g.pw; ch += g.dh; }
           }
+          a_dst += L.stage_bytes;
+          if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_dst = base + L.stages; }
         }
       }
     }
@@ -182,22 +187,30 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(128, g.BN);
-      uint32_t gk = 0, ti_local = 0;
+      // smem descriptors: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B), the low word carries
+      // (address >> 4) and is advanced by running adds -- the issue loop of this single thread paces every tile
+      // whose MMAs are short (N <= 128), so it is kept to a handful of instructions per k-block.
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4, a16 = L.a_bytes >> 4;
+      uint32_t s = 0, ph = 0, a_lo = a_lo0, ti_local = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
-          const uint32_t s = gk % (uint32_t)g.stages, it = gk / (uint32_t)g.stages;
-          mbar_wait(bar_full + 8 * s, it & 1u);
+        uint32_t acc = 0u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a = base + L.stages + s * L.stage_bytes;
-          const uint32_t b = a + L.a_bytes;
+          const uint32_t b_lo = a_lo + a16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, umma_desc(a + k * 32), umma_desc(b + k * 32), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          for (uint32_t k = 0; k < 4; ++k) {       // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle span
+            umma_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
+            acc = 1u;
+          }
           umma_commit(bar_empty + 8 * s);
+          a_lo += stage16;
+          if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
         }
         umma_commit(bar_tfull + 8 * buf);
       }

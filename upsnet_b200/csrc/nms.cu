@@ -135,6 +135,82 @@ nms_sweep_kernel(const int* __restrict__ seg_offsets, int max_seg_len,
   if (threadIdx.x == 0) keep_cnt[seg] = count;
 }
 
+// Same sweep with the segment's whole bitmask staged in shared memory first (one coalesced cp.async pass):
+// for segments of up to ~1200 boxes (every NMS of the UPSNet path: 1000 proposals per level / per class) the
+// 64 dependent steps of a diagonal word and the kept-row ORs then run at shared-memory latency instead of one
+// L2 round trip per batch of rows.  grid (S), block kSweepSmemThreads, dynamic smem = (max_seg_len + 1) * cb * 8.
+constexpr int kSweepSmemThreads = 1024;
+__global__ void __launch_bounds__(kSweepSmemThreads)
+nms_sweep_smem_kernel(const int* __restrict__ seg_offsets, int max_seg_len,
+                      const unsigned long long* __restrict__ mask, int* __restrict__ keep_out,
+                      int* __restrict__ keep_cnt) {
+  extern __shared__ __align__(16) unsigned long long sm_mask[];   // [n][cb] then removed[cb]
+  __shared__ unsigned long long kept_word;
+  __shared__ int count;
+  const int seg = blockIdx.x;
+  const int n = min(seg_offsets[seg + 1] - seg_offsets[seg], max_seg_len);
+  const int cb = ceil_div(n, kNmsTile);
+  const int max_cb = ceil_div(max_seg_len, kNmsTile);
+  const unsigned long long* seg_mask = mask + (size_t)seg * max_seg_len * max_cb;
+  int* keep = keep_out + (size_t)seg * max_seg_len;
+  unsigned long long* removed = sm_mask + (size_t)n * cb;
+  // stage rows [0,n) x words [row/64, cb): the mask kernel only writes the upper-triangular tiles
+  for (int e = threadIdx.x; e < n * cb; e += kSweepSmemThreads) {
+    const int r = e / cb, j = e - r * cb;
+    if (j >= r / kNmsTile) {
+      const unsigned int dst = (unsigned int)__cvta_generic_to_shared(sm_mask + e);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(seg_mask + (size_t)r * max_cb + j) : "memory");
+    }
+  }
+  for (int j = threadIdx.x; j < cb; j += kSweepSmemThreads) removed[j] = 0ULL;
+  if (threadIdx.x == 0) count = 0;
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int b = 0; b < cb; ++b) {
+    const int bsize = min(n - b * kNmsTile, kNmsTile);
+    if (threadIdx.x == 0) {
+      unsigned long long cur = removed[b], K = 0ULL;
+      unsigned long long d[kNmsTile];
+#pragma unroll
+      for (int t = 0; t < kNmsTile; ++t) d[t] = t < bsize ? sm_mask[(size_t)(b * kNmsTile + t) * cb + b] : 0ULL;
+#pragma unroll
+      for (int t = 0; t < kNmsTile; ++t) {
+        const bool take = (t < bsize) && !((cur >> t) & 1ULL);
+        K |= take ? (1ULL << t) : 0ULL;
+        cur |= take ? d[t] : 0ULL;
+      }
+      kept_word = K;
+    }
+    __syncthreads();
+    const unsigned long long K = kept_word;
+    const int base_cnt = count;
+    if (threadIdx.x < kNmsTile && ((K >> threadIdx.x) & 1ULL))
+      keep[base_cnt + __popcll(K & ((1ULL << threadIdx.x) - 1ULL))] = b * kNmsTile + threadIdx.x;
+    // kept rows -> removed words of the later blocks: 16 lanes per word column, 4 rows each, xor-shuffle OR
+    {
+      const int lane16 = threadIdx.x & 15, warp2 = (threadIdx.x >> 5) * 2, sub = (threadIdx.x >> 4) & 1;
+      for (int j0 = b + 1 + warp2; j0 < cb; j0 += kSweepSmemThreads / 16) {   // warp-uniform trip count
+        const int j = j0 + sub;
+        const bool ok = j < cb;
+        unsigned long long acc = 0ULL;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = lane16 * 4 + u;
+          if (ok && ((K >> t) & 1ULL)) acc |= sm_mask[(size_t)(b * kNmsTile + t) * cb + j];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o, 16);
+        if (ok && lane16 == 0) removed[j] |= acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count = base_cnt + __popcll(K);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) keep_cnt[seg] = count;
+}
+
 static size_t nms_mask_bytes(int S, int max_seg_len) {
   return (size_t)S * max_seg_len * ceil_div(max_seg_len, kNmsTile) * sizeof(unsigned long long);
 }
@@ -162,6 +238,18 @@ extern "C" int upsnet_nms_segmented(const float* boxes, const int* seg_offsets, 
   nms_mask_kernel<<<grid, kNmsTile, 0, st>>>(boxes, seg_offsets, max_seg_len, thresh,
                                              (unsigned long long*)workspace);
   UPS_CHECK_LAUNCH();
+  const size_t smem_all = ((size_t)max_seg_len + 1) * tiles * sizeof(unsigned long long);
+  if (smem_all <= 200 * 1024) {   // whole per-segment bitmask fits in shared memory
+    static bool configured = false;
+    if (!configured) {
+      UPS_CUDA(cudaFuncSetAttribute(nms_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    nms_sweep_smem_kernel<<<S, kSweepSmemThreads, smem_all, st>>>(seg_offsets, max_seg_len,
+                                                                  (const unsigned long long*)workspace, keep_out, keep_cnt);
+    UPS_CHECK_LAUNCH();
+    return 0;
+  }
   const size_t smem = (size_t)tiles * sizeof(unsigned long long);
   nms_sweep_kernel<<<S, kSweepThreads, smem, st>>>(seg_offsets, max_seg_len,
                                                    (const unsigned long long*)workspace, keep_out,
