@@ -94,7 +94,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
   const uint32_t out_slabs = BN == 64 ? 1 : 2;               // one output slab per epilogue group
   s.res = s.out + out_slabs * TM_SLAB_BYTES;
-  s.total = s.res + (has_res ? (uint32_t)(BN / 64) * TM_SLAB_BYTES : 0u);
+  s.total = s.res + (has_res ? 2u * (uint32_t)(BN / 64) * TM_SLAB_BYTES : 0u);   // two residual buffers (prefetch)
   return s;
 }
 
@@ -112,8 +112,8 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const TmaSmem L = tma_smem_layout(g.BN, g.stages, g.has_res != 0);
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
-  const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 6));
+  const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // two residual buffers
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 8));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cchunks = g.Cin / 64;
@@ -134,8 +134,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_init(bar_tfull + 8 * b, 1);
         mbar_init(bar_tempty + 8 * b, TM_EPI_WARPS);
       }
-      mbar_init(bar_rfull, 1);
-      mbar_init(bar_rempty, TM_EPI_WARPS);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_rfull + 8 * b, 1);
+        mbar_init(bar_rempty + 8 * b, TM_EPI_WARPS);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -227,11 +229,14 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int w0 = (int)(mt % g.tiles_w) * g.bw;
         const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
         const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
-        mbar_wait(bar_rempty, (ti_local & 1u) ^ 1u);
+        // residual slabs are double-buffered: tile t+1's residual streams in from HBM while tile t's epilogue runs
+        const uint32_t rb = ti_local & 1u, ruse = ti_local >> 1;
+        const uint32_t rdst = base + L.res + rb * (uint32_t)slabs * TM_SLAB_BYTES;
+        mbar_wait(bar_rempty + 8 * rb, (ruse & 1u) ^ 1u);
         // res_up2: the box of the half-resolution map that covers this tile is (bw/2, bh/2) at (w0/2, h0/2)
-        mbar_arrive_expect_tx(bar_rfull, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs);
+        mbar_arrive_expect_tx(bar_rfull + 8 * rb, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs);
         for (int s = 0; s < slabs; ++s)
-          tma_load_4d(base + L.res + s * TM_SLAB_BYTES, &tm_r, bar_rfull, nt * g.BN + s * 64, w0 >> g.res_up2,
+          tma_load_4d(rdst + s * TM_SLAB_BYTES, &tm_r, bar_rfull + 8 * rb, nt * g.BN + s * 64, w0 >> g.res_up2,
                       h0 >> g.res_up2, i0);
       }
     }
@@ -265,7 +270,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
       mbar_wait(bar_tfull + 8 * buf, use & 1u);
       tc_fence_after();
-      if (g.has_res) mbar_wait(bar_rfull, ti_local & 1u);
+      if (g.has_res) mbar_wait(bar_rfull + 8 * buf, use & 1u);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
       if (g.direct) {
         // thread = accumulator row = one output pixel of the box; the two halves split the columns
@@ -322,7 +327,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
         if (g.has_res) {
-          const uint32_t rs = base + L.res + (uint32_t)slab * TM_SLAB_BYTES + rs_row;
+          const uint32_t rs = base + L.res + (buf * (uint32_t)(g.BN / 64) + (uint32_t)slab) * TM_SLAB_BYTES + rs_row;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 rv = lds128(rs + (((jb + c) ^ rrx) << 4));
@@ -358,7 +363,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_tempty + 8 * buf);
-        if (g.has_res) mbar_arrive(bar_rempty);
+        if (g.has_res) mbar_arrive(bar_rempty + 8 * buf);
       }
     }
     if (leader) bulk_wait0();
