@@ -387,3 +387,35 @@ def test_tma_direct_store_epilogue(dev, cfg):
     assert np.abs(outs[0][1].float().cpu().numpy() - np.maximum(want - b[None, :, None, None], 0)).max() < tol
     for a, g in zip(outs[0], outs[1]):
         assert torch.equal(a, g)
+
+
+def test_pipelined_engine_matches_serial_forward(dev):
+    """The three-stream serving front end (overlapped H2D / compute / D2H) returns exactly what the serial
+    `model(data)` call returns, image after image, including when the staging slots wrap around."""
+    import upsnet_b200 as U
+    from upsnet_b200.model import UPSNetConfig
+    from upsnet_b200.synthetic import synthetic_input, synthetic_model
+    m = synthetic_model(UPSNetConfig.cityscapes_r50(), depth=(1, 1, 1, 1), seed=3, device=dev)
+    try:
+        U.set_precision("bf16")
+        imgs = [synthetic_input(256, 384, seed=10 + i) for i in range(5)]
+        with torch.no_grad():
+            want = []
+            for d in imgs:
+                o = m({"data": d["data"].to(dev), "im_info": d["im_info"]})
+                want.append({k: v.cpu() for k, v in o.items() if torch.is_tensor(v)})
+            eng = U.PipelinedEngine(m, imgs[0]["im_info"], depth=2)
+            host = [d["data"].pin_memory() for d in imgs]
+            got, tickets = [], []
+            for h in host:
+                tickets.append(eng.submit(h))
+                if len(tickets) > 1:
+                    got.append({k: v.clone() for k, v in eng.result(tickets[-2]).items()})
+            got.append({k: v.clone() for k, v in eng.result(tickets[-1]).items()})
+    finally:
+        U.set_precision("fp32")
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in ("panoptic_outputs", "fcn_outputs", "pred_boxes", "cls_probs", "cls_inds", "panoptic_cls_inds",
+                  "panoptic_cls_probs"):
+            assert torch.equal(g[k], w[k]), k

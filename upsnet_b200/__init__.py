@@ -7,7 +7,9 @@ from .operators import (DeformConv, DeformConvWithOffset, ModDeformConv, ModDefo
                         conv2d, linear, deform_conv, roi_align, fpn_roi_align, nms, nms_segmented, gpu_nms,
                         gpu_nms_wrapper, panoptic_fuse, set_precision)
 
-__all__ = ["DeformConv", "DeformConvWithOffset", "ModDeformConv", "ModDeformConvWithOffsetMask",
+from .pipeline import PipelinedEngine  # noqa: F401,E402
+
+__all__ = ["PipelinedEngine", "DeformConv", "DeformConvWithOffset", "ModDeformConv", "ModDeformConvWithOffsetMask",
            "ModulatedDeformConv", "RoIAlign", "ROIAlign", "RoIAlignFunction", "FPNRoIAlign", "PanopticHead",
            "MaskRemoval", "SegTerm",
            "conv2d", "linear", "deform_conv", "roi_align", "fpn_roi_align", "nms", "nms_segmented", "gpu_nms",

@@ -212,7 +212,15 @@ igemm_tc_kernel(const TcParams p) {
               ov.w = (b_ok && r_ok) ? hh * p.W + wh : 0;
             }
           }
-          tw[e] = wv;
+          if (XBF16) {   // bf16 gather blends in packed bf16x2: weights replicated into both halves, offsets in elements
+            ov.x *= p.Cin; ov.y *= p.Cin; ov.z *= p.Cin; ov.w *= p.Cin;
+            uint4 wp;
+            wp.x = pack_bf16x2(wv.x, wv.x); wp.y = pack_bf16x2(wv.y, wv.y);
+            wp.z = pack_bf16x2(wv.z, wv.z); wp.w = pack_bf16x2(wv.w, wv.w);
+            reinterpret_cast<uint4*>(tw)[e] = wp;
+          } else {
+            tw[e] = wv;
+          }
           to[e] = ov;
         }
       }
@@ -330,39 +338,38 @@ igemm_tc_kernel(const TcParams p) {
             }
           }
         } else if (XBF16) {
-          // deformable, bf16 activations: 8 lanes x 16 B cover a row's 64 channels; four corner reads of
-          // 8 bf16 each, blended in fp32 (sample table), repacked to bf16.
+          // deformable, bf16 activations: 4 lanes x 32 B cover a row's 64 channels (two 16-byte loads per corner,
+          // one address computation); the four corners are blended in packed bf16x2 (HFMA2.BF16: 4 ops per 8
+          // channels and corner pair instead of 8 unpack + 8 FMA + pack) with the tile's sample table, whose
+          // weights are stored as replicated bf16 pairs.  This kernel is issue-bound (ncu: 2.3 IPC, L2 16 %), so
+          // instructions per gathered element are what matters.
           const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
-#pragma unroll 2
-          for (int pass = 0; pass < TC_BM / 32; ++pass) {
-            const int r = r_first + pass * 32;
+          const int j2 = gt & 3, rr0 = gt >> 2;              // 64 rows per pass
+          const int cp0 = c0 - j * 8 + j2 * 16;              // first channel of this lane's 16-channel slice
+          const uint4* twp = reinterpret_cast<const uint4*>(tw);
+#pragma unroll 1
+          for (int pass = 0; pass < TC_BM / 64; ++pass) {
+            const int r = rr0 + pass * 64;
             const long long rb = rowinfo[r];
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
             if (rb >= 0) {
-              const __nv_bfloat16* xb = xh + rb + c0;
-              const float4 wv = tw[tap * TC_BM + r];
+              const __nv_bfloat16* xb = xh + rb + cp0;
+              const uint4 wv = twp[tap * TC_BM + r];
               const int4 ov = to[tap * TC_BM + r];
-              const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.x * p.Cin));
-              const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.y * p.Cin));
-              const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.z * p.Cin));
-              const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)ov.w * p.Cin));
-              const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w}, bw[4] = {b0.x, b0.y, b0.z, b0.w};
-              const uint32_t dw[4] = {d0.x, d0.y, d0.z, d0.w}, ew[4] = {e0.x, e0.y, e0.z, e0.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {   // bf16 -> fp32 is a 16-bit shift
-                v[2 * q] = wv.x * __uint_as_float(aw[q] << 16) + wv.y * __uint_as_float(bw[q] << 16) +
-                           wv.z * __uint_as_float(dw[q] << 16) + wv.w * __uint_as_float(ew[q] << 16);
-                v[2 * q + 1] = wv.x * __uint_as_float(aw[q] & 0xffff0000u) + wv.y * __uint_as_float(bw[q] & 0xffff0000u) +
-                               wv.z * __uint_as_float(dw[q] & 0xffff0000u) + wv.w * __uint_as_float(ew[q] & 0xffff0000u);
-              }
+              const uint4* pa = reinterpret_cast<const uint4*>(xb + ov.x);
+              const uint4* pb = reinterpret_cast<const uint4*>(xb + ov.y);
+              const uint4* pd = reinterpret_cast<const uint4*>(xb + ov.z);
+              const uint4* pe = reinterpret_cast<const uint4*>(xb + ov.w);
+              const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+              const uint4 d0 = __ldg(pd), d1 = __ldg(pd + 1), e0 = __ldg(pe), e1 = __ldg(pe + 1);
+              o0.x = bf2_blend(wv, a0.x, b0.x, d0.x, e0.x); o0.y = bf2_blend(wv, a0.y, b0.y, d0.y, e0.y);
+              o0.z = bf2_blend(wv, a0.z, b0.z, d0.z, e0.z); o0.w = bf2_blend(wv, a0.w, b0.w, d0.w, e0.w);
+              o1.x = bf2_blend(wv, a1.x, b1.x, d1.x, e1.x); o1.y = bf2_blend(wv, a1.y, b1.y, d1.y, e1.y);
+              o1.z = bf2_blend(wv, a1.z, b1.z, d1.z, e1.z); o1.w = bf2_blend(wv, a1.w, b1.w, d1.w, e1.w);
             }
-            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-            uint4 hi;
-            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(a_hi + soff) = hi;
+            const uint32_t rbase = (uint32_t)r * 128u, rx = (uint32_t)(r & 7);
+            *reinterpret_cast<uint4*>(a_hi + rbase + ((((uint32_t)j2 * 2u) ^ rx) << 4)) = o0;
+            *reinterpret_cast<uint4*>(a_hi + rbase + ((((uint32_t)j2 * 2u + 1u) ^ rx) << 4)) = o1;
           }
         } else {
           const float* xf = reinterpret_cast<const float*>(p.x);
@@ -733,6 +740,7 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   p.w_lo = p.w_hi + (size_t)p.Cout_pad * tc_kp(p.Cin, KHW);
   const bool deform = p.offset != nullptr;
   const bool smallc = (p.Cin % TC_BK) != 0;
+  if (deform && p.x_bf16 && (long long)p.H * p.W * p.Cin >= (1ll << 31)) return UPSNET_E_UNSUPPORTED;   // int32 element offsets
   if (smallc && (deform || p.x_bf16 || p.dh * (p.kh - 1) > 255 || p.dw * (p.kw - 1) > 255)) return UPSNET_E_UNSUPPORTED;
   // tile N: as wide as possible (each gathered A tile is reused by BN couts)
   int BN = p.Cout_pad;

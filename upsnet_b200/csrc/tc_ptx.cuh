@@ -128,6 +128,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// w.x*a + w.y*b + w.z*d + w.w*e on packed bf16 pairs (weights replicated into both halves)
+__device__ __forceinline__ uint32_t bf2_blend(const uint4& w, uint32_t a, uint32_t b, uint32_t d, uint32_t e) {
+  const __nv_bfloat162 wa = *reinterpret_cast<const __nv_bfloat162*>(&w.x), wb = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+  const __nv_bfloat162 wd = *reinterpret_cast<const __nv_bfloat162*>(&w.z), we = *reinterpret_cast<const __nv_bfloat162*>(&w.w);
+  __nv_bfloat162 acc = __hmul2(wa, *reinterpret_cast<const __nv_bfloat162*>(&a));
+  acc = __hfma2(wb, *reinterpret_cast<const __nv_bfloat162*>(&b), acc);
+  acc = __hfma2(wd, *reinterpret_cast<const __nv_bfloat162*>(&d), acc);
+  acc = __hfma2(we, *reinterpret_cast<const __nv_bfloat162*>(&e), acc);
+  return *reinterpret_cast<const uint32_t*>(&acc);
+}
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
 }  // namespace ups
