@@ -168,6 +168,13 @@ int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *
 int upsnet_maxpool2d_nhwc(const void *x, void *y, int N, int H, int W, int C, int k, int stride,
                           int pad, int dtype, void *stream);
 
+/* Bilinear up-sampling by an integer factor, NCHW fp32 planes, align_corners = False.
+ * replaces: models/fcn.py:88-101 nn.Upsample(scale_factor=4, mode='bilinear') of the semantic logits
+ *           (source index (dst + 0.5)/factor - 0.5 clamped at 0, as ATen's upsample_bilinear2d).
+ * x [planes,H,W] -> y [planes,H*factor,W*factor]; (W*factor) % 4 == 0. */
+int upsnet_upsample_bilinear_nchw(const float *x, float *y, int planes, int H, int W, int factor,
+                                  void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Detection glue, fused (device-resident; nothing returns to the host).
  *
@@ -190,6 +197,15 @@ int upsnet_rpn_topk_workspace_bytes(int L, size_t *bytes);
 int upsnet_rpn_topk(const float *const *probs, const int *hs, const int *ws, int L, int A,
                     int pre_nms_top_n, float *out_scores, long long *out_idx, void *workspace,
                     size_t workspace_bytes, void *stream);
+
+/* upsnet_rpn_collect: per level the first min(keep_cnt, post_nms_top_n) NMS survivors, then the post_nms_top_n
+ * best of their union by score (descending), as fixed-size outputs.
+ * replaces: operators/functions/pyramid_proposal.py:196-222 + modules/pyramid_proposal.py:61-67.
+ * keep/keep_cnt/seg_offsets from upsnet_nms_segmented over (boxes, scores) [total]; rois fp32 [post,5] =
+ * (0,x1,y1,x2,y2), rows past the live count are zero; out_scores [post]; valid uint8 [post]. */
+int upsnet_rpn_collect(const int *keep, const int *keep_cnt, const int *seg_offsets, const float *boxes,
+                       const float *scores, int S, int max_seg_len, int post_nms_top_n, float *rois,
+                       float *out_scores, unsigned char *valid, void *stream);
 
 /* upsnet_maskroi_prepare: candidate selection (prob > score_thresh, roi valid), ordering (class segment
  * ascending -- one segment when class_agnostic --, score descending, roi-major index ascending) and box decode

@@ -112,9 +112,10 @@ def cpu_ops():
     import upsnet_b200.detection as det
     import upsnet_b200.operators as ops
     names = ["conv2d", "linear", "deform_conv", "roi_align", "fpn_roi_align", "nms_segmented", "panoptic_fuse",
-             "max_pool2d"]
+             "max_pool2d", "upsample_bilinear"]
     impl = [_conv2d, _linear, _deform_conv, _roi_align, _fpn_roi_align, _nms_segmented, _panoptic_fuse,
-            lambda x, k, s, p: torch.nn.functional.max_pool2d(x, k, s, p)]
+            lambda x, k, s, p: torch.nn.functional.max_pool2d(x, k, s, p),
+            lambda x, f: torch.nn.functional.interpolate(x, None, f, mode="bilinear", align_corners=False)]
     saved = {n: getattr(ops, n) for n in names}
     saved_det = det.nms_segmented
     try:

@@ -421,3 +421,15 @@ def test_maxpool_nhwc_matches_torch(dev, dtype, shape):
     want = torch.nn.functional.max_pool2d(x.float(), 3, 2, 1)
     assert got.dtype == dtype and got.shape == want.shape
     assert torch.equal(got.float(), want)
+
+
+@pytest.mark.parametrize("shape,f", [((1, 19, 64, 96), 4), ((2, 3, 17, 5), 4), ((1, 19, 33, 50), 2), ((1, 1, 8, 8), 8)])
+def test_upsample_bilinear_matches_torch(dev, shape, f):
+    """Semantic-logit up-sampling (models/fcn.py:88-101): same source-index rule as ATen's upsample_bilinear2d."""
+    import upsnet_b200 as U
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(shape, generator=g).to(dev)
+    got = U.operators.upsample_bilinear(x, f)
+    want = torch.nn.functional.interpolate(x, None, f, mode="bilinear", align_corners=False)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 2e-6 * max(1.0, float(want.abs().max()))

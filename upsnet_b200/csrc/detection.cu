@@ -546,3 +546,147 @@ extern "C" int upsnet_rpn_topk(const float* const* probs, const int* hs, const i
   UPS_CHECK_LAUNCH();
   return 0;
 }
+
+// ----------------------------------------------------------------------------------------------
+// RPN post-NMS collect (operators/modules/pyramid_proposal.py:61-67 + functions/pyramid_proposal.py:196-222):
+// the first min(cnt, post) NMS survivors of every level, then the `post` best of their union by score, as
+// fixed-size outputs (rois [post,5] with zero rows past the live count, scores, validity flags).
+// One CTA: 45-bit keys (orderable(score) << 13 | 8191 - position in the level-major candidate list) in shared
+// memory, 4-pass radix select of the post-th largest, compaction, bitonic sort of the selected <= 2048 keys.
+// ----------------------------------------------------------------------------------------------
+namespace ups {
+
+constexpr int kColMaxCand = 8192, kColMaxPost = 2048, kColBins = 4096;
+
+__global__ void __launch_bounds__(1024, 1)
+rpn_collect_kernel(const int* __restrict__ keep, const int* __restrict__ cnt, const int* __restrict__ offs,
+                   const float* __restrict__ boxes, const float* __restrict__ scores, int S, int max_len, int post,
+                   float* __restrict__ rois, float* __restrict__ out_scores, unsigned char* __restrict__ ok) {
+  extern __shared__ unsigned long long ck[];            // [kColMaxCand] candidate keys, then [kColMaxPost] selected
+  unsigned long long* sel = ck + kColMaxCand;
+  __shared__ unsigned int hist[kColBins];
+  __shared__ int seg_base[kMaxLevels + 1];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_nsel;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < S; ++s) { seg_base[s] = acc; acc += min(min(max(cnt[s], 0), max_len), post); }
+    seg_base[S] = min(acc, kColMaxCand);
+    s_nsel = 0;
+  }
+  __syncthreads();
+  const int C = seg_base[S];
+  for (int s = 0; s < S; ++s) {
+    const int b = seg_base[s], n = min(seg_base[s + 1], kColMaxCand) - b, o = offs[s];
+    for (int j = tid; j < n; j += 1024) {
+      const int g = keep[(size_t)s * max_len + j] + o;
+      ck[b + j] = ((unsigned long long)orderable(scores[g]) << 13) | (unsigned long long)(8191 - (b + j));
+    }
+  }
+  __syncthreads();
+  unsigned long long kth = 0ull;
+  if (C > post) {
+    if (tid == 0) { s_prefix = 0ull; s_need = post; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 36 - 12 * pass;       // digits [36,48) [24,36) [12,24) [0,12) of the 45-bit key
+      const unsigned long long mask_hi = pass == 0 ? 0ull : (~0ull << (shift + 12));
+      for (int b = tid; b < kColBins; b += 1024) hist[b] = 0;
+      __syncthreads();
+      const unsigned long long pref = s_prefix;
+      for (int i = tid; i < C; i += 1024)
+        if ((ck[i] & mask_hi) == pref) atomicAdd(&hist[(unsigned int)(ck[i] >> shift) & (kColBins - 1)], 1u);
+      __syncthreads();
+      if (tid < 32) {
+        const int need = s_need, per = kColBins / 32;
+        unsigned int mine = 0;
+        for (int b = 0; b < per; ++b) mine += hist[kColBins - 1 - (tid * per + b)];
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += y;
+        }
+        const unsigned int excl = incl - mine;
+        if (excl < (unsigned int)need && incl >= (unsigned int)need) {
+          unsigned int acc = excl;
+          int d = 0;
+          for (int b = 0; b < per; ++b) {
+            const int bin = kColBins - 1 - (tid * per + b);
+            if (acc + hist[bin] >= (unsigned int)need) { d = bin; break; }
+            acc += hist[bin];
+          }
+          s_need = need - (int)acc;
+          s_prefix = pref | ((unsigned long long)d << shift);
+        }
+      }
+      __syncthreads();
+    }
+    kth = s_prefix;
+  }
+  // selected keys (all distinct): exactly min(C, post) of them; order fixed by the sort below
+  for (int i = tid; i < C; i += 1024)
+    if (ck[i] >= kth) {
+      const int pos = atomicAdd(&s_nsel, 1);
+      if (pos < kColMaxPost) sel[pos] = ck[i];
+    }
+  __syncthreads();
+  const int nsel = min(s_nsel, min(post, kColMaxPost));
+  int sortN = 64;
+  while (sortN < nsel) sortN <<= 1;
+  for (int i = nsel + tid; i < sortN; i += 1024) sel[i] = 0ull;
+  __syncthreads();
+  for (int k = 2; k <= sortN; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < sortN / 2; t += 1024) {
+        const int lo = ((t / j) * (j << 1)) + (t % j), hi = lo + j;
+        const unsigned long long a = sel[lo], b = sel[hi];
+        const bool desc = (lo & k) == 0;
+        if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < post; i += 1024) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    unsigned char live = 0;
+    if (i < nsel) {
+      const int fp = 8191 - (int)(sel[i] & 8191ull);
+      int s = 0;
+      while (s + 1 < S && fp >= seg_base[s + 1]) ++s;
+      const int g = keep[(size_t)s * max_len + (fp - seg_base[s])] + offs[s];
+      bx = reinterpret_cast<const float4*>(boxes)[g];
+      sc = scores[g];
+      live = 1;
+    }
+    rois[(size_t)i * 5] = 0.f;
+    rois[(size_t)i * 5 + 1] = bx.x; rois[(size_t)i * 5 + 2] = bx.y;
+    rois[(size_t)i * 5 + 3] = bx.z; rois[(size_t)i * 5 + 4] = bx.w;
+    out_scores[i] = sc;
+    ok[i] = live;
+  }
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_rpn_collect(const int* keep, const int* keep_cnt, const int* seg_offsets, const float* boxes,
+                                  const float* scores, int S, int max_seg_len, int post_nms_top_n, float* rois,
+                                  float* out_scores, unsigned char* valid, void* stream) {
+  using namespace ups;
+  if (!keep || !keep_cnt || !seg_offsets || !boxes || !scores || !rois || !out_scores || !valid) return UPSNET_E_BADARG;
+  if (S <= 0 || S > kMaxLevels || max_seg_len <= 0 || post_nms_top_n <= 0) return UPSNET_E_BADARG;
+  if (post_nms_top_n > kColMaxPost || (long long)S * (max_seg_len < post_nms_top_n ? max_seg_len : post_nms_top_n) > kColMaxCand)
+    return UPSNET_E_UNSUPPORTED;
+  if (((uintptr_t)boxes) & 15) return UPSNET_E_BADARG;
+  const size_t smem = (size_t)(kColMaxCand + kColMaxPost) * 8;
+  static bool configured = false;
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  rpn_collect_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(keep, keep_cnt, seg_offsets, boxes, scores, S, max_seg_len,
+                                                               post_nms_top_n, rois, out_scores, valid);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

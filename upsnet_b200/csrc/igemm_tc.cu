@@ -356,12 +356,13 @@ igemm_tc_kernel(const TcParams p) {
               const __nv_bfloat16* xb = xh + rb + cp0;
               const uint4 wv = twp[tap * TC_BM + r];
               const int4 ov = to[tap * TC_BM + r];
-              const uint4* pa = reinterpret_cast<const uint4*>(xb + ov.x);
-              const uint4* pb = reinterpret_cast<const uint4*>(xb + ov.y);
-              const uint4* pd = reinterpret_cast<const uint4*>(xb + ov.z);
-              const uint4* pe = reinterpret_cast<const uint4*>(xb + ov.w);
-              const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
-              const uint4 d0 = __ldg(pd), d1 = __ldg(pd + 1), e0 = __ldg(pe), e1 = __ldg(pe + 1);
+              // one 256-bit load per corner (LDG.E.256): 4 lanes cover a row's full 128-byte line, so the L1
+              // wavefront count stays that of the 8-lane x 16-byte mapping while the address work is halved
+              uint4 a0, a1, b0, b1, d0, d1, e0, e1;
+              ldg256(xb + ov.x, a0, a1);
+              ldg256(xb + ov.y, b0, b1);
+              ldg256(xb + ov.z, d0, d1);
+              ldg256(xb + ov.w, e0, e1);
               o0.x = bf2_blend(wv, a0.x, b0.x, d0.x, e0.x); o0.y = bf2_blend(wv, a0.y, b0.y, d0.y, e0.y);
               o0.z = bf2_blend(wv, a0.z, b0.z, d0.z, e0.z); o0.w = bf2_blend(wv, a0.w, b0.w, d0.w, e0.w);
               o1.x = bf2_blend(wv, a1.x, b1.x, d1.x, e1.x); o1.y = bf2_blend(wv, a1.y, b1.y, d1.y, e1.y);

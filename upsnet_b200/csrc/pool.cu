@@ -69,3 +69,52 @@ extern "C" int upsnet_maxpool2d_nhwc(const void* x, void* y, int N, int H, int W
   UPS_CHECK_LAUNCH();
   return 0;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Bilinear up-sampling by an integer factor on NCHW fp32 planes, align_corners = False
+// (models/fcn.py:88-101 nn.Upsample(scale_factor, mode='bilinear') of the semantic logits).
+// src = (dst + 0.5) / f - 0.5 clamped at 0 (the same source-index rule as ATen's upsample_bilinear2d);
+// one thread = 4 consecutive output pixels of one row (float4 store).  Roofline: HBM, 4*P*Ho*Wo bytes written.
+// ----------------------------------------------------------------------------------------------
+namespace ups {
+
+__global__ void __launch_bounds__(256)
+upsample_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int P, int H, int W, int f) {
+  const int Ho = H * f, Wo = W * f, Wq = Wo >> 2;
+  const long long total = (long long)P * Ho * Wq;
+  const float rf = 1.0f / (float)f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(t % Wq);
+    long long rest = t / Wq;
+    const int yo = (int)(rest % Ho);
+    const int pl = (int)(rest / Ho);
+    const float sy = fmaxf(rf * ((float)yo + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = y0 + (y0 < H - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, hy = 1.f - ly;
+    const float* r0 = x + ((size_t)pl * H + y0) * W;
+    const float* r1 = x + ((size_t)pl * H + y1) * W;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int xo = xq * 4 + e;
+      const float sx = fmaxf(rf * ((float)xo + 0.5f) - 0.5f, 0.f);
+      const int x0 = (int)sx, x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float lx = sx - (float)x0, hx = 1.f - lx;
+      o[e] = hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+    }
+    reinterpret_cast<float4*>(y)[t] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace ups
+
+extern "C" int upsnet_upsample_bilinear_nchw(const float* x, float* y, int planes, int H, int W, int factor, void* stream) {
+  if (!x || !y || planes <= 0 || H <= 0 || W <= 0 || factor <= 0) return UPSNET_E_BADARG;
+  if (((W * factor) & 3) || (((uintptr_t)y) & 15)) return UPSNET_E_UNSUPPORTED;
+  const long long total = (long long)planes * H * factor * ((W * factor) >> 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > ups::kNumSMs * 32) blocks = ups::kNumSMs * 32;
+  ups::upsample_bilinear_nchw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, planes, H, W, factor);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -128,6 +128,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 32-byte read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  lo = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+  hi = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+}
 // w.x*a + w.y*b + w.z*d + w.w*e on packed bf16 pairs (weights replicated into both halves)
 __device__ __forceinline__ uint32_t bf2_blend(const uint4& w, uint32_t a, uint32_t b, uint32_t d, uint32_t e) {
   const __nv_bfloat162 wa = *reinterpret_cast<const __nv_bfloat162*>(&w.x), wb = *reinterpret_cast<const __nv_bfloat162*>(&w.y);

@@ -251,6 +251,9 @@ class StaticProposalGenerator(ProposalGenerator):
         offs = self._offsets(lens, dev)
         max_len = max(lens)
         keep, cnt = nms_segmented(boxes, offs, max_len, self.thresh)
+        if (FUSED["on"] and dev.type == "cuda" and 0 < self.post <= 2048 and len(lens) * min(max_len, self.post) <= 8192
+                and len(lens) * min(max_len, self.post) >= self.post):
+            return _ops.rpn_collect(keep, cnt, offs, boxes, scores, self.post)
         pos = torch.arange(max_len, device=dev)[None, :]
         limit = cnt.clamp(max=self.post if self.post > 0 else max_len)[:, None]
         valid = pos < limit

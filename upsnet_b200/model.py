@@ -398,7 +398,7 @@ class FCNHead(nn.Module):
                 score = score + F.interpolate(s_l, None, 2 ** l, mode="bilinear", align_corners=False)
             ret = {"fcn_score": score}
             if self.upsample_rate != 1:
-                ret["fcn_output"] = F.interpolate(score, None, self.upsample_rate, mode="bilinear", align_corners=False)
+                ret["fcn_output"] = ops.upsample_bilinear(score, self.upsample_rate)
             return ret
         p3 = F.interpolate(p3, None, 2, mode="bilinear", align_corners=False)
         p4 = F.interpolate(p4, None, 4, mode="bilinear", align_corners=False)

@@ -295,6 +295,18 @@ def max_pool2d(x, kernel_size, stride, padding):
     return store.permute(0, 3, 1, 2)
 
 
+def upsample_bilinear(x, factor):
+    """nn.Upsample(scale_factor=factor, mode='bilinear', align_corners=False) on contiguous NCHW fp32 planes
+    (models/fcn.py:88-101: the semantic logits)."""
+    require_cuda(x)
+    x = f32c(x)
+    N, Cc, H, W = x.shape
+    y = torch.empty((N, Cc, H * factor, W * factor), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _Timed("upsample", 1, {"bytes": 4.0 * (x.numel() + y.numel())}, x.device):
+        check(lib().upsnet_upsample_bilinear_nchw(ptr(x), ptr(y), N * Cc, H, W, int(factor), stream_ptr(x.device)), "upsample")
+    return y
+
+
 def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, sampling_ratio=2, layout="nchw",
                   return_levels=False):
     """FPNRoIAlign.forward in one launch (level assignment on device, output already in roi order)."""
@@ -423,6 +435,21 @@ def rpn_topk(probs, A, pre_nms_top_n):
                                     (ci * L)(*[int(pr.shape[-1]) for pr in probs]), L, int(A), int(pre_nms_top_n),
                                     ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), stream_ptr(dev)), "rpn_topk")
     return out_s, out_i, ks
+
+
+def rpn_collect(keep, cnt, offs, boxes, scores, post_nms_top_n):
+    """Fused proposal collect after the per-level NMS -> (rois [post,5], scores [post], valid [post] bool)."""
+    require_cuda(keep, cnt, offs, boxes, scores)
+    dev = boxes.device
+    S, M = keep.shape
+    post = int(post_nms_top_n)
+    rois = torch.empty((post, 5), dtype=torch.float32, device=dev)
+    out_s = torch.empty((post,), dtype=torch.float32, device=dev)
+    ok = torch.empty((post,), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev), _Timed("rpn_collect", 1, {"bytes": 28.0 * post}, dev):
+        check(lib().upsnet_rpn_collect(ptr(keep), ptr(cnt), ptr(offs), ptr(f32c(boxes)), ptr(f32c(scores)), S, M, post,
+                                       ptr(rois), ptr(out_s), ptr(ok), stream_ptr(dev)), "rpn_collect")
+    return rois, out_s, ok
 
 
 def maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, class_agnostic, score_thresh, weights, im_h, im_w):
