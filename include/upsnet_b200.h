@@ -162,6 +162,21 @@ int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *
                         double fraction_threshold, int64_t *keep_out, int *k_out, float *mask_energy,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* RGB stem on the TMA kernel: k x k (kw <= 8) / stride 2 / pad `pad` convolution of a tiny-Cin (<= 8) fp32 NCHW
+ * image, bf16 NHWC output [N,Ho,Wo,Cout] (Cout % 64 == 0), fused bias + ReLU (UPSNET_EPI_RELU).
+ * replaces: models/resnet.py:155-162 conv1 + bn1 (folded) + relu.
+ * The call first packs the image to a zero-padded bf16 NHWC8 copy in `workspace` (upsnet_stem_workspace_bytes),
+ * then runs the tcgen05 kernel whose A tiles are boxes of a 5-D tensor map over that copy; weights are packed
+ * once with upsnet_stem_pack_weight ([Cout][kh][8][8] bf16, upsnet_stem_packed_weight_bytes).
+ * Returns UPSNET_E_UNSUPPORTED if the driver rejects the tensor map (callers fall back to upsnet_igemm_forward). */
+int upsnet_stem_workspace_bytes(int N, int H, int W, int kh, int kw, int pad, size_t *bytes);
+int upsnet_stem_packed_weight_bytes(int Cout, int kh, size_t *bytes);
+int upsnet_stem_pack_weight(const float *weight, int Cout, int Cin, int kh, int kw, void *packed,
+                            void *stream);
+int upsnet_stem_forward(const float *x, const void *packed_w, const float *bias, void *y, int N, int Cin,
+                        int H, int W, int Cout, int kh, int kw, int pad, int epi_flags, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* Max-pooling on NHWC activations (bf16 or fp32 storage; C % 8 == 0 resp. C % 4 == 0), floor output size.
  * replaces: models/resnet.py:163 nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the stem.
  * x [N,H,W,C] -> y [N,Ho,Wo,C], Ho = (H + 2*pad - k)/stride + 1; padding never wins the max. */

@@ -419,3 +419,20 @@ def test_pipelined_engine_matches_serial_forward(dev):
         for k in ("panoptic_outputs", "fcn_outputs", "pred_boxes", "cls_probs", "cls_inds", "panoptic_cls_inds",
                   "panoptic_cls_probs"):
             assert torch.equal(g[k], w[k]), k
+
+
+@pytest.mark.parametrize("cfg", [dict(N=1, H=64, W=96, k=7, pad=3, Cout=64), dict(N=2, H=38, W=54, k=7, pad=3, Cout=64),
+                                 dict(N=1, H=32, W=48, k=3, pad=1, Cout=128)])
+def test_stem_tma_vs_oracle(dev, cfg):
+    """RGB stem on the TMA kernel (packed NHWC8 image + 5-D tensor map) against the dense-conv oracle."""
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as OPS
+    rng = np.random.default_rng(41)
+    x, w, b = _case(rng, cfg["N"], 3, cfg["Cout"], cfg["H"], cfg["W"], cfg["k"])
+    x, w = _bf16_exact(x * 20), _bf16_exact(w)
+    want = np.maximum(O.conv2d(x, w, b, 2, cfg["pad"], 1), 0)
+    got = OPS.stem_conv(t(x, dev), t(w, dev), t(b, dev), cfg["pad"], relu=True)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == want.shape
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert np.abs(got.float().cpu().numpy() - want).max() < 1e-3 + (2.0 ** -8) * np.abs(want).max()

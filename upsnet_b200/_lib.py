@@ -56,6 +56,10 @@ def lib():
         L.upsnet_maxpool2d_nhwc.argtypes = [vp, vp] + [i] * 8 + [vp]
         L.upsnet_upsample_bilinear_nchw.argtypes = [vp, vp, i, i, i, i, vp]
         L.upsnet_rpn_topk_workspace_bytes.argtypes = [i, C.POINTER(sz)]
+        L.upsnet_stem_workspace_bytes.argtypes = [i] * 6 + [C.POINTER(sz)]
+        L.upsnet_stem_packed_weight_bytes.argtypes = [i, i, C.POINTER(sz)]
+        L.upsnet_stem_pack_weight.argtypes = [vp, i, i, i, i, vp, vp]
+        L.upsnet_stem_forward.argtypes = [vp] * 4 + [i] * 9 + [vp, sz, vp]
         L.upsnet_rpn_collect.argtypes = [vp] * 5 + [i] * 3 + [vp] * 4
         L.upsnet_rpn_topk.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i), i, i, i, vp, vp, vp, sz, vp]
         _lib = L
@@ -67,7 +71,8 @@ EXPORTED_SYMBOLS = [
     "upsnet_nms_workspace_bytes", "upsnet_nms_segmented", "upsnet_nms_host", "upsnet_dcn_forward",
     "upsnet_conv2d_forward", "upsnet_igemm_packed_weight_bytes", "upsnet_igemm_pack_weight",
     "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_head", "upsnet_mask_removal",
-    "upsnet_rpn_decode", "upsnet_maskroi_prepare", "upsnet_maskroi_finish", "upsnet_maxpool2d_nhwc", "upsnet_upsample_bilinear_nchw", "upsnet_rpn_topk_workspace_bytes", "upsnet_rpn_topk", "upsnet_rpn_collect",
+    "upsnet_rpn_decode", "upsnet_maskroi_prepare", "upsnet_maskroi_finish", "upsnet_maxpool2d_nhwc", "upsnet_upsample_bilinear_nchw", "upsnet_rpn_topk_workspace_bytes", "upsnet_rpn_topk", "upsnet_rpn_collect", "upsnet_stem_workspace_bytes",
+    "upsnet_stem_packed_weight_bytes", "upsnet_stem_pack_weight", "upsnet_stem_forward",
 ]
 
 

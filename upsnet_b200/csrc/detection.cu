@@ -353,7 +353,7 @@ extern "C" int upsnet_maskroi_finish(const int* keep, const int* keep_cnt, const
 // ----------------------------------------------------------------------------------------------
 namespace ups {
 
-constexpr int kTkBins = 2048, kTkThreads = 512, kTkItems = 16, kTkMaxK = 2048, kTkIdxBits = 22;
+constexpr int kTkBins = 2048, kTkThreads = 512, kTkItems = 8, kTkMaxK = 2048, kTkIdxBits = 22;
 
 struct TopkLevel {
   const float* prob;      // [A, h, w]
@@ -398,10 +398,17 @@ topk_pass_kernel(const TopkParams p, int shift, int bits, int first) {
 #pragma unroll 4
   for (int it = 0; it < kTkItems; ++it) {
     const int e = e0 + it * kTkThreads + threadIdx.x;
+    bool act = false;
+    unsigned int bin = 0xffffffffu;
     if (e < lv.L) {
       const unsigned long long key = topk_key(__ldg(lv.prob + e), topk_flat(e, lv.hw, p.A));
-      if ((key & mask_hi) == fixed) atomicAdd(&sh[(unsigned int)(key >> shift) & dmask], 1u);
+      act = (key & mask_hi) == fixed;
+      if (act) bin = (unsigned int)(key >> shift) & dmask;
     }
+    // scores cluster in a handful of exponent bins (first pass) or tie exactly (saturated sigmoid): aggregate equal
+    // bins inside the warp so that one lane issues one shared-memory atomic per distinct bin
+    const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+    if (act && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (unsigned int)__popc(peers));
   }
   __syncthreads();
   unsigned int* gh = p.hist + (size_t)l * kTkBins;

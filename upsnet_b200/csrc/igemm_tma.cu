@@ -43,6 +43,7 @@ struct TmaGeom {
   // direct-store epilogue (small / odd Cout, fp32 or NCHW outputs: offset convs, RPN / score / mask-logit heads)
   int direct, y_bf16, out_nhwc;
   void* y;
+  int stem;                             // stride-2 tiny-Cin stem: A boxes come from the packed / padded image (5-D map)
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -53,6 +54,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -173,7 +179,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t bf = bar_full + 8 * s;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(bf, tx_bytes);
-          tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
+          if (g.stem)   // k-block = filter row ky: 8 pixels x 8 channels per output pixel, input row 2*ho + ky of the padded image
+            tma_load_5d(a_dst, &tm_x, bf, 0, w0, kb & 1, h0 + (kb >> 1), i0);
+          else
+            tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
           tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, n0);
           if (++cc == cchunks) {
             cc = 0; cw += g.dw;
@@ -402,10 +411,10 @@ static EncodeTiledFn tma_encoder() {
 // bf16 tensor, innermost dimension first; box[0] = 64 elements = one 128-byte swizzle span
 static bool encode_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
                         const cuuint32_t* box, const cuuint64_t* byte_strides = nullptr) {
-  cuuint64_t strides[4];
+  cuuint64_t strides[5];
   cuuint64_t acc = 2;
   for (int i = 0; i + 1 < rank; ++i) { acc *= dims[i]; strides[i] = byte_strides ? byte_strides[i] : acc; }
-  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -519,4 +528,142 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   return 0;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// RGB stem (models/resnet.py:155-162 conv1: 7x7 / stride 2 / pad 3, Cin = 3) on the TMA kernel.
+// The fp32 NCHW image is first packed to a zero-padded bf16 NHWC8 image (stem_pack_image_kernel); the eight input
+// pixels x 8 channels an output pixel needs from filter row ky are then 128 contiguous bytes, consecutive output
+// pixels start 32 bytes apart, and even / odd input rows are split by a parity dimension -- a 5-D tensor map
+// (64 el, Wo @32 B, 2 @pitch, Hp/2 @2*pitch, N) whose boxes ARE the im2col tiles, one k-block per filter row.
+// Weights are packed [Cout][ky][8 px][8 ch] with zeros for kx >= kw and c >= Cin (K = 64*kh).
+// ----------------------------------------------------------------------------------------------
+__global__ void stem_pack_image_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int N, int C, int H, int W,
+                                       int pad, int Hp, int Wp) {
+  const long long total = (long long)N * Hp * Wp;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % Wp);
+    const long long rest = t / Wp;
+    const int r = (int)(rest % Hp), n = (int)(rest / Hp);
+    const int hi = r - pad, wi = c - pad;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(x + (((size_t)n * C + ch) * H + hi) * W + wi);
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    xp[t] = o;
+  }
+}
+
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw,
+                                        __nv_bfloat16* __restrict__ packed) {
+  const int total = Cout * kh * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 7, kx = (i >> 3) & 7, ky = (i >> 6) % kh, co = i / (64 * kh);
+    const float v = (c < Cin && kx < kw) ? w[(((size_t)co * Cin + c) * kh + ky) * kw + kx] : 0.f;
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static void stem_geometry(int H, int W, int kh, int kw, int pad, int* Ho, int* Wo, int* Hp, int* Wp) {
+  *Ho = (H + 2 * pad - kh) / 2 + 1;
+  *Wo = (W + 2 * pad - kw) / 2 + 1;
+  *Hp = 2 * (*Ho + (kh >> 1));
+  *Wp = 2 * *Wo + 8;
+}
+
 }  // namespace ups
+
+extern "C" int upsnet_stem_workspace_bytes(int N, int H, int W, int kh, int kw, int pad, size_t* bytes) {
+  if (!bytes || N <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || kw > 8 || pad < 0) return UPSNET_E_BADARG;
+  int Ho, Wo, Hp, Wp;
+  ups::stem_geometry(H, W, kh, kw, pad, &Ho, &Wo, &Hp, &Wp);
+  if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
+  *bytes = (size_t)N * Hp * Wp * 16;
+  return 0;
+}
+
+extern "C" int upsnet_stem_packed_weight_bytes(int Cout, int kh, size_t* bytes) {
+  if (!bytes || Cout <= 0 || kh <= 0) return UPSNET_E_BADARG;
+  *bytes = (size_t)Cout * kh * 64 * 2;
+  return 0;
+}
+
+extern "C" int upsnet_stem_pack_weight(const float* weight, int Cout, int Cin, int kh, int kw, void* packed, void* stream) {
+  if (!weight || !packed || Cout <= 0 || Cin <= 0 || Cin > 8 || kh <= 0 || kw <= 0 || kw > 8) return UPSNET_E_BADARG;
+  const int total = Cout * kh * 64;
+  ups::stem_pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, Cout, Cin, kh, kw,
+                                                                                         (__nv_bfloat16*)packed);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const float* bias, void* y, int N, int Cin, int H,
+                                   int W, int Cout, int kh, int kw, int pad, int epi_flags, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  using namespace ups;
+  if (!x || !packed_w || !y || !workspace) return UPSNET_E_BADARG;
+  if (N <= 0 || Cin <= 0 || Cin > 8 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || kw > 8 || pad < 0) return UPSNET_E_BADARG;
+  if ((Cout % 64) || Cout > 256 || kh > 16) return UPSNET_E_UNSUPPORTED;
+  if ((((uintptr_t)y) & 15) || (((uintptr_t)packed_w) & 15) || (((uintptr_t)workspace) & 15)) return UPSNET_E_BADARG;
+  if (bias && (((uintptr_t)bias) & 15)) return UPSNET_E_UNSUPPORTED;
+  int Ho, Wo, Hp, Wp;
+  stem_geometry(H, W, kh, kw, pad, &Ho, &Wo, &Hp, &Wp);
+  if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
+  if (workspace_bytes < (size_t)N * Hp * Wp * 16) return UPSNET_E_WORKSPACE;
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return UPSNET_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  TmaGeom g{};
+  g.bias = bias;
+  g.N = N; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout; g.Cin = 64;
+  g.kw = 1; g.KHW = kh; g.ph = 0; g.pw = 0; g.dh = 1; g.dw = 1;
+  g.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
+  g.stem = 1; g.y = y; g.y_bf16 = 1; g.out_nhwc = 1;
+  tma_pick_box(N, Ho, Wo, 1, 1, 1, 1, false, &g.bw, &g.bh, &g.bn);
+  g.tiles_w = (Wo + g.bw - 1) / g.bw;
+  g.tiles_h = (Ho + g.bh - 1) / g.bh;
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  g.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  g.n_tiles = Cout / g.BN;
+  int stages = TM_MAX_STAGES;
+  TmaSmem L = tma_smem_layout(g.BN, stages, false);
+  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(g.BN, stages, false); }
+  g.stages = stages;
+  CUtensorMap tm_x, tm_w, tm_y;
+  {
+    const cuuint64_t pitch = (cuuint64_t)Wp * 16;
+    const cuuint64_t dx[5] = {64, (cuuint64_t)Wo, 2, (cuuint64_t)(Hp / 2), (cuuint64_t)N};
+    const cuuint64_t sx[4] = {32, pitch, 2 * pitch, (cuuint64_t)Hp * pitch};
+    const cuuint32_t bx[5] = {64, (cuuint32_t)g.bw, 1, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
+    const cuuint64_t dwt[2] = {(cuuint64_t)kh * 64, (cuuint64_t)Cout};
+    const cuuint32_t bw2[2] = {64, (cuuint32_t)g.BN};
+    const cuuint64_t dy[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint32_t by[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
+    if (!encode_bf16(enc, &tm_x, workspace, 5, dx, bx, sx)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_w, packed_w, 2, dwt, bw2)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_y, y, 4, dy, by)) return UPSNET_E_UNSUPPORTED;
+  }
+  {
+    const long long total = (long long)N * Hp * Wp;
+    long long blocks = (total + 255) / 256;
+    if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+    stem_pack_image_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (uint4*)workspace, N, Cin, H, W, pad, Hp, Wp);
+    UPS_CHECK_LAUNCH();
+  }
+  static bool configured = false;
+  if (!configured) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms = v > 0 ? v : kNumSMs;
+  }
+  const long long num_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
+  igemm_tma_kernel<<<grid, TM_THREADS, L.total + 1024, st>>>(tm_x, tm_w, tm_y, tm_y, g);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}

@@ -304,34 +304,60 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     __syncthreads();
   }
   const int cnt = s_cnt;
+  // Per-instance critical path = one L2 round trip (window words + occupancy) + a block reduction: |mask| values are
+  // staged in shared memory up front, a thread's window words stay in registers between the popc and the OR pass.
+  __shared__ int s_msum[kMaxList];
+  for (int li = threadIdx.x; li < cnt; li += blockDim.x) s_msum[li] = ws.msum[list[li]];
+  __syncthreads();
+  constexpr int kRegWords = 8;
   for (int li = 0; li < cnt; ++li) {
     const int r = list[li];
     const int i = ws.order[r];
     const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
     const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;
     const int nwc = max(wx1 - wx0, 0), items = nwc * max(y1 - y0, 0);
-    const unsigned int* bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
+    const unsigned int* __restrict__ bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
     unsigned int my_ovl = 0;
-    for (int item = threadIdx.x; item < items; item += blockDim.x) {
+    unsigned int wreg[kRegWords];
+#pragma unroll
+    for (int u = 0; u < kRegWords; ++u) {
+      const int item = threadIdx.x + u * (int)blockDim.x;
+      wreg[u] = 0u;
+      if (item < items) {
+        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
+        wreg[u] = __ldg(bits + item);
+        my_ovl += __popc(wreg[u] & occ[o]);
+      }
+    }
+    for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
       const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-      my_ovl += __popc(bits[item] & occ[o]);
+      my_ovl += __popc(__ldg(bits + item) & occ[o]);
     }
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) my_ovl += __shfl_xor_sync(0xffffffffu, my_ovl, sh);
     if (lane == 0 && my_ovl) atomicAdd(&s_ovl[li & 1], my_ovl);
     __syncthreads();
-    const unsigned int ms = (unsigned int)ws.msum[r], ov = s_ovl[li & 1];
+    const unsigned int ms = (unsigned int)s_msum[li], ov = s_ovl[li & 1];
     // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
     const bool drop = (ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold);
     if (threadIdx.x == 0) {
       ws.kept_flag[r] = drop ? 0 : 1;
       s_ovl[(li + 1) & 1] = 0;            // the other counter is idle until the next instance's barrier
     }
-    if (!drop)
-      for (int item = threadIdx.x; item < items; item += blockDim.x) {
-        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-        occ[o] |= bits[item];
+    if (!drop) {
+#pragma unroll
+      for (int u = 0; u < kRegWords; ++u) {
+        const int item = threadIdx.x + u * (int)blockDim.x;
+        if (item < items && wreg[u]) {
+          const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
+          occ[o] |= wreg[u];
+        }
       }
+      for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
+        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
+        occ[o] |= __ldg(bits + item);
+      }
+    }
     __syncthreads();   // occupancy visible to the whole CTA before the next instance reads it
   }
 }

@@ -124,12 +124,22 @@ class Stem(nn.Module):
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self._f = None
+        self._stem_tma = None    # None = not probed yet, True / False = TMA stem path usable
 
     def prepare(self):
         w, b = _fold_bn(self.conv1.weight, self.bn1)
         self._f = (w.detach(), b.detach())
 
     def forward(self, x):
+        if x.is_cuda and ops.ACT_BF16["on"] and ops._PRECISION["conv"] == ops._lib.PREC_BF16 and self._stem_tma is not False:
+            try:    # TMA-fed stem; a driver that rejects the overlapping-stride tensor map leaves the gather kernel in charge
+                y = ops.stem_conv(x, self._f[0], self._f[1], 3, relu=True)
+                self._stem_tma = True
+                return ops.max_pool2d(y, 3, 2, 1)
+            except ops._lib.UpsnetError:
+                if self._stem_tma:      # it worked before: a real failure, not a capability probe
+                    raise
+                self._stem_tma = False
         x = ops.conv2d(x, self._f[0], self._f[1], stride=2, padding=3, relu=True)
         return ops.max_pool2d(x, 3, 2, 1)
 

@@ -107,6 +107,50 @@ def _packed_weight(weight):
     return buf
 
 
+_stem_cache = {}   # id(weight) -> (weakref, version, packed bf16 [Cout][kh][8][8])
+_stem_ws = None
+
+
+def stem_conv(x, weight, bias, padding, relu=True):
+    """k x k / stride-2 convolution of a tiny-Cin fp32 NCHW image (models/resnet.py:155-162 conv1) on the TMA kernel:
+    the image is packed to a zero-padded bf16 NHWC8 copy whose 5-D tensor-map boxes are the im2col tiles.
+    -> bf16 channels_last activation [N,Cout,Ho,Wo].  Raises UpsnetError(UNSUPPORTED) if the driver rejects the map."""
+    global _stem_ws
+    require_cuda(x, weight, bias)
+    x = f32c(x)
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    dev = x.device
+    hit = _stem_cache.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == dev:
+        packed = hit[2]
+    else:
+        nb = C.c_size_t(0)
+        check(lib().upsnet_stem_packed_weight_bytes(Cout, kh, C.byref(nb)), "stem_packed_weight_bytes")
+        packed = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().upsnet_stem_pack_weight(ptr(f32c(weight.detach())), Cout, Cin, kh, kw, ptr(packed), stream_ptr(dev)),
+                  "stem_pack_weight")
+        STATS["launches"] += 1
+        wid = id(weight)
+        _stem_cache[wid] = (weakref.ref(weight, lambda _r, _k=wid: _stem_cache.pop(_k, None)), weight._version, packed)
+    nb = C.c_size_t(0)
+    check(lib().upsnet_stem_workspace_bytes(N, H, W, kh, kw, int(padding), C.byref(nb)), "stem_workspace_bytes")
+    if _stem_ws is None:
+        _stem_ws = _Workspace()
+    ws = _stem_ws.get(dev, nb.value)
+    Ho, Wo = (H + 2 * padding - kh) // 2 + 1, (W + 2 * padding - kw) // 2 + 1
+    store = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "shape": "N%d %dx%d Cin%d->Cout%d k%d s2 float32->bfloat16 (stem, TMA)" % (N, H, W, Cin, Cout, kh),
+            "bytes": float(4 * x.numel() + 2 * store.numel())}
+    with torch.cuda.device(dev), _Timed("conv2d", 2, work, dev):
+        check(lib().upsnet_stem_forward(ptr(x), ptr(packed), ptr(None if bias is None else f32c(bias)), ptr(store), N, Cin, H, W,
+                                        Cout, kh, kw, int(padding), _lib.EPI_RELU if relu else 0, ptr(ws), ws.numel(),
+                                        stream_ptr(dev)), "stem_forward")
+    return store.permute(0, 3, 1, 2)
+
+
 def _tc_ok(Cin, kh, kw, dg, deform=False):
     return (Cin % 64 == 0 or (Cin <= 8 and not deform)) and dg == 1 and kh * kw <= 49
 
