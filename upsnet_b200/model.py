@@ -458,6 +458,8 @@ class resnet_upsnet(nn.Module):
                                                       cfg.panoptic_score_thresh, cfg.bbox_reg_weights)
         self.static_engine = True     # fixed shapes + device-side counts: no host sync inside the forward
         self.use_cuda_graph = True    # capture the static forward once per (shape, precision) and replay it
+        self.overlap_heads = True     # semantic head on a side stream, concurrent with the detection chain
+        self._side = {}
         self._graphs = {}
         self._prepared = False
         self.eval()
@@ -487,8 +489,25 @@ class resnet_upsnet(nn.Module):
             _, bbox, prob = self.rpn(feat)
             rpn_cls_prob.append(prob)
             rpn_bbox_pred.append(bbox)
+        # The semantic head (8 offset convs + 8 deformable convs, machine-filling kernels) does not depend on the
+        # detection chain (top-k, NMS sweeps, MaskROI: single-CTA, latency-bound kernels): fork it onto a side stream
+        # and join before the panoptic head, so the small kernels hide under the big ones (also inside the CUDA graph).
+        fork = x.is_cuda and self.overlap_heads
+        if fork:
+            cur = torch.cuda.current_stream(x.device)
+            side = self._side_stream(x.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
+                done = torch.cuda.Event()
+                done.record(side)
+            if not torch.cuda.is_current_stream_capturing():
+                fcn_output.record_stream(cur)   # eager mode: the block is consumed on `cur` (graph pools need no hint)
         rois, _, roi_valid = self.pyramid_proposal_static(rpn_cls_prob, rpn_bbox_pred, im_info)
-        fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
+        if not fork:
+            fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
         feats = [p2, p3, p4, p5]
         rcnn_output = self.rcnn(feats, rois)
         cls_prob = F.softmax(rcnn_output["cls_score"].float(), dim=1)
@@ -498,6 +517,8 @@ class resnet_upsnet(nn.Module):
         s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
         ms = self.cfg.mask_size
         mask_score = self.mask_branch(feats, b2).float().gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
+        if fork:
+            cur.wait_event(done)
         keep, labels, sem, k = ops.panoptic_fuse(fcn_output, b2[:, 1:], s2, mask_score, c2, self.panoptic_head.num_stuff,
                                                  self.panoptic_head.fraction_threshold, want_sem=True,
                                                  n_dev=n2.reshape(1))
@@ -505,6 +526,12 @@ class resnet_upsnet(nn.Module):
         return {"cls_probs": s1, "pred_boxes": b1, "mask_probs": mask_prob, "cls_inds": c1, "fcn_outputs": sem,
                 "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
                 "keep": keep, "counts": counts, "fcn_output": fcn_output}
+
+    def _side_stream(self, dev):
+        key = str(dev)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=dev)
+        return self._side[key]
 
     def _run_static(self, x, im_info):
         if not (self.use_cuda_graph and x.is_cuda):
