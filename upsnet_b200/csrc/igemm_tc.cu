@@ -112,8 +112,23 @@ igemm_tc_kernel(const TcParams p) {
   const int Kp = (Kreal + TC_BK - 1) / TC_BK * TC_BK;      // == Kreal unless SMALLC
   const int num_kb = Kp / TC_BK;
   const int n_tiles = p.Cout_pad / p.BN;
-  const long long m_tiles = (Ptot + TC_BM - 1) / TC_BM;
+  // M-tile = 128 output pixels.  Dense / stem modes: 128 consecutive pixels of the flattened (n, ho, wo) index.
+  // Deformable mode: a 16 x 8 pixel BLOCK of one image -- its nine taps x four corners then revisit ~(16+3) x (8+3)
+  // input pixels per channel chunk (27 KB: L1-resident) instead of four 131-pixel row segments.
+  constexpr int TW = 16, TH = 8;
+  const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
+  const long long m_tiles = DEFORM ? (long long)p.N * tiles_w * tiles_h : (Ptot + TC_BM - 1) / TC_BM;
   const long long num_tiles = m_tiles * n_tiles;
+  // flattened output pixel of row r of M-tile mt, or -1 when the row lies outside the tensor
+  auto tile_pixel = [&](long long mt, int r) -> long long {
+    if (DEFORM) {
+      const int tx = (int)(mt % tiles_w), ty = (int)((mt / tiles_w) % tiles_h), n = (int)(mt / ((long long)tiles_w * tiles_h));
+      const int wo = tx * TW + (r & (TW - 1)), ho = ty * TH + (r >> 4);
+      return (wo < p.Wo && ho < p.Ho) ? ((long long)n * p.Ho + ho) * p.Wo + wo : -1ll;
+    }
+    const long long pg = mt * TC_BM + r;
+    return pg < Ptot ? pg : -1ll;
+  };
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * p.BN) tmem_cols <<= 1;
 
@@ -163,7 +178,7 @@ igemm_tc_kernel(const TcParams p) {
     const bool deferred = (MODE == 0) && XBF16 && p.stages >= 3;
     int pend_s = -1;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long p0 = (tile / n_tiles) * TC_BM;
+      const long long mt = tile / n_tiles;
       const int n0 = (int)(tile % n_tiles) * p.BN;
       // Per-tile row info (image, top-left input coordinate of the receptive field) is double-buffered, so ONE
       // producer barrier per tile suffices for the dense / stem modes; the deformable sample table is a single
@@ -171,9 +186,9 @@ igemm_tc_kernel(const TcParams p) {
       long long* rowinfo = rowbase + (tile_it & 1) * TC_BM;
       if (DEFORM) producer_bar_sync();   // every producer is done with the previous tile's sample table
       for (int r = pt; r < TC_BM; r += TC_PRODUCERS) {
-        const long long pg = p0 + r;
+        const long long pg = tile_pixel(mt, r);
         long long v = -1;
-        if (pg < Ptot) {
+        if (pg >= 0) {
           const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
           const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
           if (DEFORM) v = (long long)n * p.H * p.W * (long long)p.Cin;
@@ -184,12 +199,12 @@ igemm_tc_kernel(const TcParams p) {
       // deformable: per-tile sample table (channel independent), one entry per (tap, pixel)
       for (int e = pt; e < (DEFORM ? KHW * TC_BM : 0); e += TC_PRODUCERS) {
         const int tap = e / TC_BM, r = e - tap * TC_BM;
-        const long long pg = p0 + r;
+        const long long pg = tile_pixel(mt, r);
         const int ki = tap / p.kw, kj = tap - ki * p.kw;
         {
           float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
           int4 ov = make_int4(0, 0, 0, 0);
-          if (pg < Ptot) {
+          if (pg >= 0) {
             const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
             const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
             const float* offp = p.offset + ((size_t)n * 2 * KHW + 2 * tap) * HoWo + pp;
@@ -479,14 +494,14 @@ igemm_tc_kernel(const TcParams p) {
     const bool vec_ptrs_ok = (((uintptr_t)p.y) & 15) == 0 && (!p.residual || (((uintptr_t)p.residual) & 15) == 0);
     uint32_t ti_local = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
-      const long long p0 = (tile / n_tiles) * TC_BM;
+      const long long mt = tile / n_tiles;
       const int n0 = (int)(tile % n_tiles) * p.BN;
       const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
       mbar_wait(bar_tfull + 8 * buf, use & 1u);
       tc_fence_after();
       const int m = q * 32 + lane;
-      const long long pg = p0 + m;
-      const bool row_ok = pg < Ptot;
+      const long long pg = tile_pixel(mt, m);
+      const bool row_ok = pg >= 0;
       const int n_img = row_ok ? (int)(pg / HoWo) : 0;
       const int pp = row_ok ? (int)(pg - (long long)n_img * HoWo) : 0;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)p.BN;
@@ -524,8 +539,8 @@ igemm_tc_kernel(const TcParams p) {
           if (co < p.Cout) {
             for (int it = 0; it < lpr; ++it) {
               const int row = it * rpi + rsub;
-              const long long pgr = p0 + q * 32 + row;
-              if (pgr >= Ptot) continue;
+              const long long pgr = tile_pixel(mt, q * 32 + row);
+              if (pgr < 0) continue;
               size_t ridx = (size_t)pgr * p.Cout + co;
               if (p.residual && p.res_up2) {
                 const int ni = (int)(pgr / HoWo), ppr = (int)(pgr - (long long)ni * HoWo);
@@ -762,7 +777,8 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   p.stages = stages;
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
   if (Ptot <= 0) return 0;
-  const long long num_tiles = ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN);
+  const long long num_tiles = (deform ? (long long)p.N * ((p.Wo + 15) / 16) * ((p.Ho + 7) / 8) : (Ptot + TC_BM - 1) / TC_BM) *
+                              (p.Cout_pad / BN);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0, v = kNumSMs;

@@ -513,10 +513,13 @@ class resnet_upsnet(nn.Module):
         cls_prob = F.softmax(rcnn_output["cls_score"].float(), dim=1)
         bbox_pred = rcnn_output["bbox_pred"].float()
         s1, b1, c1, n1 = self.mask_roi_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
-        mask_prob = torch.sigmoid(self.mask_branch(feats, b1).float())
         s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
+        # models/resnet_upsnet.py:203-222 runs the mask branch twice (detections, panoptic candidates).  Every roi is
+        # processed independently, so both sets go through it as ONE batch: half the launches, fuller tile waves.
+        logits = self.mask_branch(feats, torch.cat([b1, b2], 0)).float()
+        mask_prob = torch.sigmoid(logits[:b1.shape[0]])
         ms = self.cfg.mask_size
-        mask_score = self.mask_branch(feats, b2).float().gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
+        mask_score = logits[b1.shape[0]:].gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
         if fork:
             cur.wait_event(done)
         keep, labels, sem, k = ops.panoptic_fuse(fcn_output, b2[:, 1:], s2, mask_score, c2, self.panoptic_head.num_stuff,
