@@ -210,6 +210,72 @@ roi_align_nhwc_bf16_kernel(FpnFeats f, int C, const float* __restrict__ rois, in
   }
 }
 
+// Same operator, CTA = one roi: the PH*PW*gh*gw sample positions (offsets + bilinear weights) are computed ONCE
+// into shared memory, then every warp takes bins round-robin with lanes over 8-channel (16-byte) vectors -- the
+// per-sample arithmetic is no longer repeated by every channel quad, and loads are twice as wide.  Accumulation
+// order (iy, ix; four-term blend) is the one of the kernel above, so results are bit-identical.
+constexpr int kRoiMaxSamples = 1024;
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_bf16_roi_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, int PH, int PW, int sr,
+                               __nv_bfloat16* __restrict__ out, int* __restrict__ levels_out) {
+  __shared__ int4 s_off[kRoiMaxSamples];
+  __shared__ float4 s_w[kRoiMaxSamples];
+  const int n = blockIdx.x;
+  const float* r = rois + (size_t)n * 5;
+  const int b = (int)roundf(r[0]);
+  const float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+  const int lv = f.nlevels > 1 ? fpn_level_of(rx1, ry1, rx2, ry2) : 0;
+  if (levels_out && threadIdx.x == 0) levels_out[n] = lv;
+  const int H = f.H[lv], W = f.W[lv];
+  const float sc = f.scale[lv];
+  const float rsw = rx1 * sc, rsh = ry1 * sc, rew = rx2 * sc, reh = ry2 * sc;
+  const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
+  const float bsh = rh / (float)PH, bsw = rw / (float)PW;
+  const int gh = sr, gw = sr;                 // launcher guarantees sr > 0 and PH*PW*sr*sr <= kRoiMaxSamples
+  const float cnt = (float)(gh * gw);
+  const int per_bin = gh * gw, nsamp = PH * PW * per_bin;
+  for (int t = threadIdx.x; t < nsamp; t += blockDim.x) {
+    const int bin = t / per_bin, q = t - bin * per_bin;
+    const int ph = bin / PW, pw = bin - ph * PW, iy = q / gw, ix = q - iy * gw;
+    const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
+    const float x = rsw + pw * bsw + (float)(ix + .5f) * bsw / (float)gw;
+    const SamplePos sp = roi_sample(H, W, y, x);
+    s_off[t] = make_int4(sp.o00 * C, sp.o01 * C, sp.o10 * C, sp.o11 * C);
+    s_w[t] = make_float4(sp.w00, sp.w01, sp.w10, sp.w11);
+  }
+  __syncthreads();
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(f.p[lv]) + (size_t)b * H * W * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int bin = warp; bin < PH * PW; bin += nwarp) {
+    for (int c = lane * 8; c < C; c += 256) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < per_bin; ++q) {
+        const int4 o = s_off[bin * per_bin + q];
+        const float4 w = s_w[bin * per_bin + q];
+        const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + o.x + c));
+        const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + o.y + c));
+        const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + o.z + c));
+        const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + o.w + c));
+        const uint32_t a[4] = {v00.x, v00.y, v00.z, v00.w}, bq[4] = {v01.x, v01.y, v01.z, v01.w};
+        const uint32_t d[4] = {v10.x, v10.y, v10.z, v10.w}, e[4] = {v11.x, v11.y, v11.z, v11.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += (w.x * __uint_as_float(a[k] << 16) + w.y * __uint_as_float(bq[k] << 16) +
+                         w.z * __uint_as_float(d[k] << 16) + w.w * __uint_as_float(e[k] << 16));
+          acc[2 * k + 1] += (w.x * __uint_as_float(a[k] & 0xffff0000u) + w.y * __uint_as_float(bq[k] & 0xffff0000u) +
+                             w.z * __uint_as_float(d[k] & 0xffff0000u) + w.w * __uint_as_float(e[k] & 0xffff0000u));
+        }
+      }
+      uint4 wv;
+      __nv_bfloat162 o0 = __floats2bfloat162_rn(acc[0] / cnt, acc[1] / cnt), o1 = __floats2bfloat162_rn(acc[2] / cnt, acc[3] / cnt);
+      __nv_bfloat162 o2 = __floats2bfloat162_rn(acc[4] / cnt, acc[5] / cnt), o3 = __floats2bfloat162_rn(acc[6] / cnt, acc[7] / cnt);
+      wv.x = *reinterpret_cast<uint32_t*>(&o0); wv.y = *reinterpret_cast<uint32_t*>(&o1);
+      wv.z = *reinterpret_cast<uint32_t*>(&o2); wv.w = *reinterpret_cast<uint32_t*>(&o3);
+      *reinterpret_cast<uint4*>(out + ((size_t)n * PH * PW + bin) * C + c) = wv;
+    }
+  }
+}
+
 static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, int dtype, const float* rois, int R,
                             int PH, int PW, int sr, void* out_v, int* levels_out,
                             cudaStream_t stream) {
@@ -219,6 +285,13 @@ static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, int dty
     if (layout != UPSNET_LAYOUT_NHWC || (C & 3)) return UPSNET_E_UNSUPPORTED;
     for (int l = 0; l < f.nlevels; ++l) if (((uintptr_t)f.p[l]) & 7) return UPSNET_E_BADARG;
     if (((uintptr_t)out_v) & 7) return UPSNET_E_BADARG;
+    bool wide = sr > 0 && (C & 7) == 0 && (long long)PH * PW * sr * sr <= kRoiMaxSamples && (((uintptr_t)out_v) & 15) == 0;
+    for (int l = 0; l < f.nlevels; ++l) wide = wide && (((uintptr_t)f.p[l]) & 15) == 0 && (long long)f.H[l] * f.W[l] * C < (1ll << 31);
+    if (wide) {
+      roi_align_nhwc_bf16_roi_kernel<<<R, 256, 0, stream>>>(f, C, rois, R, PH, PW, sr, (__nv_bfloat16*)out_v, levels_out);
+      UPS_CHECK_LAUNCH();
+      return 0;
+    }
     const int threads = C / 4 < 32 ? 32 : (C / 4 > 256 ? 256 : (C / 4 + 31) / 32 * 32);
     roi_align_nhwc_bf16_kernel<<<R * PH, threads, 0, stream>>>(f, C, rois, R, PH, PW, sr, (__nv_bfloat16*)out_v, levels_out);
     UPS_CHECK_LAUNCH();
