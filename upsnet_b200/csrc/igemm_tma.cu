@@ -19,6 +19,7 @@
 // (x + residual + y bytes); per-SM L2->smem operand traffic is (128 + BN) * 128 B per k-block.
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is resolved at run time (no libcuda link dependency)
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -479,7 +480,15 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
   const int Cout_pad = p.Cout <= 32 ? 32 : (p.Cout + 63) / 64 * 64;      // rows of the packed weight planes (tc_cout_pad)
   int BN = (Cout_pad % 256 == 0 && !g.has_res) ? 256 : ((Cout_pad % 128 == 0) ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
-  while (BN > 64 && m_tiles * (Cout_pad / BN) < sms) BN /= 2;
+  // N tile: as wide as possible (operand bytes per flop fall with BN) while ~2/3 of the SMs still get a tile; measured
+  // on B200 (profiles/r1_bn_sweep.md): 64 m-tiles x Cout 256 -> BN 128 (128 CTAs) beats BN 64 (256 tiles) by 38 %
+  // and BN 256 (64 CTAs) by 11 %; 16 m-tiles x Cout 512 -> BN 64 (128 CTAs) stays best.
+  while (BN > 64 && m_tiles * (Cout_pad / BN) < 96) BN /= 2;
+  (void)sms;
+  if (const char* fb = getenv("UPSNET_TMA_FORCE_BN")) {     // tuning hook (scripts/bn_sweep.py): force the N tile
+    const int v = atoi(fb);
+    if ((v == 64 || v == 128 || v == 256) && Cout_pad % v == 0 && !(g.has_res && v > 128)) BN = v;
+  }
   g.BN = BN;
   g.n_tiles = Cout_pad / BN;
   g.direct = direct ? 1 : 0; g.y_bf16 = p.y_bf16; g.out_nhwc = p.out_nhwc; g.y = p.y;
