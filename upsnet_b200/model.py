@@ -388,14 +388,42 @@ class FCNHead(nn.Module):
         nn.init.normal_(self.score.weight.data, 0, 0.01)
         self.score.bias.data.zero_()
         self.fuse_score = True   # inference: score each level at its own resolution (see forward)
+        self.overlap_levels = True
+        self._streams = None
         self._f = None
 
     def prepare(self):
         w = self.score.weight.detach()
         self._f = [w[:, 128 * l:128 * (l + 1)].contiguous() for l in range(4)]
 
+    def _subnets(self, p2, p3, p4, p5):
+        """The four per-level sub-networks.  P4 / P5 have 64 / 16 output tiles -- far fewer than SMs -- so on CUDA they
+        run on two extra streams next to the P2 -> P3 chain instead of after it."""
+        if not (p2.is_cuda and self.overlap_levels):
+            return tuple(self.fcn_subnet(p) for p in (p2, p3, p4, p5))
+        cur = torch.cuda.current_stream(p2.device)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=p2.device) for _ in range(2)]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs, joins = {}, []
+        for st, (name, p) in zip(self._streams, (("p4", p4), ("p5", p5))):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                outs[name] = self.fcn_subnet(p)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+            if not torch.cuda.is_current_stream_capturing():
+                outs[name].record_stream(cur)
+        o2 = self.fcn_subnet(p2)
+        o3 = self.fcn_subnet(p3)
+        for ev in joins:
+            cur.wait_event(ev)
+        return o2, o3, outs["p4"], outs["p5"]
+
     def forward(self, p2, p3, p4, p5):
-        p2, p3, p4, p5 = (self.fcn_subnet(p) for p in (p2, p3, p4, p5))
+        p2, p3, p4, p5 = self._subnets(p2, p3, p4, p5)
         if self.fuse_score and self._f is not None:
             # models/fcn.py:94-101 computes score(cat(p2, up2(p3), up4(p4), up8(p5))).  The 1x1 score conv and the
             # bilinear upsampling are both linear and act on different axes, so they commute:
