@@ -323,9 +323,10 @@ def test_tma_conv2d_vs_oracle_and_gather_kernel(dev, cfg):
     assert np.abs(y1.float().cpu().numpy() - want1).max() < 1e-4 + (2.0 ** -8) * np.abs(want1).max()
     want2 = np.maximum(want - b[None, :, None, None], 0)
     assert np.abs(y2.float().cpu().numpy() - want2).max() < tol
-    # same MMA sequence and epilogue arithmetic as the gather kernel -> identical bf16 outputs
+    # same products and epilogue arithmetic as the gather kernel; the k-block order differs in halo mode (channel chunk
+    # outer, tap inner), so fp32 accumulation may round differently: at most one bf16 ulp apart
     for a, g in zip(outs[True], outs[False]):
-        assert torch.equal(a, g)
+        assert (a.float() - g.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, float(g.float().abs().max()))
 
 
 @pytest.mark.parametrize("cfg", [dict(N=1, Cin=256, Cout=256, H=32, W=48), dict(N=2, Cin=512, Cout=128, H=18, W=22),
@@ -386,7 +387,7 @@ def test_tma_direct_store_epilogue(dev, cfg):
     assert np.abs(outs[0][0].float().cpu().numpy() - want).max() < tol
     assert np.abs(outs[0][1].float().cpu().numpy() - np.maximum(want - b[None, :, None, None], 0)).max() < tol
     for a, g in zip(outs[0], outs[1]):
-        assert torch.equal(a, g)
+        assert (a.float() - g.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, float(g.float().abs().max()))
 
 
 def test_pipelined_engine_matches_serial_forward(dev):

@@ -45,6 +45,9 @@ struct TmaGeom {
   int direct, y_bf16, out_nhwc;
   void* y;
   int stem;                             // stride-2 tiny-Cin stem: A boxes come from the packed / padded image (5-D map)
+  // halo mode (k x k, stride 1): one (16 x PH)-pixel input PATCH per (tile, channel chunk) feeds all taps -- the A operand
+  // of tap (ky, kx) is the patch seen through a descriptor that starts (ky*dh*16 + kx*dw) rows further (tile = 8 x 16 px)
+  int halo, patch_rows, pstages, kh;
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -91,13 +94,16 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 
 struct TmaSmem {
   uint32_t stages, out, res, a_bytes, b_bytes, stage_bytes, total;
+  uint32_t patch, patch_bytes;                               // halo mode: patch ring in front of a B-only ring
 };
-__host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res) {
+__host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res, int patch_rows = 0, int pstages = 0) {
   TmaSmem s;
-  s.a_bytes = 128 * 128;
+  s.a_bytes = patch_rows ? 0u : 128 * 128;
   s.b_bytes = (uint32_t)BN * 128;
   s.stage_bytes = s.a_bytes + s.b_bytes;
-  s.stages = 1024;                                           // barriers live in the first KB
+  s.patch = 1024;                                            // barriers live in the first KB
+  s.patch_bytes = (uint32_t)patch_rows * 128u;               // multiple of 2048 (16-pixel patch rows)
+  s.stages = s.patch + s.patch_bytes * (uint32_t)pstages;
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
   const uint32_t out_slabs = BN == 64 ? 1 : 2;               // one output slab per epilogue group
   s.res = s.out + out_slabs * TM_SLAB_BYTES;
@@ -116,11 +122,12 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_dyn + (base - raw);
-  const TmaSmem L = tma_smem_layout(g.BN, g.stages, g.has_res != 0);
+  const TmaSmem L = tma_smem_layout(g.BN, g.stages, g.has_res != 0, g.halo ? g.patch_rows : 0, g.pstages);
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // two residual buffers
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 8));
+  const uint32_t bar_pfull = bar_rempty + 16, bar_pempty = bar_pfull + 32;     // up to four patch slots (halo mode)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 16));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cchunks = g.Cin / 64;
@@ -145,6 +152,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_init(bar_rfull + 8 * b, 1);
         mbar_init(bar_rempty + 8 * b, TM_EPI_WARPS);
       }
+      for (int b = 0; b < 4; ++b) {
+        mbar_init(bar_pfull + 8 * b, 1);
+        mbar_init(bar_pempty + 8 * b, 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -164,7 +175,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     // =============================== OPERAND LOADS ===============================
     if (lane == 0) {
       // ring position / phase are running counters: no division on the per-k-block path of this single thread
-      uint32_t s = 0, ph = 0;
+      uint32_t s = 0, ph = 0, sp = 0, php = 0;
       uint32_t a_dst = base + L.stages;
       const uint32_t tx_bytes = box_bytes + L.b_bytes;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -174,6 +185,25 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
         const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
         const int n0 = nt * g.BN;
+        if (g.halo) {
+          // one patch per channel chunk, then the KHW weight tiles that multiply it (K order of the packed weights is
+          // tap-major: column = tap*Cin + chunk*64)
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait(bar_pempty + 8 * sp, php ^ 1u);
+            mbar_arrive_expect_tx(bar_pfull + 8 * sp, L.patch_bytes);
+            tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, cc * 64, w0 - g.pw, h0 - g.ph, i0);
+            if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
+            for (int tap = 0; tap < g.KHW; ++tap) {
+              const uint32_t bf = bar_full + 8 * s;
+              mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+              mbar_arrive_expect_tx(bf, L.b_bytes);
+              tma_load_2d(a_dst, &tm_w, bf, tap * g.Cin + cc * 64, n0);
+              a_dst += L.stage_bytes;
+              if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_dst = base + L.stages; }
+            }
+          }
+          continue;
+        }
         int cc = 0, kj = 0;
         int cw = w0 - g.pw, ch = h0 - g.ph;         // box origin of the current tap
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -204,13 +234,44 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // whose MMAs are short (N <= 128), so it is kept to a handful of instructions per k-block.
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4, a16 = L.a_bytes >> 4;
-      uint32_t s = 0, ph = 0, a_lo = a_lo0, ti_local = 0;
+      uint32_t s = 0, ph = 0, a_lo = a_lo0, ti_local = 0, sp = 0, php = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
         uint32_t acc = 0u;
+        if (g.halo) {
+          // A descriptors: 8-row groups = 8 consecutive patch pixels of one patch row, group stride = one patch row
+          // (16 px = 2048 B); a tap shifts the start by whole 128-byte rows, so the swizzle phase of the start goes into
+          // the descriptor's base-offset field (bits 49-51 = (start >> 7) & 7).
+          const uint32_t hi_a0 = (uint32_t)(2048 >> 4) | (1u << 14) | (2u << 29);
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait(bar_pfull + 8 * sp, php);
+            tc_fence_after();
+            const uint32_t patch = base + L.patch + sp * L.patch_bytes;
+            int ky = 0, kx = 0;
+            for (int tap = 0; tap < g.KHW; ++tap) {
+              mbar_wait(bar_full + 8 * s, ph);
+              tc_fence_after();
+              const uint32_t a_start = patch + (uint32_t)((ky * g.dh * 16 + kx * g.dw) * 128);
+              const uint32_t pa_lo = (a_start >> 4) & 0x3fffu, pa_hi = hi_a0 | (((a_start >> 7) & 7u) << 17);
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k) {
+                umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, pa_hi, a_lo + 2 * k, desc_hi, idesc, acc);
+                acc = 1u;
+              }
+              umma_commit(bar_empty + 8 * s);
+              a_lo += stage16;
+              if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+              if (++kx == g.kw) { kx = 0; ++ky; }
+            }
+            umma_commit(bar_pempty + 8 * sp);     // every tap of this chunk has been issued: the patch slot may be refilled
+            if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
+          }
+          umma_commit(bar_tfull + 8 * buf);
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
@@ -474,10 +535,18 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.kw = p.kw; g.KHW = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.dh = p.dh; g.dw = p.dw;
   g.relu = p.relu; g.has_res = p.residual ? 1 : 0; g.res_up2 = p.res_up2 ? 1 : 0;
   tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, g.res_up2 != 0, &g.bw, &g.bh, &g.bn);
+  // halo mode for k x k filters (UPSNET_TMA_HALO=0 disables it, =2 also enables it for BN = 256): 8 x 16-pixel tiles,
+  // 16-pixel-wide patch rows; the patch must cover 8 + (kw-1)*dw <= 16 pixels per row
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("UPSNET_TMA_HALO"); halo_env = e ? atoi(e) : 1; }
+  const int patch_h = 16 + (p.kh - 1) * p.dh;
+  bool halo = halo_env > 0 && !strided && p.kh * p.kw > 1 && (p.kw - 1) * p.dw <= 8 && patch_h <= 48 && !g.res_up2 &&
+              p.Wo >= 8 && p.Ho >= 8;
+  if (halo) { g.bw = 8; g.bh = 16; g.bn = 1; }
   g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
   g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
   g.tiles_n = (p.N + g.bn - 1) / g.bn;
-  const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
   const int Cout_pad = p.Cout <= 32 ? 32 : (p.Cout + 63) / 64 * 64;      // rows of the packed weight planes (tc_cout_pad)
   int BN = (Cout_pad % 256 == 0 && !g.has_res) ? 256 : ((Cout_pad % 128 == 0) ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
   // N tile: as wide as possible (operand bytes per flop fall with BN) while ~2/3 of the SMs still get a tile; measured
@@ -489,12 +558,21 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
     const int v = atoi(fb);
     if ((v == 64 || v == 128 || v == 256) && Cout_pad % v == 0 && !(g.has_res && v > 128)) BN = v;
   }
+  if (halo && BN == 256 && halo_env < 2) {     // wide-N layers are MMA-bound: keep the fewest-tiles box for them
+    halo = false;
+    tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, false, &g.bw, &g.bh, &g.bn);
+    g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
+    g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
+    g.tiles_n = (p.N + g.bn - 1) / g.bn;
+    m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  }
   g.BN = BN;
   g.n_tiles = Cout_pad / BN;
   g.direct = direct ? 1 : 0; g.y_bf16 = p.y_bf16; g.out_nhwc = p.out_nhwc; g.y = p.y;
+  g.halo = halo ? 1 : 0; g.patch_rows = halo ? 16 * patch_h : 0; g.pstages = halo ? 2 : 0; g.kh = p.kh;
   int stages = TM_MAX_STAGES;
-  TmaSmem L = tma_smem_layout(BN, stages, g.has_res != 0);
-  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0); }
+  TmaSmem L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages);
+  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages); }
   if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   g.stages = stages;
 
@@ -507,8 +585,9 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
     const cuuint64_t dy[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
     const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)Cout_pad};
     const cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
+    const cuuint32_t boxp[4] = {64, 16, (cuuint32_t)patch_h, 1};            // halo mode: the input patch of a tile
     const cuuint32_t boxw[2] = {64, (cuuint32_t)BN};
-    if (!encode_bf16(enc, &tm_x, p.x, 4, dx, box, sx)) return UPSNET_E_UNSUPPORTED;
+    if (!encode_bf16(enc, &tm_x, p.x, 4, dx, halo ? boxp : box, sx)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_w, packed, 2, dwt, boxw)) return UPSNET_E_UNSUPPORTED;
     if (direct) {   // no TMA store / residual in the direct-store epilogue: the two maps are placeholders
       tm_y = tm_x;
