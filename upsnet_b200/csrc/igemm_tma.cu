@@ -243,8 +243,9 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         uint32_t acc = 0u;
         if (g.halo) {
           // A descriptors: 8-row groups = 8 consecutive patch pixels of one patch row, group stride = one patch row
-          // (16 px = 2048 B); a tap shifts the start by whole 128-byte rows, so the swizzle phase of the start goes into
-          // the descriptor's base-offset field (bits 49-51 = (start >> 7) & 7).
+          // (16 px = 2048 B); a tap shifts the START by whole 128-byte rows.  Measured on B200: the SWIZZLE_128B XOR is
+          // taken from the shared-memory ADDRESS bits [7,10) -- exactly what the TMA write used -- so a start that is
+          // not 1024-byte aligned needs no base-offset (field = 0; a non-zero value double-shifts and corrupts the tile).
           const uint32_t hi_a0 = (uint32_t)(2048 >> 4) | (1u << 14) | (2u << 29);
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait(bar_pfull + 8 * sp, php);
@@ -255,7 +256,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
               const uint32_t a_start = patch + (uint32_t)((ky * g.dh * 16 + kx * g.dw) * 128);
-              const uint32_t pa_lo = (a_start >> 4) & 0x3fffu, pa_hi = hi_a0 | (((a_start >> 7) & 7u) << 17);
+              const uint32_t pa_lo = (a_start >> 4) & 0x3fffu, pa_hi = hi_a0;
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k) {
                 umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, pa_hi, a_lo + 2 * k, desc_hi, idesc, acc);
