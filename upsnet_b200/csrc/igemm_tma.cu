@@ -48,6 +48,8 @@ struct TmaGeom {
   // halo mode (k x k, stride 1): one (16 x PH)-pixel input PATCH per (tile, channel chunk) feeds all taps -- the A operand
   // of tap (ky, kx) is the patch seen through a descriptor that starts (ky*dh*16 + kx*dw) rows further (tile = 8 x 16 px)
   int halo, patch_rows, pstages, kh;
+  int wres, wtiles;                     // halo mode with the n-tile's whole weight set (wtiles tiles) resident in smem, loaded once per CTA
+  int dbg;                              // timing experiments only (UPSNET_TMA_DEBUG): 1 alternate accumulators, 2 one MMA per k-block, 3 no MMAs
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -96,7 +98,8 @@ struct TmaSmem {
   uint32_t stages, out, res, a_bytes, b_bytes, stage_bytes, total;
   uint32_t patch, patch_bytes;                               // halo mode: patch ring in front of a B-only ring
 };
-__host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res, int patch_rows = 0, int pstages = 0) {
+__host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res, int patch_rows = 0, int pstages = 0,
+                                                  bool direct = false) {
   TmaSmem s;
   s.a_bytes = patch_rows ? 0u : 128 * 128;
   s.b_bytes = (uint32_t)BN * 128;
@@ -105,7 +108,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_
   s.patch_bytes = (uint32_t)patch_rows * 128u;               // multiple of 2048 (16-pixel patch rows)
   s.stages = s.patch + s.patch_bytes * (uint32_t)pstages;
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
-  const uint32_t out_slabs = BN == 64 ? 1 : 2;               // one output slab per epilogue group
+  const uint32_t out_slabs = direct ? 0 : (BN == 64 ? 1 : 2);   // one output slab per epilogue group (TMA-store epilogue only)
   s.res = s.out + out_slabs * TM_SLAB_BYTES;
   s.total = s.res + (has_res ? 2u * (uint32_t)(BN / 64) * TM_SLAB_BYTES : 0u);   // two residual buffers (prefetch)
   return s;
@@ -122,7 +125,8 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_dyn + (base - raw);
-  const TmaSmem L = tma_smem_layout(g.BN, g.stages, g.has_res != 0, g.halo ? g.patch_rows : 0, g.pstages);
+  const TmaSmem L = tma_smem_layout(g.BN, g.wres ? g.wtiles : g.stages, g.has_res != 0, g.halo ? g.patch_rows : 0, g.pstages,
+                                    g.direct != 0);
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // two residual buffers
@@ -176,6 +180,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (lane == 0) {
       // ring position / phase are running counters: no division on the per-k-block path of this single thread
       uint32_t s = 0, ph = 0, sp = 0, php = 0;
+      bool first_tile = true;
       uint32_t a_dst = base + L.stages;
       const uint32_t tx_bytes = box_bytes + L.b_bytes;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -186,13 +191,40 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
         const int n0 = nt * g.BN;
         if (g.halo) {
-          // one patch per channel chunk, then the KHW weight tiles that multiply it (K order of the packed weights is
-          // tap-major: column = tap*Cin + chunk*64)
-          for (int cc = 0; cc < cchunks; ++cc) {
+          // Units (tile, channel chunk) in order.  The PATCH of unit u+1 is requested before the weight tiles of unit u
+          // (its latency would otherwise be exposed once per unit: the weight ring is shorter than a unit's KHW tiles).
+          // Resident-weight mode: the n-tile's whole weight set is loaded once, up front.
+          if (first_tile) {
+            first_tile = false;
+            if (g.wres) {
+              mbar_arrive_expect_tx(bar_full, (uint32_t)(g.KHW * cchunks) * L.b_bytes);
+              for (int cc = 0; cc < cchunks; ++cc)
+                for (int tap = 0; tap < g.KHW; ++tap)
+                  tma_load_2d(base + L.stages + (uint32_t)(cc * g.KHW + tap) * L.b_bytes, &tm_w, bar_full, tap * g.Cin + cc * 64, n0);
+            }
             mbar_wait(bar_pempty + 8 * sp, php ^ 1u);
             mbar_arrive_expect_tx(bar_pfull + 8 * sp, L.patch_bytes);
-            tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, cc * 64, w0 - g.pw, h0 - g.ph, i0);
+            tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, 0, w0 - g.pw, h0 - g.ph, i0);
             if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
+          }
+          const long long ntile = tile + gridDim.x;
+          for (int cc = 0; cc < cchunks; ++cc) {
+            // next unit: next chunk of this tile, or chunk 0 of this CTA's next tile
+            if (cc + 1 < cchunks || ntile < num_tiles) {
+              int nw0 = w0, nh0 = h0, ni0 = i0, ncc = cc + 1;
+              if (cc + 1 == cchunks) {
+                const long long nmt = ntile / g.n_tiles;
+                nw0 = (int)(nmt % g.tiles_w) * g.bw;
+                nh0 = (int)((nmt / g.tiles_w) % g.tiles_h) * g.bh;
+                ni0 = (int)(nmt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+                ncc = 0;
+              }
+              mbar_wait(bar_pempty + 8 * sp, php ^ 1u);
+              mbar_arrive_expect_tx(bar_pfull + 8 * sp, L.patch_bytes);
+              tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, ncc * 64, nw0 - g.pw, nh0 - g.ph, ni0);
+              if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
+            }
+            if (g.wres) continue;
             for (int tap = 0; tap < g.KHW; ++tap) {
               const uint32_t bf = bar_full + 8 * s;
               mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -247,11 +279,32 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           // taken from the shared-memory ADDRESS bits [7,10) -- exactly what the TMA write used -- so a start that is
           // not 1024-byte aligned needs no base-offset (field = 0; a non-zero value double-shifts and corrupts the tile).
           const uint32_t hi_a0 = (uint32_t)(2048 >> 4) | (1u << 14) | (2u << 29);
+          if (g.wres && ti_local == 0) {     // the resident weight set: one barrier, once per CTA
+            mbar_wait(bar_full, 0u);
+            tc_fence_after();
+          }
           for (int cc = 0; cc < cchunks; ++cc) {
             mbar_wait(bar_pfull + 8 * sp, php);
             tc_fence_after();
             const uint32_t patch = base + L.patch + sp * L.patch_bytes;
             int ky = 0, kx = 0;
+            if (g.wres) {
+              uint32_t b_lo = a_lo0 + (uint32_t)(cc * g.KHW) * (L.b_bytes >> 4);
+              for (int tap = 0; tap < g.KHW; ++tap) {
+                const uint32_t a_start = patch + (uint32_t)((ky * g.dh * 16 + kx * g.dw) * 128);
+                const uint32_t pa_lo = (a_start >> 4) & 0x3fffu;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                  umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, hi_a0, b_lo + 2 * k, desc_hi, idesc, acc);
+                  acc = 1u;
+                }
+                b_lo += L.b_bytes >> 4;
+                if (++kx == g.kw) { kx = 0; ++ky; }
+              }
+              umma_commit(bar_pempty + 8 * sp);
+              if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
+              continue;
+            }
             for (int tap = 0; tap < g.KHW; ++tap) {
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
@@ -279,7 +332,9 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t b_lo = a_lo + a16;
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {       // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle span
-            umma_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
+            if (g.dbg == 3 || (g.dbg == 2 && k)) continue;
+            const uint32_t td = (g.dbg == 1 && (k & 1)) ? (tmem_base + (buf ^ 1u) * (uint32_t)g.BN) : tmem_d;
+            umma_bf16_lohi(td, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
             acc = 1u;
           }
           umma_commit(bar_empty + 8 * s);
@@ -570,11 +625,29 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.BN = BN;
   g.n_tiles = Cout_pad / BN;
   g.direct = direct ? 1 : 0; g.y_bf16 = p.y_bf16; g.out_nhwc = p.out_nhwc; g.y = p.y;
-  g.halo = halo ? 1 : 0; g.patch_rows = halo ? 16 * patch_h : 0; g.pstages = halo ? 2 : 0; g.kh = p.kh;
+  { const char* e = getenv("UPSNET_TMA_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+  g.halo = halo ? 1 : 0; g.patch_rows = halo ? 16 * patch_h : 0; g.pstages = halo ? 3 : 0; g.kh = p.kh;
   int stages = TM_MAX_STAGES;
-  TmaSmem L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages);
-  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages); }
-  if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  TmaSmem L;
+  // resident weights: the n-tile's KHW * Cin/64 weight tiles stay in smem for the life of the (persistent) CTA when they
+  // fit next to >= 2 patch slots -- the 64->64 3x3 bottleneck convs and the 18-channel offset convs of the semantic head
+  g.wres = 0;
+  if (halo && Cout_pad == BN) {
+    const int wtiles = g.KHW * (p.Cin / 64);
+    for (int ps = 4; ps >= 2 && !g.wres; --ps) {
+      L = tma_smem_layout(BN, wtiles, g.has_res != 0, g.patch_rows, ps, direct);
+      if (L.total + 1024 <= 227 * 1024) { g.wres = 1; g.wtiles = wtiles; g.pstages = ps; stages = 1; }
+    }
+  }
+  if (!g.wres) {
+    L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct);
+    while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct); }
+    if (L.total + 1024 > 227 * 1024 && g.pstages > 2) {
+      g.pstages = 2;
+      L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct);
+    }
+    if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  }
   g.stages = stages;
 
   const int Kp = g.KHW * p.Cin;
