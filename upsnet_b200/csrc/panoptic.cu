@@ -319,11 +319,12 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     const unsigned int* __restrict__ bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
     unsigned int my_ovl = 0;
     unsigned int wreg[kRegWords];
+    const int nit = (items + (int)blockDim.x - 1) / (int)blockDim.x;   // block-uniform: passes that have any work at all
 #pragma unroll
     for (int u = 0; u < kRegWords; ++u) {
       const int item = threadIdx.x + u * (int)blockDim.x;
       wreg[u] = 0u;
-      if (item < items) {
+      if (u < nit && item < items) {
         const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
         wreg[u] = __ldg(bits + item);
         my_ovl += __popc(wreg[u] & occ[o]);
@@ -339,7 +340,11 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     __syncthreads();
     const unsigned int ms = (unsigned int)s_msum[li], ov = s_ovl[li & 1];
     // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
-    const bool drop = (ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold);
+    // one fp64 division per WARP (lane 0), broadcast by shuffle: B200 has very few fp64 units, 1024 divisions per
+    // instance would dominate the serial pass
+    int drop_i = 0;
+    if (lane == 0) drop_i = ((ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold)) ? 1 : 0;
+    const bool drop = __shfl_sync(0xffffffffu, drop_i, 0) != 0;
     if (threadIdx.x == 0) {
       ws.kept_flag[r] = drop ? 0 : 1;
       s_ovl[(li + 1) & 1] = 0;            // the other counter is idle until the next instance's barrier
@@ -348,7 +353,7 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
 #pragma unroll
       for (int u = 0; u < kRegWords; ++u) {
         const int item = threadIdx.x + u * (int)blockDim.x;
-        if (item < items && wreg[u]) {
+        if (u < nit && item < items && wreg[u]) {
           const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
           occ[o] |= wreg[u];
         }
