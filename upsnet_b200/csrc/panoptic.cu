@@ -306,17 +306,28 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
   const int cnt = s_cnt;
   // Per-instance critical path = one L2 round trip (window words + occupancy) + a block reduction: |mask| values are
   // staged in shared memory up front, a thread's window words stay in registers between the popc and the OR pass.
-  __shared__ int s_msum[kMaxList];
-  for (int li = threadIdx.x; li < cnt; li += blockDim.x) s_msum[li] = ws.msum[list[li]];
+  // per-instance metadata of the whole class list staged in (dynamic) shared memory: inside the serial loop nothing but
+  // the window words and the occupancy words comes from L2
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  int4* s_win = reinterpret_cast<int4*>(s_dyn);                       // (wx0, nwc, y0, items)   [n_max]
+  long long* s_off = reinterpret_cast<long long*>(s_win + n_max);      // word offset in ws.bits  [n_max]
+  int* s_msum = reinterpret_cast<int*>(s_off + n_max);                 // |mask|                  [n_max]
+  for (int li = threadIdx.x; li < cnt; li += blockDim.x) {
+    const int r = list[li];
+    const int i = ws.order[r];
+    const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
+    const int wx0 = x0 >> 5, nwc = max(((x1 + 31) >> 5) - wx0, 0);
+    s_win[li] = make_int4(wx0, nwc, y0, nwc * max(y1 - y0, 0));
+    s_off[li] = ws.off[r] - (long long)rq * ws.budget;
+    s_msum[li] = ws.msum[r];
+  }
   __syncthreads();
   constexpr int kRegWords = 8;
   for (int li = 0; li < cnt; ++li) {
     const int r = list[li];
-    const int i = ws.order[r];
-    const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
-    const int wx0 = x0 >> 5, wx1 = (x1 + 31) >> 5;
-    const int nwc = max(wx1 - wx0, 0), items = nwc * max(y1 - y0, 0);
-    const unsigned int* __restrict__ bits = ws.bits + (ws.off[r] - (long long)rq * ws.budget);
+    const int4 win = s_win[li];
+    const int wx0 = win.x, nwc = win.y, y0 = win.z, items = win.w;
+    const unsigned int* __restrict__ bits = ws.bits + s_off[li];
     unsigned int my_ovl = 0;
     unsigned int wreg[kRegWords];
     const int nit = (items + (int)blockDim.x - 1) / (int)blockDim.x;   // block-uniform: passes that have any work at all
@@ -604,10 +615,17 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
   UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
+  {
+    static bool configured = false;
+    if (!configured) {   // up to kMaxList * 28 B of per-instance metadata
+      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
+      configured = true;
+    }
+  }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
     pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
     UPS_CHECK_LAUNCH();
-    pan_decide_kernel<<<num_thing, 1024, 0, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 28, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
@@ -649,10 +667,17 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   UPS_CUDA(cudaMemsetAsync(ws.kept_flag, 0, sizeof(int) * n, st));
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
+  {
+    static bool configured = false;
+    if (!configured) {   // up to kMaxList * 28 B of per-instance metadata
+      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
+      configured = true;
+    }
+  }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
     pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
     UPS_CHECK_LAUNCH();
-    pan_decide_kernel<<<num_thing, 1024, 0, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 28, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
