@@ -301,7 +301,8 @@ class StaticMaskROI(MaskROI):
             self._const[key] = (cls_flat, ridx_flat)
         return self._const[key]
 
-    def __call__(self, rois, roi_valid, bbox_delta, cls_prob, im_info):
+    def __call__(self, rois, roi_valid, bbox_delta, cls_prob, im_info, side=False):
+        """side=True: this call runs on a side stream concurrently with another MaskROI (separate NMS scratch)."""
         dev = rois.device
         C, R = self.num_classes, rois.shape[0]
         Cm = C - 1
@@ -311,7 +312,8 @@ class StaticMaskROI(MaskROI):
         if FUSED["on"] and dev.type == "cuda" and R * Cm <= 8192 and Cm <= 128:
             sc, cls, bx, offs = _ops.maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, self.class_agnostic,
                                                      self.score_thresh, self.weights, float(im_info[0]), float(im_info[1]))
-            keep, cnt = nms_segmented(bx, offs, M, self.nms_thresh)
+            keep, cnt = (_ops.nms_segmented(bx, offs, M, self.nms_thresh, side=True) if side
+                         else nms_segmented(bx, offs, M, self.nms_thresh))
             return _ops.maskroi_finish(keep, cnt, offs, sc, cls, bx, self.top_n, self.cap)
         cls_flat, ridx_flat = self._consts(R, dev)
         proposal = clip_boxes(bbox_transform(rois[:, 1:], bbox_delta, self.weights), float(im_info[0]),

@@ -540,8 +540,25 @@ class resnet_upsnet(nn.Module):
         rcnn_output = self.rcnn(feats, rois)
         cls_prob = F.softmax(rcnn_output["cls_score"].float(), dim=1)
         bbox_pred = rcnn_output["bbox_pred"].float()
+        # the two MaskROIs (detections / panoptic candidates) are independent chains of single-CTA kernels: run the second
+        # on its own stream next to the first
+        if fork:
+            side2 = self._side_stream(x.device, 1)
+            ev2 = torch.cuda.Event()
+            ev2.record(cur)
+            side2.wait_event(ev2)
+            with torch.cuda.stream(side2):
+                s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info, side=True)
+                done2 = torch.cuda.Event()
+                done2.record(side2)
+            if not torch.cuda.is_current_stream_capturing():
+                for t_ in (s2, b2, c2, n2):
+                    t_.record_stream(cur)
         s1, b1, c1, n1 = self.mask_roi_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
-        s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
+        if fork:
+            cur.wait_event(done2)
+        else:
+            s2, b2, c2, n2 = self.mask_roi_panoptic_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
         # models/resnet_upsnet.py:203-222 runs the mask branch twice (detections, panoptic candidates).  Every roi is
         # processed independently, so both sets go through it as ONE batch: half the launches, fuller tile waves.
         logits = self.mask_branch(feats, torch.cat([b1, b2], 0)).float()
@@ -558,8 +575,8 @@ class resnet_upsnet(nn.Module):
                 "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
                 "keep": keep, "counts": counts, "fcn_output": fcn_output}
 
-    def _side_stream(self, dev):
-        key = str(dev)
+    def _side_stream(self, dev, idx=0):
+        key = (str(dev), idx)
         if key not in self._side:
             self._side[key] = torch.cuda.Stream(device=dev)
         return self._side[key]

@@ -409,10 +409,11 @@ class _Workspace:
 
 
 _nms_ws = _Workspace()
+_nms_ws_side = _Workspace()   # second scratch buffer: an NMS running concurrently on another stream must not share the first
 _pan_ws = _Workspace()
 
 
-def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
+def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh, side=False):
     """boxes_sorted [total,4] fp32 sorted by descending score inside each segment; seg_offsets int32
     [S+1] (device).  Returns (keep [S,max_seg_len] int32 positions relative to segment start,
     counts [S] int32) -- both on the device, no host synchronisation."""
@@ -423,7 +424,7 @@ def nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
     dev = boxes_sorted.device
     nbytes = C.c_size_t(0)
     check(lib().upsnet_nms_workspace_bytes(S, max_seg_len, C.byref(nbytes)), "nms_workspace_bytes")
-    ws = _nms_ws.get(dev, nbytes.value)
+    ws = (_nms_ws_side if side else _nms_ws).get(dev, nbytes.value)
     keep = torch.empty((S, max_seg_len), dtype=torch.int32, device=dev)
     cnt = torch.empty((S,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _Timed("nms", 2, {"bytes": 20.0 * boxes_sorted.shape[0]}, dev):
