@@ -48,6 +48,7 @@ struct TmaGeom {
   // halo mode (k x k, stride 1): one (16 x PH)-pixel input PATCH per (tile, channel chunk) feeds all taps -- the A operand
   // of tap (ky, kx) is the patch seen through a descriptor that starts (ky*dh*16 + kx*dw) rows further (tile = 8 x 16 px)
   int halo, patch_rows, pstages, kh;
+  int rotate;                           // tile-dependent start of the K loop (see producer)
   int wres, wtiles;                     // halo mode with the n-tile's whole weight set (wtiles tiles) resident in smem, loaded once per CTA
   int dbg;                              // timing experiments only (UPSNET_TMA_DEBUG): 1 alternate accumulators, 2 one MMA per k-block, 3 no MMAs
 };
@@ -225,7 +226,9 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
             }
             if (g.wres) continue;
-            for (int tap = 0; tap < g.KHW; ++tap) {
+            for (int t_ = 0; t_ < g.KHW; ++t_) {
+              int tap = t_ + (g.rotate ? (int)(mt % g.KHW) : 0);     // same rotation as the MMA loop
+              if (tap >= g.KHW) tap -= g.KHW;
               const uint32_t bf = bar_full + 8 * s;
               mbar_wait(bar_empty + 8 * s, ph ^ 1u);
               mbar_arrive_expect_tx(bf, L.b_bytes);
@@ -236,18 +239,23 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
           continue;
         }
-        int cc = 0, kj = 0;
-        int cw = w0 - g.pw, ch = h0 - g.ph;         // box origin of the current tap
+        // The K loop starts at a tile-dependent k-block and wraps (the sum is order independent): CTAs that run the same
+        // layer in lock step would otherwise all request the SAME weight tile at the same moment (hot L2 lines).
+        int kbr = g.rotate ? (int)((mt * 5) % num_kb) : 0;
+        int tap0 = kbr / cchunks;
+        int cc = kbr - tap0 * cchunks, ki = tap0 / g.kw, kj = tap0 - ki * g.kw;
+        int cw = w0 - g.pw + kj * g.dw, ch = h0 - g.ph + ki * g.dh;         // box origin of the current tap
         for (int kb = 0; kb < num_kb; ++kb) {
           const uint32_t bf = bar_full + 8 * s;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(bf, tx_bytes);
           if (g.stem)   // k-block = filter row ky: 8 pixels x 8 channels per output pixel, input row 2*ho + ky of the padded image
-            tma_load_5d(a_dst, &tm_x, bf, 0, w0, kb & 1, h0 + (kb >> 1), i0);
+            tma_load_5d(a_dst, &tm_x, bf, 0, w0, kbr & 1, h0 + (kbr >> 1), i0);
           else
             tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
-          tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, n0);
-          if (++cc == cchunks) {
+          tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kbr * 64, n0);
+          if (++kbr == num_kb) { kbr = 0; cc = 0; kj = 0; cw = w0 - g.pw; ch = h0 - g.ph; }
+          else if (++cc == cchunks) {
             cc = 0; cw += g.dw;
             if (++kj == g.kw) { kj = 0; cw = w0 - g.pw; ch += g.dh; }
           }
@@ -305,7 +313,9 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
               continue;
             }
-            for (int tap = 0; tap < g.KHW; ++tap) {
+            const int trot = g.rotate ? (int)((tile / g.n_tiles) % g.KHW) : 0;
+            ky = trot / g.kw; kx = trot - ky * g.kw;
+            for (int t_ = 0; t_ < g.KHW; ++t_) {
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
               const uint32_t a_start = patch + (uint32_t)((ky * g.dh * 16 + kx * g.dw) * 128);
@@ -318,7 +328,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               umma_commit(bar_empty + 8 * s);
               a_lo += stage16;
               if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
-              if (++kx == g.kw) { kx = 0; ++ky; }
+              if (++kx == g.kw) { kx = 0; if (++ky == g.kh) ky = 0; }
             }
             umma_commit(bar_pempty + 8 * sp);     // every tap of this chunk has been issued: the patch slot may be refilled
             if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
@@ -626,6 +636,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.n_tiles = Cout_pad / BN;
   g.direct = direct ? 1 : 0; g.y_bf16 = p.y_bf16; g.out_nhwc = p.out_nhwc; g.y = p.y;
   { const char* e = getenv("UPSNET_TMA_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+  { static int rot_env = -1; if (rot_env < 0) { const char* e = getenv("UPSNET_TMA_ROTATE"); rot_env = e ? atoi(e) : 1; } g.rotate = rot_env; }
   g.halo = halo ? 1 : 0; g.patch_rows = halo ? 16 * patch_h : 0; g.pstages = halo ? 3 : 0; g.kh = p.kh;
   int stages = TM_MAX_STAGES;
   TmaSmem L;
