@@ -115,7 +115,10 @@ igemm_tc_kernel(const TcParams p) {
   // M-tile = 128 output pixels.  Dense / stem modes: 128 consecutive pixels of the flattened (n, ho, wo) index.
   // Deformable mode: a 16 x 8 pixel BLOCK of one image -- its nine taps x four corners then revisit ~(16+3) x (8+3)
   // input pixels per channel chunk (27 KB: L1-resident) instead of four 131-pixel row segments.
-  constexpr int TW = 16, TH = 8;
+  // (small maps use 8x8 or 8x4 blocks -- rows past the block stay empty and cost no gather work -- so that more CTAs
+  // share the serial k-block chain; the launcher picks the block)
+  const int TW = DEFORM ? p.tile_w : 16, TH = DEFORM ? p.tile_h : 8;
+  const int tw_shift = TW == 16 ? 4 : 3;
   const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
   const long long m_tiles = DEFORM ? (long long)p.N * tiles_w * tiles_h : (Ptot + TC_BM - 1) / TC_BM;
   const long long num_tiles = m_tiles * n_tiles;
@@ -123,8 +126,9 @@ igemm_tc_kernel(const TcParams p) {
   auto tile_pixel = [&](long long mt, int r) -> long long {
     if (DEFORM) {
       const int tx = (int)(mt % tiles_w), ty = (int)((mt / tiles_w) % tiles_h), n = (int)(mt / ((long long)tiles_w * tiles_h));
-      const int wo = tx * TW + (r & (TW - 1)), ho = ty * TH + (r >> 4);
-      return (wo < p.Wo && ho < p.Ho) ? ((long long)n * p.Ho + ho) * p.Wo + wo : -1ll;
+      const int ry = r >> tw_shift;
+      const int wo = tx * TW + (r & (TW - 1)), ho = ty * TH + ry;
+      return (ry < TH && wo < p.Wo && ho < p.Ho) ? ((long long)n * p.Ho + ho) * p.Wo + wo : -1ll;
     }
     const long long pg = mt * TC_BM + r;
     return pg < Ptot ? pg : -1ll;
@@ -777,14 +781,19 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   p.stages = stages;
   const long long Ptot = (long long)p.N * p.Ho * p.Wo;
   if (Ptot <= 0) return 0;
-  const long long num_tiles = (deform ? (long long)p.N * ((p.Wo + 15) / 16) * ((p.Ho + 7) / 8) : (Ptot + TC_BM - 1) / TC_BM) *
-                              (p.Cout_pad / BN);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0, v = kNumSMs;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     sms = v > 0 ? v : kNumSMs;
   }
+  p.tile_w = 16; p.tile_h = 8;
+  auto dtiles = [&]() { return (long long)p.N * ((p.Wo + p.tile_w - 1) / p.tile_w) * ((p.Ho + p.tile_h - 1) / p.tile_h) * (p.Cout_pad / BN); };
+  if (deform) {   // few tiles (coarse pyramid levels): smaller pixel blocks -> more CTAs, proportionally less gather work each
+    if (dtiles() < sms / 2) { p.tile_w = 8; p.tile_h = 8; }
+    if (dtiles() < sms / 2) { p.tile_h = 4; }
+  }
+  const long long num_tiles = (deform ? dtiles() : ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN));
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
   const size_t smem = L.total + 1024;
   // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
