@@ -368,6 +368,7 @@ struct TopkParams {
   unsigned long long* prefix;    // [nlev]  key bits fixed so far
   int* need;                     // [nlev]  how many of the k are still to be found inside the current prefix
   unsigned int* fill;            // [nlev]  gather cursor
+  int* done;                     // [nlev]  set once the bucket of the current prefix is small enough to be sorted whole
   unsigned long long* keys;      // [nlev][kTkMaxK]
   float* out_scores; long long* out_idx;
 };
@@ -387,6 +388,7 @@ topk_pass_kernel(const TopkParams p, int shift, int bits, int first) {
   const int l = blockIdx.y;
   const TopkLevel lv = p.lv[l];
   if ((int)blockIdx.x >= lv.blocks) return;
+  if (!first && p.done[l]) return;      // an earlier pass already narrowed the candidates to what the sort kernel can take
   __shared__ unsigned int sh[kTkBins];
   __shared__ int s_last;
   for (int b = threadIdx.x; b < kTkBins; b += kTkThreads) sh[b] = 0;
@@ -448,6 +450,9 @@ topk_pass_kernel(const TopkParams p, int shift, int bits, int first) {
       }
       p.need[l] = need - (int)acc;
       p.prefix[l] = fixed | ((unsigned long long)d << shift);
+      // early exit: everything above the bucket (k - need') plus the WHOLE bucket fits the sort buffer -> no need to
+      // resolve the remaining digits, the sort orders the bucket and the first k are taken
+      if ((long long)(lv.k - (need - (int)acc)) + (long long)sh[d] <= (long long)kTkMaxK) p.done[l] = 1;
     }
     if (lane == 0) { p.ticket[l] = 0; p.fill[l] = 0; }
   }
@@ -478,7 +483,8 @@ topk_sort_kernel(const TopkParams p) {
   const TopkLevel lv = p.lv[l];
   __shared__ unsigned long long sk[kTkMaxK];
   const int tid = threadIdx.x;
-  for (int i = tid; i < kTkMaxK; i += 1024) sk[i] = i < lv.k ? p.keys[(size_t)l * kTkMaxK + i] : 0ull;
+  const int nk = min((int)p.fill[l], kTkMaxK);       // == k unless a pass exited early with a whole bucket
+  for (int i = tid; i < kTkMaxK; i += 1024) sk[i] = i < nk ? p.keys[(size_t)l * kTkMaxK + i] : 0ull;
   __syncthreads();
   for (int k = 2; k <= kTkMaxK; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -502,7 +508,7 @@ topk_sort_kernel(const TopkParams p) {
 
 extern "C" int upsnet_rpn_topk_workspace_bytes(int L, size_t* bytes) {
   if (!bytes || L <= 0 || L > ups::kMaxLevels) return UPSNET_E_BADARG;
-  *bytes = (size_t)L * (ups::kTkBins * 4 + 4 + 8 + 4 + 4 + 4 + (size_t)ups::kTkMaxK * 8) + 256;
+  *bytes = (size_t)L * (ups::kTkBins * 4 + 4 + 8 + 4 + 4 + 4 + 4 + (size_t)ups::kTkMaxK * 8) + 256;
   return 0;
 }
 
@@ -524,6 +530,7 @@ extern "C" int upsnet_rpn_topk(const float* const* probs, const int* hs, const i
   p.ticket = (unsigned int*)base; base += (size_t)L * 4;
   p.need = (int*)base; base += (size_t)L * 4;
   p.fill = (unsigned int*)base; base += (size_t)L * 4;
+  p.done = (int*)base; base += (size_t)L * 4;
   p.nlev = L; p.A = A; p.out_scores = out_scores; p.out_idx = out_idx;
   int acc = 0, max_blocks = 0;
   for (int l = 0; l < L; ++l) {
@@ -540,7 +547,7 @@ extern "C" int upsnet_rpn_topk(const float* const* probs, const int* hs, const i
   cudaStream_t st = (cudaStream_t)stream;
   // histograms + tickets start at zero (every pass re-arms them for the next one)
   UPS_CUDA(cudaMemsetAsync(p.hist, 0, (size_t)L * kTkBins * 4, st));
-  UPS_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)L * 4, st));
+  UPS_CUDA(cudaMemsetAsync(p.ticket, 0, (size_t)L * 4 * 4, st));    // ticket, need, fill, done are contiguous
   const dim3 grid((unsigned)max_blocks, (unsigned)L);
   const int shifts[5] = {43, 32, 22, 11, 0}, nbits[5] = {11, 11, 10, 11, 11};
   for (int ps = 0; ps < 5; ++ps) {
