@@ -329,16 +329,17 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     const int wx0 = win.x, nwc = win.y, y0 = win.z, items = win.w;
     const unsigned int* __restrict__ bits = ws.bits + s_off[li];
     unsigned int my_ovl = 0;
-    unsigned int wreg[kRegWords];
+    unsigned int wreg[kRegWords], oreg[kRegWords];
     const int nit = (items + (int)blockDim.x - 1) / (int)blockDim.x;   // block-uniform: passes that have any work at all
 #pragma unroll
     for (int u = 0; u < kRegWords; ++u) {
       const int item = threadIdx.x + u * (int)blockDim.x;
-      wreg[u] = 0u;
+      wreg[u] = 0u; oreg[u] = 0u;
       if (u < nit && item < items) {
         const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
         wreg[u] = __ldg(bits + item);
-        my_ovl += __popc(wreg[u] & occ[o]);
+        oreg[u] = occ[o];                 // kept: the OR below is then a plain store, not a second L2 round trip
+        my_ovl += __popc(wreg[u] & oreg[u]);
       }
     }
     for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
@@ -354,7 +355,15 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     // one fp64 division per WARP (lane 0), broadcast by shuffle: B200 has very few fp64 units, 1024 divisions per
     // instance would dominate the serial pass
     int drop_i = 0;
-    if (lane == 0) drop_i = ((ms == 0) || (__ddiv_rn((double)ov, (double)ms) > fraction_threshold)) ? 1 : 0;
+    if (lane == 0) {
+      // fl(ov/ms) > thr is decided without the division whenever ov is clear of thr*ms by more than rounding could
+      // account for (1e-12 relative >> 2^-52); only the knife-edge case pays for the fp64 division itself
+      const double t = (double)ms * fraction_threshold, dov = (double)ov;
+      if (ms == 0) drop_i = 1;
+      else if (dov > t * (1.0 + 1e-12)) drop_i = 1;
+      else if (dov < t * (1.0 - 1e-12)) drop_i = 0;
+      else drop_i = (__ddiv_rn(dov, (double)ms) > fraction_threshold) ? 1 : 0;
+    }
     const bool drop = __shfl_sync(0xffffffffu, drop_i, 0) != 0;
     if (threadIdx.x == 0) {
       ws.kept_flag[r] = drop ? 0 : 1;
@@ -364,9 +373,9 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
 #pragma unroll
       for (int u = 0; u < kRegWords; ++u) {
         const int item = threadIdx.x + u * (int)blockDim.x;
-        if (u < nit && item < items && wreg[u]) {
+        if (u < nit && item < items && (wreg[u] & ~oreg[u])) {
           const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-          occ[o] |= wreg[u];
+          occ[o] = oreg[u] | wreg[u];
         }
       }
       for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
