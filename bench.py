@@ -188,6 +188,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would precede it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     U.set_precision(args.precision)
     global H, W, WORKLOAD
