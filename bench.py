@@ -81,6 +81,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL's version banner on the first
+    communicator, oneDNN / OpenMP notices): from here on file descriptor 1 points at stderr and only emit() writes to the
+    real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _best_cpu_threads():
     """The CPU arm uses the thread count that is FASTEST on this box (more threads than ~32 slow the small torch-CPU
     convs down through oversubscription): a one-second probe on a backbone-sized 3x3 convolution picks it."""
@@ -137,7 +157,7 @@ def run_reference(args, rank):
             "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg():
@@ -172,6 +192,7 @@ def main():
     ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "coco"],
                     help="cityscapes = BASELINE configs[1] (the metric); coco = configs[2] UPSNet-101-DCN 800x1344 (extra)")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -350,7 +371,7 @@ def main():
                         "api": "upsnet_b200.pipeline.PipelinedEngine: pinned-host image in, host results out; H2D / "
                                "compute / D2H of neighbouring images overlap on three streams (depth 2)"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "fp32_grade_mode": other}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
