@@ -25,14 +25,24 @@ extern "C" {
 
 #define UPSNET_LAYOUT_NCHW 0
 #define UPSNET_LAYOUT_NHWC 1
+/* upsnet_roi_align*_forward with UPSNET_DTYPE_PAIR only: out = [R][2][PH*PW*C], the hi plane of the flattened (ph,pw,c)
+ * roi feature followed by its lo plane -- i.e. a pair tensor of R 1x1 'images' with PH*PW*C channels (the RCNN fc6 input) */
+#define UPSNET_LAYOUT_FLAT_PAIR 2
 
 #define UPSNET_DTYPE_F32 0
 #define UPSNET_DTYPE_BF16 1
+/* hi/lo bf16 PAIR: an NHWC tensor with 2*C bf16 channels per pixel, [0,C) = bf16(v), [C,2C) = bf16(v - hi) -- the 16-bit
+ * storage of precision UPSNET_PREC_BF16X3 (same bytes as fp32, ~16 mantissa bits); v = hi + lo is exact in fp32 */
+#define UPSNET_DTYPE_PAIR 2
 
 /* epilogue flags for the convolution entry points */
 #define UPSNET_EPI_RELU 1
 #define UPSNET_EPI_RES_UP2 2 /* upsnet_igemm_forward only: residual is [N,Ho/2,Wo/2,Cout], read with nearest 2x upsampling */
 #define UPSNET_EPI_NO_TMA 4  /* upsnet_igemm_forward only: use the cp.async gather kernel even where the TMA-fed one qualifies */
+/* upsnet_igemm_forward, y_dtype PAIR only: store the output channels as [hi G][lo G] per group of G channels instead of
+ * [hi Cout][lo Cout] (G % 64 == 0, Cout % G == 0; 0 = Cout).  Lets a 1x1 conv that emulates a 2x2 deconvolution write
+ * its four (a,b) sub-pixel groups as four pair pixels (models/rcnn.py:62 mask_deconv1). */
+#define UPSNET_EPI_PAIR_GROUP(G) ((((G) / 64) & 0xfff) << 8)
 
 /* precision of the tensor-core convolution path */
 #define UPSNET_PREC_FP32_SIMT 0 /* fp32 FFMA tiles (exact-order-free fp32)            */
@@ -48,7 +58,9 @@ int upsnet_version(int *n_sm);
  *           -> operators/src/roi_align_kernel.cu:351 roi_align_forward_gpu_kernel_launcher
  * feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC) fp32; rois [R,5] = (batch,x1,y1,x2,y2);
  * out [R,C,PH,PW] (NCHW) or [R,PH,PW,C] (NHWC) -- same layout flag as feat.
- * dtype: UPSNET_DTYPE_F32, or UPSNET_DTYPE_BF16 (NHWC only: bf16 features in, bf16 out, fp32 accumulation).
+ * dtype: UPSNET_DTYPE_F32, or UPSNET_DTYPE_BF16 (NHWC only: bf16 features in, bf16 out, fp32 accumulation), or
+ * UPSNET_DTYPE_PAIR (NHWC: hi/lo pair features [B,H,W,2C] in, pair out [R,PH,PW,2C] or UPSNET_LAYOUT_FLAT_PAIR;
+ * sampling_ratio > 0, C % 8 == 0).
  */
 int upsnet_roi_align_forward(const void *feat, int B, int C, int H, int W, int layout, int dtype,
                              const float *rois, int R, int PH, int PW, int sampling_ratio,
@@ -116,8 +128,10 @@ int upsnet_conv2d_forward(const float *x, const float *weight, const float *bias
  * Same arithmetic contract as upsnet_conv2d_forward / upsnet_dcn_forward, but
  *   - x is NHWC [N,H,W,Cin] (Cin % 64 == 0) stored as fp32 or bf16 (x_dtype) -- or, for a tiny Cin <= 8 (the
  *     RGB stem), the fp32 NCHW image itself: K = kh*kw*Cin is flattened and zero-padded to a multiple of 64; y and residual are NHWC or
- *     NCHW (out_layout) stored as fp32 or bf16 (y_dtype); bf16 activations are copied by cp.async straight
- *     into the tensor-core layout (UPSNET_PREC_BF16 only: the hi/lo split needs fp32 activations),
+ *     NCHW (out_layout) stored as fp32 or bf16 (y_dtype); bf16 activations are copied by TMA / cp.async straight
+ *     into the tensor-core layout (UPSNET_PREC_BF16); UPSNET_PREC_BF16X3 takes fp32 activations (split in the
+ *     gather) or UPSNET_DTYPE_PAIR activations (x [N,H,W,2*Cin], y / residual [N,Ho,Wo,2*Cout]: TMA-fed, three MMAs
+ *     per k-slice, fp32 result re-split in the epilogue),
  *   - weights are pre-packed once with upsnet_igemm_pack_weight (bf16 hi/lo planes,
  *     [Cout_pad][kh*kw][Cin]); `packed` must hold upsnet_igemm_packed_weight_bytes bytes,
  *   - offset [N,2*kh*kw,Ho,Wo] / mask [N,kh*kw,Ho,Wo] stay NCHW (reference layout), NULL for a
@@ -177,7 +191,8 @@ int upsnet_stem_forward(const float *x, const void *packed_w, const float *bias,
                         int H, int W, int Cout, int kh, int kw, int pad, int epi_flags, void *workspace,
                         size_t workspace_bytes, void *stream);
 
-/* Max-pooling on NHWC activations (bf16 or fp32 storage; C % 8 == 0 resp. C % 4 == 0), floor output size.
+/* Max-pooling on NHWC activations (bf16, hi/lo pair or fp32 storage; C % 8 == 0 resp. C % 4 == 0), floor output size.
+ * UPSNET_DTYPE_PAIR: x [N,H,W,2C] -> y [N,Ho,Wo,2C], the window element with the largest hi + lo is copied.
  * replaces: models/resnet.py:163 nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the stem.
  * x [N,H,W,C] -> y [N,Ho,Wo,C], Ho = (H + 2*pad - k)/stride + 1; padding never wins the max. */
 int upsnet_maxpool2d_nhwc(const void *x, void *y, int N, int H, int W, int C, int k, int stride,

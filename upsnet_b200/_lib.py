@@ -18,6 +18,8 @@ EPI_RELU = 1
 EPI_RES_UP2 = 2
 EPI_NO_TMA = 4
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_PAIR = 0, 1, 2
+LAYOUT_FLAT_PAIR = 2
 
 _ERR = {-1: "bad argument", -2: "unsupported configuration", -3: "workspace too small"}
 

@@ -115,10 +115,16 @@ extern "C" int upsnet_igemm_forward(const void* x_nhwc, const float* offset, con
   p.no_tma = (epi_flags & UPSNET_EPI_NO_TMA) ? 1 : 0;
   if (p.res_up2 && (!residual || !p.out_nhwc || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_BADARG;
   p.x3 = precision == UPSNET_PREC_BF16X3;
-  if ((x_dtype != UPSNET_DTYPE_F32 && x_dtype != UPSNET_DTYPE_BF16) || (y_dtype != UPSNET_DTYPE_F32 && y_dtype != UPSNET_DTYPE_BF16))
+  if (x_dtype < UPSNET_DTYPE_F32 || x_dtype > UPSNET_DTYPE_PAIR || y_dtype < UPSNET_DTYPE_F32 || y_dtype > UPSNET_DTYPE_PAIR)
     return UPSNET_E_BADARG;
   p.x_bf16 = x_dtype == UPSNET_DTYPE_BF16;
   p.y_bf16 = y_dtype == UPSNET_DTYPE_BF16;
+  p.x_pair = x_dtype == UPSNET_DTYPE_PAIR;
+  p.y_pair = y_dtype == UPSNET_DTYPE_PAIR;
+  p.pair_group = 64 * ((epi_flags >> 8) & 0xfff);
+  // bf16 storage carries precision bf16; hi/lo pairs are the 16-bit storage of precision bf16x3 (the split of x)
   if (p.x_bf16 && p.x3) return UPSNET_E_UNSUPPORTED;
+  if ((p.x_pair || p.y_pair) && !p.x3) return UPSNET_E_UNSUPPORTED;
+  if (p.y_pair && !p.out_nhwc) return UPSNET_E_BADARG;
   return ups::launch_igemm_tc(p, packed, (cudaStream_t)stream);
 }

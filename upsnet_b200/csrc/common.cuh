@@ -21,6 +21,19 @@ namespace ups {
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute is per device (and context): remember which devices a kernel has been configured on, so that a
+// process driving several GPUs (the reference's thread-per-GPU DataParallel, gpu_nms(device_id)) opts in on each of them.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -316,11 +316,10 @@ extern "C" int upsnet_maskroi_prepare(const float* rois, const unsigned char* ro
     return UPSNET_E_BADARG;
   if (R <= 0 || C < 2) return UPSNET_E_BADARG;
   if ((long long)R * (C - 1) > ups::kSortN || C - 1 > 128 || score_thresh < 0.f) return UPSNET_E_UNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  static ups::PerDeviceOnce configured;
+  if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(ups::maskroi_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ups::kSortN * 8));
-    configured = true;
   }
   ups::maskroi_prepare_kernel<<<1, ups::kMrThreads, ups::kSortN * 8, (cudaStream_t)stream>>>(
       rois, roi_valid, bbox_delta, cls_prob, R, C, class_agnostic, score_thresh, weights[0], weights[1], weights[2],
@@ -694,10 +693,9 @@ extern "C" int upsnet_rpn_collect(const int* keep, const int* keep_cnt, const in
     return UPSNET_E_UNSUPPORTED;
   if (((uintptr_t)boxes) & 15) return UPSNET_E_BADARG;
   const size_t smem = (size_t)(kColMaxCand + kColMaxPost) * 8;
-  static bool configured = false;
-  if (!configured) {
+  static ups::PerDeviceOnce configured;
+  if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(rpn_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   rpn_collect_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(keep, keep_cnt, seg_offsets, boxes, scores, S, max_seg_len,
                                                                post_nms_top_n, rois, out_scores, valid);

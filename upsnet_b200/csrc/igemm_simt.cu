@@ -235,11 +235,10 @@ int launch_igemm_simt(const ConvParams& p, cudaStream_t stream) {
   const long long gx = (Ptot + TN - 1) / TN;
   if (gx > 2147483647LL) return UPSNET_E_UNSUPPORTED;
   dim3 grid((unsigned)gx, (unsigned)ceil_div(p.Cout, TM));
-  static bool configured = false;   // once per process (not per launch: CUDA-graph capture)
-  if (!configured) {
+  static ups::PerDeviceOnce configured;
+  if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     UPS_CUDA(cudaFuncSetAttribute(igemm_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   if (deform) igemm_simt_kernel<true><<<grid, NT, smem, stream>>>(p);
   else igemm_simt_kernel<false><<<grid, NT, smem, stream>>>(p);

@@ -83,9 +83,12 @@ __device__ __forceinline__ void producer_bar_sync() {
 // main loop.  Tiles: id = blockIdx.x + it*gridDim.x, n-tile fastest (concurrent CTAs share the A rows in L2).
 // MODE: 0 = dense (Cin % 64 == 0, NHWC), 1 = deformable, 2 = tiny Cin (stem: NCHW fp32 image, K = kh*kw*Cin
 // flattened and zero-padded to a multiple of 64, element-wise gather through a per-k table)
-template <int MODE, bool XBF16>
+// XM: activation storage of x -- 0 fp32, 1 bf16, 2 hi/lo bf16 pairs (NHWC with 2*Cin channels; always the 3-MMA split)
+template <int MODE, int XM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 igemm_tc_kernel(const TcParams p) {
+  constexpr bool XBF16 = XM == 1;
+  constexpr bool XPAIR = XM == 2;
   constexpr bool DEFORM = MODE == 1;
   constexpr bool SMALLC = MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -179,7 +182,7 @@ igemm_tc_kernel(const TcParams p) {
     uint32_t tile_it = 0;
     // bf16 dense mode: both operands travel by cp.async, so the producer keeps ONE k-block outstanding and
     // signals the previous one only after issuing the next (two k-blocks of loads in flight per group).
-    const bool deferred = (MODE == 0) && XBF16 && p.stages >= 3;
+    const bool deferred = (MODE == 0) && (XBF16 || XPAIR) && p.stages >= 3;
     int pend_s = -1;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long mt = tile / n_tiles;
@@ -195,7 +198,7 @@ igemm_tc_kernel(const TcParams p) {
         if (pg >= 0) {
           const int n = (int)(pg / HoWo), pp = (int)(pg - (long long)n * HoWo);
           const int ho = pp / p.Wo, wo = pp - ho * p.Wo;
-          if (DEFORM) v = (long long)n * p.H * p.W * (long long)p.Cin;
+          if (DEFORM) v = (long long)n * p.H * p.W * (long long)p.Cin * (XPAIR ? 2 : 1);
           else v = ((long long)n << 40) | ((long long)(ho * p.sh - p.ph + (1 << 19)) << 20) | (long long)(wo * p.sw - p.pw + (1 << 19));
         }
         rowinfo[r] = v;
@@ -231,7 +234,10 @@ igemm_tc_kernel(const TcParams p) {
               ov.w = (b_ok && r_ok) ? hh * p.W + wh : 0;
             }
           }
-          if (XBF16) {   // bf16 gather blends in packed bf16x2: weights replicated into both halves, offsets in elements
+          if (XPAIR) {   // pair gather: element offsets in the 2*Cin-channel tensor, fp32 weights
+            ov.x *= 2 * p.Cin; ov.y *= 2 * p.Cin; ov.z *= 2 * p.Cin; ov.w *= 2 * p.Cin;
+            tw[e] = wv;
+          } else if (XBF16) {   // bf16 gather blends in packed bf16x2: weights replicated into both halves, offsets in elements
             ov.x *= p.Cin; ov.y *= p.Cin; ov.z *= p.Cin; ov.w *= p.Cin;
             uint4 wp;
             wp.x = pack_bf16x2(wv.x, wv.x); wp.y = pack_bf16x2(wv.y, wv.y);
@@ -308,6 +314,67 @@ igemm_tc_kernel(const TcParams p) {
               lo.w = pack_bf16x2(v[6] - bf16_round(v[6]), v[7] - bf16_round(v[7]));
               *reinterpret_cast<uint4*>(a_lo + soff) = lo;
             }
+          }
+        } else if (!DEFORM && XPAIR) {
+          // dense, hi/lo pair activations: the hi and lo 128-byte rows ARE the smem rows of the two A tiles -> two cp.async
+          // of 16 B per (row, chunk) straight into the swizzled stage (zero-fill for padding / out-of-range rows)
+          const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
+#pragma unroll
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowinfo[r];
+            const int hi = (int)((rb >> 20) & 0xfffff) - (1 << 19) + tdy, wi = (int)(rb & 0xfffff) - (1 << 19) + tdx;
+            const bool ok = rb >= 0 && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const __nv_bfloat16* src = ok ? xh + (((size_t)(rb >> 40) * p.H + hi) * p.W + wi) * (size_t)(2 * p.Cin) + c0 : xh;
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            cp_async16_zfill(smem_u32(a_hi + soff), src, ok ? 16u : 0u);
+            cp_async16_zfill(smem_u32(a_lo + soff), ok ? src + p.Cin : xh, ok ? 16u : 0u);
+          }
+        } else if (DEFORM && XPAIR) {
+          // deformable, hi/lo pair activations: 8 lanes x 16 B cover a row's 64 channels of one plane; per corner one hi and
+          // one lo load, v = sum_i w_i * (hi_i + lo_i) in fp32 (hi + lo is exact), then the result is split again.
+          const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
+#pragma unroll 1
+          for (int pass = 0; pass < TC_BM / 32; ++pass) {
+            const int r = r_first + pass * 32;
+            const long long rb = rowinfo[r];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (rb >= 0) {
+              const __nv_bfloat16* xb = xh + rb + c0;
+              const float4 wv = tw[tap * TC_BM + r];
+              const int4 ov = to[tap * TC_BM + r];
+              const uint4 ha = __ldg(reinterpret_cast<const uint4*>(xb + ov.x)), la = __ldg(reinterpret_cast<const uint4*>(xb + ov.x + p.Cin));
+              const uint4 hb = __ldg(reinterpret_cast<const uint4*>(xb + ov.y)), lb = __ldg(reinterpret_cast<const uint4*>(xb + ov.y + p.Cin));
+              const uint4 hd = __ldg(reinterpret_cast<const uint4*>(xb + ov.z)), ld = __ldg(reinterpret_cast<const uint4*>(xb + ov.z + p.Cin));
+              const uint4 he = __ldg(reinterpret_cast<const uint4*>(xb + ov.w)), le = __ldg(reinterpret_cast<const uint4*>(xb + ov.w + p.Cin));
+              const uint32_t A[4] = {ha.x, ha.y, ha.z, ha.w}, a[4] = {la.x, la.y, la.z, la.w};
+              const uint32_t B[4] = {hb.x, hb.y, hb.z, hb.w}, b[4] = {lb.x, lb.y, lb.z, lb.w};
+              const uint32_t D[4] = {hd.x, hd.y, hd.z, hd.w}, d[4] = {ld.x, ld.y, ld.z, ld.w};
+              const uint32_t E[4] = {he.x, he.y, he.z, he.w}, e4[4] = {le.x, le.y, le.z, le.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] = wv.x * (__uint_as_float(A[q] << 16) + __uint_as_float(a[q] << 16)) +
+                           wv.y * (__uint_as_float(B[q] << 16) + __uint_as_float(b[q] << 16)) +
+                           wv.z * (__uint_as_float(D[q] << 16) + __uint_as_float(d[q] << 16)) +
+                           wv.w * (__uint_as_float(E[q] << 16) + __uint_as_float(e4[q] << 16));
+                v[2 * q + 1] = wv.x * (__uint_as_float(A[q] & 0xffff0000u) + __uint_as_float(a[q] & 0xffff0000u)) +
+                               wv.y * (__uint_as_float(B[q] & 0xffff0000u) + __uint_as_float(b[q] & 0xffff0000u)) +
+                               wv.z * (__uint_as_float(D[q] & 0xffff0000u) + __uint_as_float(d[q] & 0xffff0000u)) +
+                               wv.w * (__uint_as_float(E[q] & 0xffff0000u) + __uint_as_float(e4[q] & 0xffff0000u));
+              }
+            }
+            const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+            uint4 hi4, lo4;
+            hi4.x = pack_bf16x2(v[0], v[1]); hi4.y = pack_bf16x2(v[2], v[3]);
+            hi4.z = pack_bf16x2(v[4], v[5]); hi4.w = pack_bf16x2(v[6], v[7]);
+            lo4.x = pack_bf16x2(v[0] - __uint_as_float(hi4.x << 16), v[1] - __uint_as_float(hi4.x & 0xffff0000u));
+            lo4.y = pack_bf16x2(v[2] - __uint_as_float(hi4.y << 16), v[3] - __uint_as_float(hi4.y & 0xffff0000u));
+            lo4.z = pack_bf16x2(v[4] - __uint_as_float(hi4.z << 16), v[5] - __uint_as_float(hi4.z & 0xffff0000u));
+            lo4.w = pack_bf16x2(v[6] - __uint_as_float(hi4.w << 16), v[7] - __uint_as_float(hi4.w & 0xffff0000u));
+            *reinterpret_cast<uint4*>(a_hi + soff) = hi4;
+            *reinterpret_cast<uint4*>(a_lo + soff) = lo4;
           }
         } else if (!DEFORM && XBF16) {
           // dense, bf16 activations: the 128-byte row IS the smem row -> cp.async 16 B per (row, chunk)
@@ -515,7 +582,9 @@ igemm_tc_kernel(const TcParams p) {
         //      -- and every residual read -- is made of fully used 32-byte sectors instead of one 16-byte
         //      fragment per 512-byte-strided row. ----
         float* st = reinterpret_cast<float*>(sm + L.epi) + (size_t)warp * 32 * TC_EPI_PITCH;
-        const int lpr = p.y_bf16 ? 4 : 8;              // lanes per row in the write-out phase
+        const bool y16 = p.y_bf16 || p.y_pair;          // 16-bit storage: 8 columns (16 B) per lane
+        const size_t ypitch = p.y_pair ? 2 * (size_t)p.Cout : (size_t)p.Cout;   // elements per stored pixel
+        const int lpr = y16 ? 4 : 8;                    // lanes per row in the write-out phase
         const int rpi = 32 / lpr;                       // rows per iteration
         const int sub = lane % lpr, rsub = lane / lpr;
         for (int cb = 0; cb < p.BN; cb += 32) {
@@ -538,21 +607,48 @@ igemm_tc_kernel(const TcParams p) {
             }
           }
           __syncwarp();
-          const int ce = p.y_bf16 ? sub * 8 : sub * 4;   // first staged column of this lane
+          const int ce = y16 ? sub * 8 : sub * 4;        // first staged column of this lane
           const int co = n0 + cb + ce;
           if (co < p.Cout) {
             for (int it = 0; it < lpr; ++it) {
               const int row = it * rpi + rsub;
               const long long pgr = tile_pixel(mt, q * 32 + row);
               if (pgr < 0) continue;
-              size_t ridx = (size_t)pgr * p.Cout + co;
+              size_t ridx = (size_t)pgr * ypitch + co;
               if (p.residual && p.res_up2) {
                 const int ni = (int)(pgr / HoWo), ppr = (int)(pgr - (long long)ni * HoWo);
                 const int ho = ppr / p.Wo, wo = ppr - ho * p.Wo;
-                ridx = (((size_t)ni * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.Cout + co;
+                ridx = (((size_t)ni * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * ypitch + co;
               }
               const float* src = st + row * TC_EPI_PITCH + ce;
-              if (p.y_bf16) {
+              if (p.y_pair) {
+                // hi/lo pair output: residual = hi + lo (exact in fp32), result split into bf16(o) and bf16(o - hi)
+                const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+                float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (p.residual) {
+                  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + ridx;
+                  const uint4 rh = __ldg(reinterpret_cast<const uint4*>(rp)), rl = __ldg(reinterpret_cast<const uint4*>(rp + p.Cout));
+                  const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w}, lw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    o[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                    o[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  hw[e] = pack_bf16x2(o[2 * e], o[2 * e + 1]);
+                  lw[e] = pack_bf16x2(o[2 * e] - __uint_as_float(hw[e] << 16), o[2 * e + 1] - __uint_as_float(hw[e] & 0xffff0000u));
+                }
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)pgr * ypitch + co;
+                *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(yp + p.Cout) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              } else if (p.y_bf16) {
                 const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
                 float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 if (p.residual) {
@@ -760,8 +856,14 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   p.w_lo = p.w_hi + (size_t)p.Cout_pad * tc_kp(p.Cin, KHW);
   const bool deform = p.offset != nullptr;
   const bool smallc = (p.Cin % TC_BK) != 0;
-  if (deform && p.x_bf16 && (long long)p.H * p.W * p.Cin >= (1ll << 31)) return UPSNET_E_UNSUPPORTED;   // int32 element offsets
-  if (smallc && (deform || p.x_bf16 || p.dh * (p.kh - 1) > 255 || p.dw * (p.kw - 1) > 255)) return UPSNET_E_UNSUPPORTED;
+  if (deform && (p.x_bf16 || p.x_pair) && (long long)p.H * p.W * p.Cin * (p.x_pair ? 2 : 1) >= (1ll << 31)) return UPSNET_E_UNSUPPORTED;   // int32 element offsets
+  if (smallc && (deform || p.x_bf16 || p.x_pair || p.dh * (p.kh - 1) > 255 || p.dw * (p.kw - 1) > 255)) return UPSNET_E_UNSUPPORTED;
+  if (p.x_pair && !p.x3) return UPSNET_E_UNSUPPORTED;          // pairs are the storage format of precision bf16x3
+  if (p.y_pair) {
+    // pair output: the staged NHWC epilogue only (16-byte vectors), plain [hi Cout][lo Cout] grouping
+    if (!p.out_nhwc || (p.Cout & 7) || (p.pair_group && p.pair_group != p.Cout)) return UPSNET_E_UNSUPPORTED;
+    if (p.residual && (((uintptr_t)p.residual) & 15)) return UPSNET_E_UNSUPPORTED;
+  }
   // tile N: as wide as possible (each gathered A tile is reused by BN couts)
   int BN = p.Cout_pad;
   const int bn_cap = p.x3 ? 128 : 256;
@@ -797,27 +899,33 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
   const size_t smem = L.total + 1024;
   // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
-  static bool configured = false;
-  if (!configured) {
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // opt in to the full 227 KB once per device (kept out of the per-launch path: CUDA-graph capture)
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UPS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // deformable instantiations: prefer the smallest shared-memory carve-out that fits, the rest of the 256 KB is L1
-    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
-    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
-    configured = true;
+    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+    (void)cudaFuncSetAttribute(igemm_tc_kernel<1, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
   }
   if (smallc) {
-    igemm_tc_kernel<2, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    igemm_tc_kernel<2, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+  } else if (p.x_pair) {
+    if (deform) igemm_tc_kernel<1, 2><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<0, 2><<<grid, TC_THREADS, smem, stream>>>(p);
   } else if (p.x_bf16) {
-    if (p.x3) return UPSNET_E_UNSUPPORTED;   // the hi/lo split needs fp32 activations
-    if (deform) igemm_tc_kernel<1, true><<<grid, TC_THREADS, smem, stream>>>(p);
-    else igemm_tc_kernel<0, true><<<grid, TC_THREADS, smem, stream>>>(p);
+    if (p.x3) return UPSNET_E_UNSUPPORTED;   // the hi/lo split needs fp32 or pair activations
+    if (deform) igemm_tc_kernel<1, 1><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<0, 1><<<grid, TC_THREADS, smem, stream>>>(p);
   } else {
-    if (deform) igemm_tc_kernel<1, false><<<grid, TC_THREADS, smem, stream>>>(p);
-    else igemm_tc_kernel<0, false><<<grid, TC_THREADS, smem, stream>>>(p);
+    if (deform) igemm_tc_kernel<1, 0><<<grid, TC_THREADS, smem, stream>>>(p);
+    else igemm_tc_kernel<0, 0><<<grid, TC_THREADS, smem, stream>>>(p);
   }
   UPS_CHECK_LAUNCH();
   return 0;

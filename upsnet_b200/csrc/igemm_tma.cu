@@ -51,6 +51,15 @@ struct TmaGeom {
   int rotate;                           // tile-dependent start of the K loop (see producer)
   int wres, wtiles;                     // halo mode with the n-tile's whole weight set (wtiles tiles) resident in smem, loaded once per CTA
   int dbg;                              // timing experiments only (UPSNET_TMA_DEBUG): 1 alternate accumulators, 2 one MMA per k-block, 3 no MMAs
+  // PAIR mode (precision bf16x3 on the TMA kernel): activations are hi/lo bf16 PAIRS -- an NHWC tensor with 2*C channels,
+  // channels [0,C) = bf16(x), [C,2C) = bf16(x - hi) -- weights are the packed hi/lo planes, every k-slice issues three
+  // MMAs (lo*hi, hi*lo, hi*hi) and the epilogue splits the fp32 result into a pair again.
+  int x3;
+  int x_lo;                             // channel coordinate of the input's lo plane (= Cin)
+  int w_lo;                             // row coordinate of the weight lo plane (= Cout_pad)
+  int pg;                               // output / residual pair group G: channels stored [hi G][lo G] per group (G = Cout normally)
+  int res_inplace;                      // residual slabs are TMA-loaded into the (double-buffered) output slabs and updated in place
+  int opairs;                           // output slab pairs that alternate (2, or 1 when shared memory is short)
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -79,6 +88,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -95,20 +105,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// pair tensors: channel coordinate of channel n's hi value when channels are stored [hi G][lo G] per group of G (lo = +G)
+__device__ __forceinline__ int pair_chan(int n, int G) { return (n / G) * 2 * G + (n % G); }
+
 struct TmaSmem {
   uint32_t stages, out, res, a_bytes, b_bytes, stage_bytes, total;
   uint32_t patch, patch_bytes;                               // halo mode: patch ring in front of a B-only ring
+  uint32_t a_half, b_half, patch_half;                       // pair mode: offset of the lo tile inside an A / B / patch slot
+  uint32_t oslabs, res_slab;                                 // pair mode: number of (hi, lo) output slab pairs; bytes per residual slab
 };
 __host__ __device__ inline TmaSmem tma_smem_layout(int BN, int stages, bool has_res, int patch_rows = 0, int pstages = 0,
-                                                  bool direct = false) {
+                                                  bool direct = false, bool x3 = false, bool res_up2 = false,
+                                                  bool res_inplace = false, int opairs = 2) {
   TmaSmem s;
-  s.a_bytes = patch_rows ? 0u : 128 * 128;
-  s.b_bytes = (uint32_t)BN * 128;
+  const uint32_t mul = x3 ? 2u : 1u;
+  s.a_half = 128 * 128; s.b_half = (uint32_t)BN * 128; s.patch_half = (uint32_t)patch_rows * 128u;
+  s.a_bytes = patch_rows ? 0u : s.a_half * mul;
+  s.b_bytes = s.b_half * mul;
   s.stage_bytes = s.a_bytes + s.b_bytes;
   s.patch = 1024;                                            // barriers live in the first KB
-  s.patch_bytes = (uint32_t)patch_rows * 128u;               // multiple of 2048 (16-pixel patch rows)
+  s.patch_bytes = s.patch_half * mul;                        // multiple of 2048 (16-pixel patch rows)
   s.stages = s.patch + s.patch_bytes * (uint32_t)pstages;
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
+  s.res_slab = (x3 && res_up2) ? 4096u : (uint32_t)TM_SLAB_BYTES;
+  if (x3) {
+    // pair mode: the eight epilogue warps work on ONE 64-channel slab pair at a time (two pairs alternate so that a TMA
+    // store can still be reading the first while the second is written); in-place residual: one pair per slab and buffer
+    s.oslabs = direct ? 0u : (res_inplace ? 2u * (uint32_t)(BN / 64) : (uint32_t)opairs);
+    s.res = s.out + s.oslabs * 2u * TM_SLAB_BYTES;
+    s.total = s.res + ((has_res && !res_inplace) ? 2u * (uint32_t)(BN / 64) * 2u * s.res_slab : 0u);
+    return s;
+  }
+  s.oslabs = 0;
   const uint32_t out_slabs = direct ? 0 : (BN == 64 ? 1 : 2);   // one output slab per epilogue group (TMA-store epilogue only)
   s.res = s.out + out_slabs * TM_SLAB_BYTES;
   s.total = s.res + (has_res ? 2u * (uint32_t)(BN / 64) * TM_SLAB_BYTES : 0u);   // two residual buffers (prefetch)
@@ -127,7 +155,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_dyn + (base - raw);
   const TmaSmem L = tma_smem_layout(g.BN, g.wres ? g.wtiles : g.stages, g.has_res != 0, g.halo ? g.patch_rows : 0, g.pstages,
-                                    g.direct != 0);
+                                    g.direct != 0, g.x3 != 0, g.res_up2 != 0, g.res_inplace != 0, g.opairs);
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // two residual buffers
@@ -155,7 +183,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_rfull + 8 * b, 1);
-        mbar_init(bar_rempty + 8 * b, TM_EPI_WARPS);
+        mbar_init(bar_rempty + 8 * b, g.res_inplace ? 1 : TM_EPI_WARPS);
       }
       for (int b = 0; b < 4; ++b) {
         mbar_init(bar_pfull + 8 * b, 1);
@@ -183,7 +211,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       uint32_t s = 0, ph = 0, sp = 0, php = 0;
       bool first_tile = true;
       uint32_t a_dst = base + L.stages;
-      const uint32_t tx_bytes = box_bytes + L.b_bytes;
+      const uint32_t tx_bytes = (g.x3 ? 2u * box_bytes : box_bytes) + L.b_bytes;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % g.n_tiles);
         const long long mt = tile / g.n_tiles;
@@ -200,12 +228,16 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (g.wres) {
               mbar_arrive_expect_tx(bar_full, (uint32_t)(g.KHW * cchunks) * L.b_bytes);
               for (int cc = 0; cc < cchunks; ++cc)
-                for (int tap = 0; tap < g.KHW; ++tap)
-                  tma_load_2d(base + L.stages + (uint32_t)(cc * g.KHW + tap) * L.b_bytes, &tm_w, bar_full, tap * g.Cin + cc * 64, n0);
+                for (int tap = 0; tap < g.KHW; ++tap) {
+                  const uint32_t wd = base + L.stages + (uint32_t)(cc * g.KHW + tap) * L.b_bytes;
+                  tma_load_2d(wd, &tm_w, bar_full, tap * g.Cin + cc * 64, n0);
+                  if (g.x3) tma_load_2d(wd + L.b_half, &tm_w, bar_full, tap * g.Cin + cc * 64, g.w_lo + n0);
+                }
             }
             mbar_wait(bar_pempty + 8 * sp, php ^ 1u);
             mbar_arrive_expect_tx(bar_pfull + 8 * sp, L.patch_bytes);
             tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, 0, w0 - g.pw, h0 - g.ph, i0);
+            if (g.x3) tma_load_4d(base + L.patch + sp * L.patch_bytes + L.patch_half, &tm_x, bar_pfull + 8 * sp, g.x_lo, w0 - g.pw, h0 - g.ph, i0);
             if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
           }
           const long long ntile = tile + gridDim.x;
@@ -223,6 +255,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               mbar_wait(bar_pempty + 8 * sp, php ^ 1u);
               mbar_arrive_expect_tx(bar_pfull + 8 * sp, L.patch_bytes);
               tma_load_4d(base + L.patch + sp * L.patch_bytes, &tm_x, bar_pfull + 8 * sp, ncc * 64, nw0 - g.pw, nh0 - g.ph, ni0);
+              if (g.x3) tma_load_4d(base + L.patch + sp * L.patch_bytes + L.patch_half, &tm_x, bar_pfull + 8 * sp, g.x_lo + ncc * 64, nw0 - g.pw, nh0 - g.ph, ni0);
               if (++sp == (uint32_t)g.pstages) { sp = 0; php ^= 1u; }
             }
             if (g.wres) continue;
@@ -233,6 +266,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               mbar_wait(bar_empty + 8 * s, ph ^ 1u);
               mbar_arrive_expect_tx(bf, L.b_bytes);
               tma_load_2d(a_dst, &tm_w, bf, tap * g.Cin + cc * 64, n0);
+              if (g.x3) tma_load_2d(a_dst + L.b_half, &tm_w, bf, tap * g.Cin + cc * 64, g.w_lo + n0);
               a_dst += L.stage_bytes;
               if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_dst = base + L.stages; }
             }
@@ -255,6 +289,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           else
             tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
           tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kbr * 64, n0);
+          if (g.x3) {
+            tma_load_4d(a_dst + L.a_half, &tm_x, bf, g.x_lo + cc * 64, cw, ch, i0);
+            tma_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kbr * 64, g.w_lo + n0);
+          }
           if (++kbr == num_kb) { kbr = 0; cc = 0; kj = 0; cw = w0 - g.pw; ch = h0 - g.ph; }
           else if (++cc == cchunks) {
             cc = 0; cw += g.dw;
@@ -275,6 +313,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // whose MMAs are short (N <= 128), so it is kept to a handful of instructions per k-block.
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4, a16 = L.a_bytes >> 4;
+      const uint32_t ah16 = L.a_half >> 4, bh16 = L.b_half >> 4, ph16 = L.patch_half >> 4;   // pair mode: lo-tile offsets
       uint32_t s = 0, ph = 0, a_lo = a_lo0, ti_local = 0, sp = 0, php = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
@@ -304,6 +343,11 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const uint32_t pa_lo = (a_start >> 4) & 0x3fffu;
 #pragma unroll
                 for (uint32_t k = 0; k < 4; ++k) {
+                  if (g.x3) {
+                    umma_bf16_lohi2(tmem_d, pa_lo + ph16 + 2 * k, hi_a0, b_lo + 2 * k, desc_hi, idesc, acc);
+                    umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, hi_a0, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
+                    acc = 1u;
+                  }
                   umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, hi_a0, b_lo + 2 * k, desc_hi, idesc, acc);
                   acc = 1u;
                 }
@@ -323,6 +367,11 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               const uint32_t pa_lo = (a_start >> 4) & 0x3fffu, pa_hi = hi_a0;
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k) {
+                if (g.x3) {
+                  umma_bf16_lohi2(tmem_d, pa_lo + ph16 + 2 * k, pa_hi, a_lo + 2 * k, desc_hi, idesc, acc);
+                  umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, pa_hi, a_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
+                  acc = 1u;
+                }
                 umma_bf16_lohi2(tmem_d, pa_lo + 2 * k, pa_hi, a_lo + 2 * k, desc_hi, idesc, acc);
                 acc = 1u;
               }
@@ -345,6 +394,11 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           for (uint32_t k = 0; k < 4; ++k) {       // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle span
             if (g.dbg == 3 || (g.dbg == 2 && k)) continue;
             const uint32_t td = (g.dbg == 1 && (k & 1)) ? (tmem_base + (buf ^ 1u) * (uint32_t)g.BN) : tmem_d;
+            if (g.x3) {      // (hi + lo) * (hi + lo) without the lo * lo term: relative error ~2^-16
+              umma_bf16_lohi(td, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
+              umma_bf16_lohi(td, a_lo + 2 * k, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
+              acc = 1u;
+            }
             umma_bf16_lohi(td, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
             acc = 1u;
           }
@@ -371,6 +425,20 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const uint32_t rb = ti_local & 1u, ruse = ti_local >> 1;
         const uint32_t rdst = base + L.res + rb * (uint32_t)slabs * TM_SLAB_BYTES;
         mbar_wait(bar_rempty + 8 * rb, (ruse & 1u) ^ 1u);
+        if (g.x3) {
+          // pair mode: (hi, lo) slab per 64 channels; in-place mode lands them in this tile's output slab pairs
+          const uint32_t lo_off = g.res_inplace ? (uint32_t)TM_SLAB_BYTES : L.res_slab;
+          const uint32_t pdst = g.res_inplace ? base + L.out + rb * (uint32_t)slabs * 2u * TM_SLAB_BYTES
+                                              : base + L.res + rb * (uint32_t)slabs * 2u * L.res_slab;
+          mbar_arrive_expect_tx(bar_rfull + 8 * rb, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs * 2u);
+          for (int s = 0; s < slabs; ++s) {
+            const int c = pair_chan(nt * g.BN + s * 64, g.pg);
+            tma_load_4d(pdst + (uint32_t)s * 2u * lo_off, &tm_r, bar_rfull + 8 * rb, c, w0 >> g.res_up2, h0 >> g.res_up2, i0);
+            tma_load_4d(pdst + (uint32_t)s * 2u * lo_off + lo_off, &tm_r, bar_rfull + 8 * rb, c + g.pg, w0 >> g.res_up2,
+                        h0 >> g.res_up2, i0);
+          }
+          continue;
+        }
         // res_up2: the box of the half-resolution map that covers this tile is (bw/2, bh/2) at (w0/2, h0/2)
         mbar_arrive_expect_tx(bar_rfull + 8 * rb, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs);
         for (int s = 0; s < slabs; ++s)
@@ -397,7 +465,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       rrow = (w >> 1) + (g.bw >> 1) * ((h >> 1) + (g.bh >> 1) * n);
     }
     const uint32_t rs_row = (uint32_t)rrow * 128u, rrx = (uint32_t)(rrow & 7);
-    uint32_t ti_local = 0;
+    uint32_t ti_local = 0, oc = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti_local) {
       const int nt = (int)(tile % g.n_tiles);
       const long long mt = tile / g.n_tiles;
@@ -438,6 +506,91 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        continue;
+      }
+      if (g.x3) {
+        // ---- pair epilogue: all eight warps share one 64-channel (hi, lo) slab pair at a time; half h owns its columns
+        //      [32h, 32h + 32).  fp32 result -> hi = bf16(o), lo = bf16(o - hi) -> two swizzled slabs -> two TMA stores ----
+        const int nslab = g.BN / 64;
+        const uint32_t jb = (uint32_t)half * 4u;
+        const bool lead = warp == 0 && lane == 0;
+        for (int sl = 0; sl < nslab; ++sl, ++oc) {
+          const int u = 2 * sl + half;
+          uint32_t v0[16], v1[16];
+          tmem_ld16_issue(trow + (uint32_t)(u * 32), v0);
+          tmem_ld16_issue(trow + (uint32_t)(u * 32 + 16), v1);
+          uint32_t ob;
+          if (g.res_inplace) {
+            ob = base + L.out + (buf * (uint32_t)nslab + (uint32_t)sl) * 2u * TM_SLAB_BYTES;   // holds this slab's residual
+          } else {
+            ob = base + L.out + (g.opairs == 2 ? (oc & 1u) : 0u) * 2u * TM_SLAB_BYTES;
+            if (lead) {                             // the stores that last used this pair have finished reading it
+              if (g.opairs == 2) bulk_wait_read1(); else bulk_wait_read0();
+            }
+            named_bar_sync(1, 256);
+          }
+          tmem_ld_wait();
+          float o[32];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { o[e] = __uint_as_float(v0[e]); o[16 + e] = __uint_as_float(v1[e]); }
+          if (g.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + u * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 b4 = __ldg(bp + e);
+              o[4 * e] += b4.x; o[4 * e + 1] += b4.y; o[4 * e + 2] += b4.z; o[4 * e + 3] += b4.w;
+            }
+          }
+          if (g.has_res) {
+            uint32_t rh, rl, xr;
+            if (g.res_inplace) { rh = ob + sw_row; rl = rh + TM_SLAB_BYTES; xr = rx; }
+            else { rh = base + L.res + (buf * (uint32_t)nslab + (uint32_t)sl) * 2u * L.res_slab + rs_row; rl = rh + L.res_slab; xr = rrx; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 hv = lds128(rh + (((jb + c) ^ xr) << 4)), lv = lds128(rl + (((jb + c) ^ xr) << 4));
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                o[c * 8 + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                o[c * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              }
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = fmaxf(o[e], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = o[c * 8 + 2 * e], b = o[c * 8 + 2 * e + 1];
+              hw[e] = pack_bf16x2(a, b);
+              lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xffff0000u));
+            }
+            sts128(ob + sw_row + (((jb + c) ^ rx) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            sts128(ob + TM_SLAB_BYTES + sw_row + (((jb + c) ^ rx) << 4), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 256);
+          if (lead) {
+            const int c = pair_chan(n0 + sl * 64, g.pg);
+            tma_store_4d(&tm_y, ob, c, w0, h0, i0);
+            tma_store_4d(&tm_y, ob + TM_SLAB_BYTES, c + g.pg, w0, h0, i0);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_tempty + 8 * buf);
+          if (g.has_res && !g.res_inplace) mbar_arrive(bar_rempty + 8 * buf);
+        }
+        if (g.res_inplace && lead) {     // the slab pairs of this tile may be refilled once their stores have been read out
+          bulk_wait_read0();
+          mbar_arrive(bar_rempty + 8 * buf);
+        }
         continue;
       }
       for (int ui = 0; ui < upw; ++ui) {
@@ -504,7 +657,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (g.has_res) mbar_arrive(bar_rempty + 8 * buf);
       }
     }
-    if (leader) bulk_wait0();
+    if (leader || (g.x3 && warp == 0 && lane == 0)) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -574,10 +727,17 @@ static void tma_pick_box(int N, int Ho, int Wo, int kh, int kw, int dh, int dw, 
 }
 
 int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream) {
-  if (p.no_tma || p.offset || p.x3 || !p.x_bf16) return UPSNET_E_UNSUPPORTED;
-  // slab epilogue (TMA store): bf16 NHWC output with Cout % 64 == 0; everything else without a residual goes
+  if (p.no_tma || p.offset) return UPSNET_E_UNSUPPORTED;
+  // precision bf16 runs on bf16 activations, precision bf16x3 on hi/lo bf16 pairs (same tile pipeline, three MMAs)
+  const bool pair = p.x_pair != 0;
+  if (pair != (p.x3 != 0) || (!pair && !p.x_bf16)) return UPSNET_E_UNSUPPORTED;
+  if (p.y_pair && (!pair || !p.out_nhwc || (p.Cout % 64) != 0)) return UPSNET_E_UNSUPPORTED;
+  if (pair && p.y_bf16) return UPSNET_E_UNSUPPORTED;     // pair in -> pair (slab epilogue) or fp32 (direct epilogue) out
+  const int pg = p.y_pair ? (p.pair_group > 0 ? p.pair_group : p.Cout) : 0;
+  if (p.y_pair && ((pg % 64) != 0 || (p.Cout % pg) != 0)) return UPSNET_E_UNSUPPORTED;
+  // slab epilogue (TMA store): bf16 / pair NHWC output with Cout % 64 == 0; everything else without a residual goes
   // through the direct-store epilogue (small heads: Cout 9..45, fp32 planes)
-  const bool direct = !p.y_bf16 || !p.out_nhwc || (p.Cout % 64) != 0;
+  const bool direct = (!p.y_bf16 && !p.y_pair) || !p.out_nhwc || (p.Cout % 64) != 0;
   if (direct && (p.residual || p.Cout > 256)) return UPSNET_E_UNSUPPORTED;
   if (p.res_up2 && (!p.residual || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_UNSUPPORTED;
   // stride > 1 only for 1x1 / pad 0 (the ResNet down-sampling convs): the input is then addressed through a
@@ -616,6 +776,12 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
   const int Cout_pad = p.Cout <= 32 ? 32 : (p.Cout + 63) / 64 * 64;      // rows of the packed weight planes (tc_cout_pad)
   int BN = (Cout_pad % 256 == 0 && !g.has_res) ? 256 : ((Cout_pad % 128 == 0) ? 128 : (Cout_pad % 64 == 0 ? 64 : 32));
+  // pair mode: operand tiles are twice as large -- N tile <= 128, and 64 next to residual slab pairs (shared memory)
+  g.x3 = pair ? 1 : 0; g.x_lo = p.Cin; g.w_lo = Cout_pad; g.pg = pg;
+  g.res_inplace = (pair && g.has_res && !g.res_up2) ? 1 : 0;
+  g.opairs = 2;
+  if (pair && BN > 128) BN = 128;
+  if (pair && g.has_res && BN > 64) BN = 64;
   // N tile: as wide as possible (operand bytes per flop fall with BN) while ~2/3 of the SMs still get a tile; measured
   // on B200 (profiles/r1_bn_sweep.md): 64 m-tiles x Cout 256 -> BN 128 (128 CTAs) beats BN 64 (256 tiles) by 38 %
   // and BN 256 (64 CTAs) by 11 %; 16 m-tiles x Cout 512 -> BN 64 (128 CTAs) stays best.
@@ -623,7 +789,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   (void)sms;
   if (const char* fb = getenv("UPSNET_TMA_FORCE_BN")) {     // tuning hook (scripts/bn_sweep.py): force the N tile
     const int v = atoi(fb);
-    if ((v == 64 || v == 128 || v == 256) && Cout_pad % v == 0 && !(g.has_res && v > 128)) BN = v;
+    if ((v == 64 || v == 128 || v == 256) && Cout_pad % v == 0 && !(g.has_res && v > 128) && !(pair && (v > 128 || (g.has_res && v > 64)))) BN = v;
   }
   if (halo && BN == 256 && halo_env < 2) {     // wide-N layers are MMA-bound: keep the fewest-tiles box for them
     halo = false;
@@ -647,29 +813,56 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   if (halo && Cout_pad == BN) {
     const int wtiles = g.KHW * (p.Cin / 64);
     for (int ps = 4; ps >= 2 && !g.wres; --ps) {
-      L = tma_smem_layout(BN, wtiles, g.has_res != 0, g.patch_rows, ps, direct);
+      L = tma_smem_layout(BN, wtiles, g.has_res != 0, g.patch_rows, ps, direct, pair, g.res_up2 != 0, g.res_inplace != 0, g.opairs);
       if (L.total + 1024 <= 227 * 1024) { g.wres = 1; g.wtiles = wtiles; g.pstages = ps; stages = 1; }
     }
   }
   if (!g.wres) {
-    L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct);
-    while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct); }
-    if (L.total + 1024 > 227 * 1024 && g.pstages > 2) {
-      g.pstages = 2;
-      L = tma_smem_layout(BN, stages, g.has_res != 0, g.patch_rows, g.pstages, direct);
+    const uint32_t cap = 227 * 1024 - 1024;
+    auto lay = [&](int st) { return tma_smem_layout(BN, st, g.has_res != 0, g.patch_rows, g.pstages, direct, pair, g.res_up2 != 0, g.res_inplace != 0, g.opairs); };
+    // deepest ring that fits (<= TM_MAX_STAGES, >= 2); pair mode: if two alternating output slab pairs leave fewer than
+    // four stages, one pair buys another stage -- the main loop needs the depth more than the epilogue does
+    auto fit = [&]() {
+      g.opairs = 2;
+      stages = TM_MAX_STAGES;
+      while (stages > 2 && lay(stages).total > cap) --stages;
+      if (pair && !direct && !g.res_inplace && stages < 4) {
+        g.opairs = 1;
+        int st1 = 4;
+        while (st1 > 2 && lay(st1).total > cap) --st1;
+        if (st1 > stages || lay(stages).total > cap) stages = st1; else g.opairs = 2;
+      }
+      L = lay(stages);
+      return L.total <= cap;
+    };
+    if (pair && halo) g.pstages = 2;       // pair patches are 2 x 36 KB (3x3): two slots, the rest goes to the weight ring
+    bool ok = fit();
+    if (!ok && g.pstages > 2) { g.pstages = 2; ok = fit(); }
+    if (!ok && pair && halo) {
+      // pair mode: the patch slots do not fit next to a weight ring for this N tile -- plain per-tap boxes instead
+      halo = false;
+      g.halo = 0; g.patch_rows = 0; g.pstages = 0;
+      tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, g.res_up2 != 0, &g.bw, &g.bh, &g.bn);
+      g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
+      g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
+      g.tiles_n = (p.N + g.bn - 1) / g.bn;
+      m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+      ok = fit();
     }
-    if (L.total + 1024 > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+    if (!ok) return UPSNET_E_UNSUPPORTED;
   }
   g.stages = stages;
 
   const int Kp = g.KHW * p.Cin;
   CUtensorMap tm_x, tm_w, tm_y, tm_r;
   {
-    const cuuint64_t dx[4] = {(cuuint64_t)p.Cin, (cuuint64_t)(strided ? p.Wo : p.W), (cuuint64_t)(strided ? p.Ho : p.H),
+    const cuuint64_t xm = pair ? 2 : 1;      // pair tensors carry 2*C channels per pixel (hi plane, lo plane)
+    const cuuint64_t dx[4] = {(cuuint64_t)p.Cin * xm, (cuuint64_t)(strided ? p.Wo : p.W), (cuuint64_t)(strided ? p.Ho : p.H),
                               (cuuint64_t)p.N};
-    const cuuint64_t sx[3] = {(cuuint64_t)p.sw * p.Cin * 2, (cuuint64_t)p.sh * p.W * p.Cin * 2, (cuuint64_t)p.H * p.W * p.Cin * 2};
-    const cuuint64_t dy[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
-    const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)Cout_pad};
+    const cuuint64_t sx[3] = {(cuuint64_t)p.sw * p.Cin * 2 * xm, (cuuint64_t)p.sh * p.W * p.Cin * 2 * xm,
+                              (cuuint64_t)p.H * p.W * p.Cin * 2 * xm};
+    const cuuint64_t dy[4] = {(cuuint64_t)p.Cout * xm, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+    const cuuint64_t dwt[2] = {(cuuint64_t)Kp, (cuuint64_t)Cout_pad * xm};       // the packed weights ARE [hi plane][lo plane]
     const cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
     const cuuint32_t boxp[4] = {64, 16, (cuuint32_t)patch_h, 1};            // halo mode: the input patch of a tile
     const cuuint32_t boxw[2] = {64, (cuuint32_t)BN};
@@ -681,7 +874,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
     } else {
     if (!encode_bf16(enc, &tm_y, p.y, 4, dy, box)) return UPSNET_E_UNSUPPORTED;
     if (g.res_up2) {
-      const cuuint64_t dr[4] = {(cuuint64_t)p.Cout, (cuuint64_t)(p.Wo / 2), (cuuint64_t)(p.Ho / 2), (cuuint64_t)p.N};
+      const cuuint64_t dr[4] = {(cuuint64_t)p.Cout * xm, (cuuint64_t)(p.Wo / 2), (cuuint64_t)(p.Ho / 2), (cuuint64_t)p.N};
       const cuuint32_t boxr[4] = {64, (cuuint32_t)(g.bw / 2), (cuuint32_t)(g.bh / 2), (cuuint32_t)g.bn};
       if (!encode_bf16(enc, &tm_r, p.residual, 4, dr, boxr)) return UPSNET_E_UNSUPPORTED;
     } else if (!encode_bf16(enc, &tm_r, p.residual ? p.residual : p.y, 4, dy, box)) {
@@ -691,10 +884,9 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   }
   const long long num_tiles = m_tiles * g.n_tiles;
   if (num_tiles <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static ups::PerDeviceOnce configured;
+  if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
   igemm_tma_kernel<<<grid, TM_THREADS, L.total + 1024, stream>>>(tm_x, tm_w, tm_y, tm_r, g);
@@ -824,10 +1016,9 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
     stem_pack_image_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (uint4*)workspace, N, Cin, H, W, pad, Hp, Wp);
     UPS_CHECK_LAUNCH();
   }
-  static bool configured = false;
-  if (!configured) {
+  static ups::PerDeviceOnce configured;
+  if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   static int sms = 0;
   if (sms == 0) {

@@ -240,10 +240,9 @@ extern "C" int upsnet_nms_segmented(const float* boxes, const int* seg_offsets, 
   UPS_CHECK_LAUNCH();
   const size_t smem_all = ((size_t)max_seg_len + 1) * tiles * sizeof(unsigned long long);
   if (smem_all <= 200 * 1024) {   // whole per-segment bitmask fits in shared memory
-    static bool configured = false;
-    if (!configured) {
+    static ups::PerDeviceOnce configured;
+    if (configured.need()) {
       UPS_CUDA(cudaFuncSetAttribute(nms_sweep_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
     }
     nms_sweep_smem_kernel<<<S, kSweepSmemThreads, smem_all, st>>>(seg_offsets, max_seg_len,
                                                                   (const unsigned long long*)workspace, keep_out, keep_cnt);

@@ -625,10 +625,9 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
   {
-    static bool configured = false;
-    if (!configured) {   // up to kMaxList * 28 B of per-instance metadata
+    static ups::PerDeviceOnce configured;
+    if (configured.need()) {   // up to kMaxList * 28 B of per-instance metadata
       UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
-      configured = true;
     }
   }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
@@ -677,10 +676,9 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   pan_prep_kernel<<<1, 1024, 0, st>>>(boxes, cls_prob, cls_idx, n, n_dev, H, W, ws);
   UPS_CHECK_LAUNCH();
   {
-    static bool configured = false;
-    if (!configured) {   // up to kMaxList * 28 B of per-instance metadata
+    static ups::PerDeviceOnce configured;
+    if (configured.need()) {   // up to kMaxList * 28 B of per-instance metadata
       UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
-      configured = true;
     }
   }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget

@@ -47,20 +47,65 @@ __global__ void maxpool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restri
   }
 }
 
+// hi/lo pair storage ([N,H,W,2C] bf16: C hi values then C lo values per pixel): the window element with the largest
+// hi + lo (exact in fp32) is copied as it is -- both halves -- so the result is again a canonical pair.
+__global__ void maxpool_nhwc_pair_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV,
+                                         int Ho, int Wo, int k, int s, int pad) {
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    long long pix = t / CV;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+    const int h0 = ho * s - pad, w0 = wo * s - pad;
+    float best[8];
+    uint32_t bh[4], bl[4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { bh[e] = 0xff80ff80u; bl[e] = 0u; }
+    for (int i = 0; i < k; ++i) {
+      const int h = h0 + i;
+      if (h < 0 || h >= H) continue;
+      for (int j = 0; j < k; ++j) {
+        const int w = w0 + j;
+        if (w < 0 || w >= W) continue;
+        const size_t base = (((size_t)n * H + h) * W + w) * (size_t)(2 * CV);
+        const uint4 vh = __ldg(x + base + cv), vl = __ldg(x + base + CV + cv);
+        const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+          const float b = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+          if (a > best[2 * e]) { best[2 * e] = a; bh[e] = (bh[e] & 0xffff0000u) | (hw[e] & 0xffffu); bl[e] = (bl[e] & 0xffff0000u) | (lw[e] & 0xffffu); }
+          if (b > best[2 * e + 1]) { best[2 * e + 1] = b; bh[e] = (bh[e] & 0xffffu) | (hw[e] & 0xffff0000u); bl[e] = (bl[e] & 0xffffu) | (lw[e] & 0xffff0000u); }
+        }
+      }
+    }
+    const size_t ob = (size_t)(t / CV) * (size_t)(2 * CV);
+    y[ob + cv] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+    y[ob + CV + cv] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+  }
+}
+
 }  // namespace ups
 
 extern "C" int upsnet_maxpool2d_nhwc(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad,
                                      int dtype, void* stream) {
   if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0 || 2 * pad > k) return UPSNET_E_BADARG;
-  const int vec = dtype == UPSNET_DTYPE_BF16 ? 8 : 4;
-  if (dtype != UPSNET_DTYPE_BF16 && dtype != UPSNET_DTYPE_F32) return UPSNET_E_BADARG;
+  const int vec = dtype == UPSNET_DTYPE_F32 ? 4 : 8;
+  if (dtype != UPSNET_DTYPE_BF16 && dtype != UPSNET_DTYPE_F32 && dtype != UPSNET_DTYPE_PAIR) return UPSNET_E_BADARG;
   if (C % vec || (((uintptr_t)x) & 15) || (((uintptr_t)y) & 15)) return UPSNET_E_UNSUPPORTED;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
   const long long total = (long long)N * Ho * Wo * (C / vec);
   long long blocks = (total + 255) / 256;
   if (blocks > ups::kNumSMs * 32) blocks = ups::kNumSMs * 32;
-  if (dtype == UPSNET_DTYPE_BF16)
+  if (dtype == UPSNET_DTYPE_PAIR)
+    ups::maxpool_nhwc_pair_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, N, H, W, C / vec, Ho, Wo, k, stride, pad);
+  else if (dtype == UPSNET_DTYPE_BF16)
     ups::maxpool_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)x, (uint4*)y, N, H, W, C / vec, Ho, Wo, k, stride, pad);
   else

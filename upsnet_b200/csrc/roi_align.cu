@@ -276,11 +276,104 @@ roi_align_nhwc_bf16_roi_kernel(FpnFeats f, int C, const float* __restrict__ rois
   }
 }
 
+// hi/lo pair features in ([B,H,W,2C] bf16 per level), pair result out: the blend runs on hi + lo (exact in fp32) and the
+// fp32 bin average is split again.  Output addressing is (roi_stride, pix_stride, lo_off) in elements:
+//   pair pixels [R,PH,PW,2C]   (mask branch: the 14x14 roi maps feed 3x3 convs)   -> (PH*PW*2C, 2C, C)
+//   flat pair   [R,2,PH*PW*C]  (RCNN fc6: one 'pixel' per roi with PH*PW*C channels) -> (2*PH*PW*C, C, PH*PW*C)
+// Same sample arithmetic and accumulation order as the bf16 / fp32 kernels above.
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_pair_roi_kernel(FpnFeats f, int C, const float* __restrict__ rois, int R, int PH, int PW, int sr,
+                               __nv_bfloat16* __restrict__ out, long long roi_stride, int pix_stride, long long lo_off,
+                               int* __restrict__ levels_out) {
+  __shared__ int4 s_off[kRoiMaxSamples];
+  __shared__ float4 s_w[kRoiMaxSamples];
+  const int n = blockIdx.x;
+  const float* r = rois + (size_t)n * 5;
+  const int b = (int)roundf(r[0]);
+  const float rx1 = r[1], ry1 = r[2], rx2 = r[3], ry2 = r[4];
+  const int lv = f.nlevels > 1 ? fpn_level_of(rx1, ry1, rx2, ry2) : 0;
+  if (levels_out && threadIdx.x == 0) levels_out[n] = lv;
+  const int H = f.H[lv], W = f.W[lv];
+  const float sc = f.scale[lv];
+  const float rsw = rx1 * sc, rsh = ry1 * sc, rew = rx2 * sc, reh = ry2 * sc;
+  const float rw = fmaxf(rew - rsw, 1.f), rh = fmaxf(reh - rsh, 1.f);
+  const float bsh = rh / (float)PH, bsw = rw / (float)PW;
+  const int gh = sr, gw = sr;
+  const float cnt = (float)(gh * gw);
+  const int per_bin = gh * gw, nsamp = PH * PW * per_bin;
+  for (int t = threadIdx.x; t < nsamp; t += blockDim.x) {
+    const int bin = t / per_bin, q = t - bin * per_bin;
+    const int ph = bin / PW, pw = bin - ph * PW, iy = q / gw, ix = q - iy * gw;
+    const float y = rsh + ph * bsh + (float)(iy + .5f) * bsh / (float)gh;
+    const float x = rsw + pw * bsw + (float)(ix + .5f) * bsw / (float)gw;
+    const SamplePos sp = roi_sample(H, W, y, x);
+    s_off[t] = make_int4(sp.o00 * 2 * C, sp.o01 * 2 * C, sp.o10 * 2 * C, sp.o11 * 2 * C);
+    s_w[t] = make_float4(sp.w00, sp.w01, sp.w10, sp.w11);
+  }
+  __syncthreads();
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(f.p[lv]) + (size_t)b * H * W * 2 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int bin = warp; bin < PH * PW; bin += nwarp) {
+    for (int c = lane * 8; c < C; c += 256) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < per_bin; ++q) {
+        const int4 o = s_off[bin * per_bin + q];
+        const float4 w = s_w[bin * per_bin + q];
+        const __nv_bfloat16* p0 = base + o.x + c; const __nv_bfloat16* p1 = base + o.y + c;
+        const __nv_bfloat16* p2 = base + o.z + c; const __nv_bfloat16* p3 = base + o.w + c;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(p0)), l0 = __ldg(reinterpret_cast<const uint4*>(p0 + C));
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(p1)), l1 = __ldg(reinterpret_cast<const uint4*>(p1 + C));
+        const uint4 h2 = __ldg(reinterpret_cast<const uint4*>(p2)), l2 = __ldg(reinterpret_cast<const uint4*>(p2 + C));
+        const uint4 h3 = __ldg(reinterpret_cast<const uint4*>(p3)), l3 = __ldg(reinterpret_cast<const uint4*>(p3 + C));
+        const uint32_t A[4] = {h0.x, h0.y, h0.z, h0.w}, a[4] = {l0.x, l0.y, l0.z, l0.w};
+        const uint32_t B[4] = {h1.x, h1.y, h1.z, h1.w}, bq[4] = {l1.x, l1.y, l1.z, l1.w};
+        const uint32_t D[4] = {h2.x, h2.y, h2.z, h2.w}, d[4] = {l2.x, l2.y, l2.z, l2.w};
+        const uint32_t E[4] = {h3.x, h3.y, h3.z, h3.w}, e[4] = {l3.x, l3.y, l3.z, l3.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += (w.x * (__uint_as_float(A[k] << 16) + __uint_as_float(a[k] << 16)) +
+                         w.y * (__uint_as_float(B[k] << 16) + __uint_as_float(bq[k] << 16)) +
+                         w.z * (__uint_as_float(D[k] << 16) + __uint_as_float(d[k] << 16)) +
+                         w.w * (__uint_as_float(E[k] << 16) + __uint_as_float(e[k] << 16)));
+          acc[2 * k + 1] += (w.x * (__uint_as_float(A[k] & 0xffff0000u) + __uint_as_float(a[k] & 0xffff0000u)) +
+                             w.y * (__uint_as_float(B[k] & 0xffff0000u) + __uint_as_float(bq[k] & 0xffff0000u)) +
+                             w.z * (__uint_as_float(D[k] & 0xffff0000u) + __uint_as_float(d[k] & 0xffff0000u)) +
+                             w.w * (__uint_as_float(E[k] & 0xffff0000u) + __uint_as_float(e[k] & 0xffff0000u)));
+        }
+      }
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float u = acc[2 * k] / cnt, v = acc[2 * k + 1] / cnt;
+        __nv_bfloat162 hh = __floats2bfloat162_rn(u, v);
+        hw[k] = *reinterpret_cast<uint32_t*>(&hh);
+        __nv_bfloat162 ll = __floats2bfloat162_rn(u - __uint_as_float(hw[k] << 16), v - __uint_as_float(hw[k] & 0xffff0000u));
+        lw[k] = *reinterpret_cast<uint32_t*>(&ll);
+      }
+      __nv_bfloat16* op = out + (size_t)n * roi_stride + (size_t)bin * pix_stride + c;
+      *reinterpret_cast<uint4*>(op) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(op + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
+
 static int launch_roi_align(const FpnFeats& f, int B, int C, int layout, int dtype, const float* rois, int R,
                             int PH, int PW, int sr, void* out_v, int* levels_out,
                             cudaStream_t stream) {
   if (R < 0 || C <= 0 || PH <= 0 || PW <= 0 || B <= 0) return UPSNET_E_BADARG;
   if (R == 0) return 0;
+  if (dtype == UPSNET_DTYPE_PAIR) {
+    if (layout != UPSNET_LAYOUT_NHWC && layout != UPSNET_LAYOUT_FLAT_PAIR) return UPSNET_E_UNSUPPORTED;
+    if (sr <= 0 || (C & 7) || (long long)PH * PW * sr * sr > kRoiMaxSamples || (((uintptr_t)out_v) & 15)) return UPSNET_E_UNSUPPORTED;
+    for (int l = 0; l < f.nlevels; ++l)
+      if ((((uintptr_t)f.p[l]) & 15) || (long long)f.H[l] * f.W[l] * 2 * C >= (1ll << 31)) return UPSNET_E_UNSUPPORTED;
+    const long long plane = (long long)PH * PW * C;
+    const bool flat = layout == UPSNET_LAYOUT_FLAT_PAIR;
+    roi_align_nhwc_pair_roi_kernel<<<R, 256, 0, stream>>>(f, C, rois, R, PH, PW, sr, (__nv_bfloat16*)out_v, 2 * plane,
+                                                          flat ? C : 2 * C, flat ? plane : (long long)C, levels_out);
+    UPS_CHECK_LAUNCH();
+    return 0;
+  }
   if (dtype == UPSNET_DTYPE_BF16) {
     if (layout != UPSNET_LAYOUT_NHWC || (C & 3)) return UPSNET_E_UNSUPPORTED;
     for (int l = 0; l < f.nlevels; ++l) if (((uintptr_t)f.p[l]) & 7) return UPSNET_E_BADARG;

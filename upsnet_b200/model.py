@@ -212,8 +212,11 @@ class FPN(nn.Module):
     def forward(self, res2, res3, res4, res5):
         p5_1x1 = self._c(self.fpn_p5_1x1, res5)
         if hasattr(self, "fpn_gap"):
-            gap = ops.linear(res5.float().mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias)
-            p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1).to(p5_1x1.dtype)
+            gap = ops.linear(res5.float().mean(dim=(2, 3)), self.fpn_gap.weight, self.fpn_gap.bias, out_dtype=torch.float32)
+            if isinstance(p5_1x1, ops.Pair):
+                p5_1x1 = ops.Pair.from_float(p5_1x1.float() + gap.view(-1, self.feature_dim, 1, 1))
+            else:
+                p5_1x1 = p5_1x1 + gap.view(-1, self.feature_dim, 1, 1).to(p5_1x1.dtype)
         # lateral 1x1 + nearest-2x-upsampled coarser level, fused into the conv epilogue (no upsampled tensor)
         p4_plus = self._c(self.fpn_p4_1x1, res4, residual=p5_1x1, up2=True)
         p3_plus = self._c(self.fpn_p3_1x1, res3, residual=p4_plus, up2=True)
@@ -222,7 +225,7 @@ class FPN(nn.Module):
         p4 = self._c(self.fpn_p4, p4_plus, padding=1)
         p3 = self._c(self.fpn_p3, p3_plus, padding=1)
         p2 = self._c(self.fpn_p2, p2_plus, padding=1)
-        p6 = p5[:, :, ::2, ::2].contiguous()                            # MaxPool2d(kernel 1, stride 2)
+        p6 = ops.subsample2(p5)                                         # MaxPool2d(kernel 1, stride 2)
         return p2, p3, p4, p5, p6
 
 
@@ -284,6 +287,15 @@ class RCNN(nn.Module):
         self._w6_nhwc = w6.view(w6.shape[0], -1, ps, ps).permute(0, 2, 3, 1).reshape(w6.shape[0], -1).contiguous()
 
     def forward(self, feat, rois):
+        if isinstance(feat[0], ops.Pair):
+            # hi/lo pair stream: ROIAlign writes the flattened (ph, pw, c) feature as one pair 'pixel' per roi
+            ps = self.pool_size
+            pool = ops.fpn_roi_align(list(feat), rois, ps, ps, self.roi_pooling.spatial_scale, layout="flat_pair")
+            fc6 = ops.linear(pool, self._w6_nhwc, self.fc6[0].bias, relu=True)
+            fc7 = ops.linear(fc6, self.fc7[0].weight, self.fc7[0].bias, relu=True)
+            both = ops.linear(fc7, self._f[0], self._f[1], out_dtype=torch.float32).float()
+            return {"cls_score": both[:, :self.num_classes].contiguous(),
+                    "bbox_pred": both[:, self.num_classes:].contiguous(), "fc_feat": fc7}
         pool = self.roi_pooling(feat, rois)
         nhwc = pool.permute(0, 2, 3, 1)
         if self._f is not None and nhwc.is_contiguous() and not pool.is_contiguous():
@@ -327,6 +339,16 @@ class MaskBranch(nn.Module):
             c = getattr(self, "mask_conv%d" % i)[0]
             x = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
         w1, b1, cout = self._f
+        if isinstance(x, ops.Pair):
+            # pair stream: the deconv-as-1x1 conv writes its four (a, b) groups as [hi Cout][lo Cout] each, i.e. directly
+            # as the Pair of 4w 'pixels' per row that mask_score (1x1) then scores -- same commutation as below
+            yv = ops.conv2d(x, w1, b1, relu=True, pair_group=cout)                                # Pair [n, Cout, h, 4w]
+            n, _, h, w4 = yv.shape
+            w = w4 // 4
+            z = ops.conv2d(yv, self.mask_score.weight, self.mask_score.bias, out_format="nhwc", out_dtype=torch.float32)
+            K = z.shape[1]
+            z = z.permute(0, 2, 3, 1).reshape(n, h, w, 2, 2, K)
+            return z.permute(0, 5, 1, 3, 2, 4).reshape(n, K, 2 * h, 2 * w)
         y = ops.conv2d(x, w1, b1, relu=True)                 # [n, 4*Cout, h, w], channels ordered (a, b, co)
         n, _, h, w = y.shape
         if y.is_contiguous(memory_format=torch.channels_last) and y.dim() == 4:
@@ -584,7 +606,8 @@ class resnet_upsnet(nn.Module):
     def _run_static(self, x, im_info):
         if not (self.use_cuda_graph and x.is_cuda):
             return self._forward_static(x, im_info), None
-        key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], ops.ACT_BF16["on"], tuple(float(v) for v in im_info))
+        key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], ops.ACT_BF16["on"], ops.ACT_PAIR["on"],
+               tuple(float(v) for v in im_info))
         ent = self._graphs.get(key)
         if ent is None:
             static_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)

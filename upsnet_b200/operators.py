@@ -30,15 +30,79 @@ from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
 # default arithmetic of the convolution tiles; switched by upsnet_b200.set_precision()
 _PRECISION = {"conv": _lib.PREC_FP32_SIMT}
 ACT_BF16 = {"on": False}   # engine switch: store activations as bf16 (precision 'bf16' only)
+ACT_PAIR = {"on": False}   # engine switch: store activations as hi/lo bf16 pairs (precision 'bf16x3': fp32-grade results)
 USE_TMA = {"on": True}     # False forces the cp.async gather kernel where the TMA-fed one would qualify (A/B tests)
 
 
-def set_precision(name, bf16_activations=None):
+def set_precision(name, bf16_activations=None, pair_activations=None):
     """'fp32' (CUDA-core fp32 tiles), 'bf16x3' or 'bf16' (tcgen05 tiles).  With 'bf16' the engine also stores
     the NHWC activation stream as bf16 (halves HBM traffic; the gather becomes a cp.async copy) unless
-    bf16_activations=False."""
+    bf16_activations=False.  With 'bf16x3' -- the configuration that meets "fp32 logits within 1e-3" -- the stream is
+    stored as hi/lo bf16 PAIRS (class Pair: same bytes as fp32, ~16 mantissa bits) so that the TMA-fed tcgen05 kernel can
+    run the three-term split (hi*hi + lo*hi + hi*lo) without any gather threads; pair_activations=False keeps fp32
+    activations and the gather-fed kernel (round-1 behaviour, kept for A/B tests)."""
     _PRECISION["conv"] = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.PREC_BF16}[name]
     ACT_BF16["on"] = (name == "bf16") if bf16_activations is None else (bool(bf16_activations) and name == "bf16")
+    ACT_PAIR["on"] = (name == "bf16x3") if pair_activations is None else (bool(pair_activations) and name == "bf16x3")
+
+
+class Pair:
+    """An activation stored as a hi/lo bf16 pair: `store` is bf16 [N,H,W,2C] (NHWC), channels [0,C) = bf16(v) and
+    [C,2C) = bf16(v - hi); v = hi + lo is exact in fp32 (UPSNET_DTYPE_PAIR in include/upsnet_b200.h).  Quacks like the
+    logical [N,C,H,W] tensor for the few attributes the engine's module code reads."""
+    __slots__ = ("store",)
+    dtype = "pair"
+
+    def __init__(self, store):
+        assert store.dtype == torch.bfloat16 and store.dim() == 4 and store.shape[-1] % 2 == 0 and store.is_contiguous()
+        self.store = store
+
+    @staticmethod
+    def from_float(x):
+        """x: logical [N,C,H,W] float tensor (any memory format) -> Pair."""
+        xs = x.float().permute(0, 2, 3, 1)
+        hi = xs.to(torch.bfloat16)
+        lo = (xs - hi.float()).to(torch.bfloat16)
+        return Pair(torch.cat([hi, lo], dim=-1).contiguous())
+
+    @property
+    def shape(self):
+        n, h, w, c2 = self.store.shape
+        return torch.Size((n, c2 // 2, h, w))
+
+    @property
+    def device(self):
+        return self.store.device
+
+    @property
+    def is_cuda(self):
+        return self.store.is_cuda
+
+    def dim(self):
+        return 4
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def float(self):
+        """fp32 logical [N,C,H,W] (channels_last storage) = hi + lo."""
+        c = self.store.shape[-1] // 2
+        return (self.store[..., :c].float() + self.store[..., c:].float()).permute(0, 3, 1, 2)
+
+    def record_stream(self, s):
+        self.store.record_stream(s)
+
+    def subsample2(self):
+        """x[:, :, ::2, ::2] (nn.MaxPool2d(kernel_size=1, stride=2): models/fpn.py:75)."""
+        return Pair(self.store[:, ::2, ::2, :].contiguous())
+
+
+def subsample2(x):
+    return x.subsample2() if isinstance(x, Pair) else x[:, :, ::2, ::2].contiguous()
+
+
+def as_float(x):
+    return x.float()
 
 
 # launch accounting (bench.py reports gpu_launches) and optional per-call CUDA-event timing of the
@@ -156,64 +220,103 @@ def _tc_ok(Cin, kh, kw, dg, deform=False):
 
 
 def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format,
-              out_dtype=None, residual_up2=False):
-    """upsnet_igemm_forward: x logical NCHW (any memory format; fp32 or bf16), result logical NCHW whose
+              out_dtype=None, residual_up2=False, pair_group=0):
+    """upsnet_igemm_forward: x logical NCHW (any memory format; fp32 or bf16) or a Pair; result logical NCHW whose
     storage is NHWC (channels_last view, the engine layout) unless out_format == 'nchw'.
-    Output dtype: bf16 when the engine stores bf16 activations (ACT_BF16) and the result stays in the
-    NHWC activation stream; fp32 for plane-wise (NCHW) head outputs or when asked via out_dtype."""
+    Output: bf16 when the engine stores bf16 activations (ACT_BF16) / a Pair when it stores pairs (ACT_PAIR) and the
+    result stays in the NHWC activation stream; fp32 for plane-wise (NCHW) head outputs or when asked via out_dtype.
+    pair_group=G (Pair output only): channels are written as [hi G][lo G] groups and the result is returned as the Pair
+    of logical shape [N, G, Ho, Wo*Cout/G] that this storage also is (see MaskBranch)."""
     sh, sw = stride; ph, pw = padding; dh, dw = dilation
     N, Cin, H, W = x.shape
     Cout, _, kh, kw = weight.shape
     Ho, Wo = _conv_out(H, ph, dh, kh, sh), _conv_out(W, pw, dw, kw, sw)
     nhwc_out = out_format != "nchw"
-    if prec == _lib.PREC_BF16X3 and x.dtype != torch.float32:
-        x = x.float()                                      # the hi/lo split needs fp32 activations
-    if x.dtype not in (torch.float32, torch.bfloat16):
+    x3 = prec == _lib.PREC_BF16X3
+    pair_in = isinstance(x, Pair)
+    if pair_in:
+        assert x3, "Pair activations belong to precision bf16x3"
+    elif x3 and ACT_PAIR["on"] and Cin % 64 == 0:
+        x = Pair.from_float(x)                               # entry into the pair stream (API-level callers)
+        pair_in = True
+    elif x3 and x.dtype != torch.float32:
+        x = x.float()                                        # the in-kernel hi/lo split needs fp32 activations
+    elif x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
+    dev = x.device
+    pair_out = False
     if out_dtype is None:
-        out_dtype = torch.bfloat16 if (ACT_BF16["on"] and prec == _lib.PREC_BF16 and nhwc_out) else torch.float32
-    xs = f32c(x) if Cin % 64 else _nhwc(x)      # tiny-Cin (stem) mode reads the NCHW fp32 image directly
-    packed = _packed_weight(weight)
-    if nhwc_out:
-        store = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=out_dtype)
-        y = store.permute(0, 3, 1, 2)
-        res = None if residual is None else _nhwc(residual.to(out_dtype))
+        if x3 and ACT_PAIR["on"] and nhwc_out and Cout % 8 == 0:
+            pair_out = True
+        else:
+            out_dtype = torch.bfloat16 if (ACT_BF16["on"] and prec == _lib.PREC_BF16 and nhwc_out) else torch.float32
+    elif out_dtype == "pair":
+        pair_out = True
+    if pair_in:
+        xs, x_dt = x.store, _lib.DTYPE_PAIR
     else:
-        store = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=out_dtype)
-        y = store
-        res = None if residual is None else residual.to(out_dtype).contiguous()
-    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * (3 if prec == _lib.PREC_BF16X3 else 1),
+        xs = f32c(x) if Cin % 64 else _nhwc(x)      # tiny-Cin (stem) mode reads the NCHW fp32 image directly
+        x_dt = _lib.DTYPE_BF16 if xs.dtype == torch.bfloat16 else _lib.DTYPE_F32
+    packed = _packed_weight(weight)
+    if pair_out:
+        assert nhwc_out
+        store = torch.empty((N, Ho, Wo, 2 * Cout), device=dev, dtype=torch.bfloat16)
+        res = None
+        if residual is not None:
+            res = (residual if isinstance(residual, Pair) else Pair.from_float(residual)).store
+        y_dt = _lib.DTYPE_PAIR
+    elif nhwc_out:
+        store = torch.empty((N, Ho, Wo, Cout), device=dev, dtype=out_dtype)
+        res = None if residual is None else _nhwc(as_float(residual).to(out_dtype))
+        y_dt = _lib.DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.DTYPE_F32
+    else:
+        store = torch.empty((N, Cout, Ho, Wo), device=dev, dtype=out_dtype)
+        res = None if residual is None else as_float(residual).to(out_dtype).contiguous()
+        y_dt = _lib.DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.DTYPE_F32
+    xbytes = xs.numel() * xs.element_size()
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * (3 if x3 else 1),
             "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
-            "shape": "N%d %dx%d Cin%d->Cout%d k%d s%d %s->%s%s" % (N, H, W, Cin, Cout, kh, sh, str(xs.dtype)[6:] if False else str(x.dtype)[6:],
-                                                              str(out_dtype)[6:], " +res" if residual is not None else ""),
-            "bytes": float(x.numel() * x.element_size() + 4 * weight.numel() +
+            "shape": "N%d %dx%d Cin%d->Cout%d k%d s%d %s->%s%s" % (N, H, W, Cin, Cout, kh, sh, "pair" if pair_in else str(xs.dtype)[6:],
+                                                              "pair" if pair_out else str(out_dtype)[6:],
+                                                              " +res" if residual is not None else ""),
+            "bytes": float(xbytes + 4 * weight.numel() +
                            store.numel() * store.element_size() * (2 if residual is not None else 1))}
-    with torch.cuda.device(x.device), _Timed(kind, 1, work, x.device):
+    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if residual_up2 else 0) | \
+            (0 if USE_TMA["on"] else _lib.EPI_NO_TMA)
+    if pair_group:
+        assert pair_out and pair_group % 64 == 0 and Cout % pair_group == 0
+        flags |= (pair_group // 64) << 8
+    with torch.cuda.device(dev), _Timed(kind, 1, work, dev):
         check(lib().upsnet_igemm_forward(ptr(xs), ptr(offset), ptr(mask), ptr(packed), ptr(bias), ptr(res),
                                          ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
-                                         _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW,
-                                         1 if xs.dtype == torch.bfloat16 else 0, 1 if out_dtype == torch.bfloat16 else 0,
-                                         (_lib.EPI_RELU if relu else 0) | (_lib.EPI_RES_UP2 if residual_up2 else 0) |
-                                         (0 if USE_TMA["on"] else _lib.EPI_NO_TMA),
-                                         prec, stream_ptr(x.device)), kind)
-    return y
+                                         _lib.LAYOUT_NHWC if nhwc_out else _lib.LAYOUT_NCHW, x_dt, y_dt, flags,
+                                         prec, stream_ptr(dev)), kind)
+    if pair_out:
+        if pair_group:
+            return Pair(store.view(N, Ho, Wo * (Cout // pair_group), 2 * pair_group))
+        return Pair(store)
+    return store.permute(0, 3, 1, 2) if nhwc_out else store
 
 
 # ------------------------------------------------------------------------------------------------
 # functional layer
 # ------------------------------------------------------------------------------------------------
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-           out_format=None, out_dtype=None, residual_up2=False):
+           out_format=None, out_dtype=None, residual_up2=False, pair_group=0):
     """Dense conv + fused bias / residual / ReLU epilogue.  fp32 precision -> upsnet_conv2d_forward
     (NCHW CUDA-core tiles); bf16x3 / bf16 -> upsnet_igemm_forward (tcgen05 tiles, NHWC storage)."""
     require_cuda(x, weight, bias, residual)
     prec = _PRECISION["conv"] if precision is None else precision
     if prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], 1):
         if residual_up2 and out_format == "nchw":
-            residual, residual_up2 = torch.nn.functional.interpolate(residual, scale_factor=2, mode="nearest"), False
+            residual, residual_up2 = torch.nn.functional.interpolate(as_float(residual), scale_factor=2, mode="nearest"), False
         return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
                          _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype,
-                         residual_up2)
+                         residual_up2, pair_group)
+    if isinstance(x, Pair):
+        x = x.float()
+    if isinstance(residual, Pair):
+        residual = residual.float()
     if residual_up2:   # CUDA-core path: materialise the nearest-neighbour upsampling (models/fpn.py:33-34)
         residual = torch.nn.functional.interpolate(residual, scale_factor=2, mode="nearest")
     x, weight = f32c(x), f32c(weight)
@@ -238,10 +341,14 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
 
 
 def linear(x, weight, bias=None, relu=False, precision=None, out_dtype=None):
-    """y = x @ weight.T + bias as a 1x1 convolution over N 'images' of 1x1 pixels."""
+    """y = x @ weight.T + bias as a 1x1 convolution over N 'images' of 1x1 pixels.  x: [N,K] tensor, or a Pair of
+    logical shape [N,K,1,1] (then the result is a Pair too unless out_dtype says otherwise)."""
+    if isinstance(x, Pair):
+        y = conv2d(x, _as_1x1(weight), bias, relu=relu, precision=precision, out_dtype=out_dtype)
+        return y if isinstance(y, Pair) else y.reshape(y.shape[0], weight.shape[0])
     N, K = x.shape
     y = conv2d(x.reshape(N, K, 1, 1), _as_1x1(weight), bias, relu=relu, precision=precision, out_dtype=out_dtype)
-    return y.reshape(N, weight.shape[0])
+    return y if isinstance(y, Pair) else y.reshape(N, weight.shape[0])
 
 
 _view_cache = {}
@@ -279,7 +386,7 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
             assert tuple(mask.shape) == (N, kh * kw, Ho, Wo), mask.shape
         return _igemm_tc("dcn", data, offset, mask, weight, bias, None, (sh, sw), (ph, pw), (dh, dw), relu, prec,
                          out_format, out_dtype)
-    data, weight = f32c(data), f32c(weight)
+    data, weight = f32c(as_float(data)), f32c(weight)
     N, Cin, H, W = data.shape
     Cout, Cin_w, kh, kw = weight.shape
     assert Cin_w == Cin, "groups != 1 is not supported (the reference ignores `groups`)"
@@ -326,12 +433,18 @@ def max_pool2d(x, kernel_size, stride, padding):
     """nn.MaxPool2d on the engine's activation stream (models/resnet.py:163).  x is a logical NCHW tensor; the
     kernel works on NHWC storage (channels_last tensors are used as they are) in bf16 or fp32."""
     require_cuda(x)
-    if x.dtype not in (torch.float32, torch.bfloat16):
-        x = x.float()
     N, Cc, H, W = x.shape
-    xs = _nhwc(x)
     Ho = (H + 2 * padding - kernel_size) // stride + 1
     Wo = (W + 2 * padding - kernel_size) // stride + 1
+    if isinstance(x, Pair):
+        store = torch.empty((N, Ho, Wo, 2 * Cc), device=x.device, dtype=torch.bfloat16)
+        with torch.cuda.device(x.device), _Timed("maxpool", 1, {"bytes": float((x.store.numel() + store.numel()) * 2)}, x.device):
+            check(lib().upsnet_maxpool2d_nhwc(ptr(x.store), ptr(store), N, H, W, Cc, kernel_size, stride, padding,
+                                              _lib.DTYPE_PAIR, stream_ptr(x.device)), "maxpool2d")
+        return Pair(store)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    xs = _nhwc(x)
     store = torch.empty((N, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
     with torch.cuda.device(x.device), _Timed("maxpool", 1, {"bytes": float((xs.numel() + store.numel()) * x.element_size())}, x.device):
         check(lib().upsnet_maxpool2d_nhwc(ptr(xs), ptr(store), N, H, W, Cc, kernel_size, stride, padding,
@@ -358,6 +471,26 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
     require_cuda(rois, *feats)
     rois = f32c(rois)
     R = rois.shape[0]
+    if isinstance(feats[0], Pair):
+        # hi/lo pair features -> Pair result: [R,C,PH,PW] pair pixels, or (layout 'flat_pair') the [R, PH*PW*C, 1, 1]
+        # pair of the flattened (ph, pw, c) roi feature that the RCNN fc6 consumes as a 1x1 'image'
+        assert all(isinstance(f, Pair) for f in feats) and layout in ("auto", "nhwc", "flat_pair") and not return_levels
+        B, Cc = feats[0].shape[0], feats[0].shape[1]
+        flat = layout == "flat_pair"
+        if flat:
+            out = torch.empty((R, 1, 1, 2 * pooled_height * pooled_width * Cc), device=rois.device, dtype=torch.bfloat16)
+        else:
+            out = torch.empty((R, pooled_height, pooled_width, 2 * Cc), device=rois.device, dtype=torch.bfloat16)
+        if R > 0:
+            fp = (C.c_void_p * 4)(*[f.store.data_ptr() for f in feats])
+            hs = (C.c_int * 4)(*[f.shape[2] for f in feats]); ws = (C.c_int * 4)(*[f.shape[3] for f in feats])
+            sc = (C.c_float * 4)(*[float(s_) for s_ in spatial_scales])
+            with torch.cuda.device(rois.device), _Timed("roi_align_fpn", 1, {"bytes": 2.0 * out.numel()}, rois.device):
+                check(lib().upsnet_roi_align_fpn_forward(fp, hs, ws, sc, B, Cc, _lib.LAYOUT_FLAT_PAIR if flat else _lib.LAYOUT_NHWC,
+                                                         _lib.DTYPE_PAIR, ptr(rois), R, pooled_height, pooled_width,
+                                                         sampling_ratio, ptr(out), ptr(None), stream_ptr(rois.device)),
+                      "fpn_roi_align")
+        return Pair(out)
     if layout == "auto":
         # engine tensors: logical NCHW; if every level is stored channels_last use the NHWC kernel
         # (coalesced channel vectors) and hand back a logical-NCHW view of the NHWC result
