@@ -159,8 +159,12 @@ int upsnet_igemm_forward(const void *x_nhwc, const float *offset, const float *m
  * the actual count <= n, so the call can be enqueued without knowing it (static-shape engine / CUDA graphs).
  * keep_out int64 [max(n,1)] original indices of kept instances in score order, k_out int32[1];
  * labels int64 [H,W] (255 = void); sem_labels int64 [H,W] or NULL (argmax_c fcn).
+ * Workspace: upsnet_panoptic_workspace_bytes is the preferred size (the 1-bit mask windows of all n instances resident,
+ * capped at 64 MB); any size >= upsnet_panoptic_workspace_min_bytes is accepted -- the windows are then built and
+ * consumed in rounds of consecutive score ranks (at most 64), with identical results.
  */
 int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thing, size_t *bytes);
+int upsnet_panoptic_workspace_min_bytes(int n, int H, int W, int num_thing, size_t *bytes);
 int upsnet_panoptic_head(const float *fcn, int S, int H, int W, const float *boxes,
                          const float *cls_prob, const float *mask_logit, const int64_t *cls_idx,
                          int n, const int *n_dev, int num_stuff, double fraction_threshold, int64_t *keep_out,

@@ -197,7 +197,7 @@ def panoptic_head(fcn, boxes, cls_prob, mask_logit, cls_idx, num_stuff, fraction
 # oracle-of-record formula (default) or real cv2.resize (informational, needs cv2).
 # ---------------------------------------------------------------------------------------------
 def panoptic_head_literal(fcn, boxes, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                          resize="formula"):
+                          resize="formula", return_logits=False):
     fcn = _f32(fcn)
     S, H, W = fcn.shape
     im_shape = (H, W)
@@ -273,6 +273,8 @@ def panoptic_head_literal(fcn, boxes, cls_prob, mask_logit, cls_idx, num_stuff, 
     void_id = panoptic_logits.shape[1] - 1
     out = panoptic_logits.argmax(axis=1)[0].astype(np.int64)
     out[out == void_id] = 255
+    if return_logits:
+        return keep, out, panoptic_logits[0]
     return keep, out
 
 

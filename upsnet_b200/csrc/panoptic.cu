@@ -54,8 +54,11 @@ struct PanWorkspace {
   int rounds;
 };
 
+// avail = 0: the preferred layout (all bit windows resident, up to kBitsBudget).  avail > 0: the caller's workspace size
+// -- the bit-window budget shrinks to what fits (more rounds of consecutive ranks), so the round structure is a RUNTIME
+// property of the call; returns 0 when not even the minimum (one window, or all / kMaxRounds words) fits.
 static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorkspace* ws,
-                                                char* base) {
+                                                char* base, size_t avail = 0) {
   const int nn = n > 0 ? n : 1;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -71,6 +74,11 @@ static inline size_t pan_ws_layout(int n, int H, int W, int num_thing, PanWorksp
   // fit the budget, otherwise the instances are processed in rounds of consecutive ranks.
   const long long win = (long long)H * Ww, all = win * nn;
   long long budget = all < kBitsBudget ? all : kBitsBudget;
+  if (avail) {
+    const long long fit = ((long long)avail - (long long)off) / (long long)sizeof(unsigned int) - win - 64;
+    if (fit < budget) budget = fit;
+    if (budget < win || (all + budget - 1) / budget > kMaxRounds) return 0;
+  }
   if ((all + budget - 1) / budget > kMaxRounds) budget = (all + kMaxRounds - 1) / kMaxRounds;
   if (budget < win) budget = win;
   const int rounds = (int)((all + budget - 1) / budget);
@@ -616,8 +624,8 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
   if (n < 1 || H <= 0 || W <= 0 || num_thing <= 0) return UPSNET_E_BADARG;
   if (n > kMaxList) return UPSNET_E_UNSUPPORTED;
   PanWorkspace ws;
-  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace);
-  if (workspace_bytes < need) return UPSNET_E_WORKSPACE;
+  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace, workspace_bytes);
+  if (need == 0 || workspace_bytes < need) return UPSNET_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int Ww = ceil_div(W, 32);
   UPS_CUDA(cudaMemsetAsync(ws.occ, 0, (size_t)num_thing * H * Ww * sizeof(unsigned int), st));
@@ -652,6 +660,18 @@ extern "C" int upsnet_panoptic_workspace_bytes(int n, int H, int W, int num_thin
   return 0;
 }
 
+extern "C" int upsnet_panoptic_workspace_min_bytes(int n, int H, int W, int num_thing, size_t* bytes) {
+  if (!bytes || n < 0 || H <= 0 || W <= 0 || num_thing <= 0) return UPSNET_E_BADARG;
+  // fixed part + the smallest bit-window budget: max(one window, all windows / kMaxRounds), plus the spill window
+  const size_t full = ups::pan_ws_layout(n, H, W, num_thing, nullptr, nullptr);
+  const long long win = (long long)H * ups::ceil_div(W, 32), all = win * (n > 0 ? n : 1);
+  long long budget = all < ups::kBitsBudget ? all : ups::kBitsBudget;
+  long long minb = (all + ups::kMaxRounds - 1) / ups::kMaxRounds;
+  if (minb < win) minb = win;
+  *bytes = full - (size_t)(budget - minb) * sizeof(unsigned int) + 1024;
+  return 0;
+}
+
 extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const float* boxes,
                                     const float* cls_prob, const float* mask_logit,
                                     const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
@@ -667,8 +687,8 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   if (((uintptr_t)fcn & 15) || ((uintptr_t)labels & 15) || (sem_labels && ((uintptr_t)sem_labels & 15)))
     return UPSNET_E_BADARG;
   PanWorkspace ws;
-  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace);
-  if (workspace_bytes < need) return UPSNET_E_WORKSPACE;
+  const size_t need = pan_ws_layout(n, H, W, num_thing, &ws, (char*)workspace, workspace_bytes);
+  if (need == 0 || workspace_bytes < need) return UPSNET_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int Ww = ceil_div(W, 32);
   UPS_CUDA(cudaMemsetAsync(ws.occ, 0, (size_t)num_thing * H * Ww * sizeof(unsigned int), st));

@@ -511,6 +511,7 @@ class resnet_upsnet(nn.Module):
         self.overlap_heads = True     # semantic head on a side stream, concurrent with the detection chain
         self._side = {}
         self._graphs = {}
+        self.max_graphs = 4           # captured graphs kept (LRU): one activation pool each (~2 GB at 1024x2048)
         self._prepared = False
         self.eval()
 
@@ -521,6 +522,14 @@ class resnet_upsnet(nn.Module):
                 m.prepare()
         self._prepared = True
         return self
+
+    def _apply(self, fn, *a, **kw):
+        """.to() / .cuda() / .float(): the folded / fused weights made by prepare() and the captured graphs refer to the
+        old parameter storage -- rebuild them lazily on the next forward."""
+        r = super()._apply(fn, *a, **kw)
+        self._prepared = False
+        self._graphs = {}
+        return r
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         r = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -593,9 +602,15 @@ class resnet_upsnet(nn.Module):
                                                  self.panoptic_head.fraction_threshold, want_sem=True,
                                                  n_dev=n2.reshape(1))
         counts = torch.cat([n1.reshape(1).to(torch.int32), n2.reshape(1).to(torch.int32), k.reshape(1)])
-        return {"cls_probs": s1, "pred_boxes": b1, "mask_probs": mask_prob, "cls_inds": c1, "fcn_outputs": sem,
-                "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
-                "keep": keep, "counts": counts, "fcn_output": fcn_output}
+        out = {"cls_probs": s1, "pred_boxes": b1, "mask_probs": mask_prob, "cls_inds": c1, "fcn_outputs": sem,
+               "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
+               "keep": keep, "counts": counts, "fcn_output": fcn_output}
+        if getattr(self, "keep_intermediates", False):   # parity tests against the literal oracle: every stage boundary
+            out["dbg"] = {"fpn": [f.float().contiguous() for f in (p2, p3, p4, p5, p6)],
+                          "rpn_cls_prob": [t_.float() for t_ in rpn_cls_prob], "rpn_bbox_pred": [t_.float() for t_ in rpn_bbox_pred],
+                          "rois": rois, "roi_valid": roi_valid, "cls_score": rcnn_output["cls_score"].float(),
+                          "bbox_pred": bbox_pred, "mask_logits": logits}
+        return out
 
     def _side_stream(self, dev, idx=0):
         key = (str(dev), idx)
@@ -607,7 +622,7 @@ class resnet_upsnet(nn.Module):
         if not (self.use_cuda_graph and x.is_cuda):
             return self._forward_static(x, im_info), None
         key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], ops.ACT_BF16["on"], ops.ACT_PAIR["on"],
-               tuple(float(v) for v in im_info))
+               bool(getattr(self, "keep_intermediates", False)), tuple(float(v) for v in im_info))
         ent = self._graphs.get(key)
         if ent is None:
             static_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)
@@ -625,7 +640,11 @@ class resnet_upsnet(nn.Module):
             with torch.cuda.graph(graph):
                 out = self._forward_static(static_x, im_info)
             ent = (graph, static_x, out, ops.STATS["launches"] - l0)
+            while len(self._graphs) >= self.max_graphs:      # LRU: every entry pins one full activation pool
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
+        else:
+            self._graphs[key] = self._graphs.pop(key)        # most recently used last
         graph, static_x, out, n_launch = ent
         static_x.copy_(x, non_blocking=True)
         graph.replay()
@@ -655,6 +674,8 @@ class resnet_upsnet(nn.Module):
                                              "pcls_prob": cp(out["p_scores"][:n2]),
                                              "pmask_score": cp(out["p_mask_score"][:n2]),
                                              "pcls_idx": cp(out["p_cls"][:n2]), "keep_inds": cp(keep)}
+                for k_, v_ in out.get("dbg", {}).items():
+                    results["_intermediates"][k_] = [cp(t_) for t_ in v_] if isinstance(v_, list) else cp(v_)
             return results
         res2, res3, res4, res5 = self.resnet_backbone(x)
         p2, p3, p4, p5, p6 = self.fpn(res2, res3, res4, res5)

@@ -528,14 +528,21 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
 # NMS
 # ------------------------------------------------------------------------------------------------
 class _Workspace:
-    """Caller-owned, grow-only device scratch (the C ABI never allocates)."""
+    """Caller-owned, grow-only device scratch (the C ABI never allocates).  A buffer that is outgrown is RETIRED, not
+    freed: captured CUDA graphs (model._run_static) have its raw pointer baked in and keep writing to it on replay, so
+    handing the block back to the caching allocator would let a replay corrupt whatever tensor reuses it.
+    Growth is geometric (>= 1.5x), which bounds the retired bytes by about twice the final size."""
 
     def __init__(self):
         self.buf = {}
+        self.retired = []
 
     def get(self, device, nbytes):
         b = self.buf.get(device)
         if b is None or b.numel() < nbytes:
+            if b is not None:
+                self.retired.append(b)
+                nbytes = max(int(nbytes), int(b.numel() * 1.5))
             b = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
             self.buf[device] = b
         return b
@@ -836,7 +843,7 @@ class FPNRoIAlign(nn.Module):
 # panoptic head
 # ------------------------------------------------------------------------------------------------
 def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                  want_sem=False, n_dev=None):
+                  want_sem=False, n_dev=None, workspace_bytes=None):
     """Fused MaskRemoval + SegTerm + void/argmax (upsnet_panoptic_head).
     fcn_output [1,S,H,W]; mask_rois [n,4]; cls_prob [n]; mask_logit [n,1,28,28] or [n,28,28];
     cls_idx int64 [n].  Returns (keep_inds int64 [k], panoptic_output int64 [1,H,W][, sem int64 [1,H,W]]).
@@ -854,7 +861,12 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     num_thing = S - num_stuff
     nbytes = C.c_size_t(0)
     check(lib().upsnet_panoptic_workspace_bytes(n, H, W, num_thing, C.byref(nbytes)), "panoptic_workspace_bytes")
-    ws = _pan_ws.get(dev, nbytes.value)
+    if workspace_bytes is None:
+        ws = _pan_ws.get(dev, nbytes.value)
+    else:
+        # caller-chosen (smaller) workspace: the instances' bit windows are then processed in several rounds of
+        # consecutive score ranks -- same results (upsnet_panoptic_workspace_min_bytes is the floor)
+        ws = torch.empty(int(workspace_bytes), dtype=torch.uint8, device=dev)
     if n_dev is not None:
         assert n_dev.dtype == torch.int32 and n_dev.is_cuda
     keep = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)

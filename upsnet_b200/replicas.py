@@ -26,6 +26,16 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
+def all_ranks(value, device=None):
+    """The python float of every rank, in rank order (per-rank timings: names the straggler of a scaling run)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    t = torch.zeros(dist.get_world_size(), dtype=torch.float64, device=device)
+    t[dist.get_rank()] = float(value)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
 def gather_counts(local_count, device=None):
     """Per-rank processed-unit counts (whole-job throughput = sum / max time)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
