@@ -96,6 +96,17 @@ def _reference():
     return config, ref_mask_roi.MaskROI, ref_ppm.PyramidProposal, MaskRemoval, SegTerm
 
 
+def _reference_training_modules():
+    """MaskTerm (unary_logits.py:24-66) and MaskMatching (mask_matching.py:27-62); the latter's module imports matplotlib
+    (not installed, unused by MaskMatching) -- stubbed."""
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from upsnet.operators.modules.unary_logits import MaskTerm
+    from upsnet.operators.modules.mask_matching import MaskMatching
+    return MaskTerm, MaskMatching
+
+
 def reference_panoptic_glue(mask_removal, seg_term, fcn_output, mask_rois, cls_prob, mask_score, cls_idx, num_seg_classes,
                             num_classes):
     """models/resnet_upsnet.py:223-240 (enable_void branch, the one every shipped yaml takes) on the reference modules."""
@@ -211,6 +222,31 @@ def main():
         out.update({p + "im_info": info, p + "pre": np.int64(c["pre"]), p + "post": np.int64(c["post"]),
                     p + "rois": rois.numpy().astype(np.float32), p + "scores": sc.numpy().astype(np.float32)})
     out["pp_cases"] = np.int64(len(pp_cases))
+
+    # ------------------------------------------------------------------ MaskTerm / MaskMatching (a17: training twins)
+    MaskTerm, MaskMatching = _reference_training_modules()
+    H4, W4, n = 48, 80, 9
+    masks = (rng.standard_normal((n, 1, 28, 28)) * 2).astype(np.float32)
+    bx = rand_boxes(rng, n, 4 * H4, 4 * W4, 20, 200)
+    bx[0] = [-13.0, 5.0, 60.0, 90.0]            # partly outside (negative corner truncates toward zero in .long())
+    rois = np.concatenate([np.zeros((n, 1), np.float32), bx], 1)
+    cls = rng.integers(1, 9, n).astype(np.int64)
+    seg = (rng.standard_normal((1, 19, H4, W4))).astype(np.float32)
+    mt = MaskTerm(19, box_scale=1 / 4.0)
+    energy = mt(torch.from_numpy(masks), torch.from_numpy(rois), torch.from_numpy(cls), torch.from_numpy(seg))
+    out.update(mterm_masks=masks, mterm_rois=rois, mterm_cls=cls, mterm_seg_shape=np.array(seg.shape), mterm_energy=energy.numpy())
+    gt_segs = rng.integers(0, 19, (1, H4, W4)).astype(np.int64)
+    gt_segs[0, :4] = 255
+    gt_masks = np.zeros((5, H4, W4), np.int64)
+    for i in range(5):
+        y, x = rng.integers(0, H4 - 12), rng.integers(0, W4 - 16)
+        gt_masks[i, y:y + 12, x:x + 16] = 1
+    gt_masks[2, 0:3, 0:3] = 255
+    mm = MaskMatching(19, enable_void=True)
+    m_all = mm(torch.from_numpy(gt_segs), torch.from_numpy(gt_masks))
+    keep = np.array([3, 0, 4], np.int64)
+    m_keep = mm(torch.from_numpy(gt_segs), torch.from_numpy(gt_masks), torch.from_numpy(keep))
+    out.update(mmatch_gt_segs=gt_segs, mmatch_gt_masks=gt_masks, mmatch_keep=keep, mmatch_all=m_all.numpy(), mmatch_kept=m_keep.numpy())
 
     np.savez_compressed(os.path.join(HERE, "reference_modules.npz"), **out)
     print("wrote reference_modules.npz with", len(out), "arrays;",

@@ -133,3 +133,21 @@ def test_proposals_host_logic_vs_reference(ref, i):
         assert n == want_rois.shape[0] and bool(ok[:n].all())
         assert np.array_equal(s_sc[:n].numpy(), want_sc)
         np.testing.assert_allclose(s_rois[:n].numpy(), want_rois, rtol=0, atol=2e-3)
+
+
+def test_mask_term_vs_reference(ref):
+    """MaskTerm (training twin, row a17): bilinear (align_corners=False) resize + paste at 1/4 scale."""
+    from upsnet_b200.operators import MaskTerm
+    seg = torch.zeros(tuple(int(v) for v in ref["mterm_seg_shape"]))
+    got = MaskTerm(19, box_scale=1 / 4.0)(torch.from_numpy(ref["mterm_masks"]), torch.from_numpy(ref["mterm_rois"]),
+                                         torch.from_numpy(ref["mterm_cls"]), seg)
+    assert got.shape == ref["mterm_energy"].shape
+    np.testing.assert_allclose(got.numpy(), ref["mterm_energy"], rtol=0, atol=1e-6)
+
+
+def test_mask_matching_vs_reference(ref):
+    from upsnet_b200.operators import MaskMatching
+    mm = MaskMatching(19, enable_void=True)
+    segs, masks = torch.from_numpy(ref["mmatch_gt_segs"]), torch.from_numpy(ref["mmatch_gt_masks"])
+    assert np.array_equal(mm(segs, masks).numpy(), ref["mmatch_all"])
+    assert np.array_equal(mm(segs, masks, torch.from_numpy(ref["mmatch_keep"])).numpy(), ref["mmatch_kept"])

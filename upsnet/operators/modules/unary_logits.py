@@ -1,2 +1,2 @@
-"""reference path: upsnet/operators/modules/unary_logits.py (SegTerm; MaskTerm is the training twin, config #4)"""
-from upsnet_b200.operators import SegTerm  # noqa: F401
+"""reference path: upsnet/operators/modules/unary_logits.py (SegTerm :69-105; MaskTerm :24-66, the training twin)"""
+from upsnet_b200.operators import MaskTerm, SegTerm  # noqa: F401

@@ -188,6 +188,48 @@ class MaskROI:
         return sc, boxes, cls.long()
 
 
+class PyramidProposal(torch.nn.Module):
+    """operators/modules/pyramid_proposal.py:24-67 -- the reference's module signature on the device implementation:
+    forward(cls_prob [5 x [B,A,h,w]], bbox_pred [5 x [B,4A,h,w]], im_info [B,3]) -> (rois [R,5], scores [R])."""
+
+    def __init__(self, feat_stride, scales, ratios, rpn_pre_nms_top_n, rpn_post_nms_top_n, threshold, rpn_min_size,
+                 individual_proposals=False, use_softnms=False):
+        super().__init__()
+        assert individual_proposals and not use_softnms, "the shipped configuration (config.py:123): per-level NMS, hard NMS"
+        self.rpn_post_nms_top_n = rpn_post_nms_top_n
+        self.gen = ProposalGenerator(tuple(int(s) for s in feat_stride), tuple(scales), tuple(ratios), rpn_pre_nms_top_n,
+                                     rpn_post_nms_top_n, threshold, rpn_min_size)
+
+    def forward(self, cls_prob, bbox_pred, im_info, roidb=None):
+        assert roidb is None, "crowd filtering is a training-time option"
+        im_info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)
+        rois, scores = [], []
+        for i in range(im_info.shape[0]):
+            r, s = self.gen([c[[i]] for c in cls_prob], [b[[i]] for b in bbox_pred], im_info[i])
+            r = r.clone(); r[:, 0] = i                                              # batch index column
+            rois.append(r); scores.append(s)
+        rois, scores = torch.cat(rois, 0), torch.cat(scores, 0)
+        _, idx = torch.sort(-scores, 0, stable=True)                                 # modules/pyramid_proposal.py:61-66
+        idx = idx[:self.rpn_post_nms_top_n]
+        return rois[idx, :], scores[idx]
+
+
+class MaskROIModule(torch.nn.Module):
+    """operators/modules/mask_roi.py:24-36 constructor + forward signature on the device implementation."""
+
+    def __init__(self, clip_boxes, bbox_class_agnostic, top_n, num_classes, nms_thresh=None, class_agnostic=False,
+                 score_thresh=None, bbox_reg_weights=(10., 10., 5., 5.)):
+        super().__init__()
+        assert clip_boxes and not bbox_class_agnostic, "the shipped configuration (resnet_upsnet.py:57-66)"
+        self.impl = MaskROI(top_n, num_classes, 0.5 if nms_thresh is None else nms_thresh, class_agnostic,
+                            0.05 if score_thresh is None else score_thresh, bbox_reg_weights)
+
+    def forward(self, bottom_rois, bbox_delta, cls_prob, im_info, nms=True, cls_score=None, cls_label=None):
+        assert nms and cls_score is None and cls_label is None, "inference call shape (resnet_upsnet.py:203,217)"
+        info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)[0]
+        return self.impl(bottom_rois, bbox_delta, cls_prob, info)
+
+
 # ================================================================================================
 # Static-shape, synchronisation-free variants (the engine path).  Same decisions as the classes above
 # for every valid entry, but all outputs are padded to fixed sizes with a device-side count, so the

@@ -56,6 +56,31 @@ class UPSNetConfig:
             setattr(self, k, v)
 
     @classmethod
+    def from_reference_config(cls, config):
+        """Build from the reference's global `config` (upsnet/config/config.py + an experiment yaml merged by
+        update_config): the fields resnet_upsnet.__init__ reads (models/resnet_upsnet.py:42-71, resnet.py:314-340)."""
+        def get(sec, key, default):
+            d = config.get(sec, {}) if hasattr(config, "get") else getattr(config, sec, {})
+            try:
+                return d[key]
+            except (KeyError, TypeError):
+                return getattr(d, key, default)
+        return cls(num_classes=int(get("dataset", "num_classes", 9)), num_seg_classes=int(get("dataset", "num_seg_classes", 19)),
+                   backbone_with_dconv=int(get("network", "backbone_with_dconv", 100)),
+                   backbone_with_dilation=bool(get("network", "backbone_with_dilation", False)),
+                   backbone_with_dpyramid=bool(get("network", "backbone_with_dpyramid", False)),
+                   fpn_feature_dim=int(get("network", "fpn_feature_dim", 256)), fpn_with_gap=bool(get("network", "fpn_with_gap", False)),
+                   fcn_num_layers=int(get("network", "fcn_num_layers", 3)), num_anchors=int(get("network", "num_anchors", 3)),
+                   anchor_scales=tuple(get("network", "anchor_scales", (8,))), anchor_ratios=tuple(get("network", "anchor_ratios", (0.5, 1, 2))),
+                   rpn_feat_stride=tuple(get("network", "rpn_feat_stride", (4, 8, 16, 32, 64))), mask_size=int(get("network", "mask_size", 28)),
+                   bbox_reg_weights=tuple(get("network", "bbox_reg_weights", (10., 10., 5., 5.))),
+                   rpn_pre_nms_top_n=int(get("test", "rpn_pre_nms_top_n", 1000)), rpn_post_nms_top_n=int(get("test", "rpn_post_nms_top_n", 1000)),
+                   rpn_nms_thresh=float(get("test", "rpn_nms_thresh", 0.7)), rpn_min_size=int(get("test", "rpn_min_size", 0)),
+                   nms_thresh=float(get("test", "nms_thresh", 0.5)), max_det=int(get("test", "max_det", 100)),
+                   score_thresh=float(get("test", "score_thresh", 0.05)), panoptic_score_thresh=float(get("test", "panoptic_score_thresh", 0.6)),
+                   panoptic_box_keep_fraction=float(get("train", "panoptic_box_keep_fraction", 0.7)))
+
+    @classmethod
     def cityscapes_r50(cls):      # experiments/upsnet_resnet50_cityscapes_16gpu.yaml
         return cls()
 
@@ -531,11 +556,78 @@ class resnet_upsnet(nn.Module):
         self._graphs = {}
         return r
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        r = super().load_state_dict(state_dict, strict=strict, **kw)
+    # COCO -> Cityscapes head remapping of models/resnet.py:223-273 (fine-tuning a COCO checkpoint on Cityscapes)
+    _COCO2CITY_THING = {0: 0, 1: 1, 2: -1, 3: 3, 4: 8, 5: 6, 6: 7, 7: 4, 8: 2}
+    _COCO2CITY_SEG = {0: 20, 1: 43, 2: 49, 3: 51, 4: 37, 5: -1, 6: 62, 7: -1, 8: 36, 9: -1, 10: 39, 11: 53, 12: -1, 13: 55,
+                      14: 60, 15: 58, 16: 59, 17: 56, 18: 54}
+
+    @staticmethod
+    def name_mapping(name, resume=False):
+        """models/resnet.py:213-222: checkpoints of this model (`resume`) may carry DataParallel's `module.` prefix;
+        backbone-only checkpoints use torchvision / caffe names (conv1, bn1, layer1..4)."""
+        if resume:
+            return name[len("module."):] if name.startswith("module.") else name
+        if name.startswith("conv1") or name.startswith("bn1"):
+            return "resnet_backbone.conv1." + name
+        return name.replace("layer1", "resnet_backbone.res2.layers").replace("layer2", "resnet_backbone.res3.layers") \
+                   .replace("layer3", "resnet_backbone.res4.layers").replace("layer4", "resnet_backbone.res5.layers")
+
+    def load_state_dict(self, state_dict, strict=True, resume=None, **kw):
+        """nn.Module.load_state_dict, or -- when `resume` is given, the way upsnet_end2end_test.py:190-193 and the
+        training scripts call it -- the reference's own loader (models/resnet.py:224-299): key remapping, the COCO ->
+        Cityscapes head conversion, shape-checked copies with warnings instead of errors."""
+        if resume is None:
+            r = super().load_state_dict(state_dict, strict=strict, **kw)
+        else:
+            r = self._load_reference_style(dict(state_dict), bool(resume))
         self._prepared = False
         self._graphs = {}
         return r
+
+    def _load_reference_style(self, state_dict, resume):
+        import warnings
+        own = self.state_dict()
+        k = "rcnn.cls_score.weight"
+        if k in state_dict and own[k].shape[0] == 9 and state_dict[k].shape[0] == 81:          # resnet.py:227-250
+            for wn in ("rcnn.cls_score.weight", "rcnn.cls_score.bias", "rcnn.bbox_pred.weight", "rcnn.bbox_pred.bias",
+                       "mask_branch.mask_score.weight", "mask_branch.mask_score.bias"):
+                src = state_dict[wn].float()
+                mean, std = src.mean().item(), src.std().item()
+                src = src.view(*([81, -1] + list(src.shape[1:])))
+                blobs = (np.random.randn(*([9] + list(src.shape[1:]))) * std + mean).astype(np.float32)
+                for i in range(9):
+                    c = self._COCO2CITY_THING[i]
+                    if c >= 0:
+                        blobs[i] = src[c].cpu().numpy()
+                state_dict[wn] = torch.from_numpy(blobs.reshape([-1] + list(src.shape[2:])))
+        k = "fcn_head.score.weight"
+        if k in own and k in state_dict and own[k].shape[0] == 19 and state_dict[k].shape[0] == 133:   # resnet.py:252-283
+            for wn in ("fcn_head.score.weight", "fcn_head.score.bias"):
+                src = state_dict[wn].float()
+                mean, std = src.mean().item(), src.std().item()
+                blobs = (np.random.randn(*([19] + list(src.shape[1:]))) * std + mean).astype(np.float32)
+                for i in range(19):
+                    c = self._COCO2CITY_SEG[i]
+                    if c >= 0:
+                        blobs[i] = src[c].cpu().numpy()
+                state_dict[wn] = torch.from_numpy(blobs)
+        seen = set()
+        with torch.no_grad():
+            for name, param in state_dict.items():
+                name = self.name_mapping(name, resume)
+                seen.add(name)
+                if name not in own:
+                    warnings.warn('unexpected key "{}" in state_dict'.format(name))
+                    continue
+                if own[name].shape == param.shape:
+                    own[name].copy_(param)
+                else:
+                    warnings.warn("While copying the parameter named {}, whose dimensions in the models are {} and whose "
+                                  "dimensions in the checkpoint are {}, ...".format(name, own[name].size(), param.size()))
+        missing = set(own.keys()) - seen
+        if missing:
+            warnings.warn('missing keys in state_dict: "{}"'.format(missing))
+        return None
 
     # ------------------------------------------------------------------------------------------
     # static engine: every tensor has a fixed shape, counts stay on the device

@@ -945,6 +945,57 @@ class SegTerm(nn.Module):
         return seg_energy, inst
 
 
+class MaskTerm(nn.Module):
+    """operators/modules/unary_logits.py:24-66 (training twin of MaskRemoval's paste: every roi's 28x28 mask logit is
+    bilinearly resized (align_corners=False, ATen rule) to its box at 1/4 scale and pasted into [1,n,h,w]).  Tensor ops
+    on the device, differentiable through torch autograd like the reference's F.upsample."""
+
+    def __init__(self, num_seg_classes, box_scale=1 / 4.0, class_mapping=None, num_classes=9, mask_size=28):
+        super().__init__()
+        self.num_seg_classes, self.box_scale, self.mask_size = num_seg_classes, box_scale, mask_size
+        self.class_mapping = dict(zip(range(1, num_classes), range(num_seg_classes - num_classes + 1, num_seg_classes))) \
+            if class_mapping is None else class_mapping
+
+    def forward(self, masks, boxes, cls_indices, seg_score):
+        assert seg_score.shape[0] == 1, "only support batch size = 1"
+        boxes = boxes[:, 1:] * self.box_scale
+        H, W = int(seg_score.shape[2]), int(seg_score.shape[3])
+        energy = torch.zeros((1, masks.shape[0], H, W), device=seg_score.device)
+        ref = boxes.long().tolist()                                          # one host read for all boxes
+        for i, (bx0, by0, bx1, by1) in enumerate(ref):
+            w, h = max(bx1 - bx0 + 1, 1), max(by1 - by0 + 1, 1)
+            m = torch.nn.functional.interpolate(masks[i, 0].view(1, 1, self.mask_size, self.mask_size), size=(h, w),
+                                                mode="bilinear", align_corners=False)
+            x0, x1, y0, y1 = max(bx0, 0), min(bx1 + 1, W), max(by0, 0), min(by1 + 1, H)
+            if x1 > x0 and y1 > y0:
+                energy[0, i, y0:y1, x0:x1] = m[0, 0, (y0 - by0):(y1 - by0), (x0 - bx0):(x1 - bx0)]
+        return energy
+
+
+class MaskMatching(nn.Module):
+    """operators/modules/mask_matching.py:27-62: panoptic ground truth = stuff labels kept, every (kept) gt instance mask
+    painted with its channel index, the rest void (255) or the extra 'unmatched' channel."""
+
+    def __init__(self, num_seg_classes, enable_void, class_mapping=None, num_classes=9):
+        super().__init__()
+        self.class_mapping = dict(zip(range(1, num_classes), range(num_seg_classes - num_classes + 1, num_seg_classes))) \
+            if class_mapping is None else class_mapping
+        self.num_seg_classes, self.num_classes = num_seg_classes, num_classes
+        self.num_inst_classes, self.enable_void = len(self.class_mapping), enable_void
+
+    def forward(self, gt_segs, gt_masks, keep_inds=None):
+        matched = torch.ones_like(gt_segs) * -1
+        matched = torch.where(gt_segs <= self.num_seg_classes - self.num_classes, gt_segs, matched)
+        matched = torch.where(gt_segs >= 255, gt_segs, matched)
+        if keep_inds is not None:
+            gt_masks = gt_masks[keep_inds]
+        base = self.num_seg_classes - self.num_inst_classes
+        for i in range(gt_masks.shape[0]):
+            matched[(gt_masks[[i], :, :] != 0) & (gt_masks[[i], :, :] != 255)] = i + base
+        matched[matched == -1] = (base + gt_masks.shape[0]) if keep_inds is not None else 255
+        return matched
+
+
 class PanopticHead(nn.Module):
     """The parameter-free panoptic head of models/resnet_upsnet.py:217-247 as one module (the
     reference has no such class: SURVEY.md F1).  forward takes what lines 220-227 consume."""
