@@ -209,7 +209,7 @@ class PyramidProposal(torch.nn.Module):
             r = r.clone(); r[:, 0] = i                                              # batch index column
             rois.append(r); scores.append(s)
         rois, scores = torch.cat(rois, 0), torch.cat(scores, 0)
-        _, idx = torch.sort(-scores, 0, stable=True)                                 # modules/pyramid_proposal.py:61-66
+        _, idx = torch.sort(-scores, dim=0, stable=True)                               # modules/pyramid_proposal.py:61-66
         idx = idx[:self.rpn_post_nms_top_n]
         return rois[idx, :], scores[idx]
 
