@@ -260,6 +260,36 @@ int upsnet_maskroi_finish(const int *keep, const int *keep_cnt, const int *seg_o
                           const int *cls, const float *bx, int nseg, int max_seg_len, int top_n, int cap,
                           float *out_sc, float *out_bx, long long *out_cls, int *n_out, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Callers either side of the per-image forward, device resident.
+ *
+ * upsnet_unified_pan_result: the 2-channel panoptic result the PQ evaluation consumes.
+ * replaces: dataset/base_dataset.py:332-371 get_unified_pan_result (numpy on the host: np.unique per segment).
+ * seg int64 [H,W] (semantic argmax, 'fcn_outputs'), pan int64 [H,W] ('panoptic_outputs': 0..id_last_stuff stuff,
+ * id_last_stuff + 1 + j = j-th kept instance, 255 void; id_last_stuff = num_seg_classes - num_classes), cls_inds int64
+ * [k] ('panoptic_cls_inds', 1-based thing class of kept instance j); k_dev optional DEVICE count <= k.
+ * pan_2ch uint8 [H,W,3]: channel 0 = semantic class (255 void), 1 = instance number (rank among the instance ids present,
+ * from 1; 0 = stuff), 2 = 0.  A segment takes its semantic majority class when that is a stuff class holding >= half of
+ * it; stuff classes smaller than stuff_area_limit pixels become void.  err_out (optional DEVICE int): bit 0 = label out of
+ * range, bit 1 = an instance id without an entry in cls_inds (the reference raises IndexError).
+ */
+int upsnet_unified_pan_workspace_bytes(int num_seg_classes, size_t *bytes);
+int upsnet_unified_pan_result(const long long *seg, const long long *pan, const long long *cls_inds, int k,
+                              const int *k_dev, int H, int W, int num_seg_classes, int num_classes,
+                              int stuff_area_limit, unsigned char *pan_2ch, int *err_out, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
+/* upsnet_prep_image: raw uint8 HWC (BGR) image -> the network input blob.
+ * replaces: dataset/base_dataset.py:143-174 prep_im_for_blob (mean subtraction, cv2.resize INTER_LINEAR) and :898-923
+ *           im_list_to_blob (zero padding to a multiple of the FPN stride, HWC -> CHW), plus the 4x larger fp32 H2D copy.
+ * image_hwc uint8 [h,w,3] on the DEVICE; scale = the fx = fy factor handed to cv2.resize (the source step is 1/scale,
+ * as OpenCV does when factors are given); (out_h,out_w) = the resized size (cvRound(h*scale), cvRound(w*scale));
+ * (pad_h,pad_w) >= it; blob fp32 [3,pad_h,pad_w]: resized (image - pixel_means), zeros in the padding.  The means are
+ * float64 like config.network.pixel_means: numpy subtracts in double and stores float32 (base_dataset.py:154).
+ */
+int upsnet_prep_image(const unsigned char *image_hwc, int h, int w, double scale, int out_h, int out_w, int pad_h,
+                      int pad_w, const double pixel_means[3], float *blob, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

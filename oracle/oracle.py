@@ -278,6 +278,54 @@ def panoptic_head_literal(fcn, boxes, cls_prob, mask_logit, cls_idx, num_stuff, 
     return keep, out
 
 
+def unified_pan_result(seg, pan, cls_ind, num_seg_classes, num_classes, stuff_area_limit=4 * 64 * 64):
+    """dataset/base_dataset.py:332-371 get_unified_pan_result for ONE image, restated with explicit histograms (the
+    reference uses np.unique per segment).  seg / pan [H,W] ints, cls_ind [k] -> uint8 [H,W,3]."""
+    seg, pan = np.asarray(seg), np.asarray(pan)
+    id_last = num_seg_classes - num_classes
+    pan_seg = pan.copy()
+    pan_ins = np.where(pan <= id_last, 0, pan)
+    ids = np.unique(pan)
+    ids_ins = ids[ids > id_last]
+    for idx, i in enumerate(ids_ins):
+        region = pan == i
+        if i == 255:
+            pan_seg[region] = 255
+            pan_ins[region] = 0
+            continue
+        cnt = np.bincount(seg[region].astype(np.int64), minlength=num_seg_classes)
+        major = int(np.argmax(cnt))                                     # first maximum = smallest class id
+        target = int(cls_ind[i - id_last - 1]) + id_last
+        if major != target and 2 * int(cnt.max()) >= int(cnt.sum()) and major <= id_last:
+            pan_seg[region] = major
+            pan_ins[region] = 0
+        else:
+            pan_seg[region] = target
+            pan_ins[region] = idx + 1
+    for c in np.unique(pan_seg):
+        if c <= id_last and (pan_seg == c).sum() < stuff_area_limit:
+            pan_seg[pan_seg == c] = 255
+    out = np.zeros(pan.shape + (3,), np.uint8)
+    out[..., 0] = pan_seg
+    out[..., 1] = pan_ins
+    return out
+
+
+def prep_image(im_hwc_u8, pixel_means, scale, stride=32):
+    """dataset/base_dataset.py:143-174 + :898-923 for one target size: float32, mean subtraction, cv2.resize by `scale`
+    (INTER_LINEAR), CHW, zero padding to a multiple of `stride`.  Uses the real cv2 (what the reference calls)."""
+    import cv2
+    im = im_hwc_u8.astype(np.float32, copy=True)
+    im -= np.asarray(pixel_means, np.float64).reshape((1, 1, -1))      # float64 means: numpy subtracts in double, stores float32
+    im = cv2.resize(im, None, None, fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)
+    chw = im.transpose(2, 0, 1)
+    Hp = int(np.ceil(chw.shape[1] / float(stride)) * stride)
+    Wp = int(np.ceil(chw.shape[2] / float(stride)) * stride)
+    blob = np.zeros((1, 3, Hp, Wp), np.float32)
+    blob[0, :, :chw.shape[1], :chw.shape[2]] = chw
+    return blob, chw.shape[1:]
+
+
 class RefKernels:
     """The reference's own CUDA kernels (oracle/_ref/libupsnet_ref.so), torch tensors in/out."""
 

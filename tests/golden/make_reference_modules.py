@@ -248,6 +248,54 @@ def main():
     m_keep = mm(torch.from_numpy(gt_segs), torch.from_numpy(gt_masks), torch.from_numpy(keep))
     out.update(mmatch_gt_segs=gt_segs, mmatch_gt_masks=gt_masks, mmatch_keep=keep, mmatch_all=m_all.numpy(), mmatch_kept=m_keep.numpy())
 
+    # ------------------------------------------------------------------ get_unified_pan_result (f2)
+    # dataset/base_dataset.py pulls pycocotools / Cython at import: the METHOD's own source lines (332-371) are compiled
+    # from the file, unmodified, with `np` and the reference `config` as its globals.
+    import ast
+    src = open("/root/reference/upsnet/dataset/base_dataset.py").read()
+    fn = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "get_unified_pan_result"][0]
+    ns = {"np": np, "config": config}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "base_dataset.py:332-371", "exec"), ns)
+    get_unified = ns["get_unified_pan_result"]
+    uni_cases = [dict(H=96, W=160, k=14, limit=400), dict(H=128, W=192, k=30, limit=4 * 64 * 64), dict(H=64, W=64, k=0, limit=100)]
+    for ci, c in enumerate(uni_cases):
+        H, W, k = c["H"], c["W"], c["k"]
+        seg = rng.integers(0, 19, (H, W)).astype(np.int64)
+        # blocky semantic map so that majorities exist
+        seg = np.kron(rng.integers(0, 19, (H // 16, W // 16)), np.ones((16, 16), np.int64)).astype(np.int64)
+        pan = np.kron(rng.integers(0, 11, (H // 8, W // 8)), np.ones((8, 8), np.int64)).astype(np.int64)
+        cls = rng.integers(1, 9, max(k, 1)).astype(np.int64)
+        for j in range(k):
+            y, x = rng.integers(0, H - 24), rng.integers(0, W - 24)
+            hh, ww = rng.integers(6, 24), rng.integers(6, 24)
+            pan[y:y + hh, x:x + ww] = 11 + j
+            if j % 3 == 0:      # make the instance's own class the semantic majority under it
+                seg[y:y + hh, x:x + ww] = cls[j] + 10
+            elif j % 3 == 1:    # a stuff class holds the majority: the segment is re-labelled as stuff
+                seg[y:y + hh, x:x + ww] = rng.integers(0, 11)
+        pan[:3, :7] = 255
+        res = get_unified(None, [seg], [pan], [cls], stuff_area_limit=c["limit"])[0]
+        p = "uni%d_" % ci
+        out.update({p + "seg": seg, p + "pan": pan, p + "cls": cls[:k] if k else np.zeros((0,), np.int64), p + "limit": np.int64(c["limit"]),
+                    p + "out": res})
+    out["uni_cases"] = np.int64(len(uni_cases))
+
+    # ------------------------------------------------------------------ input pipeline (f3): prep_im_for_blob + im_list_to_blob
+    fnames = ("prep_im_for_blob", "im_list_to_blob")
+    fns = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name in fnames]
+    import cv2
+    ns2 = {"np": np, "config": config, "cv2": cv2}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "base_dataset.py:143-174,898-923", "exec"), ns2)
+    config.network.has_fpn = True
+    for ci, (h, w, target, max_size) in enumerate(((120, 200, 120, 400), (100, 150, 160, 1333), (97, 131, 80, 100))):
+        im = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        ims, scales = ns2["prep_im_for_blob"](None, im.copy(), config.network.pixel_means, [target], max_size)
+        blob = ns2["im_list_to_blob"](None, [ims[0].transpose(2, 0, 1)])
+        p = "prep%d_" % ci
+        out.update({p + "im": im, p + "scale": np.float64(scales[0]), p + "resized_hw": np.array(ims[0].shape[:2]), p + "blob": blob})
+    out["prep_cases"] = np.int64(3)
+    out["prep_pixel_means"] = np.asarray(config.network.pixel_means, np.float64)
+
     np.savez_compressed(os.path.join(HERE, "reference_modules.npz"), **out)
     print("wrote reference_modules.npz with", len(out), "arrays;",
           "panoptic kept:", [int(out["pan%d_keep" % i].shape[0]) for i in range(len(pan_cases))],

@@ -111,3 +111,45 @@ def test_proposal_kernels_vs_reference(ref, dev, i, fused):
             np.testing.assert_allclose(rois.cpu().numpy(), want_rois, rtol=0, atol=2e-3)
     finally:
         det.FUSED["on"] = old
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_unified_pan_kernels_vs_reference(ref, dev, i):
+    """upsnet_unified_pan_result (row f2) == the reference's get_unified_pan_result, bit for bit."""
+    import upsnet_b200 as U
+    p = "uni%d_" % i
+    got = U.unified_pan_result(t(ref[p + "seg"], dev), t(ref[p + "pan"], dev), t(ref[p + "cls"], dev), 19, 9, int(ref[p + "limit"]))
+    assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), ref[p + "out"])
+
+
+def test_unified_pan_full_size_vs_oracle(dev):
+    import upsnet_b200 as U
+    rng = np.random.default_rng(5)
+    H, W, k = 1024, 2048, 60
+    seg = np.kron(rng.integers(0, 19, (H // 32, W // 32)), np.ones((32, 32), np.int64))
+    pan = np.kron(rng.integers(0, 11, (H // 64, W // 64)), np.ones((64, 64), np.int64))
+    cls = rng.integers(1, 9, k).astype(np.int64)
+    for j in range(k):
+        y, x = rng.integers(0, H - 200), rng.integers(0, W - 300)
+        pan[y:y + rng.integers(20, 200), x:x + rng.integers(20, 300)] = 11 + j
+    pan[:9, :33] = 255
+    got = U.unified_pan_result(t(seg, dev), t(pan, dev), t(cls, dev), 19, 9)
+    assert np.array_equal(got.cpu().numpy(), O.unified_pan_result(seg, pan, cls, 19, 9))
+    with pytest.raises(IndexError):
+        U.unified_pan_result(t(seg, dev), t(pan, dev), t(cls[:10], dev), 19, 9)
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_prep_image_kernel_vs_reference(ref, dev, i):
+    """upsnet_prep_image (row f3) vs prep_im_for_blob + im_list_to_blob with the real cv2.resize: fp32 within 1e-3 (cv2's
+    SIMD rounding is not bit-reproducible), exact where no resize happens."""
+    import upsnet_b200 as U
+    p = "prep%d_" % i
+    blob, hw = U.prep_image(t(ref[p + "im"], dev), ref["prep_pixel_means"], float(ref[p + "scale"]))
+    want = ref[p + "blob"]
+    assert tuple(hw) == tuple(ref[p + "resized_hw"]) and tuple(blob.shape) == want.shape
+    assert np.abs(blob.cpu().numpy() - want).max() < 1e-3 * max(1.0, np.abs(want).max() / 30)   # ~3e-5 relative
+    im = ref[p + "im"]
+    same, _ = U.prep_image(t(im, dev), ref["prep_pixel_means"], 1.0)
+    exact, _ = O.prep_image(im, ref["prep_pixel_means"], 1.0)
+    assert np.array_equal(same.cpu().numpy(), exact)

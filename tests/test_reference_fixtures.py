@@ -151,3 +151,19 @@ def test_mask_matching_vs_reference(ref):
     segs, masks = torch.from_numpy(ref["mmatch_gt_segs"]), torch.from_numpy(ref["mmatch_gt_masks"])
     assert np.array_equal(mm(segs, masks).numpy(), ref["mmatch_all"])
     assert np.array_equal(mm(segs, masks, torch.from_numpy(ref["mmatch_keep"])).numpy(), ref["mmatch_kept"])
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_unified_pan_oracle_vs_reference(ref, i):
+    """oracle.unified_pan_result == the reference's get_unified_pan_result (its own source lines, executed)."""
+    p = "uni%d_" % i
+    got = O.unified_pan_result(ref[p + "seg"], ref[p + "pan"], ref[p + "cls"], 19, 9, int(ref[p + "limit"]))
+    assert np.array_equal(got, ref[p + "out"])
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_prep_image_oracle_vs_reference(ref, i):
+    p = "prep%d_" % i
+    blob, hw = O.prep_image(ref[p + "im"], ref["prep_pixel_means"], float(ref[p + "scale"]))
+    assert tuple(hw) == tuple(ref[p + "resized_hw"]) and blob.shape == ref[p + "blob"].shape
+    assert np.array_equal(blob, ref[p + "blob"])

@@ -1016,3 +1016,56 @@ class PanopticHead(nn.Module):
         if want_sem:
             res['fcn_outputs'] = out[2]
         return res
+
+
+# ------------------------------------------------------------------------------------------------
+# callers either side of the forward: unified panoptic result, input pipeline
+# ------------------------------------------------------------------------------------------------
+_uni_ws = _Workspace()
+
+
+def unified_pan_result(seg, pan, cls_inds, num_seg_classes, num_classes, stuff_area_limit=4 * 64 * 64, k_dev=None,
+                       check_errors=True):
+    """dataset/base_dataset.py:332-371 get_unified_pan_result for one image, on the device.
+    seg / pan: int64 [H,W] or [1,H,W] ('fcn_outputs' / 'panoptic_outputs' of the forward); cls_inds int64 [k]
+    ('panoptic_cls_inds').  -> uint8 [H,W,3] (semantic class, instance number, 0).  With check_errors (one int D2H) an
+    instance label without a cls_inds entry raises IndexError like the reference."""
+    require_cuda(seg, pan, cls_inds)
+    seg = seg.reshape(seg.shape[-2:]).to(torch.int64).contiguous()
+    pan = pan.reshape(pan.shape[-2:]).to(torch.int64).contiguous()
+    cls = cls_inds.to(torch.int64).contiguous()
+    H, W = pan.shape
+    dev = pan.device
+    nb = C.c_size_t(0)
+    check(lib().upsnet_unified_pan_workspace_bytes(int(num_seg_classes), C.byref(nb)), "unified_pan_workspace_bytes")
+    ws = _uni_ws.get(dev, nb.value)
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _Timed("unified_pan", 5, {"bytes": 19.0 * H * W}, dev):
+        check(lib().upsnet_unified_pan_result(ptr(seg), ptr(pan), ptr(cls), int(cls.numel()), ptr(k_dev), H, W,
+                                              int(num_seg_classes), int(num_classes), int(stuff_area_limit), ptr(out), ptr(err),
+                                              ptr(ws), ws.numel(), stream_ptr(dev)), "unified_pan_result")
+    if check_errors:
+        e = int(err.item())
+        if e & 2:
+            raise IndexError("panoptic label without an entry in cls_inds (base_dataset.py:350)")
+        if e & 1:
+            raise ValueError("label out of range in seg / pan")
+    return out
+
+
+def prep_image(image_hwc_u8, pixel_means, scale=1.0, stride=32):
+    """dataset/base_dataset.py:143-174 prep_im_for_blob + :898-923 im_list_to_blob on the device: uint8 [h,w,3] (BGR)
+    -> fp32 blob [1,3,Hp,Wp] (mean-subtracted, bilinearly resized by `scale`, zero-padded to a multiple of `stride`)
+    and the resized (h, w)."""
+    require_cuda(image_hwc_u8)
+    assert image_hwc_u8.dtype == torch.uint8 and image_hwc_u8.dim() == 3 and image_hwc_u8.shape[2] == 3
+    im = image_hwc_u8.contiguous()
+    h, w = int(im.shape[0]), int(im.shape[1])
+    ho, wo = int(np.rint(h * scale)), int(np.rint(w * scale))              # cvRound(src * f) (cv2.resize dsize rule)
+    Hp, Wp = int(math.ceil(ho / float(stride)) * stride), int(math.ceil(wo / float(stride)) * stride)
+    blob = torch.empty((1, 3, Hp, Wp), dtype=torch.float32, device=im.device)
+    pm = (C.c_double * 3)(*[float(v) for v in pixel_means])
+    with torch.cuda.device(im.device), _Timed("prep_image", 1, {"bytes": 3.0 * h * w + 12.0 * Hp * Wp}, im.device):
+        check(lib().upsnet_prep_image(ptr(im), h, w, float(scale), ho, wo, Hp, Wp, pm, ptr(blob), stream_ptr(im.device)), "prep_image")
+    return blob, (ho, wo)

@@ -20,10 +20,18 @@ class PipelinedEngine:
     RESULT_KEYS = ("panoptic_outputs", "fcn_outputs", "pred_boxes", "cls_probs", "cls_inds", "counts", "keep", "p_cls",
                    "p_scores")
 
-    def __init__(self, model, im_info, depth=2, with_masks=False):
+    PIXEL_MEANS = (102.9801, 115.9465, 122.7717)     # config.network.pixel_means (BGR, caffe models)
+
+    def __init__(self, model, im_info, depth=2, with_masks=False, with_unified=False, stuff_area_limit=4 * 64 * 64,
+                 pixel_means=None, im_scale=1.0):
+        """with_unified: also run get_unified_pan_result on the device (base_dataset.py:332-371) and return its uint8
+        [H,W,3] map as 'pan_2ch'.  submit() also accepts the RAW uint8 [h,w,3] BGR image (pinned): mean subtraction,
+        resize by im_scale and padding (prep_im_for_blob / im_list_to_blob) then run on the device after a 4x smaller H2D."""
         self.model, self.depth = model, depth
         self.im_info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)[0]
-        self.keys = self.RESULT_KEYS + (("mask_probs",) if with_masks else ())
+        self.keys = self.RESULT_KEYS + (("mask_probs",) if with_masks else ()) + (("pan_2ch",) if with_unified else ())
+        self.with_unified, self.stuff_area_limit = with_unified, stuff_area_limit
+        self.pixel_means, self.im_scale = (pixel_means or self.PIXEL_MEANS), float(im_scale)
         self.dev = None
         self._t = 0
         self._slots = None
@@ -36,13 +44,19 @@ class PipelinedEngine:
         self.dev = next(model.parameters()).device
         assert self.dev.type == "cuda", "no CPU fallback"
         self.h2d, self.d2h = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        x0 = torch.empty(host_image.shape, dtype=torch.float32, device=self.dev)
-        x0.copy_(host_image)
+        self.raw = host_image.dtype == torch.uint8
+        if self.raw:
+            from . import operators as ops
+            x0, _ = ops.prep_image(host_image.to(self.dev), self.pixel_means, self.im_scale)
+        else:
+            x0 = torch.empty(host_image.shape, dtype=torch.float32, device=self.dev)
+            x0.copy_(host_image)
         out, _ = model._run_static(x0, self.im_info)      # captures the graph on first use
+        out = self._post(dict(out))
         torch.cuda.synchronize(self.dev)
         self._slots = []
         for _ in range(self.depth):
-            s = {"in": torch.empty_like(x0),
+            s = {"in": torch.empty(host_image.shape, dtype=host_image.dtype, device=self.dev),
                  "out": {k: torch.empty_like(out[k]) for k in self.keys},
                  "host": {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in self.keys},
                  "in_ready": torch.cuda.Event(), "in_free": torch.cuda.Event(), "out_ready": torch.cuda.Event(),
@@ -63,7 +77,12 @@ class PipelinedEngine:
             s["in"].copy_(host_image, non_blocking=True)
             s["in_ready"].record(self.h2d)
         cur.wait_event(s["in_ready"])
-        out, _ = self.model._run_static(s["in"], self.im_info)
+        x = s["in"]
+        if self.raw:
+            from . import operators as ops
+            x, _ = ops.prep_image(s["in"], self.pixel_means, self.im_scale)
+        out, _ = self.model._run_static(x, self.im_info)
+        out = self._post(dict(out))
         s["in_free"].record(cur)
         cur.wait_event(s["done"])                          # this slot's previous results have left the device
         for k in self.keys:
@@ -76,6 +95,15 @@ class PipelinedEngine:
             s["done"].record(self.d2h)
         self._t += 1
         return self._t - 1
+
+    def _post(self, out):
+        if self.with_unified:
+            from . import operators as ops
+            m = self.model
+            out["pan_2ch"] = ops.unified_pan_result(out["fcn_outputs"], out["panoptic_outputs"], out["p_cls"][out["keep"]],
+                                                    m.num_seg_classes, m.num_classes, self.stuff_area_limit,
+                                                    k_dev=out["counts"][2:3], check_errors=False)
+        return out
 
     def result(self, ticket):
         """Blocks until image `ticket` is on the host.  The returned tensors view this slot's pinned buffers and stay
@@ -91,8 +119,10 @@ class PipelinedEngine:
                "panoptic_cls_inds": h["p_cls"][:n2][keep], "panoptic_cls_probs": h["p_scores"][:n2][keep]}
         if "mask_probs" in h:
             res["mask_probs"] = h["mask_probs"][:n1]
+        if "pan_2ch" in h:
+            res["pan_2ch"] = h["pan_2ch"]
         return res
 
     def bytes_per_image(self):
         s = self._slots[0]
-        return (s["in"].numel() * 4, sum(t.numel() * t.element_size() for t in s["host"].values()))
+        return (s["in"].numel() * s["in"].element_size(), sum(t.numel() * t.element_size() for t in s["host"].values()))
