@@ -306,7 +306,7 @@ def main():
     from upsnet_b200.model import UPSNetConfig
     from upsnet_b200.synthetic import synthetic_input, synthetic_model
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
-    numa_cpus = bind_to_gpu_numa(local)
+    numa_cpus = 0 if os.environ.get("UPSNET_BENCH_NO_NUMA") else bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -377,7 +377,7 @@ def main():
         step_e2e(i)
     drain_e2e()
     sampler = None
-    if rank == 0:
+    if rank == 0 and not os.environ.get("UPSNET_BENCH_NO_SAMPLER"):
         sampler = NvmlSampler(local)
         if not sampler.ok:
             sampler = ClockSampler(local)

@@ -102,7 +102,8 @@ def subsample2(x):
 
 
 def as_float(x):
-    return x.float()
+    """A Pair becomes its fp32 tensor (hi + lo); plain tensors pass through untouched (no dtype round trip)."""
+    return x.float() if isinstance(x, Pair) else x
 
 
 # launch accounting (bench.py reports gpu_launches) and optional per-call CUDA-event timing of the

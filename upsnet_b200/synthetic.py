@@ -58,10 +58,42 @@ def synthetic_model(cfg=None, depth=(3, 4, 6, 3), seed=0, device="cpu"):
         m.rcnn.bbox_pred.weight.copy_(torch.empty_like(m.rcnn.bbox_pred.weight).normal_(0, 0.02, generator=g))
         m.mask_branch.mask_score.bias.fill_(0.2)
         m.fcn_head.score.weight.copy_(torch.empty_like(m.fcn_head.score.weight).normal_(0, 0.1, generator=g))
+        if sum(depth) > 16:      # deeper than ResNet-50: keep the residual stream of the random-init stack bounded
+            _calibrate_residual_growth(m, g)
         _calibrate_fpn_laterals(m, g)
     m = m.to(device)
     m.prepare()
     return m
+
+
+def _calibrate_residual_growth(m, g):
+    """A random-init residual stack multiplies its activation scale by ~1.8 per block; over the 23 blocks of a ResNet-101
+    res4 stage that is 10^5 -- the DCN offset convs then ask for offsets of hundreds of pixels and the forward becomes
+    chaotic (any two fp32 implementations diverge).  One torch-only pass over a small random image rescales every
+    block's bn3 so that its residual branch has at most a quarter of the trunk's RMS (growth <= 3 % per block), like a
+    trained network's.  ResNet-50 models are left exactly as in round 1."""
+    import torch.nn.functional as F
+    bb = m.resnet_backbone
+    x = (torch.randn(1, 3, 96, 128, generator=g) * 50)
+    cpu = lambda t: t.detach().float().cpu()   # noqa: E731
+
+    def bn(t, b):
+        return F.batch_norm(t, cpu(b.running_mean), cpu(b.running_var), cpu(b.weight), cpu(b.bias), False, 0.0, b.eps)
+
+    t = F.max_pool2d(F.relu(bn(F.conv2d(x, cpu(bb.conv1.conv1.weight), None, 2, 3), bb.conv1.bn1)), 3, 2, 1)
+    for blk in (bb.res2, bb.res3, bb.res4, bb.res5):
+        for b in blk.layers:
+            out = F.relu(bn(F.conv2d(t, cpu(b.conv1.weight), None, b.stride), b.bn1))
+            out = F.relu(bn(F.conv2d(out, cpu(b.conv2.weight), None, 1, b.dilation, b.dilation), b.bn2))   # offsets ignored
+            pre = F.conv2d(out, cpu(b.conv3.weight))
+            branch = bn(pre, b.bn3)
+            res = t if b.downsample is None else bn(F.conv2d(t, cpu(b.downsample[0].weight), None, b.stride), b.downsample[1])
+            r_b, r_t = branch.pow(2).mean().sqrt().item(), res.pow(2).mean().sqrt().item()
+            if r_b > 0.25 * r_t:
+                s_ = 0.25 * r_t / r_b
+                b.bn3.weight.mul_(s_); b.bn3.bias.mul_(s_)
+                branch = bn(pre, b.bn3)
+            t = F.relu(branch + res)
 
 
 def _calibrate_fpn_laterals(m, g):
