@@ -331,6 +331,17 @@ def main():
     def step_resident(i):
         return model({"data": dev_imgs[i % n_img], "im_info": im_info})
 
+    # The resident leg drives the SYNC-FREE engine entry: one CUDA-graph replay per image, the 3-int result-size vector
+    # copied to pinned host memory asynchronously (model.forward() would block the host on it every image, which makes the
+    # number a measure of host wake-up latency: 101..151 images/s from run to run in round 2).  Everything the forward
+    # computes is computed; the sizes are checked after the timed region.
+    counts_host = torch.zeros((max(args.steps, 8), 3), dtype=torch.int32).pin_memory()
+
+    def step_graph(i):
+        out, _ = model._run_static(dev_imgs[i % n_img], im_info[0])
+        counts_host[i % counts_host.shape[0]].copy_(out["counts"], non_blocking=True)
+        return out
+
     # end-to-end leg: the pipelined serving front end (upsnet_b200/pipeline.py).  Every step submits one PINNED HOST
     # image (H2D inside the timed region) and reads the previous step's results back to the host (D2H inside the timed
     # region); the copies of neighbouring images overlap the compute of the current one on separate streams.
@@ -382,7 +393,13 @@ def main():
         if not sampler.ok:
             sampler = ClockSampler(local)
         sampler.start(); time.sleep(0.1)
-    ms, launches, per_rank = timed(step_resident, args.steps)
+    if not model._prepared:
+        model.prepare()
+    for i in range(2):
+        step_graph(i)
+    counts_host.zero_()
+    ms, launches, per_rank = timed(step_graph, args.steps)
+    assert int(counts_host[:args.steps, 0].min()) >= 1, "every image must yield at least the dummy detection"
     ms_e2e, _, per_rank_e2e = timed(step_e2e, args.steps, finish=drain_e2e)
     clocks = sampler.stop() if sampler else None
     h2d, d2h = engine.bytes_per_image()
@@ -456,8 +473,8 @@ def main():
     if args.precision == "bf16x3" and args.workload == "cityscapes":
         U.set_precision("bf16")
         for i in range(3):
-            step_resident(i)
-        ms3, _, _ = timed(step_resident, max(5, args.steps // 2))
+            step_graph(i)
+        ms3, _, _ = timed(step_graph, max(5, args.steps // 2))
         other = {"precision": "bf16", "value": world * max(5, args.steps // 2) / (ms3 * 1e-3), "unit": "images/s",
                  "note": "single tcgen05 pass on bf16 activations: bf16-level error (tests hold it to 4e-2..8e-2), reported "
                          "for reference only -- the headline is the bf16x3 pair stream that meets 'fp32 logits within 1e-3'"}
@@ -475,7 +492,8 @@ def main():
                 "config": {"workload": WORKLOAD, "parallelism": "replicas x%d (one image per GPU, no collective)" % world,
                            "l2": "no flush: each step streams >1 GB of activations (>> 126 MB L2) and rotates %d images" % n_img,
                            "weights": "random-init (upsnet_b200/synthetic.py), frozen BN folded",
-                           "engine": "static shapes, device-side counts, CUDA graph replay=%s" % bool(model.use_cuda_graph)},
+                           "engine": "static shapes, device-side counts, CUDA graph replay=%s; value = sync-free engine entry "
+                                     "(result sizes read back asynchronously), e2e = public PipelinedEngine API" % bool(model.use_cuda_graph)},
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

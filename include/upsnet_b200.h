@@ -43,6 +43,10 @@ extern "C" {
  * [hi Cout][lo Cout] (G % 64 == 0, Cout % G == 0; 0 = Cout).  Lets a 1x1 conv that emulates a 2x2 deconvolution write
  * its four (a,b) sub-pixel groups as four pair pixels (models/rcnn.py:62 mask_deconv1). */
 #define UPSNET_EPI_PAIR_GROUP(G) ((((G) / 64) & 0xfff) << 8)
+/* upsnet_igemm_forward, fp32 plane-wise (NCHW) or small-Cout outputs only: output channels >= c get a logistic sigmoid
+ * 1 / (1 + expf(-v)) after the bias (models/rpn.py:55 cls_prob = sigmoid(cls_score): the RPN head writes the logits and,
+ * from duplicated weight rows, their probabilities in one launch). */
+#define UPSNET_EPI_SIGMOID_FROM(c) ((((c) + 1) & 0x3ff) << 20)
 
 /* precision of the tensor-core convolution path */
 #define UPSNET_PREC_FP32_SIMT 0 /* fp32 FFMA tiles (exact-order-free fp32)            */
@@ -208,6 +212,13 @@ int upsnet_maxpool2d_nhwc(const void *x, void *y, int N, int H, int W, int C, in
  * x [planes,H,W] -> y [planes,H*factor,W*factor]; (W*factor) % 4 == 0. */
 int upsnet_upsample_bilinear_nchw(const float *x, float *y, int planes, int H, int W, int factor,
                                   void *stream);
+
+/* Semantic-head score assembly: out = s2 + up2(s3) + up4(s4) + up8(s5), bilinear, align_corners = False.
+ * replaces: models/fcn.py:94-101 (three F.interpolate of 128-channel maps + cat + score conv; the engine scores every level
+ *           at its own resolution first -- the 1x1 conv and the up-sampling commute -- and sums the 19-plane maps here).
+ * s2 [planes,H,W], s3 [planes,H/2,W/2], s4 [planes,H/4,W/4], s5 [planes,H/8,W/8] fp32; H % 8 == W % 8 == 0. */
+int upsnet_fcn_score_fuse(const float *s2, const float *s3, const float *s4, const float *s5, float *out,
+                          int planes, int H, int W, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Detection glue, fused (device-resident; nothing returns to the host).

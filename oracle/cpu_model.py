@@ -17,11 +17,14 @@ from . import oracle as O
 
 
 def _conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-            out_format=None, out_dtype=None, residual_up2=False):
+            out_format=None, out_dtype=None, residual_up2=False, pair_group=0, sigmoid_from=None):
     y = F.conv2d(x.float(), weight.float(), None if bias is None else bias.float(), stride, padding, dilation)
     if residual is not None:
         y = y + (F.interpolate(residual, scale_factor=2, mode="nearest") if residual_up2 else residual)
-    return F.relu(y) if relu else y
+    y = F.relu(y) if relu else y
+    if sigmoid_from is not None:
+        y = torch.cat([y[:, :sigmoid_from], torch.sigmoid(y[:, sigmoid_from:])], 1)
+    return y
 
 
 def _linear(x, weight, bias=None, relu=False, precision=None, out_dtype=None):

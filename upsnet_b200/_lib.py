@@ -17,6 +17,10 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 EPI_RELU = 1
 EPI_RES_UP2 = 2
 EPI_NO_TMA = 4
+
+
+def EPI_SIGMOID_FROM(c):
+    return ((int(c) + 1) & 0x3ff) << 20
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_PAIR = 0, 1, 2
 LAYOUT_FLAT_PAIR = 2
@@ -65,6 +69,7 @@ def lib():
         L.upsnet_stem_forward.argtypes = [vp] * 4 + [i] * 9 + [vp, sz, vp]
         L.upsnet_rpn_collect.argtypes = [vp] * 5 + [i] * 3 + [vp] * 4
         L.upsnet_rpn_topk.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i), i, i, i, vp, vp, vp, sz, vp]
+        L.upsnet_fcn_score_fuse.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
         L.upsnet_unified_pan_workspace_bytes.argtypes = [i, C.POINTER(sz)]
         L.upsnet_unified_pan_result.argtypes = [vp, vp, vp, i, vp, i, i, i, i, i, vp, vp, vp, sz, vp]
         L.upsnet_prep_image.argtypes = [vp, i, i, d, i, i, i, i, C.POINTER(d), vp, vp]
@@ -79,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_workspace_min_bytes", "upsnet_panoptic_head", "upsnet_mask_removal",
     "upsnet_rpn_decode", "upsnet_maskroi_prepare", "upsnet_maskroi_finish", "upsnet_maxpool2d_nhwc", "upsnet_upsample_bilinear_nchw", "upsnet_rpn_topk_workspace_bytes", "upsnet_rpn_topk", "upsnet_rpn_collect", "upsnet_stem_workspace_bytes",
     "upsnet_stem_packed_weight_bytes", "upsnet_stem_pack_weight", "upsnet_stem_forward",
-    "upsnet_unified_pan_workspace_bytes", "upsnet_unified_pan_result", "upsnet_prep_image",
+    "upsnet_fcn_score_fuse", "upsnet_unified_pan_workspace_bytes", "upsnet_unified_pan_result", "upsnet_prep_image",
 ]
 
 

@@ -122,6 +122,8 @@ extern "C" int upsnet_igemm_forward(const void* x_nhwc, const float* offset, con
   p.x_pair = x_dtype == UPSNET_DTYPE_PAIR;
   p.y_pair = y_dtype == UPSNET_DTYPE_PAIR;
   p.pair_group = 64 * ((epi_flags >> 8) & 0xfff);
+  p.sig_from = ((epi_flags >> 20) & 0x3ff) - 1;
+  if (p.sig_from >= 0 && (p.y_pair || p.y_bf16 || p.residual)) return UPSNET_E_UNSUPPORTED;
   // bf16 storage carries precision bf16; hi/lo pairs are the 16-bit storage of precision bf16x3 (the split of x)
   if (p.x_bf16 && p.x3) return UPSNET_E_UNSUPPORTED;
   if ((p.x_pair || p.y_pair) && !p.x3) return UPSNET_E_UNSUPPORTED;

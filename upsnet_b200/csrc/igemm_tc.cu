@@ -783,6 +783,7 @@ igemm_tc_kernel(const TcParams p) {
             } else {
               if (p.residual) o += __ldg(reinterpret_cast<const float*>(p.residual) + oidx);
               if (p.relu) o = fmaxf(o, 0.f);
+              if (p.sig_from >= 0 && co >= p.sig_from) o = 1.f / (1.f + expf(-o));
               reinterpret_cast<float*>(p.y)[oidx] = o;
             }
           }
@@ -859,6 +860,7 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   if (deform && (p.x_bf16 || p.x_pair) && (long long)p.H * p.W * p.Cin * (p.x_pair ? 2 : 1) >= (1ll << 31)) return UPSNET_E_UNSUPPORTED;   // int32 element offsets
   if (smallc && (deform || p.x_bf16 || p.x_pair || p.dh * (p.kh - 1) > 255 || p.dw * (p.kw - 1) > 255)) return UPSNET_E_UNSUPPORTED;
   if (p.x_pair && !p.x3) return UPSNET_E_UNSUPPORTED;          // pairs are the storage format of precision bf16x3
+  if (p.sig_from >= 0 && (p.out_nhwc || p.y_bf16)) return UPSNET_E_UNSUPPORTED;   // sigmoid lives in the fp32 NCHW per-lane epilogue
   if (p.y_pair) {
     // pair output: the staged NHWC epilogue only (16-byte vectors), plain [hi Cout][lo Cout] grouping
     if (!p.out_nhwc || (p.Cout & 7) || (p.pair_group && p.pair_group != p.Cout)) return UPSNET_E_UNSUPPORTED;

@@ -50,6 +50,7 @@ struct TmaGeom {
   int halo, patch_rows, pstages, kh;
   int rotate;                           // tile-dependent start of the K loop (see producer)
   int wres, wtiles;                     // halo mode with the n-tile's whole weight set (wtiles tiles) resident in smem, loaded once per CTA
+  int sig_from;                         // direct epilogue: channels >= sig_from get a logistic sigmoid (-1 = none)
   int dbg;                              // timing experiments only (UPSNET_TMA_DEBUG): 1 alternate accumulators, 2 one MMA per k-block, 3 no MMAs
   // PAIR mode (precision bf16x3 on the TMA kernel): activations are hi/lo bf16 PAIRS -- an NHWC tensor with 2*C channels,
   // channels [0,C) = bf16(x), [C,2C) = bf16(x - hi) -- weights are the packed hi/lo planes, every k-slice issues three
@@ -498,6 +499,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             float o = __uint_as_float(v[e]);
             if (g.bias) o += __ldg(g.bias + co);
             if (g.relu) o = fmaxf(o, 0.f);
+            if (g.sig_from >= 0 && co >= g.sig_from) o = 1.f / (1.f + expf(-o));
             const size_t oi = g.out_nhwc ? pix * g.Cout + co : ((size_t)ni * g.Cout + co) * HoWo + (size_t)ho * g.Wo + wo;
             if (g.y_bf16) reinterpret_cast<__nv_bfloat16*>(g.y)[oi] = __float2bfloat16_rn(o);
             else reinterpret_cast<float*>(g.y)[oi] = o;
@@ -738,6 +740,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   // slab epilogue (TMA store): bf16 / pair NHWC output with Cout % 64 == 0; everything else without a residual goes
   // through the direct-store epilogue (small heads: Cout 9..45, fp32 planes)
   const bool direct = (!p.y_bf16 && !p.y_pair) || !p.out_nhwc || (p.Cout % 64) != 0;
+  if (p.sig_from >= 0 && !direct) return UPSNET_E_UNSUPPORTED;
   if (direct && (p.residual || p.Cout > 256)) return UPSNET_E_UNSUPPORTED;
   if (p.res_up2 && (!p.residual || (p.Ho & 1) || (p.Wo & 1))) return UPSNET_E_UNSUPPORTED;
   // stride > 1 only for 1x1 / pad 0 (the ResNet down-sampling convs): the input is then addressed through a
@@ -760,7 +763,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   g.bias = p.bias;
   g.N = p.N; g.Ho = p.Ho; g.Wo = p.Wo; g.Cout = p.Cout; g.Cin = p.Cin;
   g.kw = p.kw; g.KHW = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.dh = p.dh; g.dw = p.dw;
-  g.relu = p.relu; g.has_res = p.residual ? 1 : 0; g.res_up2 = p.res_up2 ? 1 : 0;
+  g.relu = p.relu; g.has_res = p.residual ? 1 : 0; g.res_up2 = p.res_up2 ? 1 : 0; g.sig_from = p.sig_from;
   tma_pick_box(p.N, p.Ho, p.Wo, p.kh, p.kw, p.dh, p.dw, g.res_up2 != 0, &g.bw, &g.bh, &g.bn);
   // halo mode for k x k filters (UPSNET_TMA_HALO=0 disables it, =2 also enables it for BN = 256): 8 x 16-pixel tiles,
   // 16-pixel-wide patch rows; the patch must cover 8 + (kw-1)*dw <= 16 pixels per row
@@ -984,6 +987,7 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
   g.N = N; g.Ho = Ho; g.Wo = Wo; g.Cout = Cout; g.Cin = 64;
   g.kw = 1; g.KHW = kh; g.ph = 0; g.pw = 0; g.dh = 1; g.dw = 1;
   g.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
+  g.sig_from = -1;
   g.stem = 1; g.y = y; g.y_bf16 = 1; g.out_nhwc = 1;
   tma_pick_box(N, Ho, Wo, 1, 1, 1, 1, false, &g.bw, &g.bh, &g.bn);
   g.tiles_w = (Wo + g.bw - 1) / g.bw;

@@ -167,6 +167,50 @@ upsample_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y
 
 }  // namespace ups
 
+// score = s2 + up2(s3) + up4(s4) + up8(s5): the semantic head's per-level score maps (the 1x1 score conv commutes with the
+// bilinear up-sampling, models/fcn.py:94-101) summed at P2 resolution in one pass, same bilinear rule and the same order
+// of the three additions as the torch expression it replaces (F.interpolate + add, three times).
+namespace ups {
+__device__ __forceinline__ float bilin_at(const float* __restrict__ pl, int H, int W, int f, int yo, int xo) {
+  const float rf = 1.0f / (float)f;
+  const float sy = fmaxf(rf * ((float)yo + 0.5f) - 0.5f, 0.f), sx = fmaxf(rf * ((float)xo + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* r0 = pl + (size_t)y0 * W;
+  const float* r1 = pl + (size_t)y1 * W;
+  return hy * (hx * __ldg(r0 + x0) + lx * __ldg(r0 + x1)) + ly * (hx * __ldg(r1 + x0) + lx * __ldg(r1 + x1));
+}
+
+__global__ void __launch_bounds__(256)
+fcn_score_fuse_kernel(const float* __restrict__ s2, const float* __restrict__ s3, const float* __restrict__ s4,
+                      const float* __restrict__ s5, float* __restrict__ out, int P, int H, int W) {
+  const long long total = (long long)P * H * W;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % W);
+    const long long r = t / W;
+    const int y = (int)(r % H), pl = (int)(r / H);
+    float v = s2[t];
+    v = v + bilin_at(s3 + (size_t)pl * (H / 2) * (W / 2), H / 2, W / 2, 2, y, x);
+    v = v + bilin_at(s4 + (size_t)pl * (H / 4) * (W / 4), H / 4, W / 4, 4, y, x);
+    v = v + bilin_at(s5 + (size_t)pl * (H / 8) * (W / 8), H / 8, W / 8, 8, y, x);
+    out[t] = v;
+  }
+}
+}  // namespace ups
+
+extern "C" int upsnet_fcn_score_fuse(const float* s2, const float* s3, const float* s4, const float* s5, float* out,
+                                     int planes, int H, int W, void* stream) {
+  if (!s2 || !s3 || !s4 || !s5 || !out || planes <= 0 || H <= 0 || W <= 0) return UPSNET_E_BADARG;
+  if ((H & 7) || (W & 7)) return UPSNET_E_UNSUPPORTED;
+  const long long total = (long long)planes * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > ups::kNumSMs * 32) blocks = ups::kNumSMs * 32;
+  ups::fcn_score_fuse_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s2, s3, s4, s5, out, planes, H, W);
+  UPS_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int upsnet_upsample_bilinear_nchw(const float* x, float* y, int planes, int H, int W, int factor, void* stream) {
   if (!x || !y || planes <= 0 || H <= 0 || W <= 0 || factor <= 0) return UPSNET_E_BADARG;
   if (((W * factor) & 3) || (((uintptr_t)y) & 15)) return UPSNET_E_UNSUPPORTED;

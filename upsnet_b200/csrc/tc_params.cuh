@@ -17,6 +17,7 @@ struct TcParams {
   int x_bf16, y_bf16;    // activation storage: 0 = fp32, 1 = bf16 (x / y+residual)
   int x_pair, y_pair;    // activation storage: hi/lo bf16 PAIRS, NHWC with 2*C channels ([0,C) = bf16(v), [C,2C) = bf16(v - hi));
                          // precision bf16x3 on bf16 storage: same bytes as fp32, but TMA / cp.async can feed the tensor core directly
+  int sig_from;          // output channels >= sig_from get 1 / (1 + expf(-v)) (direct / per-lane epilogues only); -1 = none
   int pair_group;        // y_pair: channels are stored [hi G][lo G] per group of G channels (0 = Cout; TMA kernel only)
   int res_up2;           // residual is a half-resolution NHWC map read with nearest-neighbour 2x upsampling
   int no_tma;            // UPSNET_EPI_NO_TMA: force the cp.async gather kernel (A/B comparisons, tests)

@@ -268,17 +268,18 @@ class RPN(nn.Module):
             m.bias.data.zero_()
         self._f = None
 
-    def prepare(self):  # the two 1x1 heads share their input: one GEMM with Cout = A + 4A
-        self._f = (torch.cat([self.cls_score.weight, self.bbox_pred.weight]).detach().contiguous(),
-                   torch.cat([self.cls_score.bias, self.bbox_pred.bias]).detach().contiguous())
+    def prepare(self):
+        # the two 1x1 heads share their input: one GEMM with Cout = A + 4A + A -- the last A rows repeat cls_score and get
+        # the sigmoid in the epilogue (models/rpn.py:55), so logits, deltas and probabilities leave one launch
+        self._f = (torch.cat([self.cls_score.weight, self.bbox_pred.weight, self.cls_score.weight]).detach().contiguous(),
+                   torch.cat([self.cls_score.bias, self.bbox_pred.bias, self.cls_score.bias]).detach().contiguous())
 
     def forward(self, x):
         c = self.conv_proposal[0]
         t = ops.conv2d(x, c.weight, c.bias, padding=1, relu=True)
-        both = ops.conv2d(t, self._f[0], self._f[1], out_format="nchw")
-        both = both.float()
-        cls_score, bbox_pred = both[:, :self.num_anchors], both[:, self.num_anchors:]
-        return cls_score, bbox_pred, torch.sigmoid(cls_score)
+        A = self.num_anchors
+        both = ops.conv2d(t, self._f[0], self._f[1], out_format="nchw", sigmoid_from=5 * A).float()
+        return both[:, :A], both[:, A:5 * A], both[:, 5 * A:]
 
 
 class RCNN(nn.Module):
@@ -478,9 +479,13 @@ class FCNHead(nn.Module):
             # -- identical up to fp32 reassociation, and the three 128-channel upsampled maps plus the
             # 512-channel concat (0.5 GB of traffic at 1024x2048) are never built.
             score = ops.conv2d(p2, self._f[0], self.score.bias, out_format="nchw").float()
-            for l, feat in enumerate((p3, p4, p5), start=1):
-                s_l = ops.conv2d(feat, self._f[l], None, out_format="nchw").float()
-                score = score + F.interpolate(s_l, None, 2 ** l, mode="bilinear", align_corners=False)
+            parts = [ops.conv2d(feat, self._f[l], None, out_format="nchw").float() for l, feat in enumerate((p3, p4, p5), start=1)]
+            if score.is_cuda and score.shape[2] % 8 == 0 and score.shape[3] % 8 == 0 and \
+                    all(tuple(s_.shape[2:]) == (score.shape[2] >> l, score.shape[3] >> l) for l, s_ in enumerate(parts, start=1)):
+                score = ops.fcn_score_fuse(score, *parts)            # one launch: s2 + up2(s3) + up4(s4) + up8(s5)
+            else:
+                for l, s_l in enumerate(parts, start=1):
+                    score = score + F.interpolate(s_l, None, 2 ** l, mode="bilinear", align_corners=False)
             ret = {"fcn_score": score}
             if self.upsample_rate != 1:
                 ret["fcn_output"] = ops.upsample_bilinear(score, self.upsample_rate)

@@ -221,7 +221,7 @@ def _tc_ok(Cin, kh, kw, dg, deform=False):
 
 
 def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, dilation, relu, prec, out_format,
-              out_dtype=None, residual_up2=False, pair_group=0):
+              out_dtype=None, residual_up2=False, pair_group=0, sigmoid_from=None):
     """upsnet_igemm_forward: x logical NCHW (any memory format; fp32 or bf16) or a Pair; result logical NCHW whose
     storage is NHWC (channels_last view, the engine layout) unless out_format == 'nchw'.
     Output: bf16 when the engine stores bf16 activations (ACT_BF16) / a Pair when it stores pairs (ACT_PAIR) and the
@@ -287,6 +287,9 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
     if pair_group:
         assert pair_out and pair_group % 64 == 0 and Cout % pair_group == 0
         flags |= (pair_group // 64) << 8
+    if sigmoid_from is not None:
+        assert not pair_out and not nhwc_out and residual is None, "sigmoid epilogue: fp32 NCHW head outputs"
+        flags |= _lib.EPI_SIGMOID_FROM(sigmoid_from)
     with torch.cuda.device(dev), _Timed(kind, 1, work, dev):
         check(lib().upsnet_igemm_forward(ptr(xs), ptr(offset), ptr(mask), ptr(packed), ptr(bias), ptr(res),
                                          ptr(store), N, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
@@ -303,7 +306,7 @@ def _igemm_tc(kind, x, offset, mask, weight, bias, residual, stride, padding, di
 # functional layer
 # ------------------------------------------------------------------------------------------------
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None, relu=False, precision=None,
-           out_format=None, out_dtype=None, residual_up2=False, pair_group=0):
+           out_format=None, out_dtype=None, residual_up2=False, pair_group=0, sigmoid_from=None):
     """Dense conv + fused bias / residual / ReLU epilogue.  fp32 precision -> upsnet_conv2d_forward
     (NCHW CUDA-core tiles); bf16x3 / bf16 -> upsnet_igemm_forward (tcgen05 tiles, NHWC storage)."""
     require_cuda(x, weight, bias, residual)
@@ -313,7 +316,11 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
             residual, residual_up2 = torch.nn.functional.interpolate(as_float(residual), scale_factor=2, mode="nearest"), False
         return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
                          _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype,
-                         residual_up2, pair_group)
+                         residual_up2, pair_group, sigmoid_from)
+    if sigmoid_from is not None:      # CUDA-core path: the conv entry has no sigmoid epilogue
+        y = conv2d(x, weight, bias, stride, padding, dilation, residual, relu, precision, out_format, out_dtype, residual_up2)
+        y[:, sigmoid_from:] = torch.sigmoid(y[:, sigmoid_from:])
+        return y
     if isinstance(x, Pair):
         x = x.float()
     if isinstance(residual, Pair):
@@ -463,6 +470,20 @@ def upsample_bilinear(x, factor):
     with torch.cuda.device(x.device), _Timed("upsample", 1, {"bytes": 4.0 * (x.numel() + y.numel())}, x.device):
         check(lib().upsnet_upsample_bilinear_nchw(ptr(x), ptr(y), N * Cc, H, W, int(factor), stream_ptr(x.device)), "upsample")
     return y
+
+
+def fcn_score_fuse(s2, s3, s4, s5):
+    """s2 + up2(s3) + up4(s4) + up8(s5) on contiguous NCHW fp32 score maps (models/fcn.py:94-101 after the engine's
+    score-before-upsample rewrite), one launch instead of three F.interpolate + three adds."""
+    require_cuda(s2, s3, s4, s5)
+    s2, s3, s4, s5 = f32c(s2), f32c(s3), f32c(s4), f32c(s5)
+    N, Cc, H, W = s2.shape
+    assert s3.shape == (N, Cc, H // 2, W // 2) and s4.shape == (N, Cc, H // 4, W // 4) and s5.shape == (N, Cc, H // 8, W // 8)
+    out = torch.empty_like(s2)
+    with torch.cuda.device(s2.device), _Timed("upsample", 1, {"bytes": 4.0 * (2 * s2.numel() + s3.numel() + s4.numel() + s5.numel())}, s2.device):
+        check(lib().upsnet_fcn_score_fuse(ptr(s2), ptr(s3), ptr(s4), ptr(s5), ptr(out), N * Cc, H, W, stream_ptr(s2.device)),
+              "fcn_score_fuse")
+    return out
 
 
 def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, sampling_ratio=2, layout="nchw",
