@@ -301,6 +301,31 @@ int upsnet_unified_pan_result(const long long *seg, const long long *pan, const 
 int upsnet_prep_image(const unsigned char *image_hwc, int h, int w, double scale, int out_h, int out_w, int pad_h,
                       int pad_w, const double pixel_means[3], float *blob, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Backward kernels of the custom operators (training configuration, BASELINE config #4).  fp32 NCHW, ONE image per call
+ * for the deformable kernels (the reference loops over the batch: functions/deform_conv.py:84-104).
+ *
+ * upsnet_dcn_im2col:       col [Cin*kh*kw, Ho*Wo] = zero-padded bilinear samples (* mask)      -- d(weight) = dY * col^T
+ *   replaces: operators/src/deform_conv_kernel.cu:194-242 (K1), mod_deform_conv_kernel.cu:187-249 (K4)
+ * upsnet_dcn_col2im:       dx [Cin,H,W] (zeroed by the call) += bilinear weights * dcol (* mask)
+ *   replaces: deform_conv_kernel.cu:293-343 (K2), mod_deform_conv_kernel.cu:251-308 (K5)
+ * upsnet_dcn_col2im_coord: doffset [2*kh*kw, Ho*Wo] and, with a mask, dmask [kh*kw, Ho*Wo]
+ *   replaces: deform_conv_kernel.cu:391-449 (K3), mod_deform_conv_kernel.cu:310-381 (K6)
+ * x [Cin,H,W]; offset [2*kh*kw,Ho,Wo]; mask [kh*kw,Ho,Wo] (already activated) or NULL; deformable_groups = 1.
+ */
+int upsnet_dcn_im2col(const float *x, const float *offset, const float *mask, int Cin, int H, int W, int kh, int kw,
+                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float *col, void *stream);
+int upsnet_dcn_col2im(const float *dcol, const float *offset, const float *mask, int Cin, int H, int W, int kh, int kw,
+                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float *dx, void *stream);
+int upsnet_dcn_col2im_coord(const float *dcol, const float *x, const float *offset, const float *mask, int Cin, int H,
+                            int W, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                            float *doffset, float *dmask, void *stream);
+
+/* upsnet_roi_align_backward: dfeat [B,C,H,W] (zeroed by the call) += scatter of dout [R,C,PH,PW] to the bilinear taps.
+ * replaces: operators/src/roi_align_kernel.cu:238-348 RoIAlignBackwardFeature (K8). */
+int upsnet_roi_align_backward(const float *dout, const float *rois, int R, int B, int C, int H, int W, int PH, int PW,
+                              int sampling_ratio, float spatial_scale, float *dfeat, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

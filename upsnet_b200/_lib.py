@@ -69,6 +69,10 @@ def lib():
         L.upsnet_stem_forward.argtypes = [vp] * 4 + [i] * 9 + [vp, sz, vp]
         L.upsnet_rpn_collect.argtypes = [vp] * 5 + [i] * 3 + [vp] * 4
         L.upsnet_rpn_topk.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i), i, i, i, vp, vp, vp, sz, vp]
+        L.upsnet_dcn_im2col.argtypes = [vp, vp, vp] + [i] * 11 + [vp, vp]
+        L.upsnet_dcn_col2im.argtypes = [vp, vp, vp] + [i] * 11 + [vp, vp]
+        L.upsnet_dcn_col2im_coord.argtypes = [vp, vp, vp, vp] + [i] * 11 + [vp, vp, vp]
+        L.upsnet_roi_align_backward.argtypes = [vp, vp] + [i] * 8 + [f, vp, vp]
         L.upsnet_fcn_score_fuse.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
         L.upsnet_unified_pan_workspace_bytes.argtypes = [i, C.POINTER(sz)]
         L.upsnet_unified_pan_result.argtypes = [vp, vp, vp, i, vp, i, i, i, i, i, vp, vp, vp, sz, vp]
@@ -84,6 +88,7 @@ EXPORTED_SYMBOLS = [
     "upsnet_igemm_forward", "upsnet_panoptic_workspace_bytes", "upsnet_panoptic_workspace_min_bytes", "upsnet_panoptic_head", "upsnet_mask_removal",
     "upsnet_rpn_decode", "upsnet_maskroi_prepare", "upsnet_maskroi_finish", "upsnet_maxpool2d_nhwc", "upsnet_upsample_bilinear_nchw", "upsnet_rpn_topk_workspace_bytes", "upsnet_rpn_topk", "upsnet_rpn_collect", "upsnet_stem_workspace_bytes",
     "upsnet_stem_packed_weight_bytes", "upsnet_stem_pack_weight", "upsnet_stem_forward",
+    "upsnet_dcn_im2col", "upsnet_dcn_col2im", "upsnet_dcn_col2im_coord", "upsnet_roi_align_backward",
     "upsnet_fcn_score_fuse", "upsnet_unified_pan_workspace_bytes", "upsnet_unified_pan_result", "upsnet_prep_image",
 ]
 

@@ -24,6 +24,7 @@
 // LSU gather rate of the producers (4 corner reads per element) -- see DESIGN.md.
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -896,6 +897,11 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   if (deform) {   // few tiles (coarse pyramid levels): smaller pixel blocks -> more CTAs, proportionally less gather work each
     if (dtiles() < sms / 2) { p.tile_w = 8; p.tile_h = 8; }
     if (dtiles() < sms / 2) { p.tile_h = 4; }
+    static int tile_env = -1;     // tuning hook: UPSNET_DCN_TILE=168 | 88 | 84 forces the pixel block (pair / bf16 experiments)
+    if (tile_env < 0) { const char* e = getenv("UPSNET_DCN_TILE"); tile_env = e ? atoi(e) : 0; }
+    if (tile_env == 168) { p.tile_w = 16; p.tile_h = 8; }
+    if (tile_env == 88) { p.tile_w = 8; p.tile_h = 8; }
+    if (tile_env == 84) { p.tile_w = 8; p.tile_h = 4; }
   }
   const long long num_tiles = (deform ? dtiles() : ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN));
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));

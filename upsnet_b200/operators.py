@@ -761,6 +761,10 @@ class DeformConv(nn.Module):
             self.bias.data.uniform_(-stdv, stdv)
 
     def forward(self, data, offset):
+        if torch.is_grad_enabled() and self.deformable_groups == 1 and \
+                any(t is not None and t.requires_grad for t in (data, offset, self.weight, self.bias)):
+            from .training import DeformConvFunction      # training path: hand-written backward kernels (csrc/backward.cu)
+            return DeformConvFunction.apply(data, offset, self.weight, self.bias, self.stride, self.padding, self.dilation)
         return deform_conv(data, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
                            self.deformable_groups)
 
@@ -792,6 +796,10 @@ class ModDeformConv(DeformConv):
         offset_1, offset_2, mask = torch.chunk(offset_mask, 3, dim=1)
         offset = torch.cat((offset_1, offset_2), dim=1)
         mask = torch.sigmoid(mask) * 2
+        if torch.is_grad_enabled() and self.deformable_groups == 1 and \
+                any(t is not None and t.requires_grad for t in (data, offset_mask, self.weight, self.bias)):
+            from .training import ModDeformConvFunction
+            return ModDeformConvFunction.apply(data, offset, mask, self.weight, self.bias, self.stride, self.padding, self.dilation)
         return deform_conv(data, offset, self.weight, self.bias, self.stride, self.padding, self.dilation,
                            self.deformable_groups, mask=mask)
 
@@ -828,6 +836,9 @@ class RoIAlignFunction:
     def __call__(self, features, rois):
         if not features.is_cuda:
             raise Exception('not implemented')
+        if torch.is_grad_enabled() and features.requires_grad:
+            from .training import RoIAlignFunction as _F      # training path: upsnet_roi_align_backward
+            return _F.apply(features, rois, self.pooled_height, self.pooled_width, self.spatial_scale, self.sampling_ratio)
         return roi_align(features, rois, self.pooled_height, self.pooled_width, self.spatial_scale,
                          self.sampling_ratio)
 
