@@ -772,6 +772,10 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   const int patch_h = 16 + (p.kh - 1) * p.dh;
   bool halo = halo_env > 0 && !strided && p.kh * p.kw > 1 && (p.kw - 1) * p.dw <= 8 && patch_h <= 48 && !g.res_up2 &&
               p.Wo >= 8 && p.Ho >= 8;
+  // pair mode (measured, profiles/r2_mma_probe_pair.md): the patch slots of a hi/lo pair (2 x 36 KB per 3x3 slot) only fit next
+  // to N tiles <= 64, and there the tap-shifted (not 1024-byte aligned) A descriptors make the short N <= 64 MMAs ~2x slower
+  // than the per-tap boxes -- halo mode stays a bf16-stream optimisation (UPSNET_TMA_HALO=3 forces it for pairs)
+  if (pair && halo_env < 3) halo = false;
   if (halo) { g.bw = 8; g.bh = 16; g.bn = 1; }
   g.tiles_w = (p.Wo + g.bw - 1) / g.bw;
   g.tiles_h = (p.Ho + g.bh - 1) / g.bh;
