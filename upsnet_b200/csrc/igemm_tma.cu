@@ -670,6 +670,301 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 }
 
 // ----------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2) for the latency-bound layers of the PAIR stream.
+//
+// A cluster of two CTAs (one TPC) works on an M = 256 tile: CTA r owns output rows [128 r, 128 r + 128) -- m-tile 2p + r of
+// the same n-tile -- and stages its OWN A tiles (hi, lo) but only HALF of the weight tile (rows [n0 + r*BN/2, +BN/2) of both
+// planes); `tcgen05.mma.cta_group::2` (issued by the leader CTA's single MMA thread, M = 256) reads the B halves from both
+// CTAs' shared memory.  A pair k-block is then 48 KB per CTA instead of 64 KB, so FOUR ring stages fit next to the output
+// slab pair instead of three -- the ring is latency-bound (profiles/r2_mma_probe_pair.md), stages are throughput.
+// Protocol (CUTLASS sm100 2-SM scheme): every CTA's TMA thread issues its loads with `.cta_group::2`, their complete_tx
+// bytes go to the LEADER's full barrier (which expects the bytes of both CTAs); `tcgen05.commit ... multicast::cluster`
+// releases the stage / publishes the accumulator in BOTH CTAs; both CTAs' epilogue warps arrive on the leader's
+// tmem-empty barrier (remote mbarrier arrive for CTA 1).  Per-tap boxes only, no residual (the +res layers keep the 1-CTA
+// kernel with in-place slab pairs); slab (pair) or direct (fp32) epilogue as in the 1-CTA kernel.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_leader, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar_leader, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {      // arrive on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+struct Tma2Smem { uint32_t stages, out, a_half, b_half, a_bytes, b_bytes, stage_bytes, total; };
+__host__ __device__ inline Tma2Smem tma2_smem_layout(int BN, int stages, bool direct, int opairs) {
+  Tma2Smem s;
+  s.a_half = 128 * 128; s.b_half = (uint32_t)(BN / 2) * 128;      // this CTA's half of the weight tile, per plane
+  s.a_bytes = 2 * s.a_half; s.b_bytes = 2 * s.b_half;
+  s.stage_bytes = s.a_bytes + s.b_bytes;
+  s.stages = 1024;
+  s.out = s.stages + s.stage_bytes * (uint32_t)stages;
+  s.total = s.out + (direct ? 0u : (uint32_t)opairs * 2u * TM_SLAB_BYTES);
+  return s;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TM_THREADS, 1)
+igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                  const __grid_constant__ CUtensorMap tm_y, const TmaGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_dyn + (base - raw);
+  const Tma2Smem L = tma2_smem_layout(g.BN, g.stages, g.direct != 0, g.opairs);
+  const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 16));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  const int cchunks = g.Cin / 64;
+  const int num_kb = g.KHW * cchunks;
+  const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  const long long p_tiles = (m_tiles + 1) / 2;                      // pairs of m-tiles
+  const long long num_tiles = p_tiles * g.n_tiles;
+  const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t box_bytes = (uint32_t)(g.bw * g.bh * g.bn) * 128u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * g.BN) tmem_cols <<= 1;
+
+  if (warp == TM_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < g.stages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_tfull + 8 * b, 1);
+        mbar_init(bar_tempty + 8 * b, 2 * TM_EPI_WARPS);      // the epilogue warps of BOTH CTAs (used in the leader only)
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc2(smem_u32(tmem_ptr_smem), tmem_cols);
+  } else if (warp == TM_WARP_TMA && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_y);
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == TM_WARP_TMA) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      uint32_t a_dst = base + L.stages;
+      const uint32_t tx_both = 2u * (2u * box_bytes + L.b_bytes);       // both CTAs' A (hi, lo) boxes + B halves (hi, lo)
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int nt = (int)(tile % g.n_tiles);
+        const long long mt = 2 * (tile / g.n_tiles) + rank;
+        const int w0 = (int)(mt % g.tiles_w) * g.bw;
+        const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+        const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;     // >= N for the odd tail tile: all-zero boxes
+        const int nrow = nt * g.BN + (int)rank * (g.BN / 2);                      // this CTA's half of the weight rows
+        int cc = 0, kj = 0, cw = w0 - g.pw, ch = h0 - g.ph;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t bf_local = bar_full + 8 * s;
+          const uint32_t bf = mapa_rank(bf_local, 0);                 // complete_tx goes to the leader CTA's barrier
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          if (leader_cta) mbar_arrive_expect_tx(bf_local, tx_both);
+          tma2_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
+          tma2_load_4d(a_dst + L.a_half, &tm_x, bf, g.x_lo + cc * 64, cw, ch, i0);
+          tma2_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, nrow);
+          tma2_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kb * 64, g.w_lo + nrow);
+          if (++cc == cchunks) {
+            cc = 0; cw += g.dw;
+            if (++kj == g.kw) { kj = 0; cw = w0 - g.pw; ch += g.dh; }
+          }
+          a_dst += L.stage_bytes;
+          if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_dst = base + L.stages; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == TM_WARP_MMA) {
+    if (lane == 0 && leader_cta) {
+      const uint32_t idesc = umma_idesc(256, g.BN);
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4, a16 = L.a_bytes >> 4;
+      const uint32_t ah16 = L.a_half >> 4, bh16 = L.b_half >> 4;
+      uint32_t s = 0, ph = 0, a_lo = a_lo0, ti_local = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti_local) {
+        const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
+        uint32_t acc = 0u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t b_lo = a_lo + a16;
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            umma2_bf16_lohi(tmem_d, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
+            umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
+            umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+            acc = 1u;
+          }
+          umma2_commit_mc(bar_empty + 8 * s);
+          a_lo += stage16;
+          if (++s == (uint32_t)g.stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+        }
+        umma2_commit_mc(bar_tfull + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else if (warp < TM_EPI_WARPS) {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t sw_row = (uint32_t)row * 128u;
+    const uint32_t rx = (uint32_t)(row & 7);
+    const uint32_t tempty_leader = mapa_rank(bar_tempty, 0);
+    uint32_t ti_local = 0, oc = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti_local) {
+      const int nt = (int)(tile % g.n_tiles);
+      const long long mt = 2 * (tile / g.n_tiles) + rank;
+      const int w0 = (int)(mt % g.tiles_w) * g.bw;
+      const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+      const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+      const int n0 = nt * g.BN;
+      const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
+      mbar_wait(bar_tfull + 8 * buf, use & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      if (g.direct) {
+        const int wq = row % g.bw, hq = (row / g.bw) % g.bh, nq = row / (g.bw * g.bh);
+        const int wo = w0 + wq, ho = h0 + hq, ni = i0 + nq;
+        const bool ok = nq < g.bn && wo < g.Wo && ho < g.Ho && ni < g.N;
+        const size_t HoWo = (size_t)g.Ho * g.Wo;
+        const size_t pix = ((size_t)ni * g.Ho + ho) * g.Wo + wo;
+        const int cbeg = half * (g.BN / 2), cend = cbeg + g.BN / 2;
+        for (int cb = cbeg; cb < cend; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + (uint32_t)cb, v);
+          const int co0 = n0 + cb;
+          if (!ok || co0 >= g.Cout) continue;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int co = co0 + e;
+            if (co >= g.Cout) break;
+            float o = __uint_as_float(v[e]);
+            if (g.bias) o += __ldg(g.bias + co);
+            if (g.relu) o = fmaxf(o, 0.f);
+            if (g.sig_from >= 0 && co >= g.sig_from) o = 1.f / (1.f + expf(-o));
+            const size_t oi = g.out_nhwc ? pix * g.Cout + co : ((size_t)ni * g.Cout + co) * HoWo + (size_t)ho * g.Wo + wo;
+            reinterpret_cast<float*>(g.y)[oi] = o;
+          }
+        }
+      } else {
+        const int nslab = g.BN / 64;
+        const uint32_t jb = (uint32_t)half * 4u;
+        const bool lead = warp == 0 && lane == 0;
+        for (int sl = 0; sl < nslab; ++sl, ++oc) {
+          const int u = 2 * sl + half;
+          uint32_t v0[16], v1[16];
+          tmem_ld16_issue(trow + (uint32_t)(u * 32), v0);
+          tmem_ld16_issue(trow + (uint32_t)(u * 32 + 16), v1);
+          const uint32_t ob = base + L.out + (g.opairs == 2 ? (oc & 1u) : 0u) * 2u * TM_SLAB_BYTES;
+          if (lead) {
+            if (g.opairs == 2) bulk_wait_read1(); else bulk_wait_read0();
+          }
+          named_bar_sync(1, 256);
+          tmem_ld_wait();
+          float o[32];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { o[e] = __uint_as_float(v0[e]); o[16 + e] = __uint_as_float(v1[e]); }
+          if (g.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + u * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 b4 = __ldg(bp + e);
+              o[4 * e] += b4.x; o[4 * e + 1] += b4.y; o[4 * e + 2] += b4.z; o[4 * e + 3] += b4.w;
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = fmaxf(o[e], 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = o[c * 8 + 2 * e], b = o[c * 8 + 2 * e + 1];
+              hw[e] = pack_bf16x2(a, b);
+              lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xffff0000u));
+            }
+            sts128(ob + sw_row + (((jb + c) ^ rx) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            sts128(ob + TM_SLAB_BYTES + sw_row + (((jb + c) ^ rx) << 4), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 256);
+          if (lead) {
+            const int c = pair_chan(n0 + sl * 64, g.pg);
+            tma_store_4d(&tm_y, ob, c, w0, h0, i0);
+            tma_store_4d(&tm_y, ob + TM_SLAB_BYTES, c + g.pg, w0, h0, i0);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * buf);     // leader's barrier: 16 arrivals = both CTAs drained
+    }
+    if (warp == 0 && lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // no CTA may exit (or free TMEM) while its peer still reads its shared memory / signals its barriers
+  if (warp == TM_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side: tensor maps, tile geometry, launch
 // ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -891,6 +1186,39 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   }
   const long long num_tiles = m_tiles * g.n_tiles;
   if (num_tiles <= 0) return 0;
+  // ---- 2-CTA variant (cta_group::2): pair stream, per-tap boxes, no residual; each CTA stages half of the weight tile ----
+  static int two_env = -1;
+  if (two_env < 0) { const char* e = getenv("UPSNET_TMA_2CTA"); two_env = e ? atoi(e) : 1; }
+  if (two_env > 0 && pair && !g.halo && !g.has_res && !g.stem && BN >= 64 && m_tiles >= 2 && sms >= 2) {
+    const int opairs_1cta = g.opairs;
+    int st2 = TM_MAX_STAGES;
+    g.opairs = 2;
+    Tma2Smem L2 = tma2_smem_layout(BN, st2, direct, g.opairs);
+    while (st2 > 2 && L2.total + 1024 > 227 * 1024) { --st2; L2 = tma2_smem_layout(BN, st2, direct, g.opairs); }
+    if (!direct && st2 < 5) {           // one output slab pair buys a stage
+      int st1 = st2;
+      while (st1 < TM_MAX_STAGES && tma2_smem_layout(BN, st1 + 1, direct, 1).total + 1024 <= 227 * 1024) ++st1;
+      if (st1 > st2) { st2 = st1; g.opairs = 1; L2 = tma2_smem_layout(BN, st2, direct, 1); }
+    }
+    if (L2.total + 1024 <= 227 * 1024) {
+      g.stages = st2;
+      CUtensorMap tm_w2;
+      const cuuint64_t dwt2[2] = {(cuuint64_t)Kp, (cuuint64_t)Cout_pad * 2};
+      const cuuint32_t boxw2[2] = {64, (cuuint32_t)(BN / 2)};
+      if (encode_bf16(enc, &tm_w2, packed, 2, dwt2, boxw2)) {
+        static ups::PerDeviceOnce configured2;
+        if (configured2.need()) {
+          UPS_CUDA(cudaFuncSetAttribute(igemm_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        }
+        const long long ctiles = ((m_tiles + 1) / 2) * g.n_tiles;
+        const long long clusters = ctiles < sms / 2 ? ctiles : sms / 2;
+        igemm_tma2_kernel<<<dim3((unsigned)(2 * clusters)), TM_THREADS, L2.total + 1024, stream>>>(tm_x, tm_w2, tm_y, g);
+        UPS_CHECK_LAUNCH();
+        return 0;
+      }
+    }
+    g.stages = stages; g.opairs = opairs_1cta;     // fall through to the 1-CTA kernel with its own geometry
+  }
   static ups::PerDeviceOnce configured;
   if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
