@@ -731,28 +731,33 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {      // arrive o
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-struct Tma2Smem { uint32_t stages, out, a_half, b_half, a_bytes, b_bytes, stage_bytes, total; };
-__host__ __device__ inline Tma2Smem tma2_smem_layout(int BN, int stages, bool direct, int opairs) {
+struct Tma2Smem { uint32_t stages, out, res, res_slab, a_half, b_half, a_bytes, b_bytes, stage_bytes, total; };
+__host__ __device__ inline Tma2Smem tma2_smem_layout(int BN, int stages, bool direct, int opairs, bool has_res = false,
+                                                    bool res_up2 = false, bool res_inplace = false) {
   Tma2Smem s;
   s.a_half = 128 * 128; s.b_half = (uint32_t)(BN / 2) * 128;      // this CTA's half of the weight tile, per plane
   s.a_bytes = 2 * s.a_half; s.b_bytes = 2 * s.b_half;
   s.stage_bytes = s.a_bytes + s.b_bytes;
   s.stages = 1024;
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
-  s.total = s.out + (direct ? 0u : (uint32_t)opairs * 2u * TM_SLAB_BYTES);
+  s.res_slab = res_up2 ? 4096u : (uint32_t)TM_SLAB_BYTES;
+  const uint32_t pairs = direct ? 0u : (res_inplace ? 2u * (uint32_t)(BN / 64) : (uint32_t)opairs);
+  s.res = s.out + pairs * 2u * TM_SLAB_BYTES;
+  s.total = s.res + ((has_res && !res_inplace) ? 2u * (uint32_t)(BN / 64) * 2u * s.res_slab : 0u);
   return s;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TM_THREADS, 1)
 igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_y, const TmaGeom g) {
+                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_r, const TmaGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_dyn + (base - raw);
-  const Tma2Smem L = tma2_smem_layout(g.BN, g.stages, g.direct != 0, g.opairs);
+  const Tma2Smem L = tma2_smem_layout(g.BN, g.stages, g.direct != 0, g.opairs, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0);
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // residual slabs: CTA-local protocol
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + 8 * (2 * TM_MAX_STAGES + 16));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -777,6 +782,8 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull + 8 * b, 1);
         mbar_init(bar_tempty + 8 * b, 2 * TM_EPI_WARPS);      // the epilogue warps of BOTH CTAs (used in the leader only)
+        mbar_init(bar_rfull + 8 * b, 1);
+        mbar_init(bar_rempty + 8 * b, g.res_inplace ? 1 : TM_EPI_WARPS);
       }
       fence_mbar_init();
     }
@@ -786,6 +793,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_y);
+    if (g.has_res) prefetch_tmap(&tm_r);
   }
   tc_fence_before();
   cluster_sync_all();          // barriers of both CTAs initialised, TMEM allocated in both
@@ -856,11 +864,43 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     }
     __syncwarp();
+  } else if (warp == TM_WARP_RES) {
+    // residual slab pairs of this CTA's own m-tile: a CTA-local producer / consumer pair, exactly as in the 1-CTA kernel
+    if (lane == 0 && g.has_res) {
+      uint32_t ti_local = 0;
+      const int slabs = g.BN / 64;
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti_local) {
+        const int nt = (int)(tile % g.n_tiles);
+        const long long mt = 2 * (tile / g.n_tiles) + rank;
+        const int w0 = (int)(mt % g.tiles_w) * g.bw;
+        const int h0 = (int)((mt / g.tiles_w) % g.tiles_h) * g.bh;
+        const int i0 = (int)(mt / ((long long)g.tiles_w * g.tiles_h)) * g.bn;
+        const uint32_t rb = ti_local & 1u, ruse = ti_local >> 1;
+        mbar_wait(bar_rempty + 8 * rb, (ruse & 1u) ^ 1u);
+        const uint32_t lo_off = g.res_inplace ? (uint32_t)TM_SLAB_BYTES : L.res_slab;
+        const uint32_t pdst = g.res_inplace ? base + L.out + rb * (uint32_t)slabs * 2u * TM_SLAB_BYTES
+                                            : base + L.res + rb * (uint32_t)slabs * 2u * L.res_slab;
+        mbar_arrive_expect_tx(bar_rfull + 8 * rb, (g.res_up2 ? box_bytes / 4 : box_bytes) * (uint32_t)slabs * 2u);
+        for (int sl = 0; sl < slabs; ++sl) {
+          const int c = pair_chan(nt * g.BN + sl * 64, g.pg);
+          tma_load_4d(pdst + (uint32_t)sl * 2u * lo_off, &tm_r, bar_rfull + 8 * rb, c, w0 >> g.res_up2, h0 >> g.res_up2, i0);
+          tma_load_4d(pdst + (uint32_t)sl * 2u * lo_off + lo_off, &tm_r, bar_rfull + 8 * rb, c + g.pg, w0 >> g.res_up2,
+                      h0 >> g.res_up2, i0);
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp < TM_EPI_WARPS) {
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t sw_row = (uint32_t)row * 128u;
     const uint32_t rx = (uint32_t)(row & 7);
+    int rrow = row;
+    if (g.res_up2) {
+      const int w = row % g.bw, h = (row / g.bw) % g.bh, n = row / (g.bw * g.bh);
+      rrow = (w >> 1) + (g.bw >> 1) * ((h >> 1) + (g.bh >> 1) * n);
+    }
+    const uint32_t rs_row = (uint32_t)rrow * 128u, rrx = (uint32_t)(rrow & 7);
     const uint32_t tempty_leader = mapa_rank(bar_tempty, 0);
     uint32_t ti_local = 0, oc = 0;
     for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti_local) {
@@ -873,6 +913,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
       mbar_wait(bar_tfull + 8 * buf, use & 1u);
       tc_fence_after();
+      if (g.has_res) mbar_wait(bar_rfull + 8 * buf, use & 1u);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
       if (g.direct) {
         const int wq = row % g.bw, hq = (row / g.bw) % g.bh, nq = row / (g.bw * g.bh);
@@ -907,11 +948,16 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           uint32_t v0[16], v1[16];
           tmem_ld16_issue(trow + (uint32_t)(u * 32), v0);
           tmem_ld16_issue(trow + (uint32_t)(u * 32 + 16), v1);
-          const uint32_t ob = base + L.out + (g.opairs == 2 ? (oc & 1u) : 0u) * 2u * TM_SLAB_BYTES;
-          if (lead) {
-            if (g.opairs == 2) bulk_wait_read1(); else bulk_wait_read0();
+          uint32_t ob;
+          if (g.res_inplace) {
+            ob = base + L.out + (buf * (uint32_t)nslab + (uint32_t)sl) * 2u * TM_SLAB_BYTES;   // holds this slab's residual
+          } else {
+            ob = base + L.out + (g.opairs == 2 ? (oc & 1u) : 0u) * 2u * TM_SLAB_BYTES;
+            if (lead) {
+              if (g.opairs == 2) bulk_wait_read1(); else bulk_wait_read0();
+            }
+            named_bar_sync(1, 256);
           }
-          named_bar_sync(1, 256);
           tmem_ld_wait();
           float o[32];
 #pragma unroll
@@ -922,6 +968,21 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             for (int e = 0; e < 8; ++e) {
               const float4 b4 = __ldg(bp + e);
               o[4 * e] += b4.x; o[4 * e + 1] += b4.y; o[4 * e + 2] += b4.z; o[4 * e + 3] += b4.w;
+            }
+          }
+          if (g.has_res) {
+            uint32_t rh, rl, xr;
+            if (g.res_inplace) { rh = ob + sw_row; rl = rh + TM_SLAB_BYTES; xr = rx; }
+            else { rh = base + L.res + (buf * (uint32_t)nslab + (uint32_t)sl) * 2u * L.res_slab + rs_row; rl = rh + L.res_slab; xr = rrx; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 hv = lds128(rh + (((jb + c) ^ xr) << 4)), lv = lds128(rl + (((jb + c) ^ xr) << 4));
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                o[c * 8 + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                o[c * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              }
             }
           }
           if (g.relu) {
@@ -952,7 +1013,14 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * buf);     // leader's barrier: 16 arrivals = both CTAs drained
+      if (lane == 0) {
+        mbar_arrive_cluster(tempty_leader + 8 * buf);     // leader's barrier: 16 arrivals = both CTAs drained
+        if (g.has_res && !g.res_inplace) mbar_arrive(bar_rempty + 8 * buf);
+      }
+      if (g.res_inplace && warp == 0 && lane == 0) {      // slab pairs may be refilled once their stores have been read out
+        bulk_wait_read0();
+        mbar_arrive(bar_rempty + 8 * buf);
+      }
     }
     if (warp == 0 && lane == 0) bulk_wait0();
   }
@@ -1189,16 +1257,17 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   // ---- 2-CTA variant (cta_group::2): pair stream, per-tap boxes, no residual; each CTA stages half of the weight tile ----
   static int two_env = -1;
   if (two_env < 0) { const char* e = getenv("UPSNET_TMA_2CTA"); two_env = e ? atoi(e) : 1; }
-  if (two_env > 0 && pair && !g.halo && !g.has_res && !g.stem && BN >= 64 && m_tiles >= 2 && sms >= 2) {
+  if (two_env > 0 && pair && !g.halo && !g.stem && BN >= 32 && m_tiles >= 2 && sms >= 2 && !(direct && g.has_res)) {
     const int opairs_1cta = g.opairs;
     int st2 = TM_MAX_STAGES;
     g.opairs = 2;
-    Tma2Smem L2 = tma2_smem_layout(BN, st2, direct, g.opairs);
-    while (st2 > 2 && L2.total + 1024 > 227 * 1024) { --st2; L2 = tma2_smem_layout(BN, st2, direct, g.opairs); }
-    if (!direct && st2 < 5) {           // one output slab pair buys a stage
+    auto lay2 = [&](int st, int op) { return tma2_smem_layout(BN, st, direct, op, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0); };
+    Tma2Smem L2 = lay2(st2, g.opairs);
+    while (st2 > 2 && L2.total + 1024 > 227 * 1024) { --st2; L2 = lay2(st2, g.opairs); }
+    if (!direct && !g.res_inplace && st2 < 5) {           // one output slab pair buys a stage
       int st1 = st2;
-      while (st1 < TM_MAX_STAGES && tma2_smem_layout(BN, st1 + 1, direct, 1).total + 1024 <= 227 * 1024) ++st1;
-      if (st1 > st2) { st2 = st1; g.opairs = 1; L2 = tma2_smem_layout(BN, st2, direct, 1); }
+      while (st1 < TM_MAX_STAGES && lay2(st1 + 1, 1).total + 1024 <= 227 * 1024) ++st1;
+      if (st1 > st2) { st2 = st1; g.opairs = 1; L2 = lay2(st2, 1); }
     }
     if (L2.total + 1024 <= 227 * 1024) {
       g.stages = st2;
@@ -1212,7 +1281,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
         }
         const long long ctiles = ((m_tiles + 1) / 2) * g.n_tiles;
         const long long clusters = ctiles < sms / 2 ? ctiles : sms / 2;
-        igemm_tma2_kernel<<<dim3((unsigned)(2 * clusters)), TM_THREADS, L2.total + 1024, stream>>>(tm_x, tm_w2, tm_y, g);
+        igemm_tma2_kernel<<<dim3((unsigned)(2 * clusters)), TM_THREADS, L2.total + 1024, stream>>>(tm_x, tm_w2, tm_y, tm_r, g);
         UPS_CHECK_LAUNCH();
         return 0;
       }
