@@ -1257,7 +1257,12 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
   // ---- 2-CTA variant (cta_group::2): pair stream, per-tap boxes, no residual; each CTA stages half of the weight tile ----
   static int two_env = -1;
   if (two_env < 0) { const char* e = getenv("UPSNET_TMA_2CTA"); two_env = e ? atoi(e) : 1; }
-  if (two_env > 0 && pair && !g.halo && !g.stem && BN >= 32 && m_tiles >= 2 && sms >= 2 && !(direct && g.has_res)) {
+  // measured (profiles/r2_2cta_ab.md): -10..-20 % on the long-K tiles (3x3, FC, 1x1 with Cin >= 512), but the cross-CTA
+  // accumulator hand-shake costs more than the deeper ring buys when a tile has only 1-4 k-blocks (the HBM-bound 1x1 layers
+  // of res2 / res3, +res or not): those keep the 1-CTA kernel.  UPSNET_TMA_2CTA=2 forces the pair kernel everywhere.
+  const int num_kb_h = g.KHW * (p.Cin / 64);
+  if (two_env > 0 && (two_env > 1 || num_kb_h >= 8) && pair && !g.halo && !g.stem && BN >= 32 && m_tiles >= 2 && sms >= 2 &&
+      !(direct && g.has_res)) {
     const int opairs_1cta = g.opairs;
     int st2 = TM_MAX_STAGES;
     g.opairs = 2;
