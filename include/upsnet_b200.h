@@ -38,6 +38,7 @@ extern "C" {
 /* epilogue flags for the convolution entry points */
 #define UPSNET_EPI_RELU 1
 #define UPSNET_EPI_RES_UP2 2 /* upsnet_igemm_forward only: residual is [N,Ho/2,Wo/2,Cout], read with nearest 2x upsampling */
+#define UPSNET_EPI_STEM_PAIR 8 /* upsnet_stem_forward only: y is a hi/lo pair tensor [N,Ho,Wo,2*Cout] (precision bf16x3) */
 #define UPSNET_EPI_NO_TMA 4  /* upsnet_igemm_forward only: use the cp.async gather kernel even where the TMA-fed one qualifies */
 /* upsnet_igemm_forward, y_dtype PAIR only: store the output channels as [hi G][lo G] per group of G channels instead of
  * [hi Cout][lo Cout] (G % 64 == 0, Cout % G == 0; 0 = Cout).  Lets a 1x1 conv that emulates a 2x2 deconvolution write
@@ -185,7 +186,8 @@ int upsnet_mask_removal(const float *boxes, const float *cls_prob, const float *
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* RGB stem on the TMA kernel: k x k (kw <= 8) / stride 2 / pad `pad` convolution of a tiny-Cin (<= 8) fp32 NCHW
- * image, bf16 NHWC output [N,Ho,Wo,Cout] (Cout % 64 == 0), fused bias + ReLU (UPSNET_EPI_RELU).
+ * image, bf16 NHWC output [N,Ho,Wo,Cout] (Cout % 64 == 0) -- or, with UPSNET_EPI_STEM_PAIR, the hi/lo pair tensor
+ * [N,Ho,Wo,2*Cout] computed with the three-pass split from hi/lo copies of the image -- fused bias + ReLU (UPSNET_EPI_RELU).
  * replaces: models/resnet.py:155-162 conv1 + bn1 (folded) + relu.
  * The call first packs the image to a zero-padded bf16 NHWC8 copy in `workspace` (upsnet_stem_workspace_bytes),
  * then runs the tcgen05 kernel whose A tiles are boxes of a 5-D tensor map over that copy; weights are packed

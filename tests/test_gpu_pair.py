@@ -176,6 +176,22 @@ def test_pair_stem_maxpool(dev, pair_mode):
     assert torch.equal(mp.float(), ref)               # the winning (hi, lo) is copied verbatim
 
 
+def test_pair_stem_tma(dev, pair_mode):
+    """The TMA-fed stem on hi/lo copies of the image (upsnet_stem_forward + UPSNET_EPI_STEM_PAIR) == the gather stem == oracle."""
+    U = pair_mode
+    from upsnet_b200 import operators as ops
+    rng = np.random.default_rng(16)
+    for (H, W) in ((64, 96), (224, 320)):
+        x = (rng.standard_normal((1, 3, H, W)) * 60).astype(np.float32)
+        w = (rng.standard_normal((64, 3, 7, 7)) / 12).astype(np.float32)
+        b = rng.standard_normal(64).astype(np.float32)
+        y = ops.stem_conv(t(x, dev), t(w, dev), t(b, dev), 3, relu=True, pair=True)
+        assert isinstance(y, ops.Pair) and y.shape == (1, 64, H // 2, W // 2)
+        want = np.maximum(O.conv2d(x, w, b, 2, 3, 1), 0)
+        err = np.abs(y.float().cpu().numpy() - want).max()
+        assert err < 2e-4 * max(1.0, np.abs(want).max()), err
+
+
 def test_pair_fpn_roi_align(dev, pair_mode):
     """Pair ROIAlign (pair pixels and the flat fc6 layout) == the fp32 kernel on hi + lo, to pair rounding."""
     U = pair_mode

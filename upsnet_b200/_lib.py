@@ -17,6 +17,7 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 EPI_RELU = 1
 EPI_RES_UP2 = 2
 EPI_NO_TMA = 4
+EPI_STEM_PAIR = 8
 
 
 def EPI_SIGMOID_FROM(c):

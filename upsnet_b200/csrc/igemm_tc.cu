@@ -333,15 +333,16 @@ igemm_tc_kernel(const TcParams p) {
           }
         } else if (DEFORM && XPAIR) {
           // deformable, hi/lo pair activations: 8 lanes x 16 B cover a row's 64 channels of one plane; per corner one hi and
-          // one lo load, v = sum_i w_i * (hi_i + lo_i) in fp32 (hi + lo is exact), then the result is split again.
+          // one lo load.  The gather is ISSUE-bound (ncu: 2.4 IPC, tensor pipe 18 %), so the blend is written for instruction
+          // count: hi plane = packed fp32x2 FMAs (FFMA2: two channels per instruction, exact fp32 products of the bf16 values),
+          // lo plane = packed bf16x2 HFMA2 with bf16-rounded weights (the lo plane is 2^-9 of the value, its blend only needs
+          // 2^-9 relative accuracy -> 2^-18 overall); the two sums are added in fp32 and the result is split again.
           const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
 #pragma unroll 1
           for (int pass = 0; pass < TC_BM / 32; ++pass) {
             const int r = r_first + pass * 32;
             const long long rb = rowinfo[r];
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};      // fp32x2: channels (2q, 2q+1)
             if (rb >= 0) {
               const __nv_bfloat16* xb = xh + rb + c0;
               const float4 wv = tw[tap * TC_BM + r];
@@ -350,32 +351,44 @@ igemm_tc_kernel(const TcParams p) {
               const uint4 hb = __ldg(reinterpret_cast<const uint4*>(xb + ov.y)), lb = __ldg(reinterpret_cast<const uint4*>(xb + ov.y + p.Cin));
               const uint4 hd = __ldg(reinterpret_cast<const uint4*>(xb + ov.z)), ld = __ldg(reinterpret_cast<const uint4*>(xb + ov.z + p.Cin));
               const uint4 he = __ldg(reinterpret_cast<const uint4*>(xb + ov.w)), le = __ldg(reinterpret_cast<const uint4*>(xb + ov.w + p.Cin));
-              const uint32_t A[4] = {ha.x, ha.y, ha.z, ha.w}, a[4] = {la.x, la.y, la.z, la.w};
-              const uint32_t B[4] = {hb.x, hb.y, hb.z, hb.w}, b[4] = {lb.x, lb.y, lb.z, lb.w};
-              const uint32_t D[4] = {hd.x, hd.y, hd.z, hd.w}, d[4] = {ld.x, ld.y, ld.z, ld.w};
-              const uint32_t E[4] = {he.x, he.y, he.z, he.w}, e4[4] = {le.x, le.y, le.z, le.w};
+              const uint32_t H[4][4] = {{ha.x, ha.y, ha.z, ha.w}, {hb.x, hb.y, hb.z, hb.w}, {hd.x, hd.y, hd.z, hd.w}, {he.x, he.y, he.z, he.w}};
+              const uint32_t Lo[4][4] = {{la.x, la.y, la.z, la.w}, {lb.x, lb.y, lb.z, lb.w}, {ld.x, ld.y, ld.z, ld.w}, {le.x, le.y, le.z, le.w}};
+              const float wf[4] = {wv.x, wv.y, wv.z, wv.w};
+              __nv_bfloat162 lacc[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 wb = __float2bfloat162_rn(wf[i]);
+                unsigned long long wp;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(wp) : "r"(__float_as_uint(wf[i])));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  unsigned long long hp;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(hp) : "r"(H[i][q] << 16), "r"(H[i][q] & 0xffff0000u));
+                  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[q]) : "l"(wp), "l"(hp), "l"(acc[q]));
+                  const __nv_bfloat162 lv = *reinterpret_cast<const __nv_bfloat162*>(&Lo[i][q]);
+                  lacc[q] = i == 0 ? __hmul2(wb, lv) : __hfma2(wb, lv, lacc[q]);
+                }
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                v[2 * q] = wv.x * (__uint_as_float(A[q] << 16) + __uint_as_float(a[q] << 16)) +
-                           wv.y * (__uint_as_float(B[q] << 16) + __uint_as_float(b[q] << 16)) +
-                           wv.z * (__uint_as_float(D[q] << 16) + __uint_as_float(d[q] << 16)) +
-                           wv.w * (__uint_as_float(E[q] << 16) + __uint_as_float(e4[q] << 16));
-                v[2 * q + 1] = wv.x * (__uint_as_float(A[q] & 0xffff0000u) + __uint_as_float(a[q] & 0xffff0000u)) +
-                               wv.y * (__uint_as_float(B[q] & 0xffff0000u) + __uint_as_float(b[q] & 0xffff0000u)) +
-                               wv.z * (__uint_as_float(D[q] & 0xffff0000u) + __uint_as_float(d[q] & 0xffff0000u)) +
-                               wv.w * (__uint_as_float(E[q] & 0xffff0000u) + __uint_as_float(e4[q] & 0xffff0000u));
+                const uint32_t lw = *reinterpret_cast<const uint32_t*>(&lacc[q]);
+                unsigned long long lp;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(lp) : "r"(lw << 16), "r"(lw & 0xffff0000u));
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc[q]) : "l"(acc[q]), "l"(lp));
               }
             }
             const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-            uint4 hi4, lo4;
-            hi4.x = pack_bf16x2(v[0], v[1]); hi4.y = pack_bf16x2(v[2], v[3]);
-            hi4.z = pack_bf16x2(v[4], v[5]); hi4.w = pack_bf16x2(v[6], v[7]);
-            lo4.x = pack_bf16x2(v[0] - __uint_as_float(hi4.x << 16), v[1] - __uint_as_float(hi4.x & 0xffff0000u));
-            lo4.y = pack_bf16x2(v[2] - __uint_as_float(hi4.y << 16), v[3] - __uint_as_float(hi4.y & 0xffff0000u));
-            lo4.z = pack_bf16x2(v[4] - __uint_as_float(hi4.z << 16), v[5] - __uint_as_float(hi4.z & 0xffff0000u));
-            lo4.w = pack_bf16x2(v[6] - __uint_as_float(hi4.w << 16), v[7] - __uint_as_float(hi4.w & 0xffff0000u));
-            *reinterpret_cast<uint4*>(a_hi + soff) = hi4;
-            *reinterpret_cast<uint4*>(a_lo + soff) = lo4;
+            uint32_t hw[4], lw4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t a0, a1;
+              asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(acc[q]));
+              const float v0 = __uint_as_float(a0), v1 = __uint_as_float(a1);
+              hw[q] = pack_bf16x2(v0, v1);
+              lw4[q] = pack_bf16x2(v0 - __uint_as_float(hw[q] << 16), v1 - __uint_as_float(hw[q] & 0xffff0000u));
+            }
+            *reinterpret_cast<uint4*>(a_hi + soff) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(a_lo + soff) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
           }
         } else if (!DEFORM && XBF16) {
           // dense, bf16 activations: the 128-byte row IS the smem row -> cp.async 16 B per (row, chunk)

@@ -198,7 +198,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_y);
-    if (g.has_res) prefetch_tmap(&tm_r);
+    if (g.has_res || (g.stem && g.x3)) prefetch_tmap(&tm_r);
   }
   tc_fence_before();
   __syncthreads();
@@ -291,7 +291,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tma_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
           tma_load_2d(a_dst + L.a_bytes, &tm_w, bf, kbr * 64, n0);
           if (g.x3) {
-            tma_load_4d(a_dst + L.a_half, &tm_x, bf, g.x_lo + cc * 64, cw, ch, i0);
+            if (g.stem)   // pair stem: the lo plane of the packed image has its own tensor map (tm_r is free: no residual)
+              tma_load_5d(a_dst + L.a_half, &tm_r, bf, 0, w0, kbr & 1, h0 + (kbr >> 1), i0);
+            else
+              tma_load_4d(a_dst + L.a_half, &tm_x, bf, g.x_lo + cc * 64, cw, ch, i0);
             tma_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kbr * 64, g.w_lo + n0);
           }
           if (++kbr == num_kb) { kbr = 0; cc = 0; kj = 0; cw = w0 - g.pw; ch = h0 - g.ph; }
@@ -1312,8 +1315,8 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
 // (64 el, Wo @32 B, 2 @pitch, Hp/2 @2*pitch, N) whose boxes ARE the im2col tiles, one k-block per filter row.
 // Weights are packed [Cout][ky][8 px][8 ch] with zeros for kx >= kw and c >= Cin (K = 64*kh).
 // ----------------------------------------------------------------------------------------------
-__global__ void stem_pack_image_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int N, int C, int H, int W,
-                                       int pad, int Hp, int Wp) {
+__global__ void stem_pack_image_kernel(const float* __restrict__ x, uint4* __restrict__ xp, uint4* __restrict__ xp_lo, int N, int C,
+                                       int H, int W, int pad, int Hp, int Wp) {
   const long long total = (long long)N * Hp * Wp;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(t % Wp);
@@ -1326,6 +1329,14 @@ __global__ void stem_pack_image_kernel(const float* __restrict__ x, uint4* __res
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
     xp[t] = o;
+    if (xp_lo) {     // pair stem: second plane = bf16(v - hi)
+      uint4 l;
+      l.x = pack_bf16x2(v[0] - __uint_as_float(o.x << 16), v[1] - __uint_as_float(o.x & 0xffff0000u));
+      l.y = pack_bf16x2(v[2] - __uint_as_float(o.y << 16), v[3] - __uint_as_float(o.y & 0xffff0000u));
+      l.z = pack_bf16x2(v[4] - __uint_as_float(o.z << 16), v[5] - __uint_as_float(o.z & 0xffff0000u));
+      l.w = pack_bf16x2(v[6] - __uint_as_float(o.w << 16), v[7] - __uint_as_float(o.w & 0xffff0000u));
+      xp_lo[t] = l;
+    }
   }
 }
 
@@ -1335,7 +1346,9 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, int Cout, i
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i & 7, kx = (i >> 3) & 7, ky = (i >> 6) % kh, co = i / (64 * kh);
     const float v = (c < Cin && kx < kw) ? w[(((size_t)co * Cin + c) * kh + ky) * kw + kx] : 0.f;
-    packed[i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    packed[i] = h;
+    packed[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));      // lo plane (pair stem)
   }
 }
 
@@ -1353,13 +1366,13 @@ extern "C" int upsnet_stem_workspace_bytes(int N, int H, int W, int kh, int kw, 
   int Ho, Wo, Hp, Wp;
   ups::stem_geometry(H, W, kh, kw, pad, &Ho, &Wo, &Hp, &Wp);
   if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
-  *bytes = (size_t)N * Hp * Wp * 16;
+  *bytes = (size_t)N * Hp * Wp * 16 * 2;     // hi plane + lo plane (the lo plane is only written / read by the pair stem)
   return 0;
 }
 
 extern "C" int upsnet_stem_packed_weight_bytes(int Cout, int kh, size_t* bytes) {
   if (!bytes || Cout <= 0 || kh <= 0) return UPSNET_E_BADARG;
-  *bytes = (size_t)Cout * kh * 64 * 2;
+  *bytes = (size_t)Cout * kh * 64 * 2 * 2;   // bf16 hi plane + lo plane
   return 0;
 }
 
@@ -1384,7 +1397,9 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
   int Ho, Wo, Hp, Wp;
   stem_geometry(H, W, kh, kw, pad, &Ho, &Wo, &Hp, &Wp);
   if (Ho <= 0 || Wo <= 0) return UPSNET_E_BADARG;
-  if (workspace_bytes < (size_t)N * Hp * Wp * 16) return UPSNET_E_WORKSPACE;
+  const bool pair = (epi_flags & UPSNET_EPI_STEM_PAIR) != 0;
+  const size_t plane_bytes = (size_t)N * Hp * Wp * 16;
+  if (workspace_bytes < plane_bytes * (pair ? 2 : 1)) return UPSNET_E_WORKSPACE;
   EncodeTiledFn enc = tma_encoder();
   if (!enc) return UPSNET_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1395,27 +1410,31 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
   g.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
   g.sig_from = -1;
   g.stem = 1; g.y = y; g.y_bf16 = 1; g.out_nhwc = 1;
+  g.x3 = pair ? 1 : 0; g.w_lo = Cout; g.pg = Cout; g.opairs = 2; g.x_lo = 0;
   tma_pick_box(N, Ho, Wo, 1, 1, 1, 1, false, &g.bw, &g.bh, &g.bn);
   g.tiles_w = (Wo + g.bw - 1) / g.bw;
   g.tiles_h = (Ho + g.bh - 1) / g.bh;
   g.tiles_n = (N + g.bn - 1) / g.bn;
   g.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  if (pair && g.BN > 128) g.BN = 128;
   g.n_tiles = Cout / g.BN;
   int stages = TM_MAX_STAGES;
-  TmaSmem L = tma_smem_layout(g.BN, stages, false);
-  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(g.BN, stages, false); }
+  TmaSmem L = tma_smem_layout(g.BN, stages, false, 0, 0, false, pair, false, false, g.opairs);
+  while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(g.BN, stages, false, 0, 0, false, pair, false, false, g.opairs); }
   g.stages = stages;
-  CUtensorMap tm_x, tm_w, tm_y;
+  CUtensorMap tm_x, tm_w, tm_y, tm_lo;
   {
     const cuuint64_t pitch = (cuuint64_t)Wp * 16;
     const cuuint64_t dx[5] = {64, (cuuint64_t)Wo, 2, (cuuint64_t)(Hp / 2), (cuuint64_t)N};
     const cuuint64_t sx[4] = {32, pitch, 2 * pitch, (cuuint64_t)Hp * pitch};
     const cuuint32_t bx[5] = {64, (cuuint32_t)g.bw, 1, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
-    const cuuint64_t dwt[2] = {(cuuint64_t)kh * 64, (cuuint64_t)Cout};
+    const cuuint64_t dwt[2] = {(cuuint64_t)kh * 64, (cuuint64_t)Cout * 2};       // hi plane rows, then lo plane rows
     const cuuint32_t bw2[2] = {64, (cuuint32_t)g.BN};
-    const cuuint64_t dy[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint64_t dy[4] = {(cuuint64_t)Cout * (pair ? 2 : 1), (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
     const cuuint32_t by[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, (cuuint32_t)g.bn};
     if (!encode_bf16(enc, &tm_x, workspace, 5, dx, bx, sx)) return UPSNET_E_UNSUPPORTED;
+    tm_lo = tm_x;
+    if (pair && !encode_bf16(enc, &tm_lo, (char*)workspace + plane_bytes, 5, dx, bx, sx)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_w, packed_w, 2, dwt, bw2)) return UPSNET_E_UNSUPPORTED;
     if (!encode_bf16(enc, &tm_y, y, 4, dy, by)) return UPSNET_E_UNSUPPORTED;
   }
@@ -1423,7 +1442,8 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
     const long long total = (long long)N * Hp * Wp;
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-    stem_pack_image_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (uint4*)workspace, N, Cin, H, W, pad, Hp, Wp);
+    stem_pack_image_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, (uint4*)workspace, pair ? (uint4*)((char*)workspace + plane_bytes) : nullptr,
+                                                             N, Cin, H, W, pad, Hp, Wp);
     UPS_CHECK_LAUNCH();
   }
   static ups::PerDeviceOnce configured;
@@ -1438,7 +1458,7 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
   }
   const long long num_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
-  igemm_tma_kernel<<<grid, TM_THREADS, L.total + 1024, st>>>(tm_x, tm_w, tm_y, tm_y, g);
+  igemm_tma_kernel<<<grid, TM_THREADS, L.total + 1024, st>>>(tm_x, tm_w, tm_y, pair ? tm_lo : tm_y, g);
   UPS_CHECK_LAUNCH();
   return 0;
 }

@@ -156,9 +156,11 @@ class Stem(nn.Module):
         self._f = (w.detach(), b.detach())
 
     def forward(self, x):
-        if x.is_cuda and ops.ACT_BF16["on"] and ops._PRECISION["conv"] == ops._lib.PREC_BF16 and self._stem_tma is not False:
+        bf16_stream = ops.ACT_BF16["on"] and ops._PRECISION["conv"] == ops._lib.PREC_BF16
+        pair_stream = ops.ACT_PAIR["on"] and ops._PRECISION["conv"] == ops._lib.PREC_BF16X3
+        if x.is_cuda and (bf16_stream or pair_stream) and self._stem_tma is not False:
             try:    # TMA-fed stem; a driver that rejects the overlapping-stride tensor map leaves the gather kernel in charge
-                y = ops.stem_conv(x, self._f[0], self._f[1], 3, relu=True)
+                y = ops.stem_conv(x, self._f[0], self._f[1], 3, relu=True, pair=pair_stream)
                 self._stem_tma = True
                 return ops.max_pool2d(y, 3, 2, 1)
             except ops._lib.UpsnetError:

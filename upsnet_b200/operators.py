@@ -176,10 +176,11 @@ _stem_cache = {}   # id(weight) -> (weakref, version, packed bf16 [Cout][kh][8][
 _stem_ws = None
 
 
-def stem_conv(x, weight, bias, padding, relu=True):
+def stem_conv(x, weight, bias, padding, relu=True, pair=False):
     """k x k / stride-2 convolution of a tiny-Cin fp32 NCHW image (models/resnet.py:155-162 conv1) on the TMA kernel:
     the image is packed to a zero-padded bf16 NHWC8 copy whose 5-D tensor-map boxes are the im2col tiles.
-    -> bf16 channels_last activation [N,Cout,Ho,Wo].  Raises UpsnetError(UNSUPPORTED) if the driver rejects the map."""
+    -> bf16 channels_last activation [N,Cout,Ho,Wo]; pair=True (precision bf16x3): hi and lo copies of the image, three MMAs
+    per k-slice, -> Pair.  Raises UpsnetError(UNSUPPORTED) if the driver rejects the map."""
     global _stem_ws
     require_cuda(x, weight, bias)
     x = f32c(x)
@@ -205,15 +206,16 @@ def stem_conv(x, weight, bias, padding, relu=True):
         _stem_ws = _Workspace()
     ws = _stem_ws.get(dev, nb.value)
     Ho, Wo = (H + 2 * padding - kh) // 2 + 1, (W + 2 * padding - kw) // 2 + 1
-    store = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=dev)
-    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
-            "shape": "N%d %dx%d Cin%d->Cout%d k%d s2 float32->bfloat16 (stem, TMA)" % (N, H, W, Cin, Cout, kh),
+    store = torch.empty((N, Ho, Wo, Cout * (2 if pair else 1)), dtype=torch.bfloat16, device=dev)
+    fl = 2.0 * N * Ho * Wo * Cout * Cin * kh * kw
+    work = {"flops": fl * (3 if pair else 1), "algo_flops": fl,
+            "shape": "N%d %dx%d Cin%d->Cout%d k%d s2 float32->%s (stem, TMA)" % (N, H, W, Cin, Cout, kh, "pair" if pair else "bfloat16"),
             "bytes": float(4 * x.numel() + 2 * store.numel())}
     with torch.cuda.device(dev), _Timed("conv2d", 2, work, dev):
         check(lib().upsnet_stem_forward(ptr(x), ptr(packed), ptr(None if bias is None else f32c(bias)), ptr(store), N, Cin, H, W,
-                                        Cout, kh, kw, int(padding), _lib.EPI_RELU if relu else 0, ptr(ws), ws.numel(),
-                                        stream_ptr(dev)), "stem_forward")
-    return store.permute(0, 3, 1, 2)
+                                        Cout, kh, kw, int(padding), (_lib.EPI_RELU if relu else 0) | (_lib.EPI_STEM_PAIR if pair else 0),
+                                        ptr(ws), ws.numel(), stream_ptr(dev)), "stem_forward")
+    return Pair(store) if pair else store.permute(0, 3, 1, 2)
 
 
 def _tc_ok(Cin, kh, kw, dg, deform=False):
