@@ -517,6 +517,7 @@ def run_ops(args):
     import upsnet_b200 as U
     from oracle import oracle as O
     dev = torch.device("cuda", 0)
+    torch.set_grad_enabled(False)       # operator table = inference kernels (modules switch to the autograd path otherwise)
     pk = peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     try:

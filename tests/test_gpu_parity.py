@@ -188,7 +188,7 @@ def test_dcn_golden(dev, golden_ops, ref):
     assert np.abs(y - g["dcn_y"]).max() < 1e-4
     m = U.ModulatedDeformConv(8, 12, 3, padding=1).to(dev)
     m.weight.data.copy_(w); m.bias.data.copy_(b)
-    y2 = m(x, t(g["dcn2_om"], dev)).cpu().numpy()
+    y2 = m(x, t(g["dcn2_om"], dev)).detach().cpu().numpy()      # module call = autograd path (parameters require grad), like the reference
     assert np.abs(y2 - g["dcn2_y"]).max() < 1e-4
     if ref is not None:
         r = ref.deform_conv(x, t(g["dcn_off"], dev), w, b, pad=1, dg=2).cpu().numpy()
@@ -231,7 +231,7 @@ def test_deform_conv_with_offset_module_and_state_dict_names(dev):
     torch.manual_seed(3)
     m.conv_offset.weight.data.normal_(0, 0.3)
     x = torch.randn(1, 16, 12, 14, device=dev)
-    y = m(x).cpu().numpy()
+    y = m(x).detach().cpu().numpy()      # module call = autograd path (parameters require grad), like the reference
     off = O.conv2d(x.cpu().numpy(), m.conv_offset.weight.detach().cpu().numpy(), m.conv_offset.bias.detach().cpu().numpy(), pad=1)
     want = O.deform_conv(x.cpu().numpy(), off, m.conv.weight.detach().cpu().numpy(), m.conv.bias.detach().cpu().numpy(), pad=1)
     assert np.abs(y - want).max() < 1e-4
