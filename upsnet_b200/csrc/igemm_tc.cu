@@ -918,7 +918,12 @@ int launch_igemm_tc(TcParams p, const void* packed, cudaStream_t stream) {
   }
   const long long num_tiles = (deform ? dtiles() : ((Ptot + TC_BM - 1) / TC_BM) * (p.Cout_pad / BN));
   dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));
-  const size_t smem = L.total + 1024;
+  size_t smem = L.total + 1024;
+  if (deform) {     // experiment hook: extra (unused) dynamic shared memory shrinks L1 -- measures the gather's L1 sensitivity
+    static int extra = -1;
+    if (extra < 0) { const char* e = getenv("UPSNET_DCN_EXTRA_SMEM_KB"); extra = e ? atoi(e) : 0; }
+    if (extra > 0 && smem + (size_t)extra * 1024 <= 227 * 1024) smem += (size_t)extra * 1024;
+  }
   // opt in to the full 227 KB once per process (kept out of the per-launch path: CUDA-graph capture)
   // opt in to the full 227 KB once per device (kept out of the per-launch path: CUDA-graph capture)
   static PerDeviceOnce configured;
