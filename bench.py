@@ -447,8 +447,9 @@ def main():
     achieved = algo / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0   # ALGORITHMIC flops (x3 MMAs not counted)
     dcn_algo = sum(w.get("algo_flops", 0.0) for k_, _, _, w in trace if k_ == "dcn")
     kname = {"bf16": "igemm_tma_kernel (TMA-fed tcgen05 implicit GEMM; dense conv / FC family incl. stem)",
-             "bf16x3": "igemm_tma_kernel on hi/lo bf16 pairs (TMA-fed tcgen05 implicit GEMM, 3 MMAs per k-slice: hi*hi + "
-                       "lo*hi + hi*lo; dense conv / FC family; the RGB stem runs on igemm_tc_kernel)",
+             "bf16x3": "igemm_tma2_kernel / igemm_tma_kernel on hi/lo bf16 pairs (TMA-fed tcgen05 implicit GEMM, 3 MMAs per "
+                       "k-slice: hi*hi + lo*hi + hi*lo; 2-CTA cta_group::2 variant for tiles with >= 8 k-blocks, 1-CTA "
+                       "otherwise; dense conv / FC family incl. the RGB stem)",
              "fp32": "igemm_simt_kernel (fp32 CUDA-core tiles)"}[args.precision]
     roofline = {"kernel": kname + ", precision=%s" % args.precision, "bound": "tensor",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
