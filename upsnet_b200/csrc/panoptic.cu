@@ -280,7 +280,6 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
                   PanWorkspace ws) {
   const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
   __shared__ unsigned short list[kMaxList];   // ranks (score order) of this class's instances in this round
-  __shared__ unsigned int s_ovl[2];
   __shared__ int s_cnt;
   __shared__ int s_warp_cnt[32];
   const int c = blockIdx.x;  // 0-based class
@@ -292,7 +291,7 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
   if (r_lo >= r_hi) return;
 
   // ---- ordered list of the ranks that belong to this class ----
-  if (threadIdx.x == 0) { s_cnt = 0; s_ovl[0] = 0; s_ovl[1] = 0; }
+  if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   for (int base = r_lo; base < r_hi; base += blockDim.x) {
     const int r = base + threadIdx.x;
@@ -312,86 +311,87 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
     __syncthreads();
   }
   const int cnt = s_cnt;
-  // Per-instance critical path = one L2 round trip (window words + occupancy) + a block reduction: |mask| values are
-  // staged in shared memory up front, a thread's window words stay in registers between the popc and the OR pass.
-  // per-instance metadata of the whole class list staged in (dynamic) shared memory: inside the serial loop nothing but
+  // per-instance metadata of the whole class list staged in (dynamic) shared memory: inside the decision loops nothing but
   // the window words and the occupancy words comes from L2
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  int4* s_win = reinterpret_cast<int4*>(s_dyn);                       // (wx0, nwc, y0, items)   [n_max]
+  int4* s_win = reinterpret_cast<int4*>(s_dyn);                       // (wx0, nwc, y0, rows)    [n_max]
   long long* s_off = reinterpret_cast<long long*>(s_win + n_max);      // word offset in ws.bits  [n_max]
   int* s_msum = reinterpret_cast<int*>(s_off + n_max);                 // |mask|                  [n_max]
+  volatile int* s_state = reinterpret_cast<volatile int*>(s_msum + n_max);   // 0 undecided, 1 dropped, 2 kept   [n_max]
   for (int li = threadIdx.x; li < cnt; li += blockDim.x) {
     const int r = list[li];
     const int i = ws.order[r];
     const int x0 = ws.g.gx0[i], x1 = ws.g.gx1[i], y0 = ws.g.gy0[i], y1 = ws.g.gy1[i];
     const int wx0 = x0 >> 5, nwc = max(((x1 + 31) >> 5) - wx0, 0);
-    s_win[li] = make_int4(wx0, nwc, y0, nwc * max(y1 - y0, 0));
+    s_win[li] = make_int4(wx0, nwc, y0, max(y1 - y0, 0));
     s_off[li] = ws.off[r] - (long long)rq * ws.budget;
     s_msum[li] = ws.msum[r];
+    s_state[li] = 0;
   }
   __syncthreads();
-  constexpr int kRegWords = 8;
-  for (int li = 0; li < cnt; ++li) {
+  // The keep decision of an instance depends on the EARLIER instances of its class only through the occupancy words of its
+  // own window (mask_removal.py:62-90): two instances whose word windows are disjoint never see each other.  So the score-
+  // ordered chain is only as long as the chain of OVERLAPPING windows: eight groups of 128 threads take the instances round-
+  // robin, a group first waits for every earlier overlapping instance to be decided (shared-memory state flags), then does
+  // what the serial version did -- popc(window & occupied), the float64 ratio test, occupied |= window -- with group-local
+  // barriers.  Disjoint windows share no occupancy word, so concurrent groups never write the same word.  Decisions are
+  // identical to the serial order; per-instance latency is unchanged, independent instances overlap.
+  constexpr int kGroup = 128, kGroups = 1024 / kGroup;
+  __shared__ unsigned int s_part[kGroups][kGroup / 32];
+  const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup, gw = gt >> 5;
+  for (int li = grp; li < cnt; li += kGroups) {
     const int r = list[li];
     const int4 win = s_win[li];
-    const int wx0 = win.x, nwc = win.y, y0 = win.z, items = win.w;
-    const unsigned int* __restrict__ bits = ws.bits + s_off[li];
-    unsigned int my_ovl = 0;
-    unsigned int wreg[kRegWords], oreg[kRegWords];
-    const int nit = (items + (int)blockDim.x - 1) / (int)blockDim.x;   // block-uniform: passes that have any work at all
-#pragma unroll
-    for (int u = 0; u < kRegWords; ++u) {
-      const int item = threadIdx.x + u * (int)blockDim.x;
-      wreg[u] = 0u; oreg[u] = 0u;
-      if (u < nit && item < items) {
-        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-        wreg[u] = __ldg(bits + item);
-        oreg[u] = occ[o];                 // kept: the OR below is then a plain store, not a second L2 round trip
-        my_ovl += __popc(wreg[u] & oreg[u]);
+    const int wx0 = win.x, nwc = win.y, y0 = win.z, rows = win.w;
+    const int items = nwc * rows;
+    // ---- dependencies: every earlier instance whose word window intersects this one must have been decided ----
+    for (int lj = gt; lj < li; lj += kGroup) {
+      const int4 o = s_win[lj];
+      const bool hit = o.x < wx0 + nwc && wx0 < o.x + o.y && o.z < y0 + rows && y0 < o.z + o.w && o.y > 0 && o.w > 0 && items > 0;
+      if (hit) {
+        while (s_state[lj] == 0) { }
       }
     }
-    for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
+    __threadfence_block();                        // acquire side of the state flags: the deciders' occupancy writes are visible
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGroup) : "memory");
+    const unsigned int* __restrict__ bits = ws.bits + s_off[li];
+    unsigned int my_ovl = 0;
+    for (int item = gt; item < items; item += kGroup) {
       const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-      my_ovl += __popc(__ldg(bits + item) & occ[o]);
+      my_ovl += __popc(__ldg(bits + item) & __ldcg(occ + o));      // occupancy: L2 (another group's SM-local L1 line may be stale)
     }
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) my_ovl += __shfl_xor_sync(0xffffffffu, my_ovl, sh);
-    if (lane == 0 && my_ovl) atomicAdd(&s_ovl[li & 1], my_ovl);
-    __syncthreads();
-    const unsigned int ms = (unsigned int)s_msum[li], ov = s_ovl[li & 1];
-    // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3
-    // one fp64 division per WARP (lane 0), broadcast by shuffle: B200 has very few fp64 units, 1024 divisions per
-    // instance would dominate the serial pass
-    int drop_i = 0;
-    if (lane == 0) {
-      // fl(ov/ms) > thr is decided without the division whenever ov is clear of thr*ms by more than rounding could
-      // account for (1e-12 relative >> 2^-52); only the knife-edge case pays for the fp64 division itself
+    if (lane == 0) s_part[grp][gw] = my_ovl;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGroup) : "memory");
+    const unsigned int ov = s_part[grp][0] + s_part[grp][1] + s_part[grp][2] + s_part[grp][3];
+    const unsigned int ms = (unsigned int)s_msum[li];
+    // mask_removal.py:82: int/int true division (float64) compared with the python float 0.3; decided without the division
+    // whenever ov is clear of thr*ms by more than rounding could account for (1e-12 relative >> 2^-52) -- every thread of the
+    // group evaluates the same expression on the same operands (B200 has few fp64 units, but this is 3 flops per thread)
+    bool drop;
+    {
       const double t = (double)ms * fraction_threshold, dov = (double)ov;
-      if (ms == 0) drop_i = 1;
-      else if (dov > t * (1.0 + 1e-12)) drop_i = 1;
-      else if (dov < t * (1.0 - 1e-12)) drop_i = 0;
-      else drop_i = (__ddiv_rn(dov, (double)ms) > fraction_threshold) ? 1 : 0;
-    }
-    const bool drop = __shfl_sync(0xffffffffu, drop_i, 0) != 0;
-    if (threadIdx.x == 0) {
-      ws.kept_flag[r] = drop ? 0 : 1;
-      s_ovl[(li + 1) & 1] = 0;            // the other counter is idle until the next instance's barrier
+      if (ms == 0) drop = true;
+      else if (dov > t * (1.0 + 1e-12)) drop = true;
+      else if (dov < t * (1.0 - 1e-12)) drop = false;
+      else drop = __ddiv_rn(dov, (double)ms) > fraction_threshold;
     }
     if (!drop) {
-#pragma unroll
-      for (int u = 0; u < kRegWords; ++u) {
-        const int item = threadIdx.x + u * (int)blockDim.x;
-        if (u < nit && item < items && (wreg[u] & ~oreg[u])) {
+      for (int item = gt; item < items; item += kGroup) {
+        const unsigned int w = __ldg(bits + item);
+        if (w) {
           const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-          occ[o] = oreg[u] | wreg[u];
+          __stcg(occ + o, __ldcg(occ + o) | w);
         }
       }
-      for (int item = threadIdx.x + kRegWords * (int)blockDim.x; item < items; item += blockDim.x) {
-        const size_t o = (size_t)(y0 + item / nwc) * Ww + (wx0 + item % nwc);
-        occ[o] |= __ldg(bits + item);
-      }
     }
-    __syncthreads();   // occupancy visible to the whole CTA before the next instance reads it
+    __threadfence_block();                        // release: occupancy words before the state flag
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(kGroup) : "memory");
+    if (gt == 0) {
+      ws.kept_flag[r] = drop ? 0 : 1;
+      s_state[li] = drop ? 1 : 2;
+    }
   }
 }
 
@@ -634,14 +634,14 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
   UPS_CHECK_LAUNCH();
   {
     static ups::PerDeviceOnce configured;
-    if (configured.need()) {   // up to kMaxList * 28 B of per-instance metadata
-      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
+    if (configured.need()) {   // up to kMaxList * 32 B of per-instance metadata
+      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 32));
     }
   }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
     pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
     UPS_CHECK_LAUNCH();
-    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 28, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 32, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
@@ -697,14 +697,14 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   UPS_CHECK_LAUNCH();
   {
     static ups::PerDeviceOnce configured;
-    if (configured.need()) {   // up to kMaxList * 28 B of per-instance metadata
-      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 28));
+    if (configured.need()) {   // up to kMaxList * 32 B of per-instance metadata
+      UPS_CUDA(cudaFuncSetAttribute(pan_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxList * 32));
     }
   }
   for (int rq = 0; rq < ws.rounds; ++rq) {   // one round unless n * H * W/32 words exceed the bit-window budget
     pan_bits_kernel<<<dim3(kBitsChunks, n), kBitsThreads, 0, st>>>(mask_logit, n, n_dev, rq, ws);
     UPS_CHECK_LAUNCH();
-    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 28, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
+    pan_decide_kernel<<<num_thing, 1024, (size_t)n * 32, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
