@@ -154,6 +154,23 @@ int upsnet_igemm_forward(const void *x_nhwc, const float *offset, const float *m
                          int x_dtype, int y_dtype, int epi_flags, int precision, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Deformable convolution v1 / v2 on hi/lo PAIR activations with the bilinear corners gathered from a shared-memory
+ * window (csrc/dcn_win.cu): 3x3, stride 1, deformable_groups 1, Cin % 64 == 0, Cout % 16 == 0, precision
+ * UPSNET_PREC_BF16X3.  x [N,H,W,2*Cin] pair NHWC -> y [N,Ho,Wo,2*Cout] pair NHWC; offset / mask as in
+ * upsnet_igemm_forward; epi_flags: UPSNET_EPI_RELU.  Same arithmetic contract as upsnet_igemm_forward with an offset
+ * (samples outside the staged window are gathered from global memory: the result does not depend on the window size).
+ * `packed` comes from upsnet_dcn_pack_weight (K order: 16-channel sub-chunk, tap, channel) and holds
+ * upsnet_dcn_packed_weight_bytes bytes.  All three return UPSNET_E_UNSUPPORTED for other layer shapes: callers then use
+ * upsnet_igemm_forward.
+ * replaces: operators/functions/deform_conv.py:26-57 (deformable_im2col + torch.mm),
+ *           operators/src/deform_conv_kernel.cu:89-118,194-242, mod_deform_conv_kernel.cu (v2 mask). */
+int upsnet_dcn_packed_weight_bytes(int Cout, int Cin, int kh, int kw, size_t *bytes);
+int upsnet_dcn_pack_weight(const float *weight, int Cout, int Cin, int kh, int kw, void *packed, void *stream);
+int upsnet_dcn_pair_forward(const void *x_pair, const float *offset, const float *mask, const void *packed,
+                            const float *bias, void *y_pair, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                            int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Parameter-free panoptic head, fused: MaskRemoval + SegTerm + void/concat/argmax.
  * replaces: models/resnet_upsnet.py:223-240 with operators/modules/mask_removal.py:29-93,
  *           operators/modules/unary_logits.py:78-105.  Never materialises the [1,k,H,W] planes.

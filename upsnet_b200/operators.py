@@ -31,6 +31,7 @@ from ._lib import check, f32c, lib, ptr, require_cuda, stream_ptr
 _PRECISION = {"conv": _lib.PREC_FP32_SIMT}
 ACT_BF16 = {"on": False}   # engine switch: store activations as bf16 (precision 'bf16' only)
 ACT_PAIR = {"on": False}   # engine switch: store activations as hi/lo bf16 pairs (precision 'bf16x3': fp32-grade results)
+DCN_WINDOW = {"on": False}  # pair-stream deformable convs gather from a shared-memory window (csrc/dcn_win.cu); False = global gather (A/B tests)
 USE_TMA = {"on": True}     # False forces the cp.async gather kernel where the TMA-fed one would qualify (A/B tests)
 
 
@@ -170,6 +171,55 @@ def _packed_weight(weight):
     wid = id(weight)
     _packed_cache[wid] = (weakref.ref(weight, lambda _r, _k=wid: _packed_cache.pop(_k, None)), weight._version, buf)
     return buf
+
+
+_dcn_packed_cache = {}
+
+
+def _packed_weight_dcn(weight):
+    """upsnet_dcn_pack_weight: bf16 hi/lo planes in the window kernel's K order (16-channel sub-chunk, tap, channel);
+    None when the layer shape is not supported by that kernel.  Cached like _packed_weight."""
+    hit = _dcn_packed_cache.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and (hit[2] is None or hit[2].device == weight.device):
+        return hit[2]
+    Cout, Cin, kh, kw = weight.shape
+    nbytes = C.c_size_t(0)
+    rc = lib().upsnet_dcn_packed_weight_bytes(Cout, Cin, kh, kw, C.byref(nbytes))
+    buf = None
+    if rc == 0:
+        buf = torch.empty(nbytes.value, dtype=torch.uint8, device=weight.device)
+        w = f32c(weight.detach())
+        with torch.cuda.device(weight.device):
+            check(lib().upsnet_dcn_pack_weight(ptr(w), Cout, Cin, kh, kw, ptr(buf), stream_ptr(weight.device)), "dcn_pack_weight")
+        STATS["launches"] += 1
+    elif rc != -2:
+        check(rc, "dcn_packed_weight_bytes")
+    wid = id(weight)
+    _dcn_packed_cache[wid] = (weakref.ref(weight, lambda _r, _k=wid: _dcn_packed_cache.pop(_k, None)), weight._version, buf)
+    return buf
+
+
+def _dcn_window(x, offset, mask, weight, bias, padding, dilation, relu):
+    """upsnet_dcn_pair_forward (csrc/dcn_win.cu): Pair in, Pair out, 3x3 / stride 1.  Returns None when the layer does
+    not qualify (the caller then takes upsnet_igemm_forward)."""
+    packed = _packed_weight_dcn(weight)
+    if packed is None:
+        return None
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    ph, pw = padding; dh, dw = dilation
+    Ho, Wo = _conv_out(H, ph, dh, kh, 1), _conv_out(W, pw, dw, kw, 1)
+    store = torch.empty((N, Ho, Wo, 2 * Cout), device=x.device, dtype=torch.bfloat16)
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw * 3, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * kh * kw,
+            "shape": "N%d %dx%d Cin%d->Cout%d k%d s1 pair->pair (window)" % (N, H, W, Cin, Cout, kh),
+            "bytes": float(x.store.numel() * 2 + 4 * weight.numel() + store.numel() * 2 + offset.numel() * 4)}
+    with torch.cuda.device(x.device), _Timed("dcn", 1, work, x.device):
+        rc = lib().upsnet_dcn_pair_forward(ptr(x.store), ptr(offset), ptr(mask), ptr(packed), ptr(bias), ptr(store), N, H, W,
+                                           Cin, Cout, kh, kw, ph, pw, dh, dw, _lib.EPI_RELU if relu else 0, stream_ptr(x.device))
+    if rc == -2:
+        return None
+    check(rc, "dcn_pair_forward")
+    return Pair(store)
 
 
 _stem_cache = {}   # id(weight) -> (weakref, version, packed bf16 [Cout][kh][8][8])
@@ -394,6 +444,11 @@ def deform_conv(data, offset, weight, bias=None, stride=1, padding=0, dilation=1
         assert tuple(offset.shape) == (N, 2 * kh * kw, Ho, Wo), offset.shape
         if mask is not None:
             assert tuple(mask.shape) == (N, kh * kw, Ho, Wo), mask.shape
+        if (DCN_WINDOW["on"] and isinstance(data, Pair) and prec == _lib.PREC_BF16X3 and (sh, sw) == (1, 1) and
+                out_format != "nchw" and out_dtype in (None, "pair") and ACT_PAIR["on"]):
+            y = _dcn_window(data, offset, mask, weight, bias, (ph, pw), (dh, dw), relu)
+            if y is not None:
+                return y
         return _igemm_tc("dcn", data, offset, mask, weight, bias, None, (sh, sw), (ph, pw), (dh, dw), relu, prec,
                          out_format, out_dtype)
     data, weight = f32c(as_float(data)), f32c(weight)
