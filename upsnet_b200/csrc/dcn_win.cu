@@ -34,19 +34,20 @@ namespace ups {
 
 constexpr int DW_BM = 128;            // pixels per M tile
 constexpr int DW_BK = 64;             // K elements per k-block = 4 slices of 16 channels
-constexpr int DW_STAGES = 2;          // operand ring depth (A by the gather groups, B by TMA)
-constexpr int DW_WW = 30, DW_WH = 20; // window box in pixels
+constexpr int DW_STAGES = 3;          // operand ring depth: A stages live in TMEM (gather warps), B stages in smem (TMA)
+constexpr int DW_WW = 32, DW_WH = 24; // window box in pixels; the row pitch (32 px = 1024 B) keeps bank = f(x) only
 constexpr int DW_PLANE = DW_WW * DW_WH * 32;      // one plane (hi or lo) of a window: 16 channels x 2 B per pixel
 constexpr int DW_WIN_BYTES = 2 * DW_PLANE;
 constexpr int DW_KHW = 9;
 constexpr int DW_GROUP = 256, DW_GROUPS = 2, DW_PRODUCERS = DW_GROUP * DW_GROUPS;
 constexpr int DW_WARP_MMA = 4, DW_WARP_TMAB = 5, DW_WARP_TMAW = 6, DW_WARP_PROD0 = 7;
 constexpr int DW_THREADS = (DW_WARP_PROD0 + DW_PRODUCERS / 32) * 32;   // 736
+constexpr uint32_t DW_TMEM_A0 = 256;  // TMEM columns [0,256): two accumulators; [256 + 64 s, +64): A stage s (hi 32 cols, lo 32 cols)
 
 // shared-memory map (byte offsets from the 1024-aligned base)
-constexpr uint32_t DW_OFF_BARS = 0;        // 16 mbarriers
-constexpr uint32_t DW_OFF_TMEM = 128;
-constexpr uint32_t DW_OFF_STATS = 160;     // 2 x int[8]: min w, min h, max w, max h, sum w, sum h, count, -
+constexpr uint32_t DW_OFF_BARS = 0;        // 18 mbarriers
+constexpr uint32_t DW_OFF_TMEM = 160;
+constexpr uint32_t DW_OFF_STATS = 192;     // 2 x int[8]: min w, min h, max w, max h, sum w, sum h, count, -
 constexpr uint32_t DW_OFF_ORG = 256;       // 2 x int4: window origin (w, h), image, -
 constexpr uint32_t DW_OFF_TW = 512;        // float4 [9][128] corner weights
 constexpr uint32_t DW_OFF_TP = DW_OFF_TW + DW_KHW * DW_BM * 16;   // int [9][128] window byte offset / outlier code
@@ -83,10 +84,22 @@ __device__ __forceinline__ uint4 dw_lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void dw_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ void dw_producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DW_PRODUCERS) : "memory"); }
+// registers -> TMEM: lane i of the warp writes four consecutive 32-bit columns of TMEM lane (quadrant base + i)
+__device__ __forceinline__ void dw_tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void dw_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::f16: A = 128 TMEM lanes x 8 columns (16 bf16 of K, two per column)
+__device__ __forceinline__ void dw_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi) : "memory");
+}
 
 __global__ void __launch_bounds__(DW_THREADS, 1)
 dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const DwParams p) {
@@ -96,18 +109,18 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   uint8_t* sm = smem_dyn + (base - raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_bytes = DW_BM * 128, b_bytes = (uint32_t)p.BN * 128;
-  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
-  const uint32_t win_base = base + DW_OFF_STAGES + DW_STAGES * stage_bytes;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128;
+  const uint32_t stage_bytes = 2 * b_bytes;                                 // weight tile: hi plane, lo plane
+  const uint32_t win_base = base + DW_OFF_STAGES + DW_STAGES * stage_bytes; // 1024-aligned (stage_bytes % 1024 == 0)
   // barriers
-  const uint32_t bar_fa = base + DW_OFF_BARS;            // full_a[2]: 8 producer warps each
-  const uint32_t bar_fb = bar_fa + 16;                   // full_b[2]: weight TMA (tx)
-  const uint32_t bar_em = bar_fa + 32;                   // empty[2]: tcgen05.commit
-  const uint32_t bar_tf = bar_fa + 48;                   // tmem_full[2]
-  const uint32_t bar_te = bar_fa + 64;                   // tmem_empty[2]: 4 epilogue warps
-  const uint32_t bar_wf = bar_fa + 80;                   // win_full[2]: window TMA (tx)
-  const uint32_t bar_we = bar_fa + 96;                   // win_empty[2]: 16 producer warps
-  const uint32_t bar_og = bar_fa + 112;                  // org_full[2]: window origin of a tile published
+  const uint32_t bar_fa = base + DW_OFF_BARS;            // full_a[3]: 8 producer warps each (A stage written to TMEM)
+  const uint32_t bar_fb = bar_fa + 24;                   // full_b[3]: weight TMA (tx)
+  const uint32_t bar_em = bar_fa + 48;                   // empty[3]: tcgen05.commit (A stage in TMEM + B stage in smem consumed)
+  const uint32_t bar_tf = bar_fa + 72;                   // tmem_full[2]
+  const uint32_t bar_te = bar_fa + 88;                   // tmem_empty[2]: 4 epilogue warps
+  const uint32_t bar_wf = bar_fa + 104;                  // win_full[2]: window TMA (tx)
+  const uint32_t bar_we = bar_fa + 120;                  // win_empty[2]: 16 producer warps
+  const uint32_t bar_og = bar_fa + 136;                  // org_full[2]: window origin of a tile published
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + DW_OFF_TMEM);
   int* stats = reinterpret_cast<int*>(sm + DW_OFF_STATS);
   int4* org = reinterpret_cast<int4*>(sm + DW_OFF_ORG);
@@ -122,14 +135,16 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const int tw_shift = TW == 16 ? 4 : 3;
   const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
   const long long num_tiles = (long long)p.N * tiles_w * tiles_h * n_tiles;
-  const uint32_t tmem_cols = 2 * p.BN <= 32 ? 32 : (2 * p.BN <= 64 ? 64 : (2 * p.BN <= 128 ? 128 : 256));
+  constexpr uint32_t tmem_cols = 512;
 
   if (warp == DW_WARP_MMA) {
     if (lane == 0) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < DW_STAGES; ++s) {
         mbar_init(bar_fa + 8 * s, DW_GROUP / 32);
         mbar_init(bar_fb + 8 * s, 1);
         mbar_init(bar_em + 8 * s, 1);
+      }
+      for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tf + 8 * s, 1);
         mbar_init(bar_te + 8 * s, 4);
         mbar_init(bar_wf + 8 * s, 1);
@@ -155,16 +170,17 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 
   if (warp >= DW_WARP_PROD0) {
     // =============================== GATHER PRODUCERS ===============================
-    const int pt = tid - DW_WARP_PROD0 * 32;     // 0..511
-    const int group = pt / DW_GROUP;
-    const int gt = pt - group * DW_GROUP;
-    // lane -> (slice, row, half): LDS.128 is served per quarter-warp (8 lanes x 16 B = one 128-byte wavefront), so the eight
-    // lanes of a quarter take ONE tap's four horizontally consecutive pixels x two 16-byte halves -- four consecutive
-    // 32-byte window pixels = all 32 banks once (measured with lanes = one row x four taps: 8.5 wavefronts per LDS.128
-    // instead of 4, profiles/r2_dcn_win.md); the quarters of a warp take the four slices of the k-block
-    const int half = gt & 1, sl = (gt >> 3) & 3;
-    const int j = 2 * sl + half;                 // 16-byte chunk of the 128-byte A row
-    const int r_first = (gt >> 5) * 4 + ((gt >> 1) & 3);     // 32 rows per pass
+    // A warp owns the 32 rows of ITS TMEM lane quadrant (hardware rule: warp w reaches lanes 32 (w % 4) .. +31), lane = row:
+    // the 32 lanes of an LDS.128 read one (slice, 8-channel half) of 32 consecutive tile pixels.  The window is stored by
+    // TMA with SWIZZLE_32B (16-byte chunk ^= address bit 7, i.e. pixel bit 2), so eight horizontally consecutive pixels of
+    // one half occupy eight different 16-byte bank groups: a quarter-warp wavefront is conflict-free whenever its samples
+    // stay on consecutive pixels of any rows (row pitch 1024 B).
+    const int pt = tid - DW_WARP_PROD0 * 32;     // 0..511: sample-table work is spread over all producer threads
+    const int pw = warp - DW_WARP_PROD0;         // 0..15
+    const int group = pw >> 3;                   // alternate k-blocks
+    const int u = (pw >> 2) & 1;                 // which two of the k-block's four slices this warp gathers
+    const int quad = warp & 3;                   // TMEM lane quadrant
+    const int r = quad * 32 + lane;              // A row = tile pixel
     const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(p.x);
     uint32_t g0 = 0, wf0 = 0;                    // running k-block / window-fill counters at the start of the tile
     uint32_t wf_ready = 0;                       // window fills [0, wf_ready) have been observed complete by this thread
@@ -184,9 +200,9 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         ewv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         ehl[it] = 0; ewl[it] = 0; evalid[it] = false;
         if (e < DW_KHW * DW_BM) {
-          const int tap = e >> 7, r = e & 127;
-          const int ry = r >> tw_shift;
-          const int wo = tx * TW + (r & (TW - 1)), ho = ty * TH + ry;
+          const int tap = e >> 7, rr = e & 127;
+          const int ry = rr >> tw_shift;
+          const int wo = tx * TW + (rr & (TW - 1)), ho = ty * TH + ry;
           if (ry < TH && wo < p.Wo && ho < p.Ho) {
             const int pp = ho * p.Wo + wo;
             const int ki = tap / 3, kj = tap - ki * 3;
@@ -260,34 +276,37 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int kb = (int)((uint32_t)(group - (int)g0) & 1u); kb < num_kb; kb += DW_GROUPS) {
         const uint32_t g = g0 + (uint32_t)kb;
         const uint32_t s = g % DW_STAGES, it = g / DW_STAGES;
-        const int q = kb * 4 + sl;                    // slice index: (sub-chunk, tap)
-        const int sc = q / DW_KHW, tap = q - sc * DW_KHW;
-        const uint32_t wf = wf0 + (uint32_t)sc;
-        if (wf >= wf_ready) {                         // first touch of this window fill
-          mbar_wait(bar_wf + 8 * (wf & 1u), (wf >> 1) & 1u);
-          wf_ready = wf + 1;
-        }
         mbar_wait(bar_em + 8 * s, (it & 1u) ^ 1u);
-        const uint32_t stage = base + DW_OFF_STAGES + s * stage_bytes;
-        const uint32_t a_hi = stage, a_lo = stage + a_bytes + b_bytes;
-        const uint32_t wbuf = win_base + (wf & 1u) * DW_WIN_BYTES + (uint32_t)half * 16u;
-        const int cg = sc * 16 + half * 8;            // first channel of this thread's 8-channel vector
+        tc_fence_after();
+        const uint32_t a_col = tmem_base + ((uint32_t)(quad * 32) << 16) + DW_TMEM_A0 + s * 64u;
 #pragma unroll 1
-        for (int pass = 0; pass < DW_BM / 32; ++pass) {
-          const int r = r_first + pass * 32;
+        for (int pass = 0; pass < 4; ++pass) {
+          const int sl = 2 * u + (pass >> 1), half = pass & 1;
+          const int q = kb * 4 + sl;                    // slice index: (sub-chunk, tap)
+          const int sc = q / DW_KHW, tap = q - sc * DW_KHW;
+          const uint32_t wf = wf0 + (uint32_t)sc;
+          if (wf >= wf_ready) {                         // first touch of this window fill
+            mbar_wait(bar_wf + 8 * (wf & 1u), (wf >> 1) & 1u);
+            wf_ready = wf + 1;
+          }
+          const uint32_t wbuf = win_base + (wf & 1u) * DW_WIN_BYTES;
           const float4 wv = tw[tap * DW_BM + r];
           const int code = tp[tap * DW_BM + r];
           uint4 hc[4], lc[4];
           if (code >= 0) {
-            const uint32_t a = wbuf + (uint32_t)code;
-            hc[0] = dw_lds128(a); hc[1] = dw_lds128(a + 32); hc[2] = dw_lds128(a + DW_WW * 32); hc[3] = dw_lds128(a + DW_WW * 32 + 32);
-            lc[0] = dw_lds128(a + DW_PLANE); lc[1] = dw_lds128(a + DW_PLANE + 32);
-            lc[2] = dw_lds128(a + DW_PLANE + DW_WW * 32); lc[3] = dw_lds128(a + DW_PLANE + DW_WW * 32 + 32);
+            // SWIZZLE_32B: the 16-byte chunk of a pixel sits at (half ^ bit 7 of the pixel's byte offset)
+            const uint32_t cl = (uint32_t)code, cr = cl + 32u;
+            const uint32_t al = wbuf + cl + ((((cl >> 7) & 1u) ^ (uint32_t)half) << 4);
+            const uint32_t ar = wbuf + cr + ((((cr >> 7) & 1u) ^ (uint32_t)half) << 4);
+            hc[0] = dw_lds128(al); hc[1] = dw_lds128(ar); hc[2] = dw_lds128(al + DW_WW * 32); hc[3] = dw_lds128(ar + DW_WW * 32);
+            lc[0] = dw_lds128(al + DW_PLANE); lc[1] = dw_lds128(ar + DW_PLANE);
+            lc[2] = dw_lds128(al + DW_PLANE + DW_WW * 32); lc[3] = dw_lds128(ar + DW_PLANE + DW_WW * 32);
           } else {
             // outlier sample: the four corners come from global memory (clamped addresses; invalid corners carry weight 0)
             const int hl = (int)(((uint32_t)code >> 15) & 0xffffu) - 1, wl = (int)((uint32_t)code & 0x7fffu) - 1;
             const int h0 = max(hl, 0), h1 = min(hl + 1, p.H - 1), w0 = max(wl, 0), w1 = min(wl + 1, p.W - 1);
             const size_t pc = (size_t)(2 * p.Cin);
+            const int cg = sc * 16 + half * 8;            // first channel of this pass's 8-channel vector
             const __nv_bfloat16* b00 = ximg + ((size_t)h0 * p.W + w0) * pc + cg;
             const __nv_bfloat16* b01 = ximg + ((size_t)h0 * p.W + w1) * pc + cg;
             const __nv_bfloat16* b10 = ximg + ((size_t)h1 * p.W + w0) * pc + cg;
@@ -331,11 +350,13 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             ohi[qq] = pack_bf16x2(v0, v1);
             olo[qq] = pack_bf16x2(v0 - __uint_as_float(ohi[qq] << 16), v1 - __uint_as_float(ohi[qq] & 0xffff0000u));
           }
-          const uint32_t soff = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          dw_sts128(a_hi + soff, ohi[0], ohi[1], ohi[2], ohi[3]);
-          dw_sts128(a_lo + soff, olo[0], olo[1], olo[2], olo[3]);
+          // A operand in TMEM: K element k of the k-block = 16-bit slot k of the row's 32 columns (slice sl = columns 8 sl .. +7)
+          const uint32_t col = a_col + (uint32_t)(sl * 8 + half * 4);
+          dw_tmem_st4(col, ohi[0], ohi[1], ohi[2], ohi[3]);
+          dw_tmem_st4(col + 32u, olo[0], olo[1], olo[2], olo[3]);
         }
-        fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+        dw_tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar_fa + 8 * s);
@@ -385,8 +406,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           mbar_wait(bar_em + 8 * s, (it & 1u) ^ 1u);
           const uint32_t stage = base + DW_OFF_STAGES + s * stage_bytes;
           dw_expect_tx(bar_fb + 8 * s, 2 * b_bytes);
-          dw_tma_2d(stage + a_bytes, &tm_w, bar_fb + 8 * s, kb * DW_BK, n0);
-          dw_tma_2d(stage + 2 * a_bytes + b_bytes, &tm_w, bar_fb + 8 * s, kb * DW_BK, p.Cout_pad + n0);
+          dw_tma_2d(stage, &tm_w, bar_fb + 8 * s, kb * DW_BK, n0);
+          dw_tma_2d(stage + b_bytes, &tm_w, bar_fb + 8 * s, kb * DW_BK, p.Cout_pad + n0);
         }
       }
     }
@@ -396,9 +417,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(DW_BM, p.BN);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t a0 = ((base + DW_OFF_STAGES) >> 4) & 0x3fffu, stage16 = stage_bytes >> 4;
-      const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4;
-      uint32_t s = 0, ph = 0, a_hi = a0, ti = 0;
+      const uint32_t b0 = ((base + DW_OFF_STAGES) >> 4) & 0x3fffu, stage16 = stage_bytes >> 4, b16 = b_bytes >> 4;
+      uint32_t s = 0, ph = 0, b_hi = b0, ti = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const uint32_t buf = ti & 1u, use = ti >> 1;
         mbar_wait(bar_te + 8 * buf, (use & 1u) ^ 1u);
@@ -409,17 +429,17 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           mbar_wait(bar_fb + 8 * s, ph);
           mbar_wait(bar_fa + 8 * s, ph);
           tc_fence_after();
-          const uint32_t b_hi = a_hi + a16, a_lo = b_hi + b16, b_lo = a_lo + a16;
+          const uint32_t a_hi = tmem_base + DW_TMEM_A0 + s * 64u, a_lo = a_hi + 32u, b_lo = b_hi + b16;
 #pragma unroll
           for (uint32_t k = 0; k < DW_BK / 16; ++k) {
-            umma_bf16_lohi(tmem_d, a_lo + 2 * k, b_hi + 2 * k, desc_hi, idesc, acc);
-            umma_bf16_lohi(tmem_d, a_hi + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
-            umma_bf16_lohi(tmem_d, a_hi + 2 * k, b_hi + 2 * k, desc_hi, idesc, 1u);
+            dw_umma_ts(tmem_d, a_lo + 8 * k, b_hi + 2 * k, desc_hi, idesc, acc);
+            dw_umma_ts(tmem_d, a_hi + 8 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+            dw_umma_ts(tmem_d, a_hi + 8 * k, b_hi + 2 * k, desc_hi, idesc, 1u);
             acc = 1u;
           }
           umma_commit(bar_em + 8 * s);
-          a_hi += stage16;
-          if (++s == DW_STAGES) { s = 0; ph ^= 1u; a_hi = a0; }
+          b_hi += stage16;
+          if (++s == DW_STAGES) { s = 0; ph ^= 1u; b_hi = b0; }
         }
         umma_commit(bar_tf + 8 * buf);
       }
@@ -599,7 +619,7 @@ extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, 
     const cuuint32_t bx[4] = {16, DW_WW, DW_WH, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_pair), dx, sx, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return UPSNET_E_UNSUPPORTED;
     const cuuint64_t dwt[2] = {(cuuint64_t)(9 * Cin), (cuuint64_t)(2 * p.Cout_pad)};
     const cuuint64_t sw[1] = {(cuuint64_t)(9 * Cin) * 2};
@@ -608,7 +628,7 @@ extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, 
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return UPSNET_E_UNSUPPORTED;
   }
-  const size_t smem = DW_OFF_STAGES + (size_t)DW_STAGES * 2 * (DW_BM * 128 + p.BN * 128) + 2 * DW_WIN_BYTES + 1024;
+  const size_t smem = DW_OFF_STAGES + (size_t)DW_STAGES * 2 * (p.BN * 128) + 2 * DW_WIN_BYTES + 1024;
   if (smem > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   static PerDeviceOnce configured;
   if (configured.need()) {
