@@ -289,6 +289,8 @@ def main():
                          "hi/lo split on the hi/lo bf16 pair stream; bf16: tcgen05 single pass + bf16 activation storage "
                          "(secondary figure, bf16-level error); fp32: CUDA-core tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("UPSNET_LANES", "2")),
+                    help="images in flight per GPU: independent engine instances (CUDA-graph instance + pool + scratch) on their own streams")
     ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "coco"],
                     help="cityscapes = BASELINE configs[1] (the metric); coco = configs[2] UPSNet-101-DCN 800x1344 (extra)")
     args = ap.parse_args()
@@ -337,16 +339,25 @@ def main():
     # computes is computed; the sizes are checked after the timed region.
     counts_host = torch.zeros((max(args.steps, 8), 3), dtype=torch.int32).pin_memory()
 
+    # Engine lanes: image i runs on lane i % LANES -- an independent engine instance (own CUDA-graph instance, activation
+    # pool, output buffers, scratch) on its own stream -- so the forward passes of LANES consecutive images overlap on the
+    # GPU: the single-CTA detection kernels (top-k, NMS sweeps, MaskROI, pan_decide) and the small-grid coarse-level convs
+    # of one image hide under the machine-filling convolutions of the other.  Batch stays 1 image per step.
+    LANES = max(1, int(args.lanes))
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(LANES)]
+
     def step_graph(i):
-        out, _ = model._run_static(dev_imgs[i % n_img], im_info[0])
-        counts_host[i % counts_host.shape[0]].copy_(out["counts"], non_blocking=True)
+        l = i % LANES
+        with torch.cuda.stream(lane_streams[l]):
+            out, _ = model._run_static(dev_imgs[i % n_img], im_info[0], lane=l)
+            counts_host[i % counts_host.shape[0]].copy_(out["counts"], non_blocking=True)
         return out
 
     # end-to-end leg: the pipelined serving front end (upsnet_b200/pipeline.py).  Every step submits one PINNED HOST
     # image (H2D inside the timed region) and reads the previous step's results back to the host (D2H inside the timed
     # region); the copies of neighbouring images overlap the compute of the current one on separate streams.
     from upsnet_b200.pipeline import PipelinedEngine
-    engine = PipelinedEngine(model, im_info, depth=2, with_masks=True)   # every tensor of the reference's result dict
+    engine = PipelinedEngine(model, im_info, depth=max(2, LANES), with_masks=True, lanes=LANES)   # every tensor of the reference's result dict
     pending = []
 
     def step_e2e(i):
@@ -371,11 +382,16 @@ def main():
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ops.STATS["launches"]
+        cur = torch.cuda.current_stream(dev)
         e0.record()
+        for ls in lane_streams:
+            ls.wait_stream(cur)          # lanes start after e0 ...
         for i in range(steps):
             fn(i)
         if finish is not None:
             finish()          # host-waits for the last results: everything submitted is complete before e1
+        for ls in lane_streams:
+            cur.wait_stream(ls)          # ... and e1 is recorded after every lane has finished its images
         e1.record()
         sync_all()
         mine = e0.elapsed_time(e1)
@@ -494,7 +510,12 @@ def main():
                            "l2": "no flush: each step streams >1 GB of activations (>> 126 MB L2) and rotates %d images" % n_img,
                            "weights": "random-init (upsnet_b200/synthetic.py), frozen BN folded",
                            "engine": "static shapes, device-side counts, CUDA graph replay=%s; value = sync-free engine entry "
-                                     "(result sizes read back asynchronously), e2e = public PipelinedEngine API" % bool(model.use_cuda_graph)},
+                                     "(result sizes read back asynchronously), e2e = public PipelinedEngine API; %d engine lane(s): consecutive images "
+                                     "run on independent graph instances / streams and overlap on the GPU, one image per step" % (bool(model.use_cuda_graph), LANES),
+                           "lanes": LANES,
+                           "detections_per_image": {"n_det": float(counts_host[:args.steps, 0].float().mean()),
+                                                    "n_panoptic_candidates": float(counts_host[:args.steps, 1].float().mean()),
+                                                    "n_kept": float(counts_host[:args.steps, 2].float().mean())}},
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -1,0 +1,23 @@
+"""A/B of the 18-channel offset convs of the semantic head on the pair stream (UPSNET_TMA_HALO=3 forces halo / resident-weight
+mode for pairs).  Usage: python scripts/exp_offset_conv.py   (run once per environment setting)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import upsnet_b200 as U
+from upsnet_b200.operators import Pair
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+U.set_precision("bf16x3")
+def gpu_ms(fn, iters=20):
+    fn(); fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+for cin, h, w in [(256, 256, 512), (128, 256, 512), (256, 128, 256), (128, 128, 256), (256, 64, 128)]:
+    x = Pair.from_float(torch.randn(1, cin, h, w, device=dev))
+    wt = torch.randn(18, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+    b = torch.randn(18, device=dev)
+    ms = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, out_format="nchw"))
+    print("offset conv %d->18 @%dx%d HALO=%s: %.4f ms" % (cin, h, w, os.environ.get("UPSNET_TMA_HALO", "default"), ms), flush=True)

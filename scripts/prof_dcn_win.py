@@ -11,6 +11,7 @@ from upsnet_b200.operators import Pair
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 U.set_precision("bf16x3")
+ops.DCN_WINDOW.update(on=True, min_pixels=0)
 
 
 def act(n, c, h, w): return Pair.from_float(torch.randn(n, c, h, w, device=dev))

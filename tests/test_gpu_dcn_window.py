@@ -26,10 +26,10 @@ def pair_mode():
     import upsnet_b200 as U
     from upsnet_b200 import operators as ops
     U.set_precision("bf16x3")
-    was = ops.DCN_WINDOW["on"]
-    ops.DCN_WINDOW["on"] = True
+    was = dict(ops.DCN_WINDOW)
+    ops.DCN_WINDOW.update(on=True, min_pixels=0)
     yield U
-    ops.DCN_WINDOW["on"] = was
+    ops.DCN_WINDOW.update(was)
     U.set_precision("fp32")
 
 

@@ -543,7 +543,7 @@ class resnet_upsnet(nn.Module):
         self.overlap_heads = True     # semantic head on a side stream, concurrent with the detection chain
         self._side = {}
         self._graphs = {}
-        self.max_graphs = 4           # captured graphs kept (LRU): one activation pool each (~2 GB at 1024x2048)
+        self.max_graphs = 6           # captured graphs kept (LRU): one activation pool each (~2 GB at 1024x2048)
         self._prepared = False
         self.eval()
 
@@ -712,16 +712,28 @@ class resnet_upsnet(nn.Module):
         return out
 
     def _side_stream(self, dev, idx=0):
-        key = (str(dev), idx)
+        key = (str(dev), idx, ops.WS_SLOT["i"])
         if key not in self._side:
             self._side[key] = torch.cuda.Stream(device=dev)
         return self._side[key]
 
-    def _run_static(self, x, im_info):
+    def _run_static(self, x, im_info, lane=0):
+        """One image through the static engine on the CURRENT stream.  `lane` selects an independent engine instance (its own
+        captured graph, activation pool, output buffers and scratch workspaces): callers that keep several images in flight
+        run lane i on stream i (pipeline.PipelinedEngine, bench.py) -- the single-CTA detection kernels of one image then
+        hide under the machine-filling convolutions of the other."""
+        prev_slot = ops.WS_SLOT["i"]
+        ops.WS_SLOT["i"] = int(lane)
+        try:
+            return self._run_static_lane(x, im_info, int(lane))
+        finally:
+            ops.WS_SLOT["i"] = prev_slot
+
+    def _run_static_lane(self, x, im_info, lane):
         if not (self.use_cuda_graph and x.is_cuda):
             return self._forward_static(x, im_info), None
         key = (tuple(x.shape), str(x.device), ops._PRECISION["conv"], ops.ACT_BF16["on"], ops.ACT_PAIR["on"],
-               bool(getattr(self, "keep_intermediates", False)), tuple(float(v) for v in im_info))
+               bool(getattr(self, "keep_intermediates", False)), tuple(float(v) for v in im_info), lane)
         ent = self._graphs.get(key)
         if ent is None:
             static_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)

@@ -23,11 +23,14 @@ class PipelinedEngine:
     PIXEL_MEANS = (102.9801, 115.9465, 122.7717)     # config.network.pixel_means (BGR, caffe models)
 
     def __init__(self, model, im_info, depth=2, with_masks=False, with_unified=False, stuff_area_limit=4 * 64 * 64,
-                 pixel_means=None, im_scale=1.0):
+                 pixel_means=None, im_scale=1.0, lanes=None):
         """with_unified: also run get_unified_pan_result on the device (base_dataset.py:332-371) and return its uint8
         [H,W,3] map as 'pan_2ch'.  submit() also accepts the RAW uint8 [h,w,3] BGR image (pinned): mean subtraction,
         resize by im_scale and padding (prep_im_for_blob / im_list_to_blob) then run on the device after a 4x smaller H2D."""
         self.model, self.depth = model, depth
+        # engine lanes: slot i computes on lane i % lanes (own CUDA-graph instance, activation pool, scratch, stream), so the
+        # forward passes of `lanes` consecutive images overlap on the GPU; lanes=1 is the strictly serial compute of round 1
+        self.lanes = depth if lanes is None else max(1, min(int(lanes), depth))
         self.im_info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)[0]
         self.keys = self.RESULT_KEYS + (("mask_probs",) if with_masks else ()) + (("pan_2ch",) if with_unified else ())
         self.with_unified, self.stuff_area_limit = with_unified, stuff_area_limit
@@ -55,8 +58,10 @@ class PipelinedEngine:
         out = self._post(dict(out))
         torch.cuda.synchronize(self.dev)
         self._slots = []
-        for _ in range(self.depth):
-            s = {"in": torch.empty(host_image.shape, dtype=host_image.dtype, device=self.dev),
+        self._lane_streams = [torch.cuda.Stream(self.dev) for _ in range(self.lanes)]
+        for i in range(self.depth):
+            s = {"lane": i % self.lanes,
+                 "in": torch.empty(host_image.shape, dtype=host_image.dtype, device=self.dev),
                  "out": {k: torch.empty_like(out[k]) for k in self.keys},
                  "host": {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in self.keys},
                  "in_ready": torch.cuda.Event(), "in_free": torch.cuda.Event(), "out_ready": torch.cuda.Event(),
@@ -71,23 +76,30 @@ class PipelinedEngine:
         if self._slots is None:
             self._setup(host_image)
         s = self._slots[self._t % self.depth]
-        cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_event(s["in_free"])              # compute has consumed this slot's previous image
             s["in"].copy_(host_image, non_blocking=True)
             s["in_ready"].record(self.h2d)
-        cur.wait_event(s["in_ready"])
-        x = s["in"]
-        if self.raw:
-            from . import operators as ops
-            x, _ = ops.prep_image(s["in"], self.pixel_means, self.im_scale)
-        out, _ = self.model._run_static(x, self.im_info)
-        out = self._post(dict(out))
-        s["in_free"].record(cur)
-        cur.wait_event(s["done"])                          # this slot's previous results have left the device
-        for k in self.keys:
-            s["out"][k].copy_(out[k], non_blocking=True)
-        s["out_ready"].record(cur)
+        from . import operators as ops
+        lane = s["lane"]
+        cur = self._lane_streams[lane]
+        prev_slot = ops.WS_SLOT["i"]
+        ops.WS_SLOT["i"] = lane
+        try:
+            with torch.cuda.stream(cur):
+                cur.wait_event(s["in_ready"])
+                x = s["in"]
+                if self.raw:
+                    x, _ = ops.prep_image(s["in"], self.pixel_means, self.im_scale)
+                out, _ = self.model._run_static(x, self.im_info, lane=lane)
+                out = self._post(dict(out))
+                s["in_free"].record(cur)
+                cur.wait_event(s["done"])                          # this slot's previous results have left the device
+                for k in self.keys:
+                    s["out"][k].copy_(out[k], non_blocking=True)
+                s["out_ready"].record(cur)
+        finally:
+            ops.WS_SLOT["i"] = prev_slot
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(s["out_ready"])
             for k in self.keys:
