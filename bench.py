@@ -357,12 +357,14 @@ def main():
     # image (H2D inside the timed region) and reads the previous step's results back to the host (D2H inside the timed
     # region); the copies of neighbouring images overlap the compute of the current one on separate streams.
     from upsnet_b200.pipeline import PipelinedEngine
-    engine = PipelinedEngine(model, im_info, depth=max(2, LANES), with_masks=True, lanes=LANES)   # every tensor of the reference's result dict
+    # depth = 2 x lanes staging slots: LANES images computing, the next LANES already copied in / the previous being copied out
+    E2E_DEPTH = 2 * LANES
+    engine = PipelinedEngine(model, im_info, depth=E2E_DEPTH, with_masks=True, lanes=LANES)   # every tensor of the reference's result dict
     pending = []
 
     def step_e2e(i):
         pending.append(engine.submit(host_imgs[i % n_img]))
-        if len(pending) > 1:
+        if len(pending) >= E2E_DEPTH:
             return engine.result(pending.pop(0))
         return None
 
@@ -400,7 +402,7 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
-    for i in range(3):
+    for i in range(E2E_DEPTH + 2):
         step_e2e(i)
     drain_e2e()
     sampler = None

@@ -169,6 +169,17 @@ int upsnet_dcn_pack_weight(const float *weight, int Cout, int Cin, int kh, int k
 int upsnet_dcn_pair_forward(const void *x_pair, const float *offset, const float *mask, const void *packed,
                             const float *bias, void *y_pair, int N, int H, int W, int Cin, int Cout, int kh, int kw,
                             int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags, void *stream);
+/* Dense 3x3 / stride-1 convolution on hi/lo PAIR activations through the same window pipeline (csrc/dcn_win.cu, DENSE mode):
+ * the input window of a 16x8-pixel tile is staged once per 16-channel sub-chunk by TMA and feeds all nine taps, the A operand
+ * is copied window -> TMEM.  Meant for the small-N layers (18-channel offset convs of the semantic head, 64->64 bottleneck
+ * convs) whose per-tap TMA boxes make upsnet_igemm_forward L2->SM-bandwidth-bound.  x [N,H,W,2*Cin] pair NHWC; `packed`
+ * from upsnet_dcn_pack_weight; y = fp32 NCHW [N,Cout,Ho,Wo] (UPSNET_LAYOUT_NCHW, any Cout) or pair NHWC [N,Ho,Wo,2*Cout]
+ * (UPSNET_LAYOUT_NHWC, Cout % 16 == 0); epi_flags: UPSNET_EPI_RELU.  Same arithmetic contract as upsnet_igemm_forward
+ * (precision UPSNET_PREC_BF16X3).  UPSNET_E_UNSUPPORTED for other shapes (dilation > 7, Cin % 64 != 0).
+ * replaces: the cuDNN 3x3 convs of models/fcn.py:40-55 (conv_offset) and models/resnet.py:80-100 (conv2). */
+int upsnet_conv3x3_pair_forward(const void *x_pair, const void *packed, const float *bias, void *y, int N, int H, int W,
+                                int Cin, int Cout, int pad_h, int pad_w, int dil_h, int dil_w, int out_layout,
+                                int epi_flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Parameter-free panoptic head, fused: MaskRemoval + SegTerm + void/concat/argmax.
@@ -192,6 +203,16 @@ int upsnet_panoptic_head(const float *fcn, int S, int H, int W, const float *box
                          int n, const int *n_dev, int num_stuff, double fraction_threshold, int64_t *keep_out,
                          int *k_out, int64_t *labels, int64_t *sem_labels, void *workspace,
                          size_t workspace_bytes, void *stream);
+/* Same head on the QUARTER-resolution score map: score [S,Hs,Ws] (models/fcn.py:94-101 `score` before the final
+ * nn.Upsample(scale_factor=4, mode='bilinear')), labels / sem_labels [4*Hs,4*Ws].  The up-sampling is evaluated inside the
+ * fusion kernel with the arithmetic of upsnet_upsample_bilinear_nchw (factor 4), so the results are bit-identical to
+ * upsnet_panoptic_head on the materialised [S,4*Hs,4*Ws] logits, which are neither written nor read (159 MB each way at
+ * 19 x 1024 x 2048).  Workspace sizes: upsnet_panoptic_workspace_bytes(n, 4*Hs, 4*Ws, num_thing). */
+int upsnet_panoptic_head_up4(const float *score, int S, int Hs, int Ws, const float *boxes,
+                             const float *cls_prob, const float *mask_logit, const int64_t *cls_idx,
+                             int n, const int *n_dev, int num_stuff, double fraction_threshold, int64_t *keep_out,
+                             int *k_out, int64_t *labels, int64_t *sem_labels, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* MaskRemoval alone (API parity with operators/modules/mask_removal.py:29-93): score-ordered overlap
  * pruning; keep_out / k_out as above; mask_energy (optional, may be NULL) float [n,H,W]: planes 0..k-1

@@ -433,3 +433,30 @@ def test_upsample_bilinear_matches_torch(dev, shape, f):
     want = torch.nn.functional.interpolate(x, None, f, mode="bilinear", align_corners=False)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() < 2e-6 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("hs,ws,n", [(16, 24, 6), (64, 128, 40), (33, 17, 3)])
+def test_panoptic_head_fused_upsample_is_bit_identical(dev, hs, ws, n):
+    """upsnet_panoptic_head_up4 (x4 bilinear up-sampling of the semantic score map evaluated inside the fusion kernel,
+    models/fcn.py:88-101 + resnet_upsnet.py:217-247) against upsnet_panoptic_head on the materialised logits, and both
+    against the CPU oracle on those logits: labels, semantic argmax and keep list bit for bit."""
+    import upsnet_b200 as U
+    from upsnet_b200 import operators as ops
+    from oracle import oracle as O
+    rng = np.random.default_rng(31 + hs)
+    H, W = 4 * hs, 4 * ws
+    score = (rng.standard_normal((1, 19, hs, ws)) * 3).astype(np.float32)
+    c = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1); s = rng.uniform(6, 0.6 * min(H, W), (n, 2))
+    b = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, W - 1); b[:, 1::2] = np.clip(b[:, 1::2], 0, H - 1)
+    prob = rng.uniform(0.3, 1.0, n).astype(np.float32)
+    ml = (rng.standard_normal((n, 28, 28)) * 2 + 0.5).astype(np.float32)
+    cls = rng.integers(1, 9, n).astype(np.int64)
+    ts = torch.from_numpy(score).to(dev)
+    full = ops.upsample_bilinear(ts, 4)
+    args = [torch.from_numpy(a).to(dev) for a in (b, prob, ml[:, None], cls)]
+    k0, l0, s0 = U.panoptic_fuse(full, *args, 11, want_sem=True)
+    k1, l1, s1 = U.panoptic_fuse(ts, *args, 11, want_sem=True, up4=True)
+    assert torch.equal(k0, k1) and torch.equal(l0, l1) and torch.equal(s0, s1)
+    wk, wl = O.panoptic_head(full[0].cpu().numpy(), b, prob, ml, cls, 11)
+    assert k1.cpu().tolist() == wk.tolist() and np.array_equal(l1[0].cpu().numpy(), wl)

@@ -61,6 +61,14 @@ struct DwParams {
   const float* bias;
   void* y;                // pair NHWC [N,Ho,Wo,2*Cout]
   int N, H, W, Cin, Cout, Cout_pad, Ho, Wo, ph, pw, dh, dw, relu, BN, tile_w, tile_h;
+  // DENSE mode (offset == null): plain 3x3 / stride-1 convolution through the same pipeline -- the window of a tile is its
+  // receptive field (origin = tile origin - pad, known without a sample table), a "gather" is one LDS.128 per plane copied
+  // to the TMEM A operand, no blend.  Serves the small-N 3x3 layers of the pair stream (18-channel offset convs, 64->64
+  // bottleneck convs), which the per-tap TMA boxes of igemm_tma.cu make L2->SM-bandwidth-bound (A re-fetched per tap).
+  int dense;
+  int out_nchw;           // y = fp32 NCHW [N,Cout,Ho,Wo] (offset maps) instead of the pair NHWC tensor
+  int win_bytes;          // bytes one window fill delivers (both planes): the dense box is only tile + halo rows high
+  int win_h;              // rows of the window box (<= DW_WH)
 };
 
 __device__ __forceinline__ void dw_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -185,10 +193,22 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     uint32_t g0 = 0, wf0 = 0;                    // running k-block / window-fill counters at the start of the tile
     uint32_t wf_ready = 0;                       // window fills [0, wf_ready) have been observed complete by this thread
     uint32_t tile_it = 0;
+    const bool dense = p.dense != 0;
+    if (dense) {
+      // tile-independent table: window offset of (tap, tile pixel) relative to the tile's receptive-field origin
+      for (int e = pt; e < DW_KHW * DW_BM; e += DW_PRODUCERS) {
+        const int tap = e >> 7, rr = e & 127;
+        const int ki = tap / 3, kj = tap - ki * 3;
+        const int ry = min(rr >> tw_shift, TH - 1), rx = rr & (TW - 1);      // rows past the block read a valid (unused) pixel
+        tp[e] = ((ry + ki * p.dh) * DW_WW + rx + kj * p.dw) * 32;
+      }
+      dw_producer_bar();
+    }
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
       const long long mt = tile / n_tiles;
       const int tx = (int)(mt % tiles_w), ty = (int)((mt / tiles_w) % tiles_h), n = (int)(mt / ((long long)tiles_w * tiles_h));
       const int par = (int)(tile_it & 1u);
+      if (!dense) {
       // ---- sample table, phase 1: every thread computes up to three (tap, pixel) entries in registers ----
       float4 ewv[3];
       int ehl[3], ewl[3];
@@ -246,7 +266,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           const int a = st[0], b = st[1], cc = st[2], d = st[3];
           // the bounding box of all corners fits: start the window there; otherwise centre it on the mean sample
           ox = (cc - a + 1 <= DW_WW) ? a : (int)floorf((float)st[4] / (float)c + 1.0f) - DW_WW / 2;
-          oy = (d - b + 1 <= DW_WH) ? b : (int)floorf((float)st[5] / (float)c + 1.0f) - DW_WH / 2;
+          oy = (d - b + 1 <= p.win_h) ? b : (int)floorf((float)st[5] / (float)c + 1.0f) - p.win_h / 2;
         }
       }
 #pragma unroll
@@ -256,7 +276,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           int code = 0;
           if (evalid[it]) {
             const int dx = ewl[it] - ox, dy = ehl[it] - oy;
-            if (dx >= 0 && dx + 1 < DW_WW && dy >= 0 && dy + 1 < DW_WH) code = (dy * DW_WW + dx) * 32;
+            if (dx >= 0 && dx + 1 < DW_WW && dy >= 0 && dy + 1 < p.win_h) code = (dy * DW_WW + dx) * 32;
             else code = (int)(0x80000000u | ((uint32_t)(ehl[it] + 1) << 15) | (uint32_t)(ewl[it] + 1));   // outlier: global gather
           }
           tw[e] = ewv[it];
@@ -270,6 +290,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         mbar_arrive(bar_og + 8 * par);        // release: the window TMA thread may read the origin
       }
       dw_producer_bar();      // (C) table visible
+      }                       // !dense
       const __nv_bfloat16* ximg = xh + (size_t)n * p.H * p.W * (size_t)(2 * p.Cin);
 
       int rel = 0;            // sub-chunks of this tile this WARP has released
@@ -290,8 +311,17 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             wf_ready = wf + 1;
           }
           const uint32_t wbuf = win_base + (wf & 1u) * DW_WIN_BYTES;
-          const float4 wv = tw[tap * DW_BM + r];
           const int code = tp[tap * DW_BM + r];
+          if (dense) {        // plain copy of the tap's pixel: window -> TMEM A operand
+            const uint32_t cl = (uint32_t)code;
+            const uint32_t al = wbuf + cl + ((((cl >> 7) & 1u) ^ (uint32_t)half) << 4);
+            const uint4 h4 = dw_lds128(al), l4 = dw_lds128(al + DW_PLANE);
+            const uint32_t col = a_col + (uint32_t)(sl * 8 + half * 4);
+            dw_tmem_st4(col, h4.x, h4.y, h4.z, h4.w);
+            dw_tmem_st4(col + 32u, l4.x, l4.y, l4.z, l4.w);
+            continue;
+          }
+          const float4 wv = tw[tap * DW_BM + r];
           uint4 hc[4], lc[4];
           if (code >= 0) {
             // SWIZZLE_32B: the 16-byte chunk of a pixel sits at (half ^ bit 7 of the pixel's byte offset)
@@ -381,13 +411,20 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       uint32_t wf = 0, ti = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const uint32_t par = ti & 1u;
-        mbar_wait(bar_og + 8 * par, (ti >> 1) & 1u);
-        const volatile int* ov = reinterpret_cast<const volatile int*>(&org[par]);
-        const int4 o = make_int4(ov[0], ov[1], ov[2], 0);
+        int4 o;
+        if (p.dense) {       // receptive-field origin of the tile: no sample table, no hand-shake
+          const long long mt = tile / n_tiles;
+          o = make_int4((int)(mt % tiles_w) * TW - p.pw, (int)((mt / tiles_w) % tiles_h) * TH - p.ph,
+                        (int)(mt / ((long long)tiles_w * tiles_h)), 0);
+        } else {
+          mbar_wait(bar_og + 8 * par, (ti >> 1) & 1u);
+          const volatile int* ov = reinterpret_cast<const volatile int*>(&org[par]);
+          o = make_int4(ov[0], ov[1], ov[2], 0);
+        }
         for (int sc = 0; sc < nsc; ++sc, ++wf) {
           const uint32_t b = wf & 1u;
           mbar_wait(bar_we + 8 * b, ((wf >> 1) & 1u) ^ 1u);
-          dw_expect_tx(bar_wf + 8 * b, DW_WIN_BYTES);
+          dw_expect_tx(bar_wf + 8 * b, (uint32_t)p.win_bytes);
           const uint32_t dst = win_base + b * DW_WIN_BYTES;
           dw_tma_4d(dst, &tm_x, bar_wf + 8 * b, sc * 16, o.x, o.y, o.z);
           dw_tma_4d(dst + DW_PLANE, &tm_x, bar_wf + 8 * b, p.Cin + sc * 16, o.x, o.y, o.z);
@@ -473,15 +510,28 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(rr[e]);
         if (p.bias) {
+          if (co + 16 <= p.Cout) {
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co) + e4);
-            o[4 * e4] += bv.x; o[4 * e4 + 1] += bv.y; o[4 * e4 + 2] += bv.z; o[4 * e4 + 3] += bv.w;
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co) + e4);
+              o[4 * e4] += bv.x; o[4 * e4 + 1] += bv.y; o[4 * e4 + 2] += bv.z; o[4 * e4 + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (co + e < p.Cout) o[e] += __ldg(p.bias + co + e);
           }
         }
         if (p.relu) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+        }
+        if (p.out_nchw) {     // plane-wise fp32 output (offset maps): for a fixed channel the lanes write consecutive pixels
+          float* yf = reinterpret_cast<float*>(p.y) + ((size_t)n * p.Cout + co) * HoWo + (size_t)ho * p.Wo + wo;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (co + e < p.Cout) yf[(size_t)e * HoWo] = o[e];
+          continue;
         }
         uint32_t hw[8], lw[8];
 #pragma unroll
@@ -524,10 +574,11 @@ __global__ void dcn_win_pack_kernel(const float* __restrict__ w, int Cout, int C
   }
 }
 
-static int dw_cout_pad(int Cout) { return (Cout + 63) / 64 * 64; }
+static int dw_cout_pad(int Cout) { return Cout <= 32 ? 32 : (Cout + 63) / 64 * 64; }
 
+// packing / kernel: any Cout (rows are zero-padded); the pair NHWC epilogue additionally needs Cout % 16 == 0
 static bool dw_supported(int Cin, int Cout, int kh, int kw) {
-  return kh == 3 && kw == 3 && Cin % 64 == 0 && Cin >= 64 && Cout % 16 == 0 && Cout >= 16;
+  return kh == 3 && kw == 3 && Cin % 64 == 0 && Cin >= 64 && Cout >= 1;
 }
 
 typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -571,13 +622,14 @@ extern "C" int upsnet_dcn_pack_weight(const float* weight, int Cout, int Cin, in
   return 0;
 }
 
-extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, const float* mask, const void* packed,
-                                       const float* bias, void* y_pair, int N, int H, int W, int Cin, int Cout, int kh,
-                                       int kw, int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags, void* stream) {
+static int dw_launch(const void* x_pair, const float* offset, const float* mask, const void* packed,
+                     const float* bias, void* y_pair, int N, int H, int W, int Cin, int Cout, int kh,
+                     int kw, int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags, bool dense, bool out_nchw, void* stream) {
   using namespace ups;
-  if (!x_pair || !offset || !packed || !y_pair) return UPSNET_E_BADARG;
+  if (!x_pair || (!dense && !offset) || !packed || !y_pair) return UPSNET_E_BADARG;
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || pad_h < 0 || pad_w < 0 || dil_h <= 0 || dil_w <= 0) return UPSNET_E_BADARG;
   if (!dw_supported(Cin, Cout, kh, kw)) return UPSNET_E_UNSUPPORTED;
+  if (!out_nchw && (Cout % 16) != 0) return UPSNET_E_UNSUPPORTED;
   if (H >= 32767 || W >= 32767) return UPSNET_E_UNSUPPORTED;                 // outlier code packs (h, w) into 16 + 15 bits
   if ((((uintptr_t)x_pair) & 15) || (((uintptr_t)packed) & 15) || (((uintptr_t)y_pair) & 15) || (bias && (((uintptr_t)bias) & 15)))
     return UPSNET_E_UNSUPPORTED;
@@ -589,7 +641,8 @@ extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, 
   p.Wo = conv_out_size(W, pad_w, dil_w, 3, 1);
   if (p.Ho <= 0 || p.Wo <= 0) return UPSNET_E_BADARG;
   p.relu = (epi_flags & UPSNET_EPI_RELU) ? 1 : 0;
-  p.BN = p.Cout_pad % 128 == 0 ? 128 : 64;
+  p.BN = p.Cout_pad % 128 == 0 ? 128 : (p.Cout_pad % 64 == 0 ? 64 : 32);
+  p.dense = dense ? 1 : 0; p.out_nchw = out_nchw ? 1 : 0;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0, v = kNumSMs;
@@ -610,13 +663,26 @@ extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, 
   }
   const long long num_tiles = dtiles();
   if (num_tiles <= 0) return 0;
+  // dense: the window box is the tile's receptive field (32 px wide for the bank mapping, tile + halo rows high)
+  int win_h = DW_WH;
+  if (dense) {
+    win_h = p.tile_h + 2 * dil_h;
+    if (win_h > DW_WH || p.tile_w + 2 * dil_w > DW_WW) return UPSNET_E_UNSUPPORTED;
+  }
+  if (!dense) {     // tuning hook: UPSNET_DCN_WIN_H = rows of the deformable window box (12..24)
+    static int wh_env = -1;
+    if (wh_env < 0) { const char* e = getenv("UPSNET_DCN_WIN_H"); wh_env = e ? atoi(e) : 0; }
+    if (wh_env >= 12 && wh_env <= DW_WH) win_h = wh_env;
+  }
+  p.win_bytes = 2 * DW_WW * win_h * 32;
+  p.win_h = win_h;
   DwEncodeFn enc = dw_encoder();
   if (!enc) return UPSNET_E_UNSUPPORTED;
   CUtensorMap tm_x, tm_w;
   {
     const cuuint64_t dx[4] = {(cuuint64_t)(2 * Cin), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t sx[3] = {(cuuint64_t)(2 * Cin) * 2, (cuuint64_t)W * (2 * Cin) * 2, (cuuint64_t)H * W * (2 * Cin) * 2};
-    const cuuint32_t bx[4] = {16, DW_WW, DW_WH, 1};
+    const cuuint32_t bx[4] = {16, DW_WW, (cuuint32_t)win_h, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_pair), dx, sx, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -638,4 +704,20 @@ extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, 
   dcn_win_kernel<<<grid, DW_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, p);
   UPS_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int upsnet_dcn_pair_forward(const void* x_pair, const float* offset, const float* mask, const void* packed,
+                                       const float* bias, void* y_pair, int N, int H, int W, int Cin, int Cout, int kh,
+                                       int kw, int pad_h, int pad_w, int dil_h, int dil_w, int epi_flags, void* stream) {
+  if (!offset) return UPSNET_E_BADARG;
+  return dw_launch(x_pair, offset, mask, packed, bias, y_pair, N, H, W, Cin, Cout, kh, kw, pad_h, pad_w, dil_h, dil_w, epi_flags,
+                   false, false, stream);
+}
+
+extern "C" int upsnet_conv3x3_pair_forward(const void* x_pair, const void* packed, const float* bias, void* y, int N, int H, int W,
+                                           int Cin, int Cout, int pad_h, int pad_w, int dil_h, int dil_w, int out_layout,
+                                           int epi_flags, void* stream) {
+  if (out_layout != UPSNET_LAYOUT_NCHW && out_layout != UPSNET_LAYOUT_NHWC) return UPSNET_E_BADARG;
+  return dw_launch(x_pair, nullptr, nullptr, packed, bias, y, N, H, W, Cin, Cout, 3, 3, pad_h, pad_w, dil_h, dil_w, epi_flags,
+                   true, out_layout == UPSNET_LAYOUT_NCHW, stream);
 }

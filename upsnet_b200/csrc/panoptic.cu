@@ -22,6 +22,7 @@
 // oracle-of-record formula (oracle/upsnet_oracle.c resized_logit) in un-fused fp32 (_rn
 // intrinsics) so label maps are bit-exact.
 #include "common.cuh"
+#include "up4.cuh"
 
 namespace ups {
 
@@ -429,6 +430,10 @@ constexpr int kTileW = 128, kTileH = 8, kFuseThreads = 256;
 struct Best { float v; int i; };
 __device__ __forceinline__ void feed(Best& b, float v, int i) { if (v > b.v) { b.v = v; b.i = i; } }
 
+// UP4: `fcn` is the quarter-resolution score map [S,H/4,W/4] and the x4 bilinear up-sampling of models/fcn.py:88-101 is
+// evaluated on the fly (up4.cuh: the same inlined arithmetic as upsample_bilinear_nchw_kernel, so the logits are bit-identical
+// to a materialised fcn_output) -- the 4*S*H*W-byte tensor is neither written nor read: the kernel streams 4*S*H*W/16 bytes.
+template <bool UP4>
 __global__ void __launch_bounds__(kFuseThreads)
 pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuff,
                 const float* __restrict__ mask_logit, PanWorkspace ws,
@@ -483,6 +488,10 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
   const bool vec = (x + 3 < W) && ((W & 3) == 0);
   const int npx = vec ? 4 : min(4, W - x);
 
+  const int Hs = H >> 2, Ws = W >> 2, xq = x >> 2;       // UP4: source geometry, source column of this thread's quad
+  const size_t HWs = (size_t)Hs * Ws;
+  Up4Row urow;
+  if (UP4) urow = up4_row(y, Hs);
   Best best[4], sem[4];
   float thing_max[4];
 #pragma unroll
@@ -495,7 +504,10 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
     for (int u = 0; u < 4; ++u) {
       const int c = cb + u;
       if (c < S) {
-        if (vec) {
+        if (UP4) {
+          const float* pl = fcn + (size_t)c * HWs;
+          up4_quad(pl + (size_t)urow.y0 * Ws, pl + (size_t)urow.y1 * Ws, xq, Ws, urow.ly, urow.hy, vv[u]);
+        } else if (vec) {
           const float4 t = __ldg((const float4*)(fcn + (size_t)c * HW + p));
           vv[u][0] = t.x; vv[u][1] = t.y; vv[u][2] = t.z; vv[u][3] = t.w;
         } else {
@@ -540,7 +552,9 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
     const bool row_seg = y >= sy0 && y < sy1;
     const int dy = y - by0;
     const bool row_msk = !zero_mask && y >= gy0 && y < gy1 && dy >= 0 && dy < bh;
-    const float* seg_plane = fcn + (size_t)(num_stuff + ws.g.cls[i] - 1) * HW + p;
+    const float* seg_plane = fcn + (size_t)(num_stuff + ws.g.cls[i] - 1) * (UP4 ? HWs : HW) + (UP4 ? (size_t)0 : p);
+    float segq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (UP4 && row_seg) up4_quad(seg_plane + (size_t)urow.y0 * Ws, seg_plane + (size_t)urow.y1 * Ws, xq, Ws, urow.ly, urow.hy, segq);
     const float* Sm = mask_logit + (size_t)i * kMaskElems;
     int sy = 0; float fy = 0.f;
     if (row_msk) coef_y(dy, bh, sy, fy);
@@ -549,7 +563,7 @@ pan_fuse_kernel(const float* __restrict__ fcn, int S, int H, int W, int num_stuf
       if (q >= npx) break;
       const int xx = x + q;
       float seg = 0.f;
-      if (row_seg && xx >= sx0 && xx < sx1) seg = __ldg(seg_plane + q);
+      if (row_seg && xx >= sx0 && xx < sx1) seg = UP4 ? segq[q] : __ldg(seg_plane + q);
       float m = 0.f;
       const int dx = xx - bx0;
       if (row_msk && xx >= gx0 && xx < gx1 && dx >= 0 && dx < bw) {
@@ -672,12 +686,12 @@ extern "C" int upsnet_panoptic_workspace_min_bytes(int n, int H, int W, int num_
   return 0;
 }
 
-extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const float* boxes,
-                                    const float* cls_prob, const float* mask_logit,
-                                    const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
-                                    double fraction_threshold, int64_t* keep_out, int* k_out,
-                                    int64_t* labels, int64_t* sem_labels, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+static int panoptic_head_impl(const float* fcn, bool up4, int S, int H, int W, const float* boxes,
+                              const float* cls_prob, const float* mask_logit,
+                              const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
+                              double fraction_threshold, int64_t* keep_out, int* k_out,
+                              int64_t* labels, int64_t* sem_labels, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   using namespace ups;
   if (!fcn || !boxes || !cls_prob || !mask_logit || !cls_idx || !keep_out || !k_out || !labels || !workspace)
     return UPSNET_E_BADARG;
@@ -710,8 +724,29 @@ extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const
   pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH));
-  pan_fuse_kernel<<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels,
-                                                 sem_labels);
+  if (up4) pan_fuse_kernel<true><<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels, sem_labels);
+  else pan_fuse_kernel<false><<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels, sem_labels);
   UPS_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int upsnet_panoptic_head(const float* fcn, int S, int H, int W, const float* boxes,
+                                    const float* cls_prob, const float* mask_logit,
+                                    const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
+                                    double fraction_threshold, int64_t* keep_out, int* k_out,
+                                    int64_t* labels, int64_t* sem_labels, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return panoptic_head_impl(fcn, false, S, H, W, boxes, cls_prob, mask_logit, cls_idx, n, n_dev, num_stuff, fraction_threshold,
+                            keep_out, k_out, labels, sem_labels, workspace, workspace_bytes, stream);
+}
+
+extern "C" int upsnet_panoptic_head_up4(const float* score, int S, int Hs, int Ws, const float* boxes,
+                                        const float* cls_prob, const float* mask_logit,
+                                        const int64_t* cls_idx, int n, const int* n_dev, int num_stuff,
+                                        double fraction_threshold, int64_t* keep_out, int* k_out,
+                                        int64_t* labels, int64_t* sem_labels, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (Hs <= 0 || Ws <= 0 || Hs > (1 << 28) || Ws > (1 << 28)) return UPSNET_E_BADARG;
+  return panoptic_head_impl(score, true, S, 4 * Hs, 4 * Ws, boxes, cls_prob, mask_logit, cls_idx, n, n_dev, num_stuff,
+                            fraction_threshold, keep_out, k_out, labels, sem_labels, workspace, workspace_bytes, stream);
 }

@@ -6,6 +6,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "up4.cuh"
 
 namespace ups {
 
@@ -133,26 +134,18 @@ upsample_bilinear_nchw_kernel(const float* __restrict__ x, float* __restrict__ y
     long long rest = t / Wq;
     const int yo = (int)(rest % Ho);
     const int pl = (int)(rest / Ho);
+    float o[4];
+    if (f == 4) {      // shared with the fused panoptic head (up4.cuh): six loads per quad, explicit FMAs
+      const Up4Row rw = up4_row(yo, H);
+      up4_quad(x + ((size_t)pl * H + rw.y0) * W, x + ((size_t)pl * H + rw.y1) * W, xq, W, rw.ly, rw.hy, o);
+      reinterpret_cast<float4*>(y)[t] = make_float4(o[0], o[1], o[2], o[3]);
+      continue;
+    }
     const float sy = fmaxf(rf * ((float)yo + 0.5f) - 0.5f, 0.f);
     const int y0 = (int)sy, y1 = y0 + (y0 < H - 1 ? 1 : 0);
     const float ly = sy - (float)y0, hy = 1.f - ly;
     const float* r0 = x + ((size_t)pl * H + y0) * W;
     const float* r1 = x + ((size_t)pl * H + y1) * W;
-    float o[4];
-    if (f == 4) {
-      // outputs 4q..4q+3 read source columns q-1, q, q+1 only (fractions .625 .875 | .125 .375): six loads, not sixteen
-      const int xm = max(xq - 1, 0), xp = min(xq + 1, W - 1);
-      const float a0 = __ldg(r0 + xm), a1 = __ldg(r0 + xq), a2 = __ldg(r0 + xp);
-      const float b0 = __ldg(r1 + xm), b1 = __ldg(r1 + xq), b2 = __ldg(r1 + xp);
-      // left border (xq == 0): the source index clamps at 0, i.e. weight 1 on column 0 -- xm == xq gives the same value
-      const float l0 = xq == 0 ? 0.f : 0.625f, l1 = xq == 0 ? 0.f : 0.875f;
-      o[0] = hy * ((1.f - l0) * a0 + l0 * a1) + ly * ((1.f - l0) * b0 + l0 * b1);
-      o[1] = hy * ((1.f - l1) * a0 + l1 * a1) + ly * ((1.f - l1) * b0 + l1 * b1);
-      o[2] = hy * (0.875f * a1 + 0.125f * a2) + ly * (0.875f * b1 + 0.125f * b2);
-      o[3] = hy * (0.625f * a1 + 0.375f * a2) + ly * (0.625f * b1 + 0.375f * b2);
-      reinterpret_cast<float4*>(y)[t] = make_float4(o[0], o[1], o[2], o[3]);
-      continue;
-    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int xo = xq * 4 + e;

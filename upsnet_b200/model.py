@@ -472,7 +472,9 @@ class FCNHead(nn.Module):
             cur.wait_event(ev)
         return o2, o3, outs["p4"], outs["p5"]
 
-    def forward(self, p2, p3, p4, p5):
+    def forward(self, p2, p3, p4, p5, score_only=False):
+        """score_only (static engine): stop at the quarter-resolution score map 'fcn_score' -- the x4 up-sampling is then
+        evaluated inside the panoptic fusion kernel (ops.panoptic_fuse(..., up4=True)) and fcn_output is never materialised."""
         p2, p3, p4, p5 = self._subnets(p2, p3, p4, p5)
         if self.fuse_score and self._f is not None:
             # models/fcn.py:94-101 computes score(cat(p2, up2(p3), up4(p4), up8(p5))).  The 1x1 score conv and the
@@ -489,7 +491,7 @@ class FCNHead(nn.Module):
                 for l, s_l in enumerate(parts, start=1):
                     score = score + F.interpolate(s_l, None, 2 ** l, mode="bilinear", align_corners=False)
             ret = {"fcn_score": score}
-            if self.upsample_rate != 1:
+            if self.upsample_rate != 1 and not (score_only and self.upsample_rate == 4):
                 ret["fcn_output"] = ops.upsample_bilinear(score, self.upsample_rate)
             return ret
         p3 = F.interpolate(p3, None, 2, mode="bilinear", align_corners=False)
@@ -539,6 +541,7 @@ class resnet_upsnet(nn.Module):
         self.mask_roi_panoptic_static = StaticMaskROI(cfg.max_det, self.num_classes, 0.5, True,
                                                       cfg.panoptic_score_thresh, cfg.bbox_reg_weights)
         self.static_engine = True     # fixed shapes + device-side counts: no host sync inside the forward
+        self.fuse_upsample = True     # panoptic fusion kernel up-samples the quarter-resolution semantic score map itself
         self.use_cuda_graph = True    # capture the static forward once per (shape, precision) and replay it
         self.overlap_heads = True     # semantic head on a side stream, concurrent with the detection chain
         self._side = {}
@@ -658,14 +661,16 @@ class resnet_upsnet(nn.Module):
             ev.record(cur)
             side.wait_event(ev)
             with torch.cuda.stream(side):
-                fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
+                fcn_output, fcn_score = self._semantic(p2, p3, p4, p5, x.is_cuda)
                 done = torch.cuda.Event()
                 done.record(side)
             if not torch.cuda.is_current_stream_capturing():
-                fcn_output.record_stream(cur)   # eager mode: the block is consumed on `cur` (graph pools need no hint)
+                for t_ in (fcn_output, fcn_score):      # eager mode: consumed on `cur` (graph pools need no hint)
+                    if t_ is not None:
+                        t_.record_stream(cur)
         rois, _, roi_valid = self.pyramid_proposal_static(rpn_cls_prob, rpn_bbox_pred, im_info)
         if not fork:
-            fcn_output = self.fcn_head(p2, p3, p4, p5)["fcn_output"].float()
+            fcn_output, fcn_score = self._semantic(p2, p3, p4, p5, x.is_cuda)
         feats = [p2, p3, p4, p5]
         rcnn_output = self.rcnn(feats, rois)
         cls_prob = F.softmax(rcnn_output["cls_score"].float(), dim=1)
@@ -697,9 +702,11 @@ class resnet_upsnet(nn.Module):
         mask_score = logits[b1.shape[0]:].gather(1, c2.view(-1, 1, 1, 1).expand(-1, -1, ms, ms))
         if fork:
             cur.wait_event(done)
-        keep, labels, sem, k = ops.panoptic_fuse(fcn_output, b2[:, 1:], s2, mask_score, c2, self.panoptic_head.num_stuff,
-                                                 self.panoptic_head.fraction_threshold, want_sem=True,
-                                                 n_dev=n2.reshape(1))
+        # fused x4 up-sampling: the fusion kernel reads the quarter-resolution score map (fcn_output, when the parity tests ask
+        # for it, is the same arithmetic materialised by the stand-alone kernel)
+        keep, labels, sem, k = ops.panoptic_fuse(fcn_score if fcn_score is not None else fcn_output, b2[:, 1:], s2, mask_score, c2,
+                                                 self.panoptic_head.num_stuff, self.panoptic_head.fraction_threshold,
+                                                 want_sem=True, n_dev=n2.reshape(1), up4=fcn_score is not None)
         counts = torch.cat([n1.reshape(1).to(torch.int32), n2.reshape(1).to(torch.int32), k.reshape(1)])
         out = {"cls_probs": s1, "pred_boxes": b1, "mask_probs": mask_prob, "cls_inds": c1, "fcn_outputs": sem,
                "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
@@ -710,6 +717,18 @@ class resnet_upsnet(nn.Module):
                           "rois": rois, "roi_valid": roi_valid, "cls_score": rcnn_output["cls_score"].float(),
                           "bbox_pred": bbox_pred, "mask_logits": logits}
         return out
+
+    def _semantic(self, p2, p3, p4, p5, on_gpu=True):
+        """Semantic head of the static engine: (fcn_output or None, fcn_score or None).  With the fused score path and the
+        reference's x4 up-sampling the full-resolution logits are only materialised when a test asks for intermediates."""
+        head = self.fcn_head
+        fuse_up = on_gpu and head.fuse_score and head._f is not None and head.upsample_rate == 4 and self.fuse_upsample
+        if not fuse_up:
+            return head(p2, p3, p4, p5)["fcn_output"].float(), None
+        ret = head(p2, p3, p4, p5, score_only=not getattr(self, "keep_intermediates", False))
+        score = ret["fcn_score"].float().contiguous()
+        fo = ret.get("fcn_output")
+        return (None if fo is None else fo.float()), score
 
     def _side_stream(self, dev, idx=0):
         key = (str(dev), idx, ops.WS_SLOT["i"])

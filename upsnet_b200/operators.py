@@ -201,6 +201,40 @@ def _packed_weight_dcn(weight):
     return buf
 
 
+# small-N dense 3x3 / stride-1 convs on the pair stream through the window pipeline (csrc/dcn_win.cu DENSE mode): Cout <= max_cout
+# measured on B200 (scripts/exp_offset_conv.py): 0.18 vs 0.15 ms for the 256->18 offset conv at 256x512 -- the 32-byte rows of the
+# window boxes run into the TMA request rate (~4-5 cycles per box row and SM) -> off by default, kept for the record / tests
+DENSE_WINDOW = {"on": False, "max_cout": 64, "min_pixels": 4096}
+
+
+def _dense_window(x, weight, bias, padding, dilation, relu, nchw_out):
+    """upsnet_conv3x3_pair_forward: Pair in; fp32 NCHW (offset maps) or Pair out.  None when the layer does not qualify."""
+    N, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    ph, pw = padding; dh, dw = dilation
+    if N * H * W < DENSE_WINDOW["min_pixels"] or Cout > DENSE_WINDOW["max_cout"] or (not nchw_out and Cout % 16):
+        return None
+    packed = _packed_weight_dcn(weight)
+    if packed is None:
+        return None
+    Ho, Wo = _conv_out(H, ph, dh, 3, 1), _conv_out(W, pw, dw, 3, 1)
+    if nchw_out:
+        store = torch.empty((N, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    else:
+        store = torch.empty((N, Ho, Wo, 2 * Cout), device=x.device, dtype=torch.bfloat16)
+    work = {"flops": 2.0 * N * Ho * Wo * Cout * Cin * 9 * 3, "algo_flops": 2.0 * N * Ho * Wo * Cout * Cin * 9,
+            "shape": "N%d %dx%d Cin%d->Cout%d k3 s1 pair->%s (window)" % (N, H, W, Cin, Cout, "float32" if nchw_out else "pair"),
+            "bytes": float(x.store.numel() * 2 + 4 * weight.numel() + store.numel() * store.element_size())}
+    with torch.cuda.device(x.device), _Timed("conv2d", 1, work, x.device):
+        rc = lib().upsnet_conv3x3_pair_forward(ptr(x.store), ptr(packed), ptr(bias), ptr(store), N, H, W, Cin, Cout, ph, pw, dh, dw,
+                                               _lib.LAYOUT_NCHW if nchw_out else _lib.LAYOUT_NHWC,
+                                               _lib.EPI_RELU if relu else 0, stream_ptr(x.device))
+    if rc == -2:
+        return None
+    check(rc, "conv3x3_pair_forward")
+    return store if nchw_out else Pair(store)
+
+
 def _dcn_window(x, offset, mask, weight, bias, padding, dilation, relu):
     """upsnet_dcn_pair_forward (csrc/dcn_win.cu): Pair in, Pair out, 3x3 / stride 1.  Returns None when the layer does
     not qualify (the caller then takes upsnet_igemm_forward)."""
@@ -370,6 +404,14 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, residual=None,
     if prec != _lib.PREC_FP32_SIMT and _tc_ok(weight.shape[1], weight.shape[2], weight.shape[3], 1):
         if residual_up2 and out_format == "nchw":
             residual, residual_up2 = torch.nn.functional.interpolate(as_float(residual), scale_factor=2, mode="nearest"), False
+        if (DENSE_WINDOW["on"] and isinstance(x, Pair) and prec == _lib.PREC_BF16X3 and ACT_PAIR["on"] and USE_TMA["on"] and
+                weight.shape[2] == 3 and weight.shape[3] == 3 and _pair(stride) == (1, 1) and residual is None and
+                sigmoid_from is None and not pair_group and
+                ((out_format == "nchw" and out_dtype in (None, torch.float32)) or (out_format != "nchw" and out_dtype in (None, "pair")))):
+            y = _dense_window(x, weight, None if bias is None else f32c(bias), _pair(padding), _pair(dilation), relu,
+                              out_format == "nchw")
+            if y is not None:
+                return y
         return _igemm_tc("conv2d", x, None, None, weight, None if bias is None else f32c(bias), residual,
                          _pair(stride), _pair(padding), _pair(dilation), relu, prec, out_format, out_dtype,
                          residual_up2, pair_group, sigmoid_from)
@@ -941,16 +983,20 @@ class FPNRoIAlign(nn.Module):
 # panoptic head
 # ------------------------------------------------------------------------------------------------
 def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                  want_sem=False, n_dev=None, workspace_bytes=None):
+                  want_sem=False, n_dev=None, workspace_bytes=None, up4=False):
     """Fused MaskRemoval + SegTerm + void/argmax (upsnet_panoptic_head).
     fcn_output [1,S,H,W]; mask_rois [n,4]; cls_prob [n]; mask_logit [n,1,28,28] or [n,28,28];
     cls_idx int64 [n].  Returns (keep_inds int64 [k], panoptic_output int64 [1,H,W][, sem int64 [1,H,W]]).
     With n_dev (int32 device scalar, actual count <= n) nothing is read back: keep_inds is the padded
-    [n] buffer and the device count k is returned as an extra last element (static-shape engine path)."""
+    [n] buffer and the device count k is returned as an extra last element (static-shape engine path).
+    up4=True: `fcn_output` is the quarter-resolution score map [1,S,H/4,W/4] (FCNHead's 'fcn_score'); its x4 bilinear
+    up-sampling (models/fcn.py:88-101) is evaluated inside the kernel, bit-identical to upsample_bilinear(score, 4)."""
     require_cuda(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx)
     assert fcn_output.dim() == 4 and fcn_output.shape[0] == 1, "only support batch size = 1"
     fcn = f32c(fcn_output)
     _, S, H, W = fcn.shape
+    if up4:
+        Hs, Ws, H, W = H, W, 4 * H, 4 * W
     boxes, prob, ml = f32c(mask_rois), f32c(cls_prob).reshape(-1), f32c(mask_logit)
     cls = cls_idx.to(torch.int64).contiguous()
     n = boxes.shape[0]
@@ -971,11 +1017,16 @@ def panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuf
     k = torch.empty((1,), dtype=torch.int32, device=dev)
     labels = torch.empty((1, H, W), dtype=torch.int64, device=dev)
     sem = torch.empty((1, H, W), dtype=torch.int64, device=dev) if want_sem else None
-    work = {"bytes": 4.0 * S * H * W + 8.0 * H * W * (2 if want_sem else 1) + n * (4.0 * 784 + 24)}
+    work = {"bytes": 4.0 * S * H * W / (16 if up4 else 1) + 8.0 * H * W * (2 if want_sem else 1) + n * (4.0 * 784 + 24)}
     with torch.cuda.device(dev), _Timed("panoptic_head", 5, work, dev):
-        check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, ptr(n_dev),
-                                         num_stuff, float(fraction_threshold), ptr(keep), ptr(k), ptr(labels),
-                                         ptr(sem), ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
+        if up4:
+            check(lib().upsnet_panoptic_head_up4(ptr(fcn), S, Hs, Ws, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, ptr(n_dev),
+                                                 num_stuff, float(fraction_threshold), ptr(keep), ptr(k), ptr(labels),
+                                                 ptr(sem), ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head_up4")
+        else:
+            check(lib().upsnet_panoptic_head(ptr(fcn), S, H, W, ptr(boxes), ptr(prob), ptr(ml), ptr(cls), n, ptr(n_dev),
+                                             num_stuff, float(fraction_threshold), ptr(keep), ptr(k), ptr(labels),
+                                             ptr(sem), ptr(ws), ws.numel(), stream_ptr(dev)), "panoptic_head")
     if n_dev is not None:
         return (keep, labels, sem, k) if want_sem else (keep, labels, k)
     keep = keep[:int(k.item())]
