@@ -92,7 +92,8 @@ def _nms_segmented(boxes_sorted, seg_offsets, max_seg_len, thresh):
 
 
 def _panoptic_fuse(fcn_output, mask_rois, cls_prob, mask_logit, cls_idx, num_stuff, fraction_threshold=0.3,
-                   want_sem=False, n_dev=None):
+                   want_sem=False, n_dev=None, up4=False):
+    assert not up4, "the CPU path materialises fcn_output (model._semantic fuses the up-sampling on CUDA only)"
     n = mask_rois.shape[0] if n_dev is None else max(min(int(n_dev.item()), mask_rois.shape[0]), 1)
     r = O.panoptic_head(fcn_output[0].detach().contiguous().numpy(), mask_rois[:n].detach().contiguous().numpy(),
                         cls_prob[:n].detach().numpy(), mask_logit[:n].detach().contiguous().numpy().reshape(-1, 28, 28),
