@@ -289,6 +289,7 @@ def main():
                          "hi/lo split on the hi/lo bf16 pair stream; bf16: tcgen05 single pass + bf16 activation storage "
                          "(secondary figure, bf16-level error); fp32: CUDA-core tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[2] / configs[4] extras of the default run")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("UPSNET_LANES", "2")),
                     help="images in flight per GPU: independent engine instances (CUDA-graph instance + pool + scratch) on their own streams")
     ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "coco"],
@@ -498,6 +499,58 @@ def main():
                  "note": "single tcgen05 pass on bf16 activations: bf16-level error (tests hold it to 4e-2..8e-2), reported "
                          "for reference only -- the headline is the bf16x3 pair stream that meets 'fp32 logits within 1e-3'"}
         U.set_precision(args.precision)
+    # The other BASELINE configurations, measured in the same (driver-run) process: configs[2] UPSNet-101-DCN at 800x1344
+    # through the same engine entry, and configs[4] -- the panoptic head alone at 19x1024x2048 for n = 100..1000 instances.
+    other_cfg = None
+    if world == 1 and args.precision == "bf16x3" and args.workload == "cityscapes" and not args.no_other_configs:
+        other_cfg = {}
+        try:
+            import numpy as np
+            m3 = synthetic_model(UPSNetConfig.coco_r101_dcn(), depth=(3, 4, 23, 3), seed=0, device=dev)
+            H3, W3 = 800, 1344
+            imgs3 = [synthetic_input(H3, W3, seed=700 + s_)["data"].to(dev) for s_ in range(n_img)]
+            info3 = synthetic_input(8, 8)["im_info"]; info3[0, :2] = (H3, W3)
+            cnt3 = torch.zeros((16, 3), dtype=torch.int32).pin_memory()
+
+            def step3(i):
+                l = i % LANES
+                with torch.cuda.stream(lane_streams[l]):
+                    out, _ = m3._run_static(imgs3[i % n_img], info3[0], lane=l)
+                    cnt3[i % 16].copy_(out["counts"], non_blocking=True)
+            for i in range(2 * LANES):
+                step3(i)
+            n3 = max(6, args.steps // 2)
+            ms_c3, _, _ = timed(step3, n3)
+            other_cfg["configs[2] UPSNet-101-DCN COCO 800x1344 (padded from 1333), one image per step"] = {
+                "value": n3 / (ms_c3 * 1e-3), "unit": "images/s", "ms_per_step": ms_c3 / n3, "precision": args.precision, "lanes": LANES,
+                "detections_per_image": float(cnt3[:n3, 0].float().mean()),
+                "parity": "tests/test_gpu_fullsize.py: res2-5, FPN, fcn_output <= 6e-5 relative vs the literal model at this size"}
+            del m3, imgs3
+            rng5 = np.random.default_rng(5)
+            fcn5 = torch.randn(1, 19, 1024, 2048, device=dev) * 3
+            sweep = {}
+            for n5 in (100, 200, 500, 1000):
+                c5 = np.stack([rng5.uniform(0, 2048, n5), rng5.uniform(0, 1024, n5)], 1)
+                s5 = np.exp(rng5.uniform(np.log(16), np.log(512), (n5, 2)))
+                b5 = np.concatenate([c5 - s5 / 2, c5 + s5 / 2], 1).astype(np.float32)
+                b5[:, 0::2] = np.clip(b5[:, 0::2], 0, 2047); b5[:, 1::2] = np.clip(b5[:, 1::2], 0, 1023)
+                a5 = [torch.from_numpy(v).to(dev) for v in (b5, (0.6 + 0.4 * (rng5.permutation(n5) + 1) / (n5 + 1)).astype(np.float32),
+                                                             (rng5.standard_normal((n5, 1, 28, 28)) * 2).astype(np.float32),
+                                                             rng5.integers(1, 9, n5).astype(np.int64))]
+                nd5 = torch.tensor([n5], dtype=torch.int32, device=dev)
+                run5 = lambda: U.panoptic_fuse(fcn5, a5[0], a5[1], a5[2], a5[3], 11, n_dev=nd5)
+                run5(); run5(); torch.cuda.synchronize()
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0_.record()
+                for _ in range(10):
+                    run5()
+                e1_.record(); torch.cuda.synchronize()
+                sweep["n=%d" % n5] = round(e0_.elapsed_time(e1_) / 10, 4)
+            other_cfg["configs[4] panoptic head (MaskRemoval + SegTerm + void/argmax) at 19x1024x2048, fp32 logits in HBM"] = {
+                "ms_per_call": sweep, "unit": "ms", "parity": "tests/test_gpu_parity.py: bit-exact vs the oracle for n = 100..1000 at this size"}
+            del fcn5
+        except Exception as exc:      # the extra configurations must never cost the headline line
+            other_cfg["error"] = repr(exc)[:300]
     if rank == 0:
         cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline and args.workload == "cityscapes":
@@ -522,9 +575,9 @@ def main():
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "upsnet_b200.pipeline.PipelinedEngine: pinned-host image in, host results out; H2D / "
-                               "compute / D2H of neighbouring images overlap on three streams (depth 2)"},
+                               "compute / D2H of neighbouring images overlap (%d staging slots, %d engine lanes)" % (E2E_DEPTH, LANES)},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-                "secondary_mode": other, "per_rank_ms": {"value": per_rank, "e2e": per_rank_e2e},
+                "secondary_mode": other, "other_configs": other_cfg, "per_rank_ms": {"value": per_rank, "e2e": per_rank_e2e},
                 "numa_cpus_bound": numa_cpus}
         emit(line)
     if world > 1:

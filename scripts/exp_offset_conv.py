@@ -25,10 +25,12 @@ for cin, h, w in [(256, 256, 512), (128, 256, 512), (256, 128, 256), (128, 128, 
     ops.DENSE_WINDOW["on"] = False
     ms0 = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, out_format="nchw"))
     print("offset conv %d->18 @%dx%d: window %.4f ms   per-tap TMA %.4f ms" % (cin, h, w, ms, ms0), flush=True)
-x = Pair.from_float(torch.randn(1, 64, 256, 512, device=dev)); wt = torch.randn(64, 64, 3, 3, device=dev) / 24; b = torch.randn(64, device=dev)
 from upsnet_b200 import operators as ops
-ops.DENSE_WINDOW["on"] = True
-ms = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, relu=True))
-ops.DENSE_WINDOW["on"] = False
-ms0 = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, relu=True))
-print("res2 conv2 64->64 @256x512: window %.4f ms   per-tap TMA %.4f ms" % (ms, ms0), flush=True)
+ops.DENSE_WINDOW.update(max_cout=256, min_pixels=0)
+for cin, cout, h, w in [(64, 64, 256, 512), (128, 128, 128, 256), (256, 256, 64, 128), (256, 256, 128, 256)]:
+    x = Pair.from_float(torch.randn(1, cin, h, w, device=dev)); wt = torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5); b = torch.randn(cout, device=dev)
+    ops.DENSE_WINDOW["on"] = True
+    ms = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, relu=True))
+    ops.DENSE_WINDOW["on"] = False
+    ms0 = gpu_ms(lambda: U.conv2d(x, wt, b, 1, 1, 1, relu=True))
+    print("conv3x3 %d->%d @%dx%d pair->pair: window %.4f ms   TMA kernels %.4f ms" % (cin, cout, h, w, ms, ms0), flush=True)

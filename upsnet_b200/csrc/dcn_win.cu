@@ -69,6 +69,12 @@ struct DwParams {
   int out_nchw;           // y = fp32 NCHW [N,Cout,Ho,Wo] (offset maps) instead of the pair NHWC tensor
   int win_bytes;          // bytes one window fill delivers (both planes): the dense box is only tile + halo rows high
   int win_h;              // rows of the window box (<= DW_WH)
+  // DENSE mode window geometry: one fill = a 64-channel chunk (four 16-channel sub-chunks), 128-byte pixels, SWIZZLE_128B --
+  // the 32-byte box rows of the deformable window would make the plain copy loop TMA-request-bound (~4.5 cycles per box row)
+  int win_pitch;          // pixels per window row (dense: 24)
+  int win_plane;          // bytes of one plane of a window buffer
+  int win_buf;            // bytes of one window buffer (both planes)
+  int stages;             // operand ring depth (2 or 3)
 };
 
 __device__ __forceinline__ void dw_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -119,7 +125,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t b_bytes = (uint32_t)p.BN * 128;
   const uint32_t stage_bytes = 2 * b_bytes;                                 // weight tile: hi plane, lo plane
-  const uint32_t win_base = base + DW_OFF_STAGES + DW_STAGES * stage_bytes; // 1024-aligned (stage_bytes % 1024 == 0)
+  const uint32_t NST = (uint32_t)p.stages;
+  const uint32_t win_base = base + DW_OFF_STAGES + NST * stage_bytes;       // 1024-aligned (stage_bytes % 1024 == 0)
   // barriers
   const uint32_t bar_fa = base + DW_OFF_BARS;            // full_a[3]: 8 producer warps each (A stage written to TMEM)
   const uint32_t bar_fb = bar_fa + 24;                   // full_b[3]: weight TMA (tx)
@@ -137,6 +144,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 
   const int HoWo = p.Ho * p.Wo;
   const int nsc = p.Cin / 16;                         // 16-channel sub-chunks
+  const int spf = p.dense ? 4 : 1;                    // sub-chunks per window fill
+  const int nfill = nsc / spf;                        // window fills per tile
   const int num_kb = nsc * DW_KHW / 4;                // Cin % 64 == 0 -> integral
   const int n_tiles = p.Cout_pad / p.BN;
   const int TW = p.tile_w, TH = p.tile_h;
@@ -200,7 +209,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const int tap = e >> 7, rr = e & 127;
         const int ki = tap / 3, kj = tap - ki * 3;
         const int ry = min(rr >> tw_shift, TH - 1), rx = rr & (TW - 1);      // rows past the block read a valid (unused) pixel
-        tp[e] = ((ry + ki * p.dh) * DW_WW + rx + kj * p.dw) * 32;
+        tp[e] = (ry + ki * p.dh) * p.win_pitch + rx + kj * p.dw;      // window PIXEL index
       }
       dw_producer_bar();
     }
@@ -296,7 +305,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       int rel = 0;            // sub-chunks of this tile this WARP has released
       for (int kb = (int)((uint32_t)(group - (int)g0) & 1u); kb < num_kb; kb += DW_GROUPS) {
         const uint32_t g = g0 + (uint32_t)kb;
-        const uint32_t s = g % DW_STAGES, it = g / DW_STAGES;
+        const uint32_t s = g % NST, it = g / NST;
         mbar_wait(bar_em + 8 * s, (it & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t a_col = tmem_base + ((uint32_t)(quad * 32) << 16) + DW_TMEM_A0 + s * 64u;
@@ -305,17 +314,18 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           const int sl = 2 * u + (pass >> 1), half = pass & 1;
           const int q = kb * 4 + sl;                    // slice index: (sub-chunk, tap)
           const int sc = q / DW_KHW, tap = q - sc * DW_KHW;
-          const uint32_t wf = wf0 + (uint32_t)sc;
+          const uint32_t wf = wf0 + (uint32_t)(dense ? (sc >> 2) : sc);      // dense: one fill per 64-channel chunk
           if (wf >= wf_ready) {                         // first touch of this window fill
             mbar_wait(bar_wf + 8 * (wf & 1u), (wf >> 1) & 1u);
             wf_ready = wf + 1;
           }
-          const uint32_t wbuf = win_base + (wf & 1u) * DW_WIN_BYTES;
+          const uint32_t wbuf = win_base + (wf & 1u) * (uint32_t)p.win_buf;
           const int code = tp[tap * DW_BM + r];
           if (dense) {        // plain copy of the tap's pixel: window -> TMEM A operand
-            const uint32_t cl = (uint32_t)code;
-            const uint32_t al = wbuf + cl + ((((cl >> 7) & 1u) ^ (uint32_t)half) << 4);
-            const uint4 h4 = dw_lds128(al), l4 = dw_lds128(al + DW_PLANE);
+            // SWIZZLE_128B window: a pixel is one 128-byte row (64 channels), 16-byte chunk c sits at c ^ (pixel & 7)
+            const uint32_t pix = (uint32_t)code, ch = (uint32_t)((sc & 3) * 2 + half);
+            const uint32_t al = wbuf + pix * 128u + ((ch ^ (pix & 7u)) << 4);
+            const uint4 h4 = dw_lds128(al), l4 = dw_lds128(al + (uint32_t)p.win_plane);
             const uint32_t col = a_col + (uint32_t)(sl * 8 + half * 4);
             dw_tmem_st4(col, h4.x, h4.y, h4.z, h4.w);
             dw_tmem_st4(col + 32u, l4.x, l4.y, l4.z, l4.w);
@@ -391,7 +401,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         if (lane == 0) {
           mbar_arrive(bar_fa + 8 * s);
           // window buffers this warp will not read again: its next k-block (kb + 2) starts at slice 4 * (kb + 2)
-          while (rel < nsc && DW_KHW * (rel + 1) <= 4 * (kb + DW_GROUPS)) {
+          while (rel < nfill && DW_KHW * spf * (rel + 1) <= 4 * (kb + DW_GROUPS)) {
             mbar_arrive(bar_we + 8 * ((wf0 + (uint32_t)rel) & 1u));
             ++rel;
           }
@@ -399,11 +409,11 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         rel = __shfl_sync(0xffffffffu, rel, 0);
       }
       if (lane == 0) {
-        while (rel < nsc) { mbar_arrive(bar_we + 8 * ((wf0 + (uint32_t)rel) & 1u)); ++rel; }
+        while (rel < nfill) { mbar_arrive(bar_we + 8 * ((wf0 + (uint32_t)rel) & 1u)); ++rel; }
       }
       __syncwarp();
       g0 += (uint32_t)num_kb;
-      wf0 += (uint32_t)nsc;
+      wf0 += (uint32_t)nfill;
     }
   } else if (warp == DW_WARP_TMAW) {
     // =============================== WINDOW TMA ===============================
@@ -421,13 +431,14 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           const volatile int* ov = reinterpret_cast<const volatile int*>(&org[par]);
           o = make_int4(ov[0], ov[1], ov[2], 0);
         }
-        for (int sc = 0; sc < nsc; ++sc, ++wf) {
+        const int cstep = 16 * spf;
+        for (int f = 0; f < nfill; ++f, ++wf) {
           const uint32_t b = wf & 1u;
           mbar_wait(bar_we + 8 * b, ((wf >> 1) & 1u) ^ 1u);
           dw_expect_tx(bar_wf + 8 * b, (uint32_t)p.win_bytes);
-          const uint32_t dst = win_base + b * DW_WIN_BYTES;
-          dw_tma_4d(dst, &tm_x, bar_wf + 8 * b, sc * 16, o.x, o.y, o.z);
-          dw_tma_4d(dst + DW_PLANE, &tm_x, bar_wf + 8 * b, p.Cin + sc * 16, o.x, o.y, o.z);
+          const uint32_t dst = win_base + b * (uint32_t)p.win_buf;
+          dw_tma_4d(dst, &tm_x, bar_wf + 8 * b, f * cstep, o.x, o.y, o.z);
+          dw_tma_4d(dst + (uint32_t)p.win_plane, &tm_x, bar_wf + 8 * b, p.Cin + f * cstep, o.x, o.y, o.z);
         }
       }
     }
@@ -439,7 +450,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (int)(tile % n_tiles) * p.BN;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const uint32_t s = g % DW_STAGES, it = g / DW_STAGES;
+          const uint32_t s = g % NST, it = g / NST;
           mbar_wait(bar_em + 8 * s, (it & 1u) ^ 1u);
           const uint32_t stage = base + DW_OFF_STAGES + s * stage_bytes;
           dw_expect_tx(bar_fb + 8 * s, 2 * b_bytes);
@@ -476,7 +487,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           }
           umma_commit(bar_em + 8 * s);
           b_hi += stage16;
-          if (++s == DW_STAGES) { s = 0; ph ^= 1u; b_hi = b0; }
+          if (++s == NST) { s = 0; ph ^= 1u; b_hi = b0; }
         }
         umma_commit(bar_tf + 8 * buf);
       }
@@ -663,29 +674,37 @@ static int dw_launch(const void* x_pair, const float* offset, const float* mask,
   }
   const long long num_tiles = dtiles();
   if (num_tiles <= 0) return 0;
-  // dense: the window box is the tile's receptive field (32 px wide for the bank mapping, tile + halo rows high)
+  // dense: the window box is the tile's receptive field: 24 pixels x (tile + halo) rows x 64 channels (128-byte pixels)
   int win_h = DW_WH;
+  p.win_pitch = DW_WW; p.win_plane = DW_PLANE; p.win_buf = DW_WIN_BYTES; p.stages = DW_STAGES;
   if (dense) {
     win_h = p.tile_h + 2 * dil_h;
-    if (win_h > DW_WH || p.tile_w + 2 * dil_w > DW_WW) return UPSNET_E_UNSUPPORTED;
+    p.win_pitch = 24;
+    if (win_h > 16 || p.tile_w + 2 * dil_w > p.win_pitch) return UPSNET_E_UNSUPPORTED;
+    p.win_plane = p.win_pitch * win_h * 128;
+    p.win_plane = (p.win_plane + 1023) / 1024 * 1024;     // SWIZZLE_128B destinations: 1024-byte aligned planes
+    p.win_buf = 2 * p.win_plane;
   }
   if (!dense) {     // tuning hook: UPSNET_DCN_WIN_H = rows of the deformable window box (12..24)
     static int wh_env = -1;
     if (wh_env < 0) { const char* e = getenv("UPSNET_DCN_WIN_H"); wh_env = e ? atoi(e) : 0; }
     if (wh_env >= 12 && wh_env <= DW_WH) win_h = wh_env;
   }
-  p.win_bytes = 2 * DW_WW * win_h * 32;
+  p.win_bytes = dense ? 2 * p.win_pitch * win_h * 128 : 2 * DW_WW * win_h * 32;
   p.win_h = win_h;
+  auto smem_need = [&]() { return (size_t)DW_OFF_STAGES + (size_t)p.stages * 2 * (p.BN * 128) + 2 * (size_t)p.win_buf + 1024; };
+  if (smem_need() > 227 * 1024 && p.stages > 2) p.stages = 2;
+  if (smem_need() > 227 * 1024) return UPSNET_E_UNSUPPORTED;
   DwEncodeFn enc = dw_encoder();
   if (!enc) return UPSNET_E_UNSUPPORTED;
   CUtensorMap tm_x, tm_w;
   {
     const cuuint64_t dx[4] = {(cuuint64_t)(2 * Cin), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t sx[3] = {(cuuint64_t)(2 * Cin) * 2, (cuuint64_t)W * (2 * Cin) * 2, (cuuint64_t)H * W * (2 * Cin) * 2};
-    const cuuint32_t bx[4] = {16, DW_WW, (cuuint32_t)win_h, 1};
+    const cuuint32_t bx[4] = {(cuuint32_t)(dense ? 64 : 16), (cuuint32_t)p.win_pitch, (cuuint32_t)win_h, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_pair), dx, sx, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            dense ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return UPSNET_E_UNSUPPORTED;
     const cuuint64_t dwt[2] = {(cuuint64_t)(9 * Cin), (cuuint64_t)(2 * p.Cout_pad)};
     const cuuint64_t sw[1] = {(cuuint64_t)(9 * Cin) * 2};
@@ -694,8 +713,7 @@ static int dw_launch(const void* x_pair, const float* offset, const float* mask,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return UPSNET_E_UNSUPPORTED;
   }
-  const size_t smem = DW_OFF_STAGES + (size_t)DW_STAGES * 2 * (p.BN * 128) + 2 * DW_WIN_BYTES + 1024;
-  if (smem > 227 * 1024) return UPSNET_E_UNSUPPORTED;
+  const size_t smem = smem_need();
   static PerDeviceOnce configured;
   if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(dcn_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -61,6 +61,12 @@ struct TmaGeom {
   int pg;                               // output / residual pair group G: channels stored [hi G][lo G] per group (G = Cout normally)
   int res_inplace;                      // residual slabs are TMA-loaded into the (double-buffered) output slabs and updated in place
   int opairs;                           // output slab pairs that alternate (2, or 1 when shared memory is short)
+  // 2-CTA kernel, N tile <= 64: the hi*hi and hi*lo products share ONE instruction -- B operand = [W_hi ; W_lo] (N = 2 BN, CTA 0
+  // stages the hi rows, CTA 1 the lo rows), accumulated in columns [0, 2 BN); lo*hi goes to columns [0, BN); the epilogue adds
+  // the two column groups.  A tcgen05.mma of M = 256 takes ~100 cycles whatever N <= 128 is (measured: the 18-channel offset
+  // convs and the 64->64 3x3 convs run at 12 instructions x ~100 cycles per k-block), so two instructions per K slice instead
+  // of three is a third less time on these instruction-bound layers.
+  int wide;
 };
 
 // ---- PTX: TMA (bulk tensor) copies ----
@@ -736,10 +742,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {      // arrive o
 
 struct Tma2Smem { uint32_t stages, out, res, res_slab, a_half, b_half, a_bytes, b_bytes, stage_bytes, total; };
 __host__ __device__ inline Tma2Smem tma2_smem_layout(int BN, int stages, bool direct, int opairs, bool has_res = false,
-                                                    bool res_up2 = false, bool res_inplace = false) {
+                                                    bool res_up2 = false, bool res_inplace = false, bool wide = false) {
   Tma2Smem s;
   s.a_half = 128 * 128; s.b_half = (uint32_t)(BN / 2) * 128;      // this CTA's half of the weight tile, per plane
-  s.a_bytes = 2 * s.a_half; s.b_bytes = 2 * s.b_half;
+  // wide: [Y: BN rows = this CTA's half of [W_hi ; W_lo]] [X: BN/2 rows = this CTA's half of W_hi]
+  s.a_bytes = 2 * s.a_half; s.b_bytes = (wide ? 3u : 2u) * s.b_half;
   s.stage_bytes = s.a_bytes + s.b_bytes;
   s.stages = 1024;
   s.out = s.stages + s.stage_bytes * (uint32_t)stages;
@@ -757,7 +764,9 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_dyn + (base - raw);
-  const Tma2Smem L = tma2_smem_layout(g.BN, g.stages, g.direct != 0, g.opairs, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0);
+  const Tma2Smem L = tma2_smem_layout(g.BN, g.stages, g.direct != 0, g.opairs, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0,
+                                      g.wide != 0);
+  const uint32_t acc_cols = (uint32_t)(g.wide ? 2 * g.BN : g.BN);      // TMEM columns of one accumulator buffer
   const uint32_t bar_full = base, bar_empty = base + 8 * TM_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * TM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 16;     // residual slabs: CTA-local protocol
@@ -774,7 +783,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const uint32_t box_bytes = (uint32_t)(g.bw * g.bh * g.bn) * 128u;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * g.BN) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
   if (warp == TM_WARP_MMA) {
     if (lane == 0) {
@@ -807,7 +816,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       uint32_t a_dst = base + L.stages;
-      const uint32_t tx_both = 2u * (2u * box_bytes + L.b_bytes);       // both CTAs' A (hi, lo) boxes + B halves (hi, lo)
+      const uint32_t tx_both = 2u * (2u * box_bytes + L.b_bytes);       // both CTAs' A (hi, lo) boxes + B parts
       for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int nt = (int)(tile % g.n_tiles);
         const long long mt = 2 * (tile / g.n_tiles) + rank;
@@ -823,8 +832,15 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (leader_cta) mbar_arrive_expect_tx(bf_local, tx_both);
           tma2_load_4d(a_dst, &tm_x, bf, cc * 64, cw, ch, i0);
           tma2_load_4d(a_dst + L.a_half, &tm_x, bf, g.x_lo + cc * 64, cw, ch, i0);
-          tma2_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, nrow);
-          tma2_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kb * 64, g.w_lo + nrow);
+          if (g.wide) {
+            const int yrow = (rank ? g.w_lo : 0) + nt * g.BN;              // CTA 0: the hi rows of the n-tile, CTA 1: its lo rows
+            tma2_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, yrow);
+            tma2_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kb * 64, yrow + g.BN / 2);
+            tma2_load_2d(a_dst + L.a_bytes + 2 * L.b_half, &tm_w, bf, kb * 64, nrow);     // X: this CTA's half of W_hi
+          } else {
+            tma2_load_2d(a_dst + L.a_bytes, &tm_w, bf, kb * 64, nrow);
+            tma2_load_2d(a_dst + L.a_bytes + L.b_half, &tm_w, bf, kb * 64, g.w_lo + nrow);
+          }
           if (++cc == cchunks) {
             cc = 0; cw += g.dw;
             if (++kj == g.kw) { kj = 0; cw = w0 - g.pw; ch += g.dh; }
@@ -837,7 +853,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncwarp();
   } else if (warp == TM_WARP_MMA) {
     if (lane == 0 && leader_cta) {
-      const uint32_t idesc = umma_idesc(256, g.BN);
+      const uint32_t idesc = umma_idesc(256, g.BN), idesc_w = umma_idesc(256, 2 * g.BN);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = ((base + L.stages) >> 4) & 0x3fffu, stage16 = L.stage_bytes >> 4, a16 = L.a_bytes >> 4;
       const uint32_t ah16 = L.a_half >> 4, bh16 = L.b_half >> 4;
@@ -846,7 +862,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
+        const uint32_t tmem_d = tmem_base + buf * acc_cols;
         uint32_t acc = 0u;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
@@ -854,9 +870,14 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const uint32_t b_lo = a_lo + a16;
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {
-            umma2_bf16_lohi(tmem_d, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
-            umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
-            umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+            if (g.wide) {
+              umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc_w, acc);                 // hi * [hi ; lo] -> columns [0, 2 BN)
+              umma2_bf16_lohi(tmem_d, a_lo + ah16 + 2 * k, b_lo + 2 * bh16 + 2 * k, desc_hi, idesc, 1u);  // lo * hi      -> columns [0, BN)
+            } else {
+              umma2_bf16_lohi(tmem_d, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
+              umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
+              umma2_bf16_lohi(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+            }
             acc = 1u;
           }
           umma2_commit_mc(bar_empty + 8 * s);
@@ -917,7 +938,7 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_wait(bar_tfull + 8 * buf, use & 1u);
       tc_fence_after();
       if (g.has_res) mbar_wait(bar_rfull + 8 * buf, use & 1u);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols;
       if (g.direct) {
         const int wq = row % g.bw, hq = (row / g.bw) % g.bh, nq = row / (g.bw * g.bh);
         const int wo = w0 + wq, ho = h0 + hq, ni = i0 + nq;
@@ -927,7 +948,16 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int cbeg = half * (g.BN / 2), cend = cbeg + g.BN / 2;
         for (int cb = cbeg; cb < cend; cb += 16) {
           uint32_t v[16];
-          tmem_ld16(trow + (uint32_t)cb, v);
+          if (g.wide) {       // hi*hi + lo*hi in column cb, hi*lo in column BN + cb
+            uint32_t v2[16];
+            tmem_ld16_issue(trow + (uint32_t)cb, v);
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + cb), v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+          } else {
+            tmem_ld16(trow + (uint32_t)cb, v);
+          }
           const int co0 = n0 + cb;
           if (!ok || co0 >= g.Cout) continue;
 #pragma unroll
@@ -965,6 +995,13 @@ igemm_tma2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           float o[32];
 #pragma unroll
           for (int e = 0; e < 16; ++e) { o[e] = __uint_as_float(v0[e]); o[16 + e] = __uint_as_float(v1[e]); }
+          if (g.wide) {       // + the hi*lo column group
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + u * 32), v0);
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + u * 32 + 16), v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { o[e] += __uint_as_float(v0[e]); o[16 + e] += __uint_as_float(v1[e]); }
+          }
           if (g.bias) {
             const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + u * 32);
 #pragma unroll
@@ -1269,7 +1306,10 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
     const int opairs_1cta = g.opairs;
     int st2 = TM_MAX_STAGES;
     g.opairs = 2;
-    auto lay2 = [&](int st, int op) { return tma2_smem_layout(BN, st, direct, op, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0); };
+    static int wide_env = -1;
+    if (wide_env < 0) { const char* e = getenv("UPSNET_TMA_WIDE"); wide_env = e ? atoi(e) : 1; }
+    g.wide = (wide_env > 0 && BN <= 64 && !g.has_res) ? 1 : 0;
+    auto lay2 = [&](int st, int op) { return tma2_smem_layout(BN, st, direct, op, g.has_res != 0, g.res_up2 != 0, g.res_inplace != 0, g.wide != 0); };
     Tma2Smem L2 = lay2(st2, g.opairs);
     while (st2 > 2 && L2.total + 1024 > 227 * 1024) { --st2; L2 = lay2(st2, g.opairs); }
     if (!direct && !g.res_inplace && st2 < 5) {           // one output slab pair buys a stage
@@ -1294,7 +1334,7 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
         return 0;
       }
     }
-    g.stages = stages; g.opairs = opairs_1cta;     // fall through to the 1-CTA kernel with its own geometry
+    g.stages = stages; g.opairs = opairs_1cta; g.wide = 0;     // fall through to the 1-CTA kernel with its own geometry
   }
   static ups::PerDeviceOnce configured;
   if (configured.need()) {
