@@ -342,6 +342,23 @@ int upsnet_prep_image(const unsigned char *image_hwc, int h, int w, double scale
                       int pad_w, const double pixel_means[3], float *blob, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Instance-mask post-processing of the test loop on the device.
+ * replaces: upsnet_end2end_test.py:95-152 `im_post` (expand_boxes bbox/bbox_transform.py:365-381 -> int32 boxes,
+ *           (M+2)x(M+2) zero-padded mask -> cv2.resize -> > 0.5 -> paste into [H,W] -> pycocotools.mask.encode), run by the
+ *           reference on the host with numpy + cv2 + pycocotools for every detection.
+ * mask_probs [n,C,M,M] fp32 (M <= 28; the plane of cls_inds[d] is used when C > 1, plane 0 otherwise), boxes [n,4]
+ * (x1,y1,x2,y2 = pred_boxes[:,1:]), cls_inds int64 [n]; n_dev (optional device count <= n); image H <= 2048, W <= 2048.
+ * counts [n][cap] uint32: the UNCOMPRESSED COCO run lengths of detection d (column-major, starting with the zeros run,
+ * exactly maskApi.c rleEncode); run_len [n] their number (0 for d >= *n_dev); *overflow = 1 if some detection needs more
+ * than cap counts (run_len then holds the needed size).  The compressed `counts` string of the COCO dict is a pure
+ * function of these numbers (rleToString), applied on the host by upsnet_b200.operators.im_post.
+ * Workspace: upsnet_im_post_workspace_bytes(n, cap). */
+int upsnet_im_post_workspace_bytes(int n, int cap, size_t *bytes);
+int upsnet_im_post_rle(const float *mask_probs, int C, int M, const float *boxes, const int64_t *cls_inds, int n,
+                       const int *n_dev, int H, int W, uint32_t *counts, int cap, int *run_len, int *overflow,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Backward kernels of the custom operators (training configuration, BASELINE config #4).  fp32 NCHW, ONE image per call
  * for the deformable kernels (the reference loops over the batch: functions/deform_conv.py:84-104).
  *

@@ -389,3 +389,145 @@ class RefKernels:
         num = np.zeros(1, np.int32)
         self.L.ref_nms(keep, num, sorted_dets, n, thresh, device_id)
         return order[keep[:num[0]]].tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# Row f4: im_post (upsnet_end2end_test.py:95-152) -- mask paste + COCO RLE.  Plain numpy restatement.
+# The RLE codec is pycocotools' (cocoapi common/maskApi.c rleEncode / rleToString / rleFrString; the reference imports
+# `pycocotools.mask.encode` at upsnet_end2end_test.py:48 without pinning a version; the package is not in this image):
+# restated from its published algorithm -- "parity unpinned" for the codec itself, the paste semantics are pinned to the
+# reference's own im_post executed with real cv2 (tests/golden/make_reference_impost.py).
+# ---------------------------------------------------------------------------------------------
+def resize_linear(src, w, h):
+    """cv2.resize(src, (w, h)) for a float32 image, INTER_LINEAR, OpenCV's documented formula in un-fused float32
+    (SURVEY A.5): float64 scale, float32 source coordinate; columns clamp the tap and zero the fraction at both borders,
+    rows clamp the taps only; horizontal pass first."""
+    src = _f32(src)
+    sh, sw = src.shape
+
+    def coef(n_dst, n_src):
+        scale = np.float64(n_src) / np.float64(n_dst)
+        f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int32)
+        return s, (f - s.astype(np.float32)).astype(np.float32)
+    sx, fx = coef(w, sw)
+    lo, hi = sx < 0, sx >= sw - 1
+    sx[lo] = 0; fx[lo] = 0
+    sx[hi] = sw - 1; fx[hi] = 0
+    sx1 = np.minimum(sx + 1, sw - 1)
+    sy, fy = coef(h, sh)
+    y0, y1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    a0 = (np.float32(1) - fx).astype(np.float32)
+    hrow = (src[:, sx] * a0 + src[:, sx1] * fx).astype(np.float32)            # [sh, w]
+    b0 = (np.float32(1) - fy).astype(np.float32)[:, None]
+    return (hrow[y0] * b0 + hrow[y1] * fy[:, None]).astype(np.float32)
+
+
+def expand_boxes(boxes, scale):
+    """bbox/bbox_transform.py:365-381 on float32 boxes (the arithmetic stays float32, the result array is float64)."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    w_half = (boxes[:, 2] - boxes[:, 0]) * np.float32(.5)
+    h_half = (boxes[:, 3] - boxes[:, 1]) * np.float32(.5)
+    x_c = (boxes[:, 2] + boxes[:, 0]) * np.float32(.5)
+    y_c = (boxes[:, 3] + boxes[:, 1]) * np.float32(.5)
+    w_half = w_half * np.float32(scale)
+    h_half = h_half * np.float32(scale)
+    out = np.zeros(boxes.shape)
+    out[:, 0] = x_c - w_half; out[:, 2] = x_c + w_half
+    out[:, 1] = y_c - h_half; out[:, 3] = y_c + h_half
+    return out
+
+
+def im_post_masks(pred_boxes, pred_masks, cls_inds, im_h, im_w, resize="formula"):
+    """The [n, im_h, im_w] uint8 images im_post pastes (upsnet_end2end_test.py:100-139), detection order (not per class).
+    pred_boxes [n,4]; pred_masks [n,C,M,M] probabilities; cls_inds [n]."""
+    pred_masks = _f32(pred_masks)
+    n, C, M, _ = pred_masks.shape
+    ref = expand_boxes(pred_boxes, (M + 2.0) / M).astype(np.int32)
+    out = np.zeros((n, im_h, im_w), np.uint8)
+    padded = np.zeros((M + 2, M + 2), np.float32)
+    for i in range(n):
+        padded[1:-1, 1:-1] = pred_masks[i, int(cls_inds[i]) if C > 1 else 0]
+        rb = ref[i]
+        w = max(int(rb[2] - rb[0] + 1), 1); h = max(int(rb[3] - rb[1] + 1), 1)
+        if resize == "cv2":
+            import cv2
+            m = cv2.resize(padded, (w, h))
+        else:
+            m = resize_linear(padded, w, h)
+        m = np.array(m > 0.5, dtype=np.uint8)
+        x_0, x_1 = max(int(rb[0]), 0), min(int(rb[2]) + 1, im_w)
+        y_0, y_1 = max(int(rb[1]), 0), min(int(rb[3]) + 1, im_h)
+        if x_1 > x_0 and y_1 > y_0:
+            out[i, y_0:y_1, x_0:x_1] = m[(y_0 - rb[1]):(y_1 - rb[1]), (x_0 - rb[0]):(x_1 - rb[0])]
+    return out
+
+
+def rle_counts(mask):
+    """maskApi.c rleEncode: run lengths of the column-major (Fortran) flattening, starting with the zeros run."""
+    v = np.asarray(mask, np.uint8).flatten(order="F")
+    if v.size == 0:
+        return np.zeros(0, np.uint32)
+    change = np.flatnonzero(v[1:] != v[:-1]) + 1
+    edges = np.concatenate([[0], change, [v.size]])
+    cnts = np.diff(edges)
+    if v[0] != 0:
+        cnts = np.concatenate([[0], cnts])
+    return cnts.astype(np.uint32)
+
+
+def rle_to_string(cnts):
+    """maskApi.c rleToString: LEB128-like, 5 data bits per character, differences against the count two back."""
+    out = bytearray()
+    cnts = [int(c) for c in cnts]
+    for i, x in enumerate(cnts):
+        if i > 2:
+            x -= cnts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def rle_from_string(s):
+    """maskApi.c rleFrString (inverse of rle_to_string)."""
+    if isinstance(s, str):
+        s = s.encode()
+    cnts, p = [], 0
+    while p < len(s):
+        x, k, more = 0, 0, True
+        while more:
+            c = s[p] - 48
+            x |= (c & 0x1f) << (5 * k)
+            more = bool(c & 0x20)
+            p += 1; k += 1
+            if not more and (c & 0x10):
+                x |= -1 << (5 * k)
+        if len(cnts) > 2:
+            x += cnts[-2]
+        cnts.append(x)
+    return np.asarray(cnts, np.uint32)
+
+
+def rle_decode(cnts, h, w):
+    v = np.zeros(h * w, np.uint8)
+    p, val = 0, 0
+    for c in cnts:
+        c = int(c)
+        if val:
+            v[p:p + c] = 1
+        p += c; val ^= 1
+    return v.reshape((h, w), order="F")
+
+
+def mask_encode(mask):
+    """pycocotools.mask.encode for one [H,W] (or [H,W,1]) uint8 mask: {'size': [H,W], 'counts': bytes}."""
+    m = np.asarray(mask)
+    if m.ndim == 3:
+        m = m[:, :, 0]
+    return {"size": [int(m.shape[0]), int(m.shape[1])], "counts": rle_to_string(rle_counts(m))}

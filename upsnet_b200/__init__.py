@@ -5,7 +5,7 @@ from .operators import (DeformConv, DeformConvWithOffset, ModDeformConv, ModDefo
                         ModulatedDeformConv, RoIAlign, ROIAlign, RoIAlignFunction, FPNRoIAlign, PanopticHead,
                         MaskRemoval, SegTerm, MaskTerm, MaskMatching,
                         conv2d, linear, deform_conv, roi_align, fpn_roi_align, nms, nms_segmented, gpu_nms,
-                        gpu_nms_wrapper, panoptic_fuse, set_precision, unified_pan_result, prep_image)
+                        gpu_nms_wrapper, panoptic_fuse, set_precision, unified_pan_result, prep_image, im_post, im_post_rle)
 
 from .pipeline import PipelinedEngine  # noqa: F401,E402
 
@@ -13,4 +13,4 @@ __all__ = ["PipelinedEngine", "DeformConv", "DeformConvWithOffset", "ModDeformCo
            "ModulatedDeformConv", "RoIAlign", "ROIAlign", "RoIAlignFunction", "FPNRoIAlign", "PanopticHead",
            "MaskRemoval", "SegTerm", "MaskTerm", "MaskMatching",
            "conv2d", "linear", "deform_conv", "roi_align", "fpn_roi_align", "nms", "nms_segmented", "gpu_nms",
-           "gpu_nms_wrapper", "panoptic_fuse", "set_precision", "unified_pan_result", "prep_image"]
+           "gpu_nms_wrapper", "panoptic_fuse", "set_precision", "unified_pan_result", "prep_image", "im_post", "im_post_rle"]

@@ -82,6 +82,8 @@ def lib():
         L.upsnet_fcn_score_fuse.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
         L.upsnet_unified_pan_workspace_bytes.argtypes = [i, C.POINTER(sz)]
         L.upsnet_unified_pan_result.argtypes = [vp, vp, vp, i, vp, i, i, i, i, i, vp, vp, vp, sz, vp]
+        L.upsnet_im_post_workspace_bytes.argtypes = [i, i, C.POINTER(sz)]
+        L.upsnet_im_post_rle.argtypes = [vp, i, i, vp, vp, i, vp, i, i, vp, i, vp, vp, vp, sz, vp]
         L.upsnet_prep_image.argtypes = [vp, i, i, d, i, i, i, i, C.POINTER(d), vp, vp]
         _lib = L
     return _lib
@@ -96,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "upsnet_stem_packed_weight_bytes", "upsnet_stem_pack_weight", "upsnet_stem_forward",
     "upsnet_dcn_im2col", "upsnet_dcn_col2im", "upsnet_dcn_col2im_coord", "upsnet_roi_align_backward",
     "upsnet_dcn_packed_weight_bytes", "upsnet_dcn_pack_weight", "upsnet_dcn_pair_forward", "upsnet_conv3x3_pair_forward",
-    "upsnet_fcn_score_fuse", "upsnet_unified_pan_workspace_bytes", "upsnet_unified_pan_result", "upsnet_prep_image",
+    "upsnet_fcn_score_fuse", "upsnet_unified_pan_workspace_bytes", "upsnet_unified_pan_result", "upsnet_prep_image", "upsnet_im_post_workspace_bytes", "upsnet_im_post_rle",
 ]
 
 

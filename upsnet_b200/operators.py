@@ -1218,3 +1218,74 @@ def prep_image(image_hwc_u8, pixel_means, scale=1.0, stride=32):
     with torch.cuda.device(im.device), _Timed("prep_image", 1, {"bytes": 3.0 * h * w + 12.0 * Hp * Wp}, im.device):
         check(lib().upsnet_prep_image(ptr(im), h, w, float(scale), ho, wo, Hp, Wp, pm, ptr(blob), stream_ptr(im.device)), "prep_image")
     return blob, (ho, wo)
+
+
+# ------------------------------------------------------------------------------------------------
+# Row f4: im_post (upsnet_end2end_test.py:95-152) -- mask paste + COCO RLE
+# ------------------------------------------------------------------------------------------------
+_impost_ws = _Workspace()
+
+
+def rle_to_string(cnts):
+    """pycocotools maskApi.c rleToString: the compressed `counts` bytes of a COCO RLE from its run lengths (host side; a
+    pure function of the numbers the device kernel produces)."""
+    out = bytearray()
+    cnts = [int(c) for c in cnts]
+    for i, x in enumerate(cnts):
+        if i > 2:
+            x -= cnts[i - 2]
+        more = True
+        while more:
+            c = x & 0x1f
+            x >>= 5
+            more = (x != -1) if (c & 0x10) else (x != 0)
+            if more:
+                c |= 0x20
+            out.append(c + 48)
+    return bytes(out)
+
+
+def im_post_rle(pred_boxes, pred_masks, cls_inds, im_h, im_w, n_dev=None, cap=None):
+    """upsnet_im_post_rle: the COCO run lengths of every detection's pasted mask, computed on the device without
+    materialising the [H,W] images.  pred_boxes [n,4] or [n,5] (batch index first, like the model's `pred_boxes`),
+    pred_masks [n,C,M,M] probabilities, cls_inds [n].  Returns (counts uint32 [n,cap] as int64-viewable tensor, run_len
+    int32 [n]) on the device; raises if a detection needs more than `cap` counts (default 16 per image column)."""
+    require_cuda(pred_boxes, pred_masks, cls_inds)
+    boxes = f32c(pred_boxes[:, 1:] if pred_boxes.shape[1] == 5 else pred_boxes)
+    masks = f32c(pred_masks)
+    n, Cc, M, M2 = masks.shape
+    assert M == M2 and boxes.shape == (n, 4) and cls_inds.numel() == n
+    cls = cls_inds.to(torch.int64).contiguous()
+    dev = masks.device
+    cap = int(cap) if cap else 16 * int(im_w) + 64
+    nb = C.c_size_t(0)
+    check(lib().upsnet_im_post_workspace_bytes(n, cap, C.byref(nb)), "im_post_workspace_bytes")
+    ws = _impost_ws.get(dev, nb.value)
+    counts = torch.empty((max(n, 1), cap), dtype=torch.int32, device=dev)      # uint32 payload
+    run_len = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
+    ovf = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _Timed("im_post", 1, {"bytes": 4.0 * masks.numel()}, dev):
+        check(lib().upsnet_im_post_rle(ptr(masks), Cc, M, ptr(boxes), ptr(cls), n, ptr(n_dev), int(im_h), int(im_w), ptr(counts),
+                                       cap, ptr(run_len), ptr(ovf), ptr(ws), ws.numel(), stream_ptr(dev)), "im_post_rle")
+    return counts[:n], run_len[:n], ovf
+
+
+def im_post(boxes_all, masks_all, scores, pred_boxes, pred_masks, cls_inds, num_classes, im_info):
+    """Drop-in for upsnet_end2end_test.py:95-152 `im_post` (same arguments, same side effects on boxes_all / masks_all):
+    device tensors in, per-class lists of [x1,y1,x2,y2,score] arrays and COCO RLE dicts out.  One kernel launch and one
+    D2H copy of the run lengths per image instead of n x (cv2.resize + paste + pycocotools encode) on the host."""
+    H, W = int(im_info[0]), int(im_info[1])
+    counts, run_len, ovf = im_post_rle(pred_boxes, pred_masks, cls_inds, H, W)
+    if int(ovf.item()):
+        raise UpsnetError("im_post: a mask needs more RLE counts than the buffer holds (pass a larger cap)")
+    rl = run_len.cpu().numpy()
+    cn = counts.cpu().numpy().view(np.uint32)
+    boxes_np = (pred_boxes[:, 1:] if pred_boxes.shape[1] == 5 else pred_boxes).float().cpu().numpy()
+    sc = scores.float().cpu().numpy().reshape(-1, 1)
+    ci = cls_inds.cpu().numpy()
+    for idx in range(1, num_classes):
+        sel = np.flatnonzero(ci == idx)
+        cls_boxes = np.hstack([boxes_np[sel], sc[sel]]) if sel.size else np.zeros((0, 5), np.float32)
+        segms = [{"size": [H, W], "counts": rle_to_string(cn[d, :rl[d]]).decode()} for d in sel]
+        boxes_all[idx].append(cls_boxes)
+        masks_all[idx].append(segms)
