@@ -175,8 +175,10 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const long long m_tiles = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
   const long long num_tiles = m_tiles * g.n_tiles;
   const uint32_t box_bytes = (uint32_t)(g.bw * g.bh * g.bn) * 128u;
+  // wide-B (pair mode, N tile <= 64, per-tap boxes / stem): B operand = the contiguous [W_hi ; W_lo] tile of the stage (N = 2 BN)
+  const uint32_t acc_cols = (uint32_t)(g.wide ? 2 * g.BN : g.BN);      // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * g.BN) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
   if (warp == TM_WARP_MMA) {
     if (lane == 0) {
@@ -317,7 +319,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   } else if (warp == TM_WARP_MMA) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, g.BN);
+      const uint32_t idesc = umma_idesc(128, g.BN), idesc_w = umma_idesc(128, 2 * g.BN);
       // smem descriptors: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B), the low word carries
       // (address >> 4) and is advanced by running adds -- the issue loop of this single thread paces every tile
       // whose MMAs are short (N <= 128), so it is kept to a handful of instructions per k-block.
@@ -329,7 +331,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const uint32_t buf = ti_local & 1u, use = ti_local >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * (uint32_t)g.BN;
+        const uint32_t tmem_d = tmem_base + buf * acc_cols;
         uint32_t acc = 0u;
         if (g.halo) {
           // A descriptors: 8-row groups = 8 consecutive patch pixels of one patch row, group stride = one patch row
@@ -403,7 +405,13 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {       // 16 bf16 = 32 bytes = 2 descriptor units inside the swizzle span
             if (g.dbg == 3 || (g.dbg == 2 && k)) continue;
-            const uint32_t td = (g.dbg == 1 && (k & 1)) ? (tmem_base + (buf ^ 1u) * (uint32_t)g.BN) : tmem_d;
+            const uint32_t td = (g.dbg == 1 && (k & 1)) ? (tmem_base + (buf ^ 1u) * acc_cols) : tmem_d;
+            if (g.wide) {    // two instructions per K slice: hi * [hi ; lo] -> columns [0, 2 BN), lo * hi -> columns [0, BN)
+              umma_bf16_lohi(td, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc_w, acc);
+              umma_bf16_lohi(td, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1u);
+              acc = 1u;
+              continue;
+            }
             if (g.x3) {      // (hi + lo) * (hi + lo) without the lo * lo term: relative error ~2^-16
               umma_bf16_lohi(td, a_lo + ah16 + 2 * k, b_lo + 2 * k, desc_hi, idesc, acc);
               umma_bf16_lohi(td, a_lo + 2 * k, b_lo + bh16 + 2 * k, desc_hi, idesc, 1u);
@@ -487,7 +495,7 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       mbar_wait(bar_tfull + 8 * buf, use & 1u);
       tc_fence_after();
       if (g.has_res) mbar_wait(bar_rfull + 8 * buf, use & 1u);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)g.BN;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols;
       if (g.direct) {
         // thread = accumulator row = one output pixel of the box; the two halves split the columns
         const int wq = row % g.bw, hq = (row / g.bw) % g.bh, nq = row / (g.bw * g.bh);
@@ -498,7 +506,16 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int cbeg = half * (g.BN / 2), cend = cbeg + g.BN / 2;
         for (int cb = cbeg; cb < cend; cb += 16) {
           uint32_t v[16];
-          tmem_ld16(trow + (uint32_t)cb, v);         // warp-collective
+          if (g.wide) {       // hi*hi + lo*hi in column cb, hi*lo in column BN + cb
+            uint32_t v2[16];
+            tmem_ld16_issue(trow + (uint32_t)cb, v);
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + cb), v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+          } else {
+            tmem_ld16(trow + (uint32_t)cb, v);         // warp-collective
+          }
           const int co0 = n0 + cb;
           if (!ok || co0 >= g.Cout) continue;
 #pragma unroll
@@ -544,6 +561,13 @@ igemm_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           float o[32];
 #pragma unroll
           for (int e = 0; e < 16; ++e) { o[e] = __uint_as_float(v0[e]); o[16 + e] = __uint_as_float(v1[e]); }
+          if (g.wide) {       // + the hi*lo column group
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + u * 32), v0);
+            tmem_ld16_issue(trow + (uint32_t)(g.BN + u * 32 + 16), v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { o[e] += __uint_as_float(v0[e]); o[16 + e] += __uint_as_float(v1[e]); }
+          }
           if (g.bias) {
             const float4* bp = reinterpret_cast<const float4*>(g.bias + n0 + u * 32);
 #pragma unroll
@@ -1336,6 +1360,11 @@ int launch_igemm_tma(const TcParams& p, const void* packed, cudaStream_t stream)
     }
     g.stages = stages; g.opairs = opairs_1cta; g.wide = 0;     // fall through to the 1-CTA kernel with its own geometry
   }
+  {   // 1-CTA kernel, pair stream, N tile <= 64, per-tap boxes (incl. the in-place +res layers): two MMAs per K slice
+    static int wide1_env = -1;
+    if (wide1_env < 0) { const char* e = getenv("UPSNET_TMA_WIDE"); wide1_env = e ? atoi(e) : 1; }
+    g.wide = (wide1_env > 0 && pair && BN <= 64 && !g.halo && !g.wres) ? 1 : 0;
+  }
   static ups::PerDeviceOnce configured;
   if (configured.need()) {
     UPS_CUDA(cudaFuncSetAttribute(igemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1458,6 +1487,10 @@ extern "C" int upsnet_stem_forward(const float* x, const void* packed_w, const f
   g.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   if (pair && g.BN > 128) g.BN = 128;
   g.n_tiles = Cout / g.BN;
+  {   // pair stem, N tile 64: two MMAs per K slice over [W_hi ; W_lo] (see TmaGeom::wide)
+    const char* e = getenv("UPSNET_TMA_WIDE");
+    g.wide = (pair && g.BN <= 64 && (!e || atoi(e) > 0)) ? 1 : 0;
+  }
   int stages = TM_MAX_STAGES;
   TmaSmem L = tma_smem_layout(g.BN, stages, false, 0, 0, false, pair, false, false, g.opairs);
   while (stages > 2 && L.total + 1024 > 227 * 1024) { --stages; L = tma_smem_layout(g.BN, stages, false, 0, 0, false, pair, false, false, g.opairs); }
