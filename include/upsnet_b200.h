@@ -306,7 +306,9 @@ int upsnet_maskroi_prepare(const float *rois, const unsigned char *roi_valid, co
 /* upsnet_maskroi_finish: NMS survivors (class-major) -> keep scores >= the top_n-th largest -> `cap` output
  * slots (score, (0,x1,y1,x2,y2), class) + device count; no survivor -> one dummy detection (score 1, zero box,
  * class 0).  replaces: operators/modules/mask_roi.py:96-139.  keep/keep_cnt/seg_offsets as produced by
- * upsnet_nms_segmented on bx; nseg <= 128. */
+ * upsnet_nms_segmented on bx; nseg <= 128.  n_out int32 [2]: [0] = number of detections, [1] = truncation flags (the
+ * reference keeps every survivor and every box tied at the top-n threshold): bit 0 = more NMS survivors than the 4096
+ * candidate slots, bit 1 = more boxes at / above the threshold than `cap` output slots. */
 int upsnet_maskroi_finish(const int *keep, const int *keep_cnt, const int *seg_offsets, const float *sc,
                           const int *cls, const float *bx, int nseg, int max_seg_len, int top_n, int cap,
                           float *out_sc, float *out_bx, long long *out_cls, int *n_out, void *stream);

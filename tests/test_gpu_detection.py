@@ -107,3 +107,29 @@ def test_rpn_topk_matches_stable_sort(dev, quant):
             assert torch.equal(idx[o:o + k], want_i[:k])
             assert torch.equal(sc[o:o + k], want_s[:k])
             o += k
+
+
+def test_maskroi_finish_reports_truncation(dev):
+    """the fixed-size MaskROI buffers must not drop detections silently.  n_out[1] of upsnet_maskroi_finish:
+    bit 1 = more boxes tied at / above the top-n threshold than output slots, bit 0 = more NMS survivors than the 4096
+    candidate slots (the reference keeps them all, mask_roi.py:96-121)."""
+    from upsnet_b200 import operators as ops
+    def run(nseg, M, scores, top_n, cap):
+        n = nseg * M
+        keep = torch.arange(M, dtype=torch.int32, device=dev).repeat(nseg, 1).contiguous()
+        cnt = torch.full((nseg,), M, dtype=torch.int32, device=dev)
+        offs = (torch.arange(nseg + 1, dtype=torch.int32, device=dev) * M).contiguous()
+        sc = scores.to(dev).float().contiguous()
+        cls = torch.ones(n, dtype=torch.int32, device=dev)
+        bx = torch.rand(n, 4, device=dev)
+        o_sc, o_bx, o_cls, n_out, flags = ops.maskroi_finish(keep, cnt, offs, sc, cls, bx, top_n, cap)
+        return int(n_out.item()), int(flags.item()), o_sc.cpu()
+    # 200 boxes with the same score: the tie at the threshold (all 200) does not fit 128 slots
+    n, f, sc = run(1, 200, torch.full((200,), 0.9), 100, 128)
+    assert n == 128 and f == 2 and bool((sc == 0.9).all())
+    # distinct scores: exactly top_n survive, nothing dropped
+    n, f, sc = run(1, 200, torch.linspace(0.1, 0.9, 200), 100, 128)
+    assert n == 100 and f == 0
+    # 5 x 1000 survivors > 4096 candidate slots
+    n, f, sc = run(5, 1000, torch.rand(5000), 100, 128)
+    assert (f & 1) == 1

@@ -279,7 +279,13 @@ maskroi_finish_kernel(const int* __restrict__ keep, const int* __restrict__ cnt,
 #pragma unroll
     for (int e = 0; e < 5; ++e) out_bx[(size_t)sidx * 5 + e] = 0.f;
   }
-  if (tid == 0) *n_out = n_sel == 0 ? 1 : n_sel;
+  if (tid == 0) {
+    n_out[0] = n_sel == 0 ? 1 : n_sel;
+    // truncation flags (the reference keeps every survivor / every box tied at the top-n threshold, mask_roi.py:96-121):
+    // bit 0: more NMS survivors than the kAllCap candidate slots (the tail of the class-major list was not considered),
+    // bit 1: more boxes at or above the top-n threshold than the `cap` output slots (the surplus of the tie was dropped)
+    n_out[1] = (seg_base[nseg] > all_cap ? 1 : 0) | (total > cap ? 2 : 0);
+  }
 }
 
 }  // namespace ups

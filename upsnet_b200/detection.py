@@ -332,6 +332,7 @@ class StaticMaskROI(MaskROI):
     def __init__(self, *a, slack=28, **kw):
         super().__init__(*a, **kw)
         self.cap = self.top_n + slack
+        self.last_flags = None        # device int32 scalar of the last call: != 0 when the fixed-size buffers dropped detections
         self._const = {}
 
     def _consts(self, R, dev):
@@ -356,7 +357,8 @@ class StaticMaskROI(MaskROI):
                                                      self.score_thresh, self.weights, float(im_info[0]), float(im_info[1]))
             keep, cnt = (_ops.nms_segmented(bx, offs, M, self.nms_thresh, side=True) if side
                          else nms_segmented(bx, offs, M, self.nms_thresh))
-            return _ops.maskroi_finish(keep, cnt, offs, sc, cls, bx, self.top_n, self.cap)
+            o_sc, o_bx, o_cls, n_out, self.last_flags = _ops.maskroi_finish(keep, cnt, offs, sc, cls, bx, self.top_n, self.cap)
+            return o_sc, o_bx, o_cls, n_out
         cls_flat, ridx_flat = self._consts(R, dev)
         proposal = clip_boxes(bbox_transform(rois[:, 1:], bbox_delta, self.weights), float(im_info[0]),
                               float(im_info[1])).reshape(R, C, 4)
@@ -380,12 +382,15 @@ class StaticMaskROI(MaskROI):
         # 1st compaction: class-major, NMS order inside (mask_roi.py:96-104)
         all_cap = min(nseg * M, 4096)
         (kidx,), nk = _compact([gidx], valid, all_cap, dev)
+        n_surv = valid.sum()
         live = torch.arange(all_cap, device=dev) < nk
         ks = torch.where(live, sc[kidx], torch.full((all_cap,), NEG_INF, device=dev))
         # global top-n: keep scores >= the top_n-th largest (mask_roi.py:106-121); fewer than top_n => keep all
         kth = torch.topk(ks, min(self.top_n, all_cap), sorted=True)[0][-1] if self.top_n > 0 else NEG_INF
         sel = live & (ks >= kth)
         (oidx,), n_out = _compact([kidx], sel, self.cap, dev)
+        # truncation flags like upsnet_maskroi_finish: bit 0 survivors beyond the candidate slots, bit 1 tie beyond the slack
+        self.last_flags = ((n_surv > all_cap).to(torch.int32) + 2 * (sel.sum() > self.cap).to(torch.int32)).to(torch.int32)
         slot_live = torch.arange(self.cap, device=dev) < n_out
         out_sc = torch.where(slot_live, sc[oidx], torch.zeros(self.cap, device=dev))
         out_bx = torch.cat([torch.zeros((self.cap, 1), device=dev), bx[oidx]], 1) * slot_live[:, None]

@@ -687,7 +687,7 @@ class resnet_upsnet(nn.Module):
                 done2 = torch.cuda.Event()
                 done2.record(side2)
             if not torch.cuda.is_current_stream_capturing():
-                for t_ in (s2, b2, c2, n2):
+                for t_ in (s2, b2, c2, n2, self.mask_roi_panoptic_static.last_flags):
                     t_.record_stream(cur)
         s1, b1, c1, n1 = self.mask_roi_static(rois, roi_valid, bbox_pred, cls_prob, im_info)
         if fork:
@@ -708,9 +708,12 @@ class resnet_upsnet(nn.Module):
                                                  self.panoptic_head.num_stuff, self.panoptic_head.fraction_threshold,
                                                  want_sem=True, n_dev=n2.reshape(1), up4=fcn_score is not None)
         counts = torch.cat([n1.reshape(1).to(torch.int32), n2.reshape(1).to(torch.int32), k.reshape(1)])
+        # != 0 when a static MaskROI buffer dropped detections the reference would have kept (see StaticMaskROI.last_flags)
+        trunc = torch.stack([self.mask_roi_static.last_flags.reshape(()).to(torch.int32),
+                             self.mask_roi_panoptic_static.last_flags.reshape(()).to(torch.int32)])
         out = {"cls_probs": s1, "pred_boxes": b1, "mask_probs": mask_prob, "cls_inds": c1, "fcn_outputs": sem,
                "panoptic_outputs": labels, "p_scores": s2, "p_cls": c2, "p_boxes": b2, "p_mask_score": mask_score,
-               "keep": keep, "counts": counts, "fcn_output": fcn_output}
+               "keep": keep, "counts": counts, "trunc_flags": trunc, "fcn_output": fcn_output}
         if getattr(self, "keep_intermediates", False):   # parity tests against the literal oracle: every stage boundary
             out["dbg"] = {"fpn": [f.float().contiguous() for f in (p2, p3, p4, p5, p6)],
                           "rpn_cls_prob": [t_.float() for t_ in rpn_cls_prob], "rpn_bbox_pred": [t_.float() for t_ in rpn_bbox_pred],

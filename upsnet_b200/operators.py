@@ -789,19 +789,21 @@ def maskroi_prepare(rois, roi_valid, bbox_delta, cls_prob, class_agnostic, score
 
 
 def maskroi_finish(keep, cnt, offs, sc, cls, bx, top_n, cap):
-    """Fused MaskROI back half -> (scores [cap], boxes [cap,5], cls int64 [cap], n int32 device scalar)."""
+    """Fused MaskROI back half -> (scores [cap], boxes [cap,5], cls int64 [cap], n int32 device scalar, flags int32 device
+    scalar).  flags != 0 means the static buffers truncated what the reference would have kept: bit 0 = more NMS survivors
+    than candidate slots, bit 1 = a tie at the top-n threshold larger than the output slack."""
     require_cuda(keep, cnt, offs, sc, cls, bx)
     dev = sc.device
     nseg, M = keep.shape
     out_sc = torch.empty((cap,), dtype=torch.float32, device=dev)
     out_bx = torch.empty((cap, 5), dtype=torch.float32, device=dev)
     out_cls = torch.empty((cap,), dtype=torch.int64, device=dev)
-    n_out = torch.empty((), dtype=torch.int32, device=dev)
+    n_out = torch.empty((2,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _Timed("maskroi", 1, {"bytes": 32.0 * cap}, dev):
         check(lib().upsnet_maskroi_finish(ptr(keep), ptr(cnt), ptr(offs), ptr(sc), ptr(cls), ptr(bx), nseg, M, int(top_n),
                                           int(cap), ptr(out_sc), ptr(out_bx), ptr(out_cls), ptr(n_out), stream_ptr(dev)),
               "maskroi_finish")
-    return out_sc, out_bx, out_cls, n_out
+    return out_sc, out_bx, out_cls, n_out[0], n_out[1]
 
 
 def nms(boxes, scores, thresh):

@@ -18,7 +18,7 @@ import torch
 
 class PipelinedEngine:
     RESULT_KEYS = ("panoptic_outputs", "fcn_outputs", "pred_boxes", "cls_probs", "cls_inds", "counts", "keep", "p_cls",
-                   "p_scores")
+                   "p_scores", "trunc_flags")
 
     PIXEL_MEANS = (102.9801, 115.9465, 122.7717)     # config.network.pixel_means (BGR, caffe models)
 
@@ -129,6 +129,8 @@ class PipelinedEngine:
         res = {"cls_probs": h["cls_probs"][:n1], "pred_boxes": h["pred_boxes"][:n1], "cls_inds": h["cls_inds"][:n1],
                "fcn_outputs": h["fcn_outputs"], "panoptic_outputs": h["panoptic_outputs"],
                "panoptic_cls_inds": h["p_cls"][:n2][keep], "panoptic_cls_probs": h["p_scores"][:n2][keep]}
+        # [detections, panoptic candidates]: != 0 when the fixed-size MaskROI buffers dropped boxes the reference keeps
+        res["truncated"] = [int(v) for v in h["trunc_flags"].tolist()]
         if "mask_probs" in h:
             res["mask_probs"] = h["mask_probs"][:n1]
         if "pan_2ch" in h:
