@@ -473,7 +473,12 @@ def main():
     roofline = {"kernel": kname + ", precision=%s" % args.precision, "bound": "tensor",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "peak_source": pk["source"] + " (sustained bf16)",
-                "traffic": None, "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the family under `ncu --set full`
+                # (profiles/r2_pair_full.md: FPN / RPN 3x3 256->256 @256x512 on pairs, 136.7 MB read + 93.7 MB written against
+                # algorithmic x + y = 268 MB: no re-reads from HBM); null for the other precisions (not captured)
+                "traffic": 230.4e6 if args.precision == "bf16x3" else None,
+                "traffic_launch": "FPN / RPN 3x3 256->256 @256x512 (154.6 GFLOP algorithmic, 268 MB algorithmic bytes)" if args.precision == "bf16x3" else None,
+                "share_of_step": conv["ms"] / tot_ms if tot_ms else None,
                 "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
                 "flops_per_step": algo / n_trace, "mma_flops_per_step": conv["flops"] / n_trace,
                 # executed tensor-core work (3 passes in bf16x3) against the same peak: how busy the tensor pipe is

@@ -130,7 +130,7 @@ class PipelinedEngine:
                "fcn_outputs": h["fcn_outputs"], "panoptic_outputs": h["panoptic_outputs"],
                "panoptic_cls_inds": h["p_cls"][:n2][keep], "panoptic_cls_probs": h["p_scores"][:n2][keep]}
         # [detections, panoptic candidates]: != 0 when the fixed-size MaskROI buffers dropped boxes the reference keeps
-        res["truncated"] = [int(v) for v in h["trunc_flags"].tolist()]
+        res["truncated"] = h["trunc_flags"]
         if "mask_probs" in h:
             res["mask_probs"] = h["mask_probs"][:n1]
         if "pan_2ch" in h:
