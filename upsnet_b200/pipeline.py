@@ -23,7 +23,7 @@ class PipelinedEngine:
     PIXEL_MEANS = (102.9801, 115.9465, 122.7717)     # config.network.pixel_means (BGR, caffe models)
 
     def __init__(self, model, im_info, depth=2, with_masks=False, with_unified=False, stuff_area_limit=4 * 64 * 64,
-                 pixel_means=None, im_scale=1.0, lanes=None):
+                 pixel_means=None, im_scale=1.0, lanes=None, label_maps=True):
         """with_unified: also run get_unified_pan_result on the device (base_dataset.py:332-371) and return its uint8
         [H,W,3] map as 'pan_2ch'.  submit() also accepts the RAW uint8 [h,w,3] BGR image (pinned): mean subtraction,
         resize by im_scale and padding (prep_im_for_blob / im_list_to_blob) then run on the device after a 4x smaller H2D."""
@@ -33,6 +33,9 @@ class PipelinedEngine:
         self.lanes = depth if lanes is None else max(1, min(int(lanes), depth))
         self.im_info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)[0]
         self.keys = self.RESULT_KEYS + (("mask_probs",) if with_masks else ()) + (("pan_2ch",) if with_unified else ())
+        if not label_maps:      # serving format: the unified 2-channel map replaces the two int64 label maps on the way out
+            assert with_unified, "label_maps=False needs with_unified=True (pan_2ch carries class and instance id)"
+            self.keys = tuple(k for k in self.keys if k not in ("panoptic_outputs", "fcn_outputs"))
         self.with_unified, self.stuff_area_limit = with_unified, stuff_area_limit
         self.pixel_means, self.im_scale = (pixel_means or self.PIXEL_MEANS), float(im_scale)
         self.dev = None
@@ -127,8 +130,9 @@ class PipelinedEngine:
         n1, n2, k = (int(v) for v in h["counts"].tolist())
         keep = h["keep"][:k]
         res = {"cls_probs": h["cls_probs"][:n1], "pred_boxes": h["pred_boxes"][:n1], "cls_inds": h["cls_inds"][:n1],
-               "fcn_outputs": h["fcn_outputs"], "panoptic_outputs": h["panoptic_outputs"],
                "panoptic_cls_inds": h["p_cls"][:n2][keep], "panoptic_cls_probs": h["p_scores"][:n2][keep]}
+        if "panoptic_outputs" in h:
+            res["fcn_outputs"], res["panoptic_outputs"] = h["fcn_outputs"], h["panoptic_outputs"]
         # [detections, panoptic candidates]: != 0 when the fixed-size MaskROI buffers dropped boxes the reference keeps
         res["truncated"] = h["trunc_flags"]
         if "mask_probs" in h:
