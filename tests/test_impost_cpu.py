@@ -67,3 +67,40 @@ def test_rle_known_answers():
         m = (rng.uniform(0, 1, (h, w)) > rng.uniform(0.2, 0.8)).astype(np.uint8)
         c = O.rle_counts(m)
         assert np.array_equal(O.rle_decode(O.rle_from_string(O.rle_to_string(c)), h, w), m)
+
+
+def test_operators_rle_to_string_matches_oracle_codec():
+    """The host half of operators.im_post (rleToString over the device's run lengths) is the same codec as the oracle's."""
+    from upsnet_b200 import operators as ops
+    rng = np.random.default_rng(4)
+    for _ in range(30):
+        h, w = int(rng.integers(1, 60)), int(rng.integers(1, 60))
+        m = (rng.uniform(0, 1, (h, w)) > rng.uniform(0.1, 0.9)).astype(np.uint8)
+        c = O.rle_counts(m)
+        assert ops.rle_to_string(c) == O.rle_to_string(c)
+    assert ops.rle_to_string([0, 15]) == b"0?" and ops.rle_to_string([40]) == b"X1"
+
+
+def test_workspaces_are_per_engine_lane():
+    """operators._Workspace: one scratch buffer per (device, engine lane) -- two lanes running concurrently must never share
+    scratch (model._run_static sets WS_SLOT around a lane's work); an outgrown buffer is retired, not freed (captured graphs
+    keep its pointer)."""
+    import torch
+    from upsnet_b200 import operators as ops
+    ws = ops._Workspace()
+    dev = torch.device("cpu")
+    was = ops.WS_SLOT["i"]
+    try:
+        ops.WS_SLOT["i"] = 0
+        a = ws.get(dev, 100)
+        assert ws.get(dev, 50) is a
+        ops.WS_SLOT["i"] = 1
+        b = ws.get(dev, 100)
+        assert b is not a and b.data_ptr() != a.data_ptr()
+        ops.WS_SLOT["i"] = 0
+        a2 = ws.get(dev, 1000)
+        assert a2 is not a and a2.numel() >= 1000 and any(r is a for r in ws.retired)
+        ops.WS_SLOT["i"] = 1
+        assert ws.get(dev, 10) is b
+    finally:
+        ops.WS_SLOT["i"] = was
