@@ -131,11 +131,14 @@ pan_prep_kernel(const float* __restrict__ boxes, const float* __restrict__ prob,
                 PanWorkspace ws) {
   const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;   // device-side instance count (static-shape engine)
   if (threadIdx.x == 0) ws.meta[2] = n;
+  __shared__ float s_prob[kMaxList];            // n <= kMaxList (checked by the entry point): the rank loop reads shared memory
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_prob[i] = prob[i];
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float p = prob[i];
+    const float p = s_prob[i];
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const float q = prob[j];
+      const float q = s_prob[j];
       rank += (q > p) || (q == p && j < i);
     }
     ws.order[rank] = i;
@@ -337,6 +340,8 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
   // what the serial version did -- popc(window & occupied), the float64 ratio test, occupied |= window -- with group-local
   // barriers.  Disjoint windows share no occupancy word, so concurrent groups never write the same word.  Decisions are
   // identical to the serial order; per-instance latency is unchanged, independent instances overlap.
+  // (measured and rejected: one warp per instance -- 32 in flight instead of 8 -- is 4x slower, 191 vs 53 us at n = 100: the
+  // item loops of an instance are a chain of L2 round trips per thread, so fewer threads per instance lengthen every link)
   constexpr int kGroup = 128, kGroups = 1024 / kGroup;
   __shared__ unsigned int s_part[kGroups][kGroup / 32];
   const int grp = threadIdx.x / kGroup, gt = threadIdx.x % kGroup, gw = gt >> 5;
@@ -396,26 +401,39 @@ pan_decide_kernel(int n_max, const int* __restrict__ n_dev, int H, int W, double
   }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(1024)
 pan_compact_kernel(int n_max, const int* __restrict__ n_dev, PanWorkspace ws, int64_t* __restrict__ keep_out,
                    int* __restrict__ k_out) {
+  __shared__ int s_wcnt[32];
+  __shared__ int s_base;
   const int n = n_dev ? max(min(*n_dev, n_max), 1) : n_max;
-  const int lane = threadIdx.x;
-  int k = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int r = base + lane;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {          // ordered (rank order) compaction, 1024 ranks per step
+    const int r = base + threadIdx.x;
     const bool kept = r < n && ws.kept_flag[r] != 0;
     const unsigned int m = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w2 = 0; w2 < warp; ++w2) off += s_wcnt[w2];
     if (kept) {
-      const int pos = k + __popc(m & ((1u << lane) - 1u));
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
       const int i = ws.order[r];
       ws.kept_list[pos] = i;
       keep_out[pos] = i;
     }
-    k += __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w2 = 0; w2 < 32; ++w2) tot += s_wcnt[w2];
+      s_base += tot;
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    int zero_mask = 0;
+  if (threadIdx.x == 0) {
+    int k = s_base, zero_mask = 0;
     if (k == 0) {  // mask_removal.py:89-92 (and :55-57): keep=[0] with an all-zero mask plane
       ws.kept_list[0] = 0; keep_out[0] = 0; k = 1; zero_mask = 1;
     }
@@ -658,7 +676,7 @@ extern "C" int upsnet_mask_removal(const float* boxes, const float* cls_prob, co
     pan_decide_kernel<<<num_thing, 1024, (size_t)n * 32, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
-  pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
+  pan_compact_kernel<<<1, 1024, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   if (mask_energy) {
     dim3 grid((unsigned)min((size_t)kNumSMs * 8, ((size_t)H * W + 255) / 256), (unsigned)n);
@@ -721,7 +739,7 @@ static int panoptic_head_impl(const float* fcn, bool up4, int S, int H, int W, c
     pan_decide_kernel<<<num_thing, 1024, (size_t)n * 32, st>>>(n, n_dev, H, W, fraction_threshold, rq, ws);
     UPS_CHECK_LAUNCH();
   }
-  pan_compact_kernel<<<1, 32, 0, st>>>(n, n_dev, ws, keep_out, k_out);
+  pan_compact_kernel<<<1, 1024, 0, st>>>(n, n_dev, ws, keep_out, k_out);
   UPS_CHECK_LAUNCH();
   dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH));
   if (up4) pan_fuse_kernel<true><<<grid, kFuseThreads, 0, st>>>(fcn, S, H, W, num_stuff, mask_logit, ws, labels, sem_labels);
