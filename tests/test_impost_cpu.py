@@ -104,3 +104,21 @@ def test_workspaces_are_per_engine_lane():
         assert ws.get(dev, 10) is b
     finally:
         ops.WS_SLOT["i"] = was
+
+
+def test_workspace_lane_is_thread_local():
+    import threading
+    from upsnet_b200 import operators as ops
+    seen = {}
+
+    def worker():
+        seen["initial"] = ops.WS_SLOT["i"]
+        ops.WS_SLOT["i"] = 3
+        seen["set"] = ops.WS_SLOT["i"]
+    was = ops.WS_SLOT["i"]
+    ops.WS_SLOT["i"] = 1
+    try:
+        th = threading.Thread(target=worker); th.start(); th.join()
+        assert seen == {"initial": 0, "set": 3} and ops.WS_SLOT["i"] == 1
+    finally:
+        ops.WS_SLOT["i"] = was

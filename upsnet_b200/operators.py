@@ -652,7 +652,25 @@ def fpn_roi_align(feats, rois, pooled_height, pooled_width, spatial_scales, samp
 # ------------------------------------------------------------------------------------------------
 # NMS
 # ------------------------------------------------------------------------------------------------
-WS_SLOT = {"i": 0}   # engine lane whose scratch buffers the C-ABI calls use (model._run_static sets it around a lane's work)
+import threading
+
+
+class _WsSlot(threading.local):
+    """Engine lane whose scratch buffers the C-ABI calls of THIS THREAD use (model._run_static / PipelinedEngine set it around
+    a lane's work).  Thread-local: the reference's thread-per-GPU DataParallel usage (one Python thread per device) must not
+    see another thread's lane.  Dict-style access (`WS_SLOT["i"]`) is kept for the callers."""
+    i = 0
+
+    def __getitem__(self, k):
+        assert k == "i"
+        return self.i
+
+    def __setitem__(self, k, v):
+        assert k == "i"
+        self.i = int(v)
+
+
+WS_SLOT = _WsSlot()
 
 
 class _Workspace:
