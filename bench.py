@@ -514,6 +514,9 @@ def main():
                 # executed tensor-core work (3 passes in bf16x3) against the same peak: how busy the tensor pipe is
                 "mma_achieved": conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0,
                 "mma_frac": (conv["flops"] / (conv["ms"] * 1e-3) / 1e12 / pk["tf_sustained"]) if conv["ms"] > 0 else 0.0,
+                # `frac` counts ALGORITHMIC flops (2*P*Cout*Cin*k^2, one pass); the fp32-grade product of precision bf16x3 executes
+                # three bf16 tensor-core passes per algorithmic flop, so frac <= 1/3 by construction -- mma_frac counts the passes
+                "frac_ceiling": (1.0 / 3.0) if args.precision == "bf16x3" else 1.0,
                 "families_ms_per_step": {k: round(v["ms"] / n_trace, 4) for k, v in sorted(fam.items())}}
     if "dcn" in fam and fam["dcn"]["ms"] > 0:
         roofline["dcn_tflops"] = dcn_algo / (fam["dcn"]["ms"] * 1e-3) / 1e12
